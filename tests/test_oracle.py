@@ -1,0 +1,140 @@
+"""Pin the CPU oracle against the reference's own outputs (tests/golden made by
+oracle/make_golden.py from /root/reference) -- CPU only."""
+import numpy as np
+import pytest
+
+from oracle import faithful, fast, ref_import
+from tests._util import (assert_kf_threshold_parity, edge_keys, load_golden, small_goldens)
+
+
+@pytest.fixture(params=small_goldens(), ids=lambda p: p.split("small_")[-1][:-4])
+def golden(request):
+    return load_golden(request.param)
+
+
+def _budget_binds(n_nodes, topk, n_ref_edges):
+    if topk is None:
+        return False
+    n = int(n_nodes**2 * topk)
+    return n != 0 and n_ref_edges == n
+
+
+def test_golden_files_present():
+    assert len(small_goldens()) >= 5
+
+
+def test_faithful_matches_reference(golden):
+    g = golden
+    _, pf = faithful.weighted_directed_edges(g["reads"], k=g["k"], stride=g["stride"], inlcudeUNK=False)
+    assert [p[0] for p in pf] == g["pair_u"].tolist()
+    assert [p[1] for p in pf] == g["pair_v"].tolist()
+    assert list(pf.values()) == g["pair_count"].tolist()
+    graph = faithful.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=g["create_all_kmers"])
+    d = faithful.from_networkx(graph)
+    assert d["nodes"] == g["nodes"].tolist()
+    assert np.array_equal(d["edge_index"], g["edge_index"])
+    assert np.array_equal(d["weight"], g["weight64"].astype(np.float32))
+    for s in g["small_ks"]:
+        x = faithful.node_embedding_initial(graph, "kmer_frequency", g["k"], s)
+        assert x.dtype == np.float64 and np.array_equal(x, g[f"x_s{s}"])
+        for j, (thr, topk) in enumerate(g["kf_settings"]):
+            ei, w = faithful.cosine_similarity_to_edge_index_weight(np.vstack(x), threshold=thr, keep_top_k=topk)
+            assert np.array_equal(ei, g[f"kf_s{s}_{j}_edge_index"])
+            assert np.array_equal(w, g[f"kf_s{s}_{j}_weight"])
+
+
+def test_fast_matches_reference(golden):
+    g = golden
+    k = g["k"]
+    u, v, cnt, first = fast.count_pairs(g["reads"], k, g["stride"])
+    assert fast.decode_kmers(u, k) == g["pair_u"].tolist()
+    assert fast.decode_kmers(v, k) == g["pair_v"].tolist()
+    assert cnt.tolist() == g["pair_count"].tolist()
+    assert np.all(np.diff(first) > 0)
+    nodes, ei, w = fast.build_db(u, v, cnt, k, normalise=True, create_all_kmers=g["create_all_kmers"])
+    assert fast.decode_kmers(nodes, k) == g["nodes"].tolist()
+    assert np.array_equal(ei, g["edge_index"])
+    assert np.array_equal(w, g["weight64"])
+    for s in g["small_ks"]:
+        counts = fast.subkmer_counts(nodes, k, s)
+        x, keep = fast.features_from_counts(counts, k, s)
+        assert np.array_equal(x, g[f"x_s{s}"])
+        for j, (thr, topk) in enumerate(g["kf_settings"]):
+            ei_ref, w_ref = g[f"kf_s{s}_{j}_edge_index"], g[f"kf_s{s}_{j}_weight"]
+            ei_o, w_o = fast.kf_edges_exact(counts[:, keep], thr, topk)
+            assert np.all(ei_o[0] < ei_o[1])
+            if _budget_binds(len(nodes), topk, ei_ref.shape[1]):
+                r = fast.tie_aware_compare(ei_o, w_o, ei_ref, w_ref)
+                assert r["ok"], r
+            else:
+                assert_kf_threshold_parity(ei_o, w_o, ei_ref, w_ref, thr)
+                if topk is None and thr in (0.0, 0.8):
+                    # no equality-band artefacts for these thresholds: exact, ordered
+                    assert np.array_equal(ei_o, ei_ref)
+
+
+def test_min_dot_table_is_exact():
+    tab = fast.min_dot_table(0.8, 49 * 49)
+    # cos == 0.8 exactly (dot=4, P=25) must NOT pass: fl(0.8) > 4/5
+    assert tab[25] == 5
+    assert tab[100] == 9          # 8/10 == 0.8 rejected, 9/10 passes
+    tab0 = fast.min_dot_table(0.0, 16)
+    assert np.all(tab0[1:] == 1)
+    with pytest.raises(ValueError):
+        fast.min_dot_table(-0.1, 4)
+
+
+def test_top_n_budget_quirks():
+    assert fast.top_n_budget(100, None, 77) == 77
+    assert fast.top_n_budget(100, 0.01, 1000) == 100
+    assert fast.top_n_budget(100, 0.01, 50) == 50
+    assert fast.top_n_budget(5, 0.01, 9) == 9      # int(25*0.01)=0 -> [-0:] keeps all
+
+
+def test_empty_and_short_reads():
+    for reads in ([], [""], ["AC"], ["ACG"], ["NNNNNN"], ["ACGNACG"]):
+        u, v, c, f = fast.count_pairs(reads, 3, 1)
+        _, pf = faithful.weighted_directed_edges(reads, k=3, stride=1, inlcudeUNK=False)
+        assert len(pf) == u.shape[0]
+    with pytest.raises(IndexError):
+        faithful.build_deBruijn_graph({}, normalise=True)
+    with pytest.raises(ValueError):
+        fast.count_pairs(["ACGX"], 3)
+
+
+def test_internal_N_bridges_non_overlapping_pair():
+    # utils.py:31,79-82: k-mers holding N are deleted before pairing, so the
+    # k-mer before an N run is paired with the first clean k-mer after it.
+    _, pf = faithful.weighted_directed_edges(["ACGTNTTGA"], k=3, stride=1, inlcudeUNK=False)
+    assert ("CGT", "TTG") in pf
+    u, v, c, f = fast.count_pairs(["ACGTNTTGA"], 3)
+    assert list(zip(fast.decode_kmers(u, 3), fast.decode_kmers(v, 3))) == list(pf.keys())
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_live_reference_random_cross_check():
+    ref = ref_import.load()
+    rng = np.random.default_rng(7)
+    for k, stride in [(3, 1), (4, 1), (4, 2), (5, 1)]:
+        reads = []
+        for _ in range(120):
+            ln = int(rng.integers(0, 50))
+            s = "".join("ACGT"[c] for c in rng.integers(0, 4, ln))
+            s = "".join(("N" if rng.random() < 0.04 else ch) for ch in s) + "N" * int(rng.integers(0, 4))
+            reads.append(s)
+        with ref_import.quiet():
+            _, pf = ref.weighted_directed_edges(reads, k=k, stride=stride, inlcudeUNK=False)
+        u, v, cnt, _ = fast.count_pairs(reads, k, stride)
+        assert list(zip(fast.decode_kmers(u, k), fast.decode_kmers(v, k))) == list(pf.keys())
+        assert cnt.tolist() == list(pf.values())
+        for cak in (False, True):
+            for thr, topk in ((None, None), (1.0 / 4**k, 0.3)):
+                with ref_import.quiet():
+                    gr = ref.build_deBruijn_graph(dict(pf), normalise=True, remove_N=True, create_all_kmers=cak,
+                                                  edge_weight_threshold=thr, keep_top_k=topk)
+                nodes, ei, w = fast.build_db(u, v, cnt, k, True, cak, thr, topk)
+                assert fast.decode_kmers(nodes, k) == list(gr.nodes())
+                idx = {n: i for i, n in enumerate(gr.nodes())}
+                ref_ei = np.array([[idx[a], idx[b]] for a, b in gr.edges()], dtype=np.int64).T.reshape(2, -1)
+                assert np.array_equal(ref_ei, ei)
+                assert np.array_equal(np.array([d for _, _, d in gr.edges(data="weight")]), w)
