@@ -1,0 +1,95 @@
+"""ctypes binding of libgg_b200.so (include/gg_b200.h).
+
+The CUDA library IS the product: if it is missing and cannot be built this
+module raises -- there is no CPU or PyTorch fallback behind it.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgg_b200.so")
+
+GG_OK = 0
+GG_SEP = 10
+GG_MAX_K = 13
+GG_KF_BLOCK = 1024
+GG_NO_POS = 0xFFFFFFFFFFFFFFFF
+ST_BAD_BYTES, ST_BRIDGES, ST_CURSOR, ST_REMAINING, ST_NONZERO, ST_WORDS = 0, 1, 2, 3, 4, 8
+KF_IMPL = {"auto": 0, "dp4a": 1, "tcgen05": 2, "naive": 3}
+
+
+class KfParams(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("d", C.c_int32),
+        ("iblock_begin", C.c_int32),
+        ("iblock_end", C.c_int32),
+        ("p_max", C.c_int32),
+        ("fast_shift", C.c_int32),
+        ("impl", C.c_int32),
+    ]
+
+
+_P, _I64, _I32, _SZ, _DBL = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
+
+# name -> (restype, argtypes); mirrors include/gg_b200.h one to one
+SIGNATURES = {
+    "gg_abi_version": (_I32, []),
+    "gg_last_error": (C.c_char_p, []),
+    "gg_stream_padded_bytes": (_SZ, [_I64]),
+    "gg_hist_bins": (_SZ, [_I32]),
+    "gg_count_reset": (_I32, [_I32, _P, _P, _P, _P]),
+    "gg_count_kp1mers": (_I32, [_P, _I64, _I64, _I32, _I64, _P, _P, _I64, _P, _P]),
+    "gg_first_occurrence": (_I32, [_P, _I64, _I64, _I32, _I64, _P, _P, _P, _P]),
+    "gg_db_workspace_bytes": (_SZ, [_I32, _I64]),
+    "gg_db_build": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _DBL, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "gg_kf_counts": (_I32, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "gg_kf_features_f32": (_I32, [_P, _I64, _I32, _P, _I32, _P, _P, _P]),
+    "gg_kf_rowcnt_elems": (_SZ, [_I64, _I32, _I32]),
+    "gg_kf_emit": (_I32, [C.POINTER(KfParams), _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "gg_kf_finalize_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "gg_kf_finalize": (_I32, [C.POINTER(KfParams), _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gg_kf_class_hist": (_I32, [_P, _P, _P, _I64, _P, _I32, _P, _P]),
+    "gg_kf_select_workspace_bytes": (_SZ, [_I64]),
+    "gg_kf_select": (_I32, [_P, _P, _P, _P, _I64, _P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+}
+
+_lib = None
+
+
+class GGError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if the .so is absent) and type the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+
+        try:
+            _build.build()
+        except Exception as exc:  # loud: no fallback path exists
+            raise GGError(f"libgg_b200.so is missing and could not be built: {exc}") from exc
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gg_abi_version() != 1:
+        raise GGError("libgg_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != GG_OK:
+        msg = load().gg_last_error().decode("utf-8", "replace")
+        raise GGError(f"{what} failed with status {rc}: {msg}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,413 @@
+"""Device-level pipeline over the C ABI: torch supplies device memory and
+streams, every computation is a kernel of libgg_b200.so.
+
+Stages: count -> first occurrence -> De Bruijn assembly
+-> sub-k-mer counts / features -> KF edges (threshold, global top-n).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from fractions import Fraction
+from functools import lru_cache
+from math import isqrt
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GGError, KfParams, check, ptr
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise GGError("genomic_gnn_b200 needs a CUDA device: the graph-construction path has no CPU fallback")
+
+
+# --------------------------------------------------------------------------- input marshalling
+@dataclass
+class ReadStream:
+    """ASCII reads resident on the device.  fixed_len > 0: rows of that many
+    bytes back to back; fixed_len == 0: one '\\n' after every read."""
+    data: torch.Tensor  # uint8, padded to gg_stream_padded_bytes
+    n_bytes: int
+    fixed_len: int
+    n_reads: int
+    pos_base: int = 0
+
+
+def _padded(n_bytes):
+    return int(_lib.load().gg_stream_padded_bytes(n_bytes))
+
+
+def pack_reads_host(sequences):
+    """Host-side marshalling: -> (uint8 ndarray view, fixed_len, n_reads)."""
+    if isinstance(sequences, np.ndarray):
+        if sequences.dtype != np.uint8 or sequences.ndim != 2:
+            raise ValueError("ndarray input must be uint8 [n_reads, read_len] ASCII")
+        arr = np.ascontiguousarray(sequences)
+        return arr.reshape(-1), int(arr.shape[1]), int(arr.shape[0])
+    if isinstance(sequences, (bytes, bytearray)):
+        raise ValueError("pass a list of reads, a uint8 [R, L] array or a ReadStream")
+    seqs = list(sequences)
+    if not seqs:
+        return np.zeros(0, np.uint8), 0, 0
+    joined = "\n".join(seqs) + "\n"
+    return np.frombuffer(joined.encode("ascii"), dtype=np.uint8), 0, len(seqs)
+
+
+def upload_reads(sequences, device=None, pos_base=0) -> ReadStream:
+    _require_cuda()
+    if isinstance(sequences, ReadStream):
+        return sequences
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if isinstance(sequences, torch.Tensor):
+        if sequences.dtype != torch.uint8 or sequences.dim() != 2:
+            raise ValueError("tensor input must be uint8 [n_reads, read_len] ASCII")
+        n_reads, fixed_len = int(sequences.shape[0]), int(sequences.shape[1])
+        n_bytes = n_reads * fixed_len
+        buf = torch.empty(_padded(n_bytes), dtype=torch.uint8, device=device)
+        buf[:n_bytes].copy_(sequences.reshape(-1), non_blocking=True)
+        return ReadStream(buf, n_bytes, fixed_len, n_reads, pos_base)
+    flat, fixed_len, n_reads = pack_reads_host(sequences)
+    n_bytes = int(flat.shape[0])
+    buf = torch.empty(_padded(n_bytes), dtype=torch.uint8, device=device)
+    if n_bytes:
+        host = torch.from_numpy(flat)
+        buf[:n_bytes].copy_(host, non_blocking=False)
+    return ReadStream(buf, n_bytes, fixed_len, n_reads, pos_base)
+
+
+# --------------------------------------------------------------------------- K1
+@dataclass
+class CountResult:
+    k: int
+    hist: torch.Tensor        # uint32 as int32 storage [4^(k+1)]
+    first_pos: torch.Tensor   # uint64 as int64 storage [4^(k+1)]
+    bridges: torch.Tensor     # int32 [cap, 4] (u, v, pos_lo, pos_hi) = gg_bridge_t
+    n_bridges: int
+    status: torch.Tensor      # int64 [8]
+    n_nonzero: int = -1
+
+
+def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, first_occurrence: bool = True,
+                  sync: bool = True) -> CountResult:
+    """K1 (+ first-occurrence scan).  Reference: src/utils.py:15-31,52-84."""
+    _require_cuda()
+    lib = _lib.load()
+    if not (1 <= k <= _lib.GG_MAX_K):
+        raise ValueError(f"k must be in [1, {_lib.GG_MAX_K}] for the dense (k+1)-mer histogram")
+    dev = stream.data.device
+    bins = int(lib.gg_hist_bins(k))
+    hist = torch.empty(bins, dtype=torch.int32, device=dev)
+    first = torch.empty(bins, dtype=torch.int64, device=dev)
+    status = torch.empty(_lib.ST_WORDS, dtype=torch.int64, device=dev)
+    while True:
+        bridges = torch.empty((max(bridge_capacity, 1), 4), dtype=torch.int32, device=dev)
+        st = _stream()
+        check(lib.gg_count_reset(k, ptr(hist), ptr(first), ptr(status), st), "gg_count_reset")
+        check(lib.gg_count_kp1mers(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base, ptr(hist),
+                                   ptr(bridges), bridge_capacity, ptr(status), st), "gg_count_kp1mers")
+        if first_occurrence:
+            check(lib.gg_first_occurrence(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
+                                          ptr(hist), ptr(first), ptr(status), st), "gg_first_occurrence")
+        if not sync:
+            return CountResult(k, hist, first, bridges, -1, status)
+        st_host = status.cpu()
+        if int(st_host[_lib.ST_BAD_BYTES]) > 0:
+            raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN "
+                             "(the reference fails on these at gnn_utils.py:471)")
+        nb = int(st_host[_lib.ST_BRIDGES])
+        if nb <= bridge_capacity:
+            return CountResult(k, hist, first, bridges, nb, status, int(st_host[_lib.ST_NONZERO]))
+        bridge_capacity = nb  # rare: many internal N runs -- run again with room for all of them
+
+
+# --------------------------------------------------------------------------- K2
+@dataclass
+class DBGraph:
+    k: int
+    num_nodes: int
+    num_edges: int
+    node_codes: torch.Tensor    # int64 [N] k-mer code of node i
+    code_to_node: torch.Tensor  # int32 [4^k] (-1 = absent)
+    edge_index: torch.Tensor    # int64 [2, E]
+    weight: torch.Tensor        # float32 [E]
+    weight64: torch.Tensor      # float64 [E]
+
+
+def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weight_threshold=None) -> DBGraph:
+    """K2.  Reference: src/utils.py:87-165 + from_networkx."""
+    lib = _lib.load()
+    dev = cr.hist.device
+    k = cr.k
+    bins = cr.hist.numel()
+    cap = bins + cr.n_bridges
+    ws_bytes = int(lib.gg_db_workspace_bytes(k, cr.n_bridges))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    node_codes = torch.empty(4**k, dtype=torch.int64, device=dev)
+    code_to_node = torch.empty(4**k, dtype=torch.int32, device=dev)
+    edges = torch.empty((2, cap), dtype=torch.int64, device=dev)
+    w64 = torch.empty(cap, dtype=torch.float64, device=dev)
+    w32 = torch.empty(cap, dtype=torch.float32, device=dev)
+    ne = torch.empty(2, dtype=torch.int64, device=dev)
+    thr = -1.0 if edge_weight_threshold is None else float(edge_weight_threshold)
+    if edge_weight_threshold is not None and thr < 0:
+        thr = 0.0 if thr == 0 else -1.0  # a negative threshold keeps every edge
+    check(lib.gg_db_build(ptr(cr.hist), ptr(cr.first_pos), ptr(cr.bridges), cr.n_bridges, k, int(bool(normalise)),
+                          int(bool(create_all_kmers)), thr, ptr(node_codes), ptr(code_to_node), ptr(edges[0]),
+                          ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes, _stream()),
+          "gg_db_build")
+    n, e = (int(x) for x in ne.cpu())
+    return DBGraph(k, n, e, node_codes[:n], code_to_node, edges[:, :e].contiguous(), w32[:e], w64[:e])
+
+
+# --------------------------------------------------------------------------- K3
+@dataclass
+class KFCounts:
+    k: int
+    s: int
+    counts: torch.Tensor       # uint8 [N, 4^s]
+    sqnorm: torch.Tensor       # int32 [N]
+    col_keep: torch.Tensor     # int32 [D'] columns that occur at least once
+    @property
+    def m(self):
+        return self.k - self.s + 1
+
+
+def kf_counts(node_codes: torch.Tensor, k: int, s: int) -> KFCounts:
+    """K3.  Reference: gnn_utils.py:454-481."""
+    lib = _lib.load()
+    dev = node_codes.device
+    n = int(node_codes.numel())
+    d = 4**s
+    counts = torch.empty((n, d), dtype=torch.uint8, device=dev)
+    sqnorm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    present = torch.empty(d, dtype=torch.int32, device=dev)
+    check(lib.gg_kf_counts(ptr(node_codes), n, k, s, ptr(counts), ptr(sqnorm), ptr(present), _stream()),
+          "gg_kf_counts")
+    col_keep = torch.nonzero(present, as_tuple=False).reshape(-1).to(torch.int32)
+    return KFCounts(k, s, counts, sqnorm[:n], col_keep)
+
+
+def value_lut(m: int) -> np.ndarray:
+    """float64 feature value of count c: scipy scales the sparse count matrix by the
+    reciprocal (gnn_utils.py:484-485), i.e. c * (1.0 / m), not c / m."""
+    return np.arange(256, dtype=np.float64) * (1.0 / m)
+
+
+def kf_features_f32(kc: KFCounts) -> torch.Tensor:
+    """float32 [N, D'] node features as the GNN receives them
+    (torch.tensor(labels, dtype=torch.float), gnn_tasks/utils.py:38)."""
+    lib = _lib.load()
+    dev = kc.counts.device
+    n, d = kc.counts.shape
+    dk = int(kc.col_keep.numel())
+    lut = torch.from_numpy(value_lut(kc.m).astype(np.float32)).to(dev)
+    x = torch.empty((n, dk), dtype=torch.float32, device=dev)
+    check(lib.gg_kf_features_f32(ptr(kc.counts), n, d, ptr(kc.col_keep), dk, ptr(lut), ptr(x), _stream()),
+          "gg_kf_features_f32")
+    return x
+
+
+# --------------------------------------------------------------------------- K4-K6
+@lru_cache(maxsize=64)
+def threshold_tables(threshold: float, sq_max: int):
+    """Exact-rational threshold tables (host, tiny).
+    dmin[P]: smallest integer dot with dot / sqrt(P) > threshold.
+    fast_scale[sq] = floor(threshold^2 * sq * 2^shift): conservative pre-filter."""
+    if threshold < 0:
+        raise ValueError("negative KF threshold is not supported (the reference would then emit zero-weight "
+                         "lower-triangle pairs)")
+    fr = Fraction(threshold)
+    a2, b2 = fr.numerator**2, fr.denominator**2
+    p_max = sq_max * sq_max
+    dmin = np.empty(p_max + 1, dtype=np.uint16)
+    for p in range(p_max + 1):
+        dmin[p] = min(isqrt((a2 * p) // b2) + 1, 65535)
+    dmin[0] = 65535
+    shift = 31 - max(p_max, 1).bit_length()
+    shift = max(0, min(shift, 24))
+    scale = np.array([(a2 * sq << shift) // b2 for sq in range(sq_max + 1)], dtype=np.uint64)
+    assert int(scale.max()) * sq_max < 2**32 and (p_max << shift) < 2**32
+    return dmin, scale.astype(np.uint32), shift, p_max
+
+
+def top_n_budget(n_nodes: int, keep_top_k: Optional[float], n_candidates: int) -> int:
+    """gnn_utils.py:311-317, including that top_n == 0 keeps everything ([-0:])."""
+    if keep_top_k is None:
+        return n_candidates
+    top_n = min(int(n_nodes**2 * keep_top_k), n_candidates)
+    return n_candidates if top_n == 0 else top_n
+
+
+@dataclass
+class KFEdges:
+    edge_index: torch.Tensor   # int64 [2, E], s < t, reference emission order
+    weight64: torch.Tensor     # float64 [E]
+    weight: torch.Tensor       # float32 [E]
+    n_candidates: int          # pairs above the threshold before the top-n cut
+    cutoff: Optional[float] = None   # score of the cut-off class when top-n was binding
+    tie_kept: int = 0
+    tie_total: int = 0
+    impl: str = "auto"
+
+
+def _row_blocks(n):
+    return (n + _lib.GG_KF_BLOCK - 1) // _lib.GG_KF_BLOCK
+
+
+def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max: int, iblock_begin=0,
+            iblock_end=None, impl="auto", rec_capacity=None):
+    """Score all pairs of the row-block shard and stage the candidates.
+    Returns (recs, n_recs, rowcnt, params)."""
+    lib = _lib.load()
+    dev = counts.device
+    n, d = int(counts.shape[0]), int(counts.shape[1])
+    nb = _row_blocks(n)
+    iblock_end = nb if iblock_end is None else iblock_end
+    dmin, scale, shift, p_max = threshold_tables(float(threshold), int(sq_max))
+    dmin_d = torch.from_numpy(dmin.view(np.int16)).to(dev)
+    scale_d = torch.from_numpy(scale.view(np.int32)).to(dev)
+    params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl])
+    rc_elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
+    rowcnt = torch.empty(max(rc_elems, 1), dtype=torch.int32, device=dev)
+    status = torch.empty(4, dtype=torch.int64, device=dev)
+    if rec_capacity is None:
+        rec_capacity = 1 << 22
+    while True:
+        recs = torch.empty((max(rec_capacity, 1), 4), dtype=torch.int32, device=dev)
+        check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
+                             rec_capacity, ptr(rowcnt), ptr(status), _stream()), "gg_kf_emit")
+        found = int(status[0].item())
+        if found <= rec_capacity:
+            return recs, found, rowcnt, params
+        del recs
+        rec_capacity = found
+
+
+def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=False):
+    lib = _lib.load()
+    dev = sqnorm.device
+    edges = torch.empty((2, max(n_recs, 1)), dtype=torch.int64, device=dev)
+    w64 = torch.empty(max(n_recs, 1), dtype=torch.float64, device=dev)
+    w32 = torch.empty(max(n_recs, 1), dtype=torch.float32, device=dev)
+    dot = torch.empty(max(n_recs, 1), dtype=torch.int32, device=dev) if want_dot else None
+    if n_recs:
+        ws_bytes = int(lib.gg_kf_finalize_workspace_bytes(params.n, params.iblock_begin, params.iblock_end))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.gg_kf_finalize(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(sqnorm), ptr(edges[0]),
+                                 ptr(edges[1]), ptr(w64), ptr(w32), ptr(dot), ptr(ws), ws_bytes, _stream()),
+              "gg_kf_finalize")
+    return edges[:, :n_recs], w64[:n_recs], w32[:n_recs], (dot[:n_recs] if want_dot else None)
+
+
+def choose_cutoff(class_hist: np.ndarray, p_max: int, budget: int):
+    """Host side of K5: order the exact score classes (dot, P) by dot^2 / P as
+    rationals, keep whole classes while they fit, and mark the class that
+    straddles the budget.  Returns (action uint8 table, tie_budget, cutoff score,
+    tie_total)."""
+    keys = np.nonzero(class_hist)[0]
+    dots, ps = keys // (p_max + 1), keys % (p_max + 1)
+    cnt = class_hist[keys].astype(np.int64)
+    vals = [Fraction(int(d) ** 2, int(p)) for d, p in zip(dots, ps)]
+    order = sorted(range(len(keys)), key=lambda i: vals[i], reverse=True)
+    action = np.zeros(class_hist.shape[0], dtype=np.uint8)
+    taken, i = 0, 0
+    tie_budget, cutoff, tie_total = 0, None, 0
+    while i < len(order) and taken < budget:
+        j = i
+        while j < len(order) and vals[order[j]] == vals[order[i]]:
+            j += 1
+        grp = [order[x] for x in range(i, j)]
+        size = int(cnt[grp].sum())
+        if taken + size <= budget:
+            action[keys[grp]] = 1
+            taken += size
+        else:
+            action[keys[grp]] = 2
+            tie_budget, tie_total = budget - taken, size
+            cutoff = float(dots[grp[0]]) / float(np.sqrt(float(ps[grp[0]])))
+            taken = budget
+        i = j
+    return action, tie_budget, cutoff, tie_total
+
+
+def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
+             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None,
+             n_nodes_for_budget: Optional[int] = None) -> KFEdges:
+    """K4-K6 on one GPU.  Reference: gnn_utils.py:240-322."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = counts.device
+    n = int(counts.shape[0])
+    empty = KFEdges(torch.zeros((2, 0), dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.float64, device=dev),
+                    torch.zeros(0, dtype=torch.float32, device=dev), 0, impl=impl)
+    if threshold < 0:
+        raise ValueError("negative KF threshold is not supported")
+    if n < 2 or threshold >= 1.0:
+        return empty
+    if sq_max is None:
+        sq_max = int(sqnorm.max().item())
+    if sq_max == 0:
+        return empty
+    recs, n_recs, rowcnt, params = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl)
+    budget = top_n_budget(n if n_nodes_for_budget is None else n_nodes_for_budget, keep_top_k, n_recs)
+    need_cut = budget < n_recs
+    ei, w64, w32, dot = kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=need_cut)
+    del recs, rowcnt
+    if not need_cut:
+        return KFEdges(ei.contiguous(), w64, w32, n_recs, impl=impl)
+    p_max = params.p_max
+    n_classes = (sq_max + 1) * (p_max + 1)
+    hist = torch.zeros(n_classes, dtype=torch.int64, device=dev)
+    src, dst = ei[0].contiguous(), ei[1].contiguous()
+    check(lib.gg_kf_class_hist(ptr(src), ptr(dst), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(hist), _stream()),
+          "gg_kf_class_hist")
+    action, tie_budget, cutoff, tie_total = choose_cutoff(hist.cpu().numpy(), p_max, budget)
+    action_d = torch.from_numpy(action).to(dev)
+    out = torch.empty((2, budget), dtype=torch.int64, device=dev)
+    o64 = torch.empty(budget, dtype=torch.float64, device=dev)
+    o32 = torch.empty(budget, dtype=torch.float32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int64, device=dev)
+    ws_bytes = int(lib.gg_kf_select_workspace_bytes(n_recs))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.gg_kf_select(ptr(src), ptr(dst), ptr(w64), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(action_d),
+                           tie_budget, ptr(out[0]), ptr(out[1]), ptr(o64), ptr(o32), ptr(cnt), ptr(ws), ws_bytes,
+                           _stream()), "gg_kf_select")
+    kept = int(cnt.item())
+    if kept != budget:
+        raise GGError(f"top-n select kept {kept} edges, expected {budget}")
+    return KFEdges(out, o64, o32, n_recs, cutoff, tie_budget, tie_total, impl)
+
+
+# --------------------------------------------------------------------------- whole path on one GPU
+@dataclass
+class BuiltGraph:
+    k: int
+    db: DBGraph
+    kf_counts: List[KFCounts]
+    x: List[torch.Tensor]              # float32 [N, D'_i] per small_k
+    kf: List[KFEdges] = field(default_factory=list)
+
+
+def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_threshold=0.0, edges_keep_top_k=None,
+                kf_impl="auto", with_kf=True) -> BuiltGraph:
+    """kmer_ssgnn.py:162-213 + sampling_task.py:128-161 on one GPU."""
+    stream = upload_reads(sequences)
+    cr = count_kp1mers(stream, k)
+    if cr.n_nonzero == 0 and cr.n_bridges == 0:
+        raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
+    db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
+    small = [int(s) for s in str(small_k).split(",")]
+    kcs = [kf_counts(db.node_codes, k, s) for s in small]
+    xs = [kf_features_f32(kc) for kc in kcs]
+    out = BuiltGraph(k, db, kcs, xs)
+    if with_kf:
+        for kc in kcs:
+            out.kf.append(kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m,
+                                   impl=kf_impl))
+    return out

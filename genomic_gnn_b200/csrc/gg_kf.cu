@@ -1,0 +1,482 @@
+// K4-K6: KF cosine-similarity edges -- SIMT scoring kernels, ordered
+// compaction and the global top-n select.
+//
+// Replaces cosine_similarity_to_edge_index_weight (reference
+// gnn_utils.py:240-322).  Feature rows are small integer counts, so
+// cos(i,j) = dot / sqrt(sq_i sq_j) with integer dot and the strict test
+// cos > threshold is evaluated exactly as dot >= dmin[sq_i * sq_j].
+//
+//   kf_dp4a_kernel<W>   D = 4W <= 64 columns: the row lives in registers, the
+//                       1024-column panel of block J in shared memory; 4 dp4a
+//                       per pair at D = 16.  ALU-issue bound (K = 16 is too
+//                       shallow for the tensor pipe to matter).
+//   kf_generic_kernel   any D that is a multiple of 64: register-tiled 128x32
+//                       scores per pass, dp4a over 64-byte slabs.  Validation
+//                       and fall-back path for the tcgen05 kernel (gg_kf_mma.cu).
+#include <cub/cub.cuh>
+
+#include "gg_kf_emit.cuh"
+
+namespace ggkf {
+int emit_tcgen05(const KfArgs& a, cudaStream_t s);  // gg_kf_mma.cu
+}
+
+namespace {
+
+using namespace ggkf;
+
+struct Unit {
+  int i_block, i_local, j_block, strip;
+  bool active;
+};
+
+__device__ __forceinline__ Unit decode_unit(const KfArgs& a) {
+  Unit u;
+  const long long id = blockIdx.x;
+  u.strip = static_cast<int>(id % kStripsPerBlock);
+  const long long rest = id / kStripsPerBlock;
+  u.j_block = static_cast<int>(rest % a.n_jblocks);
+  u.i_local = static_cast<int>(rest / a.n_jblocks);
+  u.i_block = a.ib0 + u.i_local;
+  u.active = u.j_block >= u.i_block && static_cast<long long>(u.i_block) * kBlock + u.strip * kStrip < a.n;
+  return u;
+}
+
+__device__ __forceinline__ bool fast_pass(uint32_t dot, uint32_t scale_i, uint32_t sq_j, int shift) {
+  return ((dot * dot) << shift) > scale_i * sq_j;
+}
+
+// ---------------------------------------------------------------------------- D <= 64
+template <int W>
+__global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* colw = reinterpret_cast<uint32_t*>(smem_raw);                         // [kBlock][W]
+  uint16_t* sqn = reinterpret_cast<uint16_t*>(colw + kBlock * W);                 // [kBlock]
+  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kBlock);                 // [4]
+
+  const Unit un = decode_unit(a);
+  if (!un.active) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpStage& ws = stages[warp];
+  if (lane == 0) ws.fill = 0;
+  __syncwarp();
+
+  const long long col0 = static_cast<long long>(un.j_block) * kBlock;
+  const int cols_in_block = static_cast<int>(min(static_cast<long long>(kBlock), a.n - col0));
+  for (int c = tid; c < kBlock; c += kStrip) {
+    const bool ok = c < cols_in_block;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.counts + (col0 + c) * a.d);
+#pragma unroll
+    for (int w = 0; w < W; ++w) colw[c * W + w] = ok ? __ldg(src + w) : 0u;
+    sqn[c] = ok ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
+  }
+
+  const int r = un.strip * kStrip + tid;  // block-local row
+  const long long s = static_cast<long long>(un.i_block) * kBlock + r;
+  const bool row_ok = s < a.n;
+  uint32_t row[W];
+  uint32_t sq_i = 0, scale_i = 0;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.counts + (row_ok ? s : 0) * a.d);
+#pragma unroll
+    for (int w = 0; w < W; ++w) row[w] = row_ok ? __ldg(src + w) : 0u;
+    if (row_ok) {
+      sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
+      scale_i = __ldg(a.fast_scale + sq_i);
+    }
+  }
+  __syncthreads();
+
+  const bool diag = un.i_block == un.j_block;
+  uint32_t row_cnt = 0;
+  // diagonal block: columns <= r contribute nothing, skip whole chunks below the strip
+  const int c_begin = diag ? (un.strip * kStrip) & ~31 : 0;
+  for (int c0 = c_begin; c0 < cols_in_block; c0 += 32) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t* cw = colw + (c0 + b) * W;
+      uint32_t dot = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) dot = __dp4a(row[w], cw[w], dot);
+      mask |= static_cast<uint32_t>(fast_pass(dot, scale_i, sqn[c0 + b], a.fast_shift)) << b;
+    }
+    mask &= chunk_col_mask(cols_in_block, c0);
+    if (diag) mask &= chunk_diag_mask(r, c0);
+    if (!row_ok) mask = 0;
+    if (__any_sync(0xFFFFFFFFu, mask != 0)) {
+      int n_l = 0;
+      for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {
+        const int b = __ffs(m2) - 1;
+        const uint32_t* cw = colw + (c0 + b) * W;
+        uint32_t dot = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) dot = __dp4a(row[w], cw[w], dot);
+        if (dot >= __ldg(a.dmin + sq_i * sqn[c0 + b])) ws.scratch[n_l++][lane] = static_cast<uint16_t>((dot << 5) | b);
+      }
+      stage_commit(ws, a.out, lane, n_l, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), row_cnt);
+    }
+  }
+  stage_flush(ws, a.out, lane);
+  if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r)] = row_cnt;
+}
+
+// ---------------------------------------------------------------------------- any D % 64 == 0
+constexpr int kSlabWords = 16;  // 64 bytes of a row per pass
+
+__global__ void __launch_bounds__(kStrip) kf_generic_kernel(KfArgs a) {
+  __shared__ __align__(16) uint32_t colw[32 * kSlabWords];
+  __shared__ uint16_t sqn[32];
+  __shared__ WarpStage stages[kStrip / 32];
+
+  const Unit un = decode_unit(a);
+  if (!un.active) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpStage& ws = stages[warp];
+  if (lane == 0) ws.fill = 0;
+  __syncwarp();
+
+  const long long col0 = static_cast<long long>(un.j_block) * kBlock;
+  const int cols_in_block = static_cast<int>(min(static_cast<long long>(kBlock), a.n - col0));
+  const int r = un.strip * kStrip + tid;
+  const long long s = static_cast<long long>(un.i_block) * kBlock + r;
+  const bool row_ok = s < a.n;
+  uint32_t sq_i = 0, scale_i = 0;
+  if (row_ok) {
+    sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
+    scale_i = __ldg(a.fast_scale + sq_i);
+  }
+  const uint4* row_ptr = reinterpret_cast<const uint4*>(a.counts + (row_ok ? s : 0) * a.d);
+  const int n_slabs = a.d / (4 * kSlabWords);
+  const bool diag = un.i_block == un.j_block;
+  uint32_t row_cnt = 0;
+  const int c_begin = diag ? (un.strip * kStrip) & ~31 : 0;
+
+  for (int c0 = c_begin; c0 < cols_in_block; c0 += 32) {
+    uint32_t acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0;
+    for (int slab = 0; slab < n_slabs; ++slab) {
+      __syncthreads();
+      {  // 128 threads x one uint4 = 32 columns x 64 bytes
+        const int c = tid >> 2, part = tid & 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c0 + c < cols_in_block)
+          v = __ldg(reinterpret_cast<const uint4*>(a.counts + (col0 + c0 + c) * a.d) + slab * 4 + part);
+        reinterpret_cast<uint4*>(colw)[c * 4 + part] = v;
+        if (slab == 0 && tid < 32)
+          sqn[tid] = (c0 + tid < cols_in_block) ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c0 + tid)) : 0;
+      }
+      __syncthreads();
+      uint32_t row[kSlabWords];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = row_ok ? __ldg(row_ptr + slab * 4 + q) : make_uint4(0, 0, 0, 0);
+        row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+#pragma unroll
+        for (int w = 0; w < kSlabWords; ++w) acc[b] = __dp4a(row[w], colw[b * kSlabWords + w], acc[b]);
+      }
+    }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) mask |= static_cast<uint32_t>(fast_pass(acc[b], scale_i, sqn[b], a.fast_shift)) << b;
+    mask &= chunk_col_mask(cols_in_block, c0);
+    if (diag) mask &= chunk_diag_mask(r, c0);
+    if (!row_ok) mask = 0;
+    if (__any_sync(0xFFFFFFFFu, mask != 0)) {
+      int n_l = 0;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        if ((mask >> b) & 1u) {
+          if (acc[b] >= __ldg(a.dmin + sq_i * sqn[b])) ws.scratch[n_l++][lane] = static_cast<uint16_t>((acc[b] << 5) | b);
+        }
+      }
+      stage_commit(ws, a.out, lane, n_l, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), row_cnt);
+    }
+  }
+  stage_flush(ws, a.out, lane);
+  if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r)] = row_cnt;
+}
+
+template <int W>
+int launch_dp4a(const KfArgs& a, long long units, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(kBlock) * W * 4 + kBlock * 2 + (kStrip / 32) * sizeof(WarpStage);
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kf_dp4a_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  kf_dp4a_kernel<W><<<static_cast<unsigned>(units), kStrip, smem, s>>>(a);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+// ---------------------------------------------------------------------------- ordered compaction
+struct ToU64 {
+  __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
+};
+
+__global__ void __launch_bounds__(256) scatter_kernel(const gg_kf_rec_t* recs, long long n_recs,
+                                                      const unsigned long long* offsets, const int32_t* sqnorm,
+                                                      int ib0, int n_jblocks, int64_t* src, int64_t* dst, double* w64,
+                                                      float* w32, uint32_t* dot_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_recs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 rc = __ldg(reinterpret_cast<const uint4*>(recs) + i);
+    const uint32_t s = rc.x, t = rc.y;
+    const long long idx = rowcnt_index(static_cast<int>(s / kBlock) - ib0, n_jblocks, static_cast<int>(t / kBlock),
+                                       static_cast<int>(s % kBlock));
+    const unsigned long long pos = offsets[idx] + rc.z;
+    src[pos] = s;
+    dst[pos] = t;
+    const double p = static_cast<double>(static_cast<long long>(sqnorm[s]) * static_cast<long long>(sqnorm[t]));
+    const double w = static_cast<double>(rc.w) / sqrt(p);
+    if (w64) w64[pos] = w;
+    if (w32) w32[pos] = static_cast<float>(w);
+    if (dot_out) dot_out[pos] = rc.w;
+  }
+}
+
+// ---------------------------------------------------------------------------- global top-n
+__device__ __forceinline__ uint32_t class_key(const int64_t* src, const int64_t* dst, const uint32_t* dot,
+                                              const int32_t* sqnorm, int32_t p_max, long long i) {
+  const uint32_t p = static_cast<uint32_t>(sqnorm[src[i]]) * static_cast<uint32_t>(sqnorm[dst[i]]);
+  return dot[i] * static_cast<uint32_t>(p_max + 1) + p;
+}
+
+__global__ void __launch_bounds__(256) class_hist_kernel(const int64_t* src, const int64_t* dst, const uint32_t* dot,
+                                                         long long n, const int32_t* sqnorm, int32_t p_max,
+                                                         unsigned long long* hist) {
+  for (long long base = blockIdx.x * static_cast<long long>(blockDim.x); base < n;
+       base += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const bool ok = i < n;
+    const uint32_t key = ok ? class_key(src, dst, dot, sqnorm, p_max, i) : 0xFFFFFFFFu;
+    // few distinct classes: one atomic per class per warp
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (ok && (__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(hist + key, static_cast<unsigned long long>(__popc(peers)));
+  }
+}
+
+__global__ void __launch_bounds__(256) tie_flag_kernel(const int64_t* src, const int64_t* dst, const uint32_t* dot,
+                                                       long long n, const int32_t* sqnorm, int32_t p_max,
+                                                       const uint8_t* action, uint8_t* act_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    act_out[i] = action[class_key(src, dst, dot, sqnorm, p_max, i)];
+}
+
+struct IsTie {
+  __host__ __device__ unsigned long long operator()(uint8_t a) const { return a == 2 ? 1ull : 0ull; }
+};
+
+__global__ void __launch_bounds__(256) keep_flag_kernel(const uint8_t* act, const unsigned long long* tie_rank,
+                                                        long long n, long long tie_budget, uint8_t* keep) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    keep[i] = act[i] == 1 || (act[i] == 2 && static_cast<long long>(tie_rank[i]) < tie_budget);
+}
+
+struct IsKept {
+  __host__ __device__ unsigned long long operator()(uint8_t a) const { return a ? 1ull : 0ull; }
+};
+
+__global__ void __launch_bounds__(256) select_scatter_kernel(const uint8_t* keep, const unsigned long long* pos,
+                                                             long long n, const int64_t* src, const int64_t* dst,
+                                                             const double* w64, int64_t* o_src, int64_t* o_dst,
+                                                             double* o_w64, float* o_w32, int64_t* out_count) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (keep[i]) {
+      const unsigned long long p = pos[i];
+      o_src[p] = src[i];
+      o_dst[p] = dst[i];
+      if (o_w64) o_w64[p] = w64[i];
+      if (o_w32) o_w32[p] = static_cast<float>(w64[i]);
+    }
+    if (i == n - 1) *out_count = static_cast<int64_t>(pos[i] + (keep[i] ? 1 : 0));
+  }
+}
+
+inline int grid_for(long long n) {
+  long long g = (n + 255) / 256;
+  const long long cap = static_cast<long long>(gg::sm_count()) * 8;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : static_cast<int>(g);
+}
+
+template <typename Op, typename In>
+size_t scan_temp_bytes(long long n) {
+  size_t bytes = 0;
+  cub::TransformInputIterator<unsigned long long, Op, const In*> it(nullptr, Op());
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, static_cast<unsigned long long*>(nullptr), n);
+  return bytes;
+}
+
+int check_params(const gg_kf_params_t* p) {
+  GG_REQUIRE(p != nullptr, GG_ERR_ARG, "null params");
+  GG_REQUIRE(p->n >= 0 && p->n <= (1ll << 24), GG_ERR_ARG, "n outside [0, 2^24]");
+  GG_REQUIRE(p->d >= 4 && p->d % 4 == 0, GG_ERR_ARG, "d must be a positive multiple of 4");
+  const int n_blocks = static_cast<int>((p->n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
+  GG_REQUIRE(p->iblock_begin >= 0 && p->iblock_begin <= p->iblock_end && p->iblock_end <= n_blocks, GG_ERR_ARG,
+             "row-block shard outside [0, ceil(n/1024)]");
+  GG_REQUIRE(p->p_max >= 0 && p->fast_shift >= 0 && p->fast_shift < 32, GG_ERR_ARG, "bad threshold tables");
+  return GG_OK;
+}
+
+}  // namespace
+
+extern "C" size_t gg_kf_rowcnt_elems(int64_t n, int iblock_begin, int iblock_end) {
+  if (n <= 0 || iblock_end <= iblock_begin) return 0;
+  const size_t nj = static_cast<size_t>((n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
+  return static_cast<size_t>(iblock_end - iblock_begin) * nj * GG_KF_BLOCK;
+}
+
+extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const int32_t* sqnorm, const uint16_t* dmin,
+                          const uint32_t* fast_scale, gg_kf_rec_t* recs, int64_t rec_capacity, uint32_t* rowcnt,
+                          int64_t* kf_status, gg_stream_t st) {
+  if (int rc = check_params(p)) return rc;
+  GG_REQUIRE(kf_status, GG_ERR_ARG, "null status");
+  cudaStream_t s = gg::as_stream(st);
+  GG_CUDA_CHECK(cudaMemsetAsync(kf_status, 0, 4 * sizeof(int64_t), s));
+  const size_t rc_elems = gg_kf_rowcnt_elems(p->n, p->iblock_begin, p->iblock_end);
+  if (rc_elems == 0) return GG_OK;
+  GG_REQUIRE(counts && sqnorm && dmin && fast_scale && rowcnt, GG_ERR_ARG, "null buffer");
+  GG_REQUIRE(rec_capacity >= 0 && (rec_capacity == 0 || recs), GG_ERR_ARG, "record buffer");
+  GG_REQUIRE((reinterpret_cast<uintptr_t>(counts) & 15) == 0 && (reinterpret_cast<uintptr_t>(recs) & 15) == 0,
+             GG_ERR_ARG, "counts / recs must be 16-byte aligned");
+  GG_CUDA_CHECK(cudaMemsetAsync(rowcnt, 0, rc_elems * sizeof(uint32_t), s));
+
+  KfArgs a;
+  a.counts = counts;
+  a.sqnorm = sqnorm;
+  a.dmin = dmin;
+  a.fast_scale = fast_scale;
+  a.n = p->n;
+  a.d = p->d;
+  a.ib0 = p->iblock_begin;
+  a.ib1 = p->iblock_end;
+  a.n_jblocks = static_cast<int>((p->n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
+  a.fast_shift = p->fast_shift;
+  a.rowcnt = rowcnt;
+  a.out.recs = recs;
+  a.out.capacity = rec_capacity;
+  a.out.status = reinterpret_cast<unsigned long long*>(kf_status);
+
+  int impl = p->impl;
+  if (impl == GG_KF_IMPL_AUTO) impl = p->d <= 64 ? GG_KF_IMPL_DP4A : GG_KF_IMPL_NAIVE;  // TODO tcgen05 once validated
+  const long long units = static_cast<long long>(a.ib1 - a.ib0) * a.n_jblocks * kStripsPerBlock;
+  GG_REQUIRE(units < (1ll << 31), GG_ERR_ARG, "too many work units for one launch; shard the row blocks");
+  switch (impl) {
+    case GG_KF_IMPL_DP4A:
+      if (p->d == 4) return launch_dp4a<1>(a, units, s);
+      if (p->d == 16) return launch_dp4a<4>(a, units, s);
+      if (p->d == 64) return launch_dp4a<16>(a, units, s);
+      gg::set_error("dp4a KF kernel supports d in {4, 16, 64}, got %d", p->d);
+      return GG_ERR_ARG;
+    case GG_KF_IMPL_TCGEN05:
+      GG_REQUIRE(p->d % 128 == 0, GG_ERR_ARG, "tcgen05 KF kernel needs d % 128 == 0");
+      return ggkf::emit_tcgen05(a, s);
+    case GG_KF_IMPL_NAIVE:
+      GG_REQUIRE(p->d % 64 == 0, GG_ERR_ARG, "generic KF kernel needs d % 64 == 0");
+      kf_generic_kernel<<<static_cast<unsigned>(units), kStrip, 0, s>>>(a);
+      GG_CUDA_CHECK(cudaGetLastError());
+      return GG_OK;
+    default:
+      gg::set_error("unknown KF impl %d", impl);
+      return GG_ERR_ARG;
+  }
+}
+
+extern "C" size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end) {
+  const size_t elems = gg_kf_rowcnt_elems(n, iblock_begin, iblock_end);
+  gg::Carver c(nullptr);
+  c.take<unsigned long long>(elems ? elems : 1);
+  c.take<char>(scan_temp_bytes<ToU64, uint32_t>(static_cast<long long>(elems ? elems : 1)));
+  return c.used();
+}
+
+extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, int64_t n_recs, const uint32_t* rowcnt,
+                              const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64,
+                              float* weight32, uint32_t* dot_out, void* workspace, size_t workspace_bytes,
+                              gg_stream_t st) {
+  if (int rc = check_params(p)) return rc;
+  GG_REQUIRE(n_recs >= 0, GG_ERR_ARG, "negative record count");
+  if (n_recs == 0) return GG_OK;
+  GG_REQUIRE(recs && rowcnt && sqnorm && edge_src && edge_dst && workspace, GG_ERR_ARG, "null buffer");
+  GG_REQUIRE(workspace_bytes >= gg_kf_finalize_workspace_bytes(p->n, p->iblock_begin, p->iblock_end),
+             GG_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t s = gg::as_stream(st);
+  const long long elems = static_cast<long long>(gg_kf_rowcnt_elems(p->n, p->iblock_begin, p->iblock_end));
+  gg::Carver c(workspace);
+  unsigned long long* offsets = c.take<unsigned long long>(elems);
+  size_t tb = scan_temp_bytes<ToU64, uint32_t>(elems);
+  void* temp = c.take<char>(tb);
+  cub::TransformInputIterator<unsigned long long, ToU64, const uint32_t*> it(rowcnt, ToU64());
+  GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb, it, offsets, elems, s));
+  const int n_jblocks = static_cast<int>((p->n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
+  scatter_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, sqnorm, p->iblock_begin, n_jblocks, edge_src,
+                                                  edge_dst, weight64, weight32, dot_out);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+extern "C" int gg_kf_class_hist(const int64_t* edge_src, const int64_t* edge_dst, const uint32_t* dot, int64_t n_edges,
+                                const int32_t* sqnorm, int32_t p_max, unsigned long long* class_hist, gg_stream_t st) {
+  GG_REQUIRE(n_edges >= 0 && p_max >= 0, GG_ERR_ARG, "bad size");
+  if (n_edges == 0) return GG_OK;
+  GG_REQUIRE(edge_src && edge_dst && dot && sqnorm && class_hist, GG_ERR_ARG, "null buffer");
+  class_hist_kernel<<<grid_for(n_edges), 256, 0, gg::as_stream(st)>>>(edge_src, edge_dst, dot, n_edges, sqnorm, p_max,
+                                                                     class_hist);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+extern "C" size_t gg_kf_select_workspace_bytes(int64_t n_edges) {
+  const long long n = n_edges > 0 ? n_edges : 1;
+  gg::Carver c(nullptr);
+  c.take<uint8_t>(n);
+  c.take<uint8_t>(n);
+  c.take<unsigned long long>(n);
+  c.take<unsigned long long>(n);
+  c.take<char>(scan_temp_bytes<IsTie, uint8_t>(n));
+  return c.used();
+}
+
+extern "C" int gg_kf_select(const int64_t* edge_src, const int64_t* edge_dst, const double* weight64,
+                            const uint32_t* dot, int64_t n_edges, const int32_t* sqnorm, int32_t p_max,
+                            const uint8_t* class_action, int64_t tie_budget, int64_t* out_src, int64_t* out_dst,
+                            double* out_w64, float* out_w32, int64_t* out_count, void* workspace,
+                            size_t workspace_bytes, gg_stream_t st) {
+  GG_REQUIRE(n_edges >= 0 && p_max >= 0 && out_count, GG_ERR_ARG, "bad size");
+  cudaStream_t s = gg::as_stream(st);
+  GG_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(int64_t), s));
+  if (n_edges == 0) return GG_OK;
+  GG_REQUIRE(edge_src && edge_dst && weight64 && dot && sqnorm && class_action && out_src && out_dst && workspace,
+             GG_ERR_ARG, "null buffer");
+  GG_REQUIRE(workspace_bytes >= gg_kf_select_workspace_bytes(n_edges), GG_ERR_WORKSPACE, "workspace too small");
+  gg::Carver c(workspace);
+  uint8_t* act = c.take<uint8_t>(n_edges);
+  uint8_t* keep = c.take<uint8_t>(n_edges);
+  unsigned long long* tie_rank = c.take<unsigned long long>(n_edges);
+  unsigned long long* pos = c.take<unsigned long long>(n_edges);
+  size_t tb = scan_temp_bytes<IsTie, uint8_t>(n_edges);
+  void* temp = c.take<char>(tb);
+  const int g = grid_for(n_edges);
+  tie_flag_kernel<<<g, 256, 0, s>>>(edge_src, edge_dst, dot, n_edges, sqnorm, p_max, class_action, act);
+  {
+    cub::TransformInputIterator<unsigned long long, IsTie, const uint8_t*> it(act, IsTie());
+    size_t b = tb;
+    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, b, it, tie_rank, n_edges, s));
+  }
+  keep_flag_kernel<<<g, 256, 0, s>>>(act, tie_rank, n_edges, tie_budget, keep);
+  {
+    cub::TransformInputIterator<unsigned long long, IsKept, const uint8_t*> it(keep, IsKept());
+    size_t b = tb;
+    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, b, it, pos, n_edges, s));
+  }
+  select_scatter_kernel<<<g, 256, 0, s>>>(keep, pos, n_edges, edge_src, edge_dst, weight64, out_src, out_dst, out_w64,
+                                          out_w32, out_count);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}

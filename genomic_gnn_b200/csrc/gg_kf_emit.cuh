@@ -1,0 +1,112 @@
+// Candidate emission shared by every KF scoring kernel (SIMT dp4a, SIMT
+// generic, tcgen05).  One thread owns one row s of a 128-row strip and walks
+// the columns of a reference block pair (I, J) in increasing t, so the rank of
+// a candidate inside (row, block pair) is a running per-thread counter; that
+// rank plus a prefix sum over per-row counts reproduces the reference's
+// emission order (gnn_utils.py:262-301) without sorting.
+#pragma once
+#include "gg_common.cuh"
+
+namespace ggkf {
+
+constexpr int kBlock = GG_KF_BLOCK;  // rows / columns of a reference block
+constexpr int kStrip = 128;          // rows per CTA (one per thread)
+constexpr int kStripsPerBlock = kBlock / kStrip;
+constexpr int kStageCap = 128;       // records staged per warp before a coalesced flush
+
+struct EmitOut {
+  gg_kf_rec_t* recs;
+  long long capacity;
+  unsigned long long* status;  // [0] candidates (also the global write cursor)
+};
+
+struct KfArgs {
+  const uint8_t* counts;
+  const int32_t* sqnorm;
+  const uint16_t* dmin;
+  const uint32_t* fast_scale;
+  long long n;
+  int d;
+  int ib0, ib1;
+  int n_jblocks;
+  int fast_shift;
+  uint32_t* rowcnt;
+  EmitOut out;
+};
+
+struct WarpStage {
+  uint4 rec[kStageCap];
+  uint16_t scratch[32][32];  // [entry][lane]: (dot << 5) | column bit
+  int fill;
+  int pad[3];
+};
+
+__device__ __forceinline__ void stage_flush(WarpStage& ws, const EmitOut& out, int lane) {
+  const int fill = ws.fill;  // warp-uniform
+  if (fill == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(out.status, static_cast<unsigned long long>(fill));
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  uint4* dst = reinterpret_cast<uint4*>(out.recs);
+  for (int i = lane; i < fill; i += 32)
+    if (static_cast<long long>(base + i) < out.capacity) dst[base + i] = ws.rec[i];
+  __syncwarp();
+  if (lane == 0) ws.fill = 0;
+  __syncwarp();
+}
+
+// Every lane has pushed n_l entries into ws.scratch[.][lane]; turn them into
+// records.  Must be called by the whole warp.
+__device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, int lane, int n_l, uint32_t s,
+                                             uint32_t t0, uint32_t& row_cnt) {
+  int incl = n_l;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  if (total == 0) return;
+  const int off = incl - n_l;
+  if (total > kStageCap) {  // dense chunk: bypass the stage
+    stage_flush(ws, out, lane);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(out.status, static_cast<unsigned long long>(total));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0) + off;
+    uint4* dst = reinterpret_cast<uint4*>(out.recs);
+    for (int i = 0; i < n_l; ++i) {
+      const uint32_t e = ws.scratch[i][lane];
+      if (static_cast<long long>(base + i) < out.capacity)
+        dst[base + i] = make_uint4(s, t0 + (e & 31u), row_cnt + i, e >> 5);
+    }
+  } else {
+    if (ws.fill + total > kStageCap) stage_flush(ws, out, lane);
+    const int fill = ws.fill;
+    for (int i = 0; i < n_l; ++i) {
+      const uint32_t e = ws.scratch[i][lane];
+      ws.rec[fill + off + i] = make_uint4(s, t0 + (e & 31u), row_cnt + i, e >> 5);
+    }
+    __syncwarp();
+    if (lane == 0) ws.fill = fill + total;
+    __syncwarp();
+  }
+  row_cnt += n_l;
+}
+
+// valid-column bits of the 32-column chunk starting at block-local column c0
+__device__ __forceinline__ uint32_t chunk_col_mask(int cols_in_block, int c0) {
+  const int left = cols_in_block - c0;
+  return left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+}
+
+// strict upper triangle inside a diagonal block: keep block-local columns > r
+__device__ __forceinline__ uint32_t chunk_diag_mask(int r, int c0) {
+  const int first = r + 1 - c0;  // first kept bit
+  return first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : ~((1u << first) - 1u));
+}
+
+__device__ __forceinline__ long long rowcnt_index(int i_local, int n_jblocks, int j, int r) {
+  return (static_cast<long long>(i_local) * n_jblocks + j) * kBlock + r;
+}
+
+}  // namespace ggkf

@@ -1,0 +1,197 @@
+/*
+ * gg_b200.h -- C ABI of the B200-native k-mer graph-construction hot path.
+ *
+ * This is the drop-in boundary for the graph-construction path of
+ * ratschlab/genomic-gnn.  The reference is pure Python and has no FFI of its
+ * own; each entry point below states which reference function it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with "h_";
+ *   - every call is asynchronous on the caller's stream (gg_stream_t is a
+ *     cudaStream_t) and allocates nothing: workspaces are caller-owned and
+ *     sized by the *_workspace_bytes() queries;
+ *   - return value: GG_OK or a negative GG_ERR_* (argument / launch errors
+ *     only -- data-dependent results such as "bad byte seen" or "capacity
+ *     exceeded" are written to the device status words documented per call,
+ *     because the host does not synchronise inside these calls);
+ *   - no global state: calls are re-entrant, one stream per call.
+ *
+ * k-mer code: base-4 value of the string with A,C,G,T = 0,1,2,3 and the first
+ * base most significant (reference: itertools.product(ALPHABET, repeat=k),
+ * src/utils.py:125 and gnn_utils.py:458-459).
+ */
+#ifndef GG_B200_H
+#define GG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gg_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define GG_API __attribute__((visibility("default")))
+#else
+#define GG_API
+#endif
+
+#define GG_ABI_VERSION 1
+#define GG_OK 0
+#define GG_ERR_ARG (-1)      /* null pointer, negative size, misaligned buffer */
+#define GG_ERR_K (-2)        /* k / small_k outside the supported range */
+#define GG_ERR_CUDA (-5)     /* a CUDA runtime call failed; see gg_last_error() */
+#define GG_ERR_WORKSPACE (-6)/* workspace smaller than *_workspace_bytes() */
+
+#define GG_SEP 10            /* '\n': hard read boundary in a separator-delimited stream */
+#define GG_MAX_K 13          /* dense (k+1)-mer histogram: 4^(k+1) uint32 bins */
+#define GG_KF_BLOCK 1024     /* reference chunk_size (gnn_utils.py:241); fixes edge order */
+#define GG_NO_POS 0xFFFFFFFFFFFFFFFFull
+
+GG_API int gg_abi_version(void);
+GG_API const char* gg_last_error(void); /* thread-local, valid until the next failing call */
+
+/* ------------------------------------------------------------------------
+ * K1  counting.  Replaces seq_to_kmers + weighted_directed_edges
+ *     (src/utils.py:15-31, 52-84) for stride 1, inlcudeUNK=False.
+ *
+ * Input: ASCII bytes.  fixed_len > 0: reads are back-to-back rows of exactly
+ * fixed_len bytes; fixed_len == 0: every read is followed by one GG_SEP byte.
+ * Bytes allowed: A C G T N (and GG_SEP when fixed_len == 0); anything else is
+ * counted in status[GG_ST_BAD_BYTES] (the reference would fail later with a
+ * KeyError at gnn_utils.py:471).  The buffer must be 16-byte aligned and
+ * readable up to gg_stream_padded_bytes(n_bytes); padding content is ignored.
+ *
+ * A pair of consecutive clean k-mers is one (k+1)-mer: hist[(u << 2) | last
+ * base of v] += 1.  k-mers holding an N are deleted before pairing
+ * (utils.py:31), so the k-mer before an N run pairs with the first clean k-mer
+ * after it: such "bridge" pairs that are not (k-1)-overlapping go to the
+ * bridges list, overlapping ones are folded into hist.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  uint32_t u, v; /* k-mer codes */
+  uint64_t pos;  /* global stream offset of u's first base */
+} gg_bridge_t;
+
+enum {
+  GG_ST_BAD_BYTES = 0, /* bytes outside the alphabet */
+  GG_ST_BRIDGES = 1,   /* bridge records found (may exceed capacity: then re-run larger) */
+  GG_ST_CURSOR = 2,    /* internal: chunk cursor of gg_first_occurrence */
+  GG_ST_REMAINING = 3, /* internal: bins whose first occurrence is still unknown */
+  GG_ST_NONZERO = 4,   /* non-zero (k+1)-mer bins */
+  GG_ST_WORDS = 8
+};
+
+GG_API size_t gg_stream_padded_bytes(int64_t n_bytes);
+GG_API size_t gg_hist_bins(int k); /* 4^(k+1) */
+
+/* zero hist, set first_pos to GG_NO_POS, zero status[GG_ST_WORDS] */
+GG_API int gg_count_reset(int k, uint32_t* hist, uint64_t* first_pos, int64_t* status, gg_stream_t st);
+
+/* accumulate one shard of reads into hist (may be called repeatedly). pos_base is
+ * the global stream offset of stream[0] (multi-GPU / multi-call first-occurrence keys). */
+GG_API int gg_count_kp1mers(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len, int k, int64_t pos_base,
+                     uint32_t* hist, gg_bridge_t* bridges, int64_t bridge_capacity, int64_t* status,
+                     gg_stream_t st);
+
+/* first_pos[e] = min global offset at which (k+1)-mer e starts.  Scans the shard
+ * in order and stops as soon as every non-zero bin of `hist` has been seen
+ * (hist must already hold this shard's counts).  Defines dict insertion order
+ * (utils.py:82) and, through it, node order (utils.py:131-143). */
+GG_API int gg_first_occurrence(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len, int k, int64_t pos_base,
+                        const uint32_t* hist, uint64_t* first_pos, int64_t* status, gg_stream_t st);
+
+/* ------------------------------------------------------------------------
+ * K2  De Bruijn graph.  Replaces build_deBruijn_graph (src/utils.py:87-165)
+ *     + torch_geometric.utils.from_networkx (gnn_tasks/utils.py:37).
+ *
+ * Nodes in first-occurrence order (or lexicographic when create_all_kmers);
+ * edges grouped by source in node order, inside a source by first occurrence
+ * of the pair; weight = count / out-count(source) in float64 (normalise) or
+ * the raw count.  edge_weight_threshold < 0 disables the strict `>` filter
+ * of utils.py:139-141.  out_ne[0] = N, out_ne[1] = E.
+ * ------------------------------------------------------------------------ */
+GG_API size_t gg_db_workspace_bytes(int k, int64_t n_bridges);
+GG_API int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, const gg_bridge_t* bridges, int64_t n_bridges,
+                int k, int normalise, int create_all_kmers, double edge_weight_threshold,
+                int64_t* node_codes, int32_t* code_to_node, int64_t* edge_src, int64_t* edge_dst,
+                double* weight64, float* weight32, int64_t edge_capacity, int64_t* out_ne,
+                void* workspace, size_t workspace_bytes, gg_stream_t st);
+
+/* ------------------------------------------------------------------------
+ * K3  node features.  Replaces node_embedding_initial(method="kmer_frequency")
+ *     (gnn_utils.py:428-493).  counts[i, c] = occurrences of s-mer c in node i;
+ *     sqnorm[i] = sum_c counts^2; col_present[c] != 0 iff some node has it
+ *     (gnn_utils.py:474-481 drops the others).  gg_kf_features_f32 gathers the
+ *     kept columns through a 256-entry value table (float32(c * (1/(k-s+1)))).
+ * ------------------------------------------------------------------------ */
+GG_API int gg_kf_counts(const int64_t* node_codes, int64_t n, int k, int s, uint8_t* counts, int32_t* sqnorm,
+                 uint32_t* col_present, gg_stream_t st);
+GG_API int gg_kf_features_f32(const uint8_t* counts, int64_t n, int d, const int32_t* col_keep, int d_keep,
+                       const float* value_lut, float* x, gg_stream_t st);
+
+/* ------------------------------------------------------------------------
+ * K4-K6  KF similarity edges.  Replaces cosine_similarity_to_edge_index_weight
+ *     (gnn_utils.py:240-322).
+ *
+ * cos(i,j) = dot / sqrt(sqnorm_i * sqnorm_j) with integer dot: the strict test
+ * cos > threshold is evaluated exactly as dot >= dmin[sqnorm_i * sqnorm_j]
+ * (dmin built on the host from the float64 threshold as a rational).
+ *
+ * gg_kf_emit scores every pair s < t with s in the row blocks
+ * [iblock_begin, iblock_end) (GG_KF_BLOCK rows each; multi-GPU sharding unit),
+ * writes one record per candidate (unordered) and per-(block pair,row) counts.
+ * gg_kf_finalize turns the counts into offsets and scatters the records into
+ * the reference's emission order: block (I, J >= I), then row, then column.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  uint32_t s, t;
+  uint32_t rank; /* rank of t among the candidates of row s inside block pair (I,J) */
+  uint32_t dot;
+} gg_kf_rec_t;
+
+enum { GG_KF_IMPL_AUTO = 0, GG_KF_IMPL_DP4A = 1, GG_KF_IMPL_TCGEN05 = 2, GG_KF_IMPL_NAIVE = 3 };
+
+typedef struct {
+  int64_t n;            /* nodes */
+  int32_t d;            /* columns of counts (4^s, multiple of 4) */
+  int32_t iblock_begin; /* row-block shard */
+  int32_t iblock_end;
+  int32_t p_max;        /* dmin has p_max + 1 entries */
+  int32_t fast_shift;   /* fast pre-filter: (dot*dot) << fast_shift > fast_scale[sqnorm_i] * sqnorm_j */
+  int32_t impl;         /* GG_KF_IMPL_* */
+} gg_kf_params_t;
+
+/* kf_status (device int64[4]): [0] candidates found (may exceed rec_capacity: re-run larger),
+ * [1] records written, [2..3] reserved. */
+GG_API size_t gg_kf_rowcnt_elems(int64_t n, int iblock_begin, int iblock_end);
+GG_API int gg_kf_emit(const gg_kf_params_t* h_params, const uint8_t* counts, const int32_t* sqnorm,
+               const uint16_t* dmin, const uint32_t* fast_scale /* [max sqnorm + 1] */,
+               gg_kf_rec_t* recs, int64_t rec_capacity, uint32_t* rowcnt, int64_t* kf_status, gg_stream_t st);
+
+GG_API size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end);
+GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint32_t* rowcnt,
+                   const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
+                   uint32_t* dot_out /* nullable: dot per edge, for top-n */, void* workspace, size_t workspace_bytes,
+                   gg_stream_t st);
+
+/* K5  global top-n (gnn_utils.py:311-317).  Histogram of exact score classes
+ * (dot, P = sqnorm_s * sqnorm_t) over finalised edges, then a stable select:
+ * class_action[dot * (p_max+1) + P] = 1 keep, 2 cut-off class (keep the first
+ * `tie_budget` in emission order), 0 drop.  out_count[0] = edges kept. */
+GG_API int gg_kf_class_hist(const int64_t* edge_src, const int64_t* edge_dst, const uint32_t* dot, int64_t n_edges,
+                     const int32_t* sqnorm, int32_t p_max, unsigned long long* class_hist, gg_stream_t st);
+GG_API size_t gg_kf_select_workspace_bytes(int64_t n_edges);
+GG_API int gg_kf_select(const int64_t* edge_src, const int64_t* edge_dst, const double* weight64, const uint32_t* dot,
+                 int64_t n_edges, const int32_t* sqnorm, int32_t p_max, const uint8_t* class_action,
+                 int64_t tie_budget, int64_t* out_src, int64_t* out_dst, double* out_w64, float* out_w32,
+                 int64_t* out_count, void* workspace, size_t workspace_bytes, gg_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_B200_H */

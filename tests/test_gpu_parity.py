@@ -1,0 +1,272 @@
+"""CUDA path vs the reference (golden fixtures) and vs the CPU oracle.
+
+All tests call through the reference-signature API / the C ABI of
+libgg_b200.so.  Bar: bit-exact counts, node order, DB edge_index and float32
+weights; KF edge sets exact outside the |cos - thr| <= 1e-12 equality band,
+float32 KF weights bit-exact, float64 within 1e-12 relative.
+"""
+import hashlib
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fast
+from tests._util import GOLDEN, assert_kf_threshold_parity, load_golden, small_goldens, sort_edges
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gg():
+    import genomic_gnn_b200 as g
+
+    return g
+
+
+def _sha(arr):
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+def _budget_binds(n_nodes, topk, n_ref_edges):
+    if topk is None:
+        return False
+    n = int(n_nodes**2 * topk)
+    return n != 0 and n_ref_edges == n
+
+
+# --------------------------------------------------------------------------- reference goldens
+@pytest.mark.parametrize("path", small_goldens(), ids=lambda p: os.path.basename(p)[6:-4])
+def test_api_matches_reference_golden(gg, path):
+    g = load_golden(path)
+    k = g["k"]
+    if g["stride"] != 1:
+        with pytest.raises(NotImplementedError):
+            gg.weighted_directed_edges(g["reads"], k=k, stride=g["stride"], inlcudeUNK=False)
+        return
+    item, pf = gg.weighted_directed_edges(g["reads"], k=k, stride=1, inlcudeUNK=False)
+    assert [p[0] for p in pf] == g["pair_u"].tolist()
+    assert [p[1] for p in pf] == g["pair_v"].tolist()
+    assert list(pf.values()) == g["pair_count"].tolist()
+    assert sum(item.values()) == int(g["pair_count"].sum())
+    graph = gg.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=g["create_all_kmers"])
+    assert graph.nodes() == g["nodes"].tolist()
+    assert graph.number_of_nodes() == len(g["nodes"])
+    assert np.array_equal(graph.edge_index.cpu().numpy(), g["edge_index"])
+    assert graph.edge_index.dtype == torch.int64 and graph.weight.dtype == torch.float32
+    assert np.array_equal(graph.weight.cpu().numpy().view(np.int32), g["weight64"].astype(np.float32).view(np.int32))
+    assert np.array_equal(graph.db.weight64.cpu().numpy(), g["weight64"])
+    for s in g["small_ks"]:
+        lab = gg.node_embedding_initial(graph, method="kmer_frequency", k=k, small_k=s)
+        x_ref = g[f"x_s{s}"]
+        assert lab.shape == x_ref.shape
+        assert np.array_equal(np.asarray(lab), x_ref)
+        assert np.array_equal(lab.to_torch_float32().cpu().numpy(), x_ref.astype(np.float32))
+        for j, (thr, topk) in enumerate(g["kf_settings"]):
+            ei_ref, w_ref = g[f"kf_s{s}_{j}_edge_index"], g[f"kf_s{s}_{j}_weight"]
+            for X in (lab, np.vstack(lab)):  # device-resident labels and the plain ndarray the reference passes
+                ei, w = gg.cosine_similarity_to_edge_index_weight(X, threshold=thr, keep_top_k=topk)
+                assert ei.dtype == np.int64 and w.dtype == np.float64 and ei.shape[0] == 2
+                assert np.all(ei[0] < ei[1])
+                if _budget_binds(len(g["nodes"]), topk, ei_ref.shape[1]):
+                    r = fast.tie_aware_compare(ei, w, ei_ref, w_ref)
+                    assert r["ok"], r
+                else:
+                    assert_kf_threshold_parity(ei, w, ei_ref, w_ref, thr)
+                    if topk is None and thr in (0.0, 0.8):
+                        assert np.array_equal(ei, ei_ref)  # same emission order as the reference
+
+
+def test_plain_dict_input_to_build(gg):
+    g = load_golden(os.path.join(GOLDEN, "small_k4_ragged_N.npz"))
+    pf = {(u, v): int(c) for u, v, c in zip(g["pair_u"], g["pair_v"], g["pair_count"])}
+    graph = gg.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=False)
+    assert graph.nodes() == g["nodes"].tolist()
+    assert np.array_equal(graph.edge_index.cpu().numpy(), g["edge_index"])
+    assert np.array_equal(graph.db.weight64.cpu().numpy(), g["weight64"])
+
+
+# --------------------------------------------------------------------------- digests of full reference runs
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "digest_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[7:-4])
+def test_matches_reference_digest(gg, path):
+    z = np.load(path)
+    n_reads, k, seed = int(z["n_reads"]), int(z["k"]), int(z["seed"])
+    thr = float(z["threshold"])
+    topk = None if float(z["keep_top_k"]) < 0 else float(z["keep_top_k"])
+    small_ks = sorted(int(f.split("_")[1][1:]) for f in z.files if f.endswith("_E"))
+    reads = fast.synthetic_reads(n_reads, 150, seed=seed)
+    from genomic_gnn_b200 import core
+
+    built = core.build_graph(reads, k, ",".join(map(str, small_ks)), edges_threshold=thr, edges_keep_top_k=topk)
+    db = built.db
+    assert db.num_nodes == int(z["num_nodes"]) and db.num_edges == int(z["num_db_edges"])
+    assert _sha(db.node_codes.cpu().numpy()) == str(z["node_codes_sha"])
+    assert _sha(db.edge_index.cpu().numpy()) == str(z["db_edge_index_sha"])
+    assert _sha(db.weight.cpu().numpy()) == str(z["db_weight_sha"])
+    for i, s in enumerate(small_ks):
+        assert _sha(built.x[i].cpu().numpy()) == str(z[f"x_s{s}_sha_f32"])
+        kf = built.kf[i]
+        ei, w32 = kf.edge_index.cpu().numpy(), kf.weight.cpu().numpy()
+        assert ei.shape[1] == int(z[f"kf_s{s}_E"])
+        budget = int(db.num_nodes**2 * topk) if topk is not None else None
+        if budget and ei.shape[1] == budget and kf.cutoff is not None:
+            # top-n bound: everything strictly above the cut-off class must match the reference
+            wmin = float(z[f"kf_s{s}_wmin"])
+            above = kf.weight64.cpu().numpy() > wmin * (1 + 1e-9)
+            assert int(above.sum()) == int(z[f"kf_s{s}_n_above_wmin"])
+            keys, _ = sort_edges(ei[:, above], w32[above])
+            assert _sha(keys) == str(z[f"kf_s{s}_above_set_sha"])
+            rest = kf.weight64.cpu().numpy()[~above]
+            assert np.all(np.abs(rest - wmin) <= 1e-9 * wmin)
+            assert abs(kf.cutoff - wmin) <= 1e-12
+        else:
+            keys, ws = sort_edges(ei, w32)
+            assert _sha(keys) == str(z[f"kf_s{s}_set_sha"])
+            assert _sha(ws) == str(z[f"kf_s{s}_w32_sha"])
+
+
+# --------------------------------------------------------------------------- oracle on seeded inputs
+@pytest.mark.parametrize("k,n_reads,small_k,thr,topk", [
+    (3, 10_000, "2", 0.0, None),          # BASELINE config 1
+    (6, 20_000, "2,5", 0.0, 0.01),        # config 2 shape, top-n binding
+    (7, 30_000, "2,5", 0.8, 0.01),        # config 3 shape, threshold binding
+    (5, 3_000, "1,3", 0.55, None),
+])
+def test_pipeline_matches_oracle(gg, k, n_reads, small_k, thr, topk):
+    from genomic_gnn_b200 import core
+
+    reads = fast.synthetic_reads(n_reads, 150, seed=k)
+    want = fast.build_graph(reads, k, small_k, edges_threshold=thr, edges_keep_top_k=topk)
+    got = core.build_graph(reads, k, small_k, edges_threshold=thr, edges_keep_top_k=topk)
+    assert np.array_equal(got.db.node_codes.cpu().numpy(), want["node_codes"])
+    assert np.array_equal(got.db.edge_index.cpu().numpy(), want["edge_index"])
+    assert np.array_equal(got.db.weight.cpu().numpy().view(np.int32), want["weight"].view(np.int32))
+    for i in range(len(small_k.split(","))):
+        assert np.array_equal(got.kf_counts[i].counts.cpu().numpy(), want[f"counts_{i}"])
+        assert np.array_equal(got.x[i].cpu().numpy(), want[f"y_{i}"])
+        # the oracle states the same deterministic tie policy, so even the top-n case is exact and ordered
+        assert np.array_equal(got.kf[i].edge_index.cpu().numpy(), want[f"edge_index_KF{i}"])
+        assert np.array_equal(got.kf[i].weight64.cpu().numpy(), want[f"edge_weight_KF{i}"])
+
+
+def test_kf_impls_agree(gg):
+    """dp4a (D = 64) and the generic slab kernel must emit identical edges."""
+    from genomic_gnn_b200 import core
+
+    reads = fast.synthetic_reads(4000, 150, seed=11)
+    built = core.build_graph(reads, 6, "3", with_kf=False)
+    kc = built.kf_counts[0]
+    a = core.kf_edges(kc.counts, kc.sqnorm, 0.5, None, sq_max=kc.m**2, impl="dp4a")
+    b = core.kf_edges(kc.counts, kc.sqnorm, 0.5, None, sq_max=kc.m**2, impl="naive")
+    assert a.edge_index.shape[1] > 0
+    assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
+
+
+def test_kf_row_block_shards_concatenate(gg):
+    """Row-block shards (the multi-GPU unit) concatenate to the single-GPU result."""
+    from genomic_gnn_b200 import core
+
+    reads = fast.synthetic_reads(5000, 150, seed=3)
+    built = core.build_graph(reads, 6, "2", with_kf=False)   # N = 4096 -> 4 row blocks
+    kc = built.kf_counts[0]
+    full = core.kf_edges(kc.counts, kc.sqnorm, 0.8, None, sq_max=kc.m**2)
+    parts = [core.kf_edges(kc.counts, kc.sqnorm, 0.8, None, sq_max=kc.m**2, iblock_begin=b, iblock_end=b + 1)
+             for b in range(4)]
+    assert torch.equal(torch.cat([p.edge_index for p in parts], dim=1), full.edge_index)
+    assert torch.equal(torch.cat([p.weight64 for p in parts]), full.weight64)
+
+
+# --------------------------------------------------------------------------- edge cases
+def test_input_forms_agree(gg):
+    from genomic_gnn_b200 import core
+
+    arr = fast.synthetic_reads(500, 37, seed=5)
+    strs = fast.reads_to_strings(arr)
+    outs = []
+    for inp in (arr, strs, torch.from_numpy(arr).cuda()):
+        b = core.build_graph(inp, 4, "2", with_kf=False)
+        outs.append((b.db.node_codes.cpu().numpy(), b.db.edge_index.cpu().numpy(), b.db.weight.cpu().numpy()))
+    for o in outs[1:]:
+        for x, y in zip(outs[0], o):
+            assert np.array_equal(x, y)
+
+
+def test_degenerate_inputs(gg):
+    with pytest.raises((ValueError, IndexError)):
+        _, pf = gg.weighted_directed_edges([], k=3, inlcudeUNK=False)
+        gg.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=False)
+    with pytest.raises((ValueError, IndexError)):
+        _, pf = gg.weighted_directed_edges(["AC", "", "NNNNNNN", "ACG"], k=3, inlcudeUNK=False)
+        assert len(pf) == 0
+        gg.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=False)
+    with pytest.raises(ValueError):
+        gg.weighted_directed_edges(["ACGTXACGT"], k=3, inlcudeUNK=False)
+    with pytest.raises(ValueError):
+        gg.weighted_directed_edges(["acgtacgt"], k=3, inlcudeUNK=False)
+    with pytest.raises(NotImplementedError):
+        gg.weighted_directed_edges(["ACGT"], k=3, inlcudeUNK=True)
+    with pytest.raises(ValueError):
+        gg.node_embedding_initial(_FakeGraph(), method="kmer_frequency", k=3)
+
+
+class _FakeGraph:
+    def number_of_nodes(self):
+        return 0
+
+
+def test_internal_n_bridge(gg):
+    _, pf = gg.weighted_directed_edges(["ACGTNTTGA", "ACGTNTTGA", "CCCNNNCCCC"], k=3, inlcudeUNK=False)
+    u, v, c, _ = fast.count_pairs(["ACGTNTTGA", "ACGTNTTGA", "CCCNNNCCCC"], 3)
+    assert list(pf.keys()) == list(zip(fast.decode_kmers(u, 3), fast.decode_kmers(v, 3)))
+    assert list(pf.values()) == c.tolist()
+    assert pf[("CGT", "TTG")] == 2          # non-overlapping bridge
+    assert pf[("CCC", "CCC")] == 3          # overlapping bridge folded into the (k+1)-mer bin + 2 ordinary
+
+
+def test_skewed_low_complexity_reads(gg):
+    from genomic_gnn_b200 import core
+
+    rng = np.random.default_rng(9)
+    reads = ["A" * 150] * 400 + ["AC" * 75] * 300 + ["ACGT" * 37 + "AC"] * 300
+    reads += fast.reads_to_strings(fast.synthetic_reads(200, 150, seed=2))
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    want = fast.build_graph(reads, 5, "2", edges_threshold=0.8)
+    got = core.build_graph(reads, 5, "2", edges_threshold=0.8)
+    assert np.array_equal(got.db.node_codes.cpu().numpy(), want["node_codes"])
+    assert np.array_equal(got.db.edge_index.cpu().numpy(), want["edge_index"])
+    assert np.array_equal(got.db.weight.cpu().numpy(), want["weight"])
+    assert np.array_equal(got.kf[0].edge_index.cpu().numpy(), want["edge_index_KF0"])
+
+
+# --------------------------------------------------------------------------- full-size properties (BASELINE config 4)
+def test_full_size_properties_k8_1m(gg):
+    from genomic_gnn_b200 import core
+
+    n_reads, k, length = 1_000_000, 8, 150
+    reads = fast.synthetic_reads(n_reads, length, seed=0)
+    stream = core.upload_reads(reads)
+    cr = core.count_kp1mers(stream, k)
+    hist = cr.hist.cpu().numpy().view(np.uint32)
+    assert int(hist.astype(np.int64).sum()) == n_reads * (length - k)       # every window counted once
+    first = cr.first_pos.cpu().numpy().view(np.uint64)
+    assert np.all(first[hist > 0] < n_reads * length) and len(np.unique(first[hist > 0])) == int((hist > 0).sum())
+    # checksum of checksums: the first 100k reads alone reproduce the reference digest's DB graph order
+    db = core.build_db(cr)
+    assert db.num_nodes == 4**k and db.num_edges == 4 ** (k + 1)
+    z = np.load(os.path.join(GOLDEN, "digest_cfg4_k8_100k.npz"))
+    # node order is decided by first occurrences, all of which lie in the first 100k reads for this seed
+    assert _sha(db.node_codes.cpu().numpy()) == str(z["node_codes_sha"])
+    assert _sha(db.edge_index.cpu().numpy()) == str(z["db_edge_index_sha"])
+    w = db.weight64.cpu().numpy()
+    src = db.edge_index[0].cpu().numpy()
+    assert np.all(np.diff(src) >= 0)                                        # grouped by source in node order
+    assert np.allclose(np.bincount(src, weights=w), 1.0, rtol=0, atol=1e-12)
+    kc = core.kf_counts(db.node_codes, k, 2)
+    kf = core.kf_edges(kc.counts, kc.sqnorm, 0.8, 0.01, sq_max=kc.m**2)
+    assert kf.edge_index.shape[1] == int(z["kf_s2_E"])                       # depends on the node set only
+    keys, ws = sort_edges(kf.edge_index.cpu().numpy(), kf.weight.cpu().numpy())
+    assert _sha(keys) == str(z["kf_s2_set_sha"]) and _sha(ws) == str(z["kf_s2_w32_sha"])
