@@ -76,8 +76,10 @@ def upload_reads(sequences, device=None, pos_base=0) -> ReadStream:
     n_bytes = int(flat.shape[0])
     buf = torch.empty(_padded(n_bytes), dtype=torch.uint8, device=device)
     if n_bytes:
-        host = torch.from_numpy(flat)
-        buf[:n_bytes].copy_(host, non_blocking=False)
+        staging = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+        staging.numpy()[:] = flat
+        buf[:n_bytes].copy_(staging, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # staging buffer is released on return
     return ReadStream(buf, n_bytes, fixed_len, n_reads, pos_base)
 
 

@@ -223,7 +223,7 @@ def test_internal_n_bridge(gg):
     assert list(pf.keys()) == list(zip(fast.decode_kmers(u, 3), fast.decode_kmers(v, 3)))
     assert list(pf.values()) == c.tolist()
     assert pf[("CGT", "TTG")] == 2          # non-overlapping bridge
-    assert pf[("CCC", "CCC")] == 3          # overlapping bridge folded into the (k+1)-mer bin + 2 ordinary
+    assert pf[("CCC", "CCC")] == 2          # one overlapping bridge folded into the (k+1)-mer bin + one ordinary
 
 
 def test_skewed_low_complexity_reads(gg):
