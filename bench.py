@@ -1,0 +1,376 @@
+"""bench.py -- k=8 graph-build throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step is ONE full graph construction over one batch of synthetic reads:
+counts -> first occurrences -> De Bruijn assembly -> sub-k-mer features ->
+all KF edge sets.  Workload = BASELINE config 4 (k=8, small_k=2,5,
+threshold 0.8, top-k 0.01, 1M synthetic 150-bp reads); with N GPUs the SAME
+1M reads are split over the ranks (strong scaling).
+
+value  reads/s with the reads already resident in HBM (CUDA events, max over ranks)
+e2e    reads/s through the public API from pinned HOST reads, H2D of the reads and
+       D2H of every graph tensor inside the timed region
+The reference arm (--impl reference) times the oracle's faithful CPU port of the
+reference (pure-Python counting, blocked float64 numpy cosine) on the host cores
+of the same box, on a bounded sample scaled to the full workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_FLUSH_BYTES = 256 << 20
+# kernels of libgg_b200.so launched by one step (CUB sort/scan kernels and memsets not counted):
+# K1 count+pending+first = 3, K2 = 6, K3 counts+features = 2 per small_k, K4 emit + K6 scatter = 2 per small_k
+OUR_LAUNCHES_PER_STEP = lambda n_small: 3 + 6 + 4 * n_small  # noqa: E731
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--k", type=int, default=8)
+    ap.add_argument("--small-k", default="2,5")
+    ap.add_argument("--threshold", type=float, default=0.8)
+    ap.add_argument("--top-k", type=float, default=0.01)
+    ap.add_argument("--kf-impl", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end loop")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"config4: k={a.k}, small_k={a.small_k}, KF threshold={a.threshold}, top_k={a.top_k}, "
+            f"{a.reads} synthetic {a.read_len}-bp reads (uniform ACGT, seed 0)")
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p["bf16_tflops"]), "source": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_sample(a, reads_arr, count_reads=20_000, kf_row_blocks=1, feat_nodes=8192):
+    """Bounded sample of the reference's CPU path, scaled to the full workload.
+    Returns (estimated seconds for the full workload, description, detail dict)."""
+    from oracle import fast, faithful
+
+    k, n_total = a.k, a.reads
+    count_reads = min(count_reads, n_total)
+    sample = fast.reads_to_strings(reads_arr[:count_reads])
+    t0 = time.perf_counter()
+    _, pf = faithful.weighted_directed_edges(sample, k=k, stride=1, inlcudeUNK=False)
+    t_count = (time.perf_counter() - t0) * (n_total / count_reads)
+    t0 = time.perf_counter()
+    g = faithful.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=False)
+    t_db = time.perf_counter() - t0
+    nodes = g.nodes()
+    n_nodes = len(nodes)
+    codes = None
+    detail = {"count_s_scaled": t_count, "db_s": t_db, "n_nodes": n_nodes}
+    t_feat = t_kf = 0.0
+    nb = (n_nodes + 1023) // 1024
+    rb = min(kf_row_blocks, nb)
+    pair_scale = (nb * (nb + 1) / 2) / sum(nb - i for i in range(rb))
+    for s in (int(x) for x in a.small_k.split(",")):
+        sub = nodes[: min(feat_nodes, n_nodes)]
+        t0 = time.perf_counter()
+        faithful.node_embedding_initial(sub, "kmer_frequency", k, s)
+        tf = (time.perf_counter() - t0) * (n_nodes / len(sub))
+        if codes is None:
+            lut = np.zeros(256, np.int64)
+            lut[np.frombuffer(b"ACGT", np.uint8)] = np.arange(4)
+            arr = np.frombuffer("".join(nodes).encode(), np.uint8).reshape(n_nodes, k)
+            codes = np.zeros(n_nodes, np.int64)
+            for j in range(k):
+                codes = codes * 4 + lut[arr[:, j]]
+        x, _ = fast.features_from_counts(fast.subkmer_counts(codes, k, s), k, s)  # untimed: input of the timed KF sample
+        t0 = time.perf_counter()
+        faithful.cosine_similarity_to_edge_index_weight(x, threshold=a.threshold, keep_top_k=None, row_blocks=rb)
+        tk = (time.perf_counter() - t0) * pair_scale
+        detail[f"feat_s{s}_s_scaled"] = tf
+        detail[f"kf_s{s}_s_scaled"] = tk
+        t_feat += tf
+        t_kf += tk
+    total = t_count + t_db + t_feat + t_kf
+    desc = (f"counting: first {count_reads} reads x{n_total / count_reads:.0f}; DB assembly in full; features: first "
+            f"{min(feat_nodes, n_nodes)} nodes x{n_nodes / min(feat_nodes, n_nodes):.0f}; KF: first {rb} of {nb} row blocks "
+            f"x{pair_scale:.1f} by block pairs; counting/features are single-thread Python, KF is numpy/BLAS")
+    return total, desc, detail
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(a, rank):
+    if rank != 0:
+        return
+    from genomic_gnn_b200.synth import synthetic_reads
+
+    reads = synthetic_reads(min(a.reads, 50_000), a.read_len, seed=0)
+    vals, desc, detail = [], "", {}
+    for i in range(a.warmup + a.steps):
+        total_s, desc, detail = cpu_reference_sample(a, reads)
+        if i >= a.warmup:
+            vals.append(total_s)
+    sec = statistics.mean(vals)
+    value = a.reads / sec
+    line = {
+        "impl": "reference", "metric": f"k={a.k} graph-build reads/sec", "value": value, "unit": "reads/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": blas_threads(), "kind": "port", "sample": desc,
+                         "host_cpus": os.cpu_count(), "detail": detail},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        import torch
+
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.file.read().strip().splitlines():
+            cols = [c.strip() for c in row.split(",")]
+            if len(cols) < 7:
+                continue
+            try:
+                sm.append(float(cols[0]))
+                mx.append(float(cols[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, cols[3:7]):
+                if val == "Active":
+                    reasons.add(name)
+        os.unlink(self.file.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- our arm
+def to_host_pinned(tensors):
+    """Async D2H of every tensor into pinned memory; returns (host tensors, bytes)."""
+    import torch
+
+    out, nbytes = [], 0
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        out.append(h)
+        nbytes += t.numel() * t.element_size()
+    return out, nbytes
+
+
+def graph_tensors(built):
+    ts = [built.db.node_codes, built.db.edge_index, built.db.weight]
+    ts += list(built.x)
+    for kf in built.kf:
+        ts += [kf.edge_index, kf.weight]
+    return ts
+
+
+def run_ours(a):
+    import torch
+
+    from genomic_gnn_b200 import core, dist as ggdist
+    from genomic_gnn_b200.synth import synthetic_reads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = ggdist.TorchComm()
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+
+    reads_all = synthetic_reads(a.reads, a.read_len, seed=0)
+    lo, hi = ggdist.shard_bounds(a.reads, world, rank)
+    reads_host = torch.from_numpy(reads_all[lo:hi].copy()).pin_memory()
+    pos_base = lo * a.read_len
+    resident = core.upload_reads(reads_host, pos_base=pos_base)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    n_small = len(a.small_k.split(","))
+    kw = dict(k=a.k, small_k=a.small_k, edges_threshold=a.threshold, edges_keep_top_k=a.top_k, kf_impl=a.kf_impl,
+              comm=comm)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return core.build_graph(resident, **kw)
+
+    def step_e2e():
+        stream = core.upload_reads(reads_host, pos_base=pos_base)     # H2D of this step's reads (pinned source)
+        built = core.build_graph(stream, **kw)
+        host, nbytes = to_host_pinned(graph_tensors(built)) if rank == 0 else ([], 0)
+        torch.cuda.current_stream().synchronize()                     # results are on the host
+        return built, nbytes
+
+    def timed_loop(fn, steps, warmup, timer=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        core.set_timer(timer)
+        total_ms, last = 0.0, None
+        for _ in range(steps):
+            flush.fill_(1)                                            # evict L2 between timed iterations
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            last = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        core.set_timer(None)
+        barrier()
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), last
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    timer = core.StageTimer()
+    total_ms, built = timed_loop(step_resident, a.steps, a.warmup, timer)
+    stage_ms = {k_: statistics.mean(v) for k_, v in timer.summary().items()}
+    if a.no_e2e:
+        e2e_ms, d2h_bytes = float("nan"), 0
+    else:
+        e2e_ms, (_, d2h_bytes) = timed_loop(step_e2e, a.steps, max(a.warmup, 3))
+    clock_info = clocks.stop() if clocks else None
+
+    ms_per_step = total_ms / a.steps
+    value = a.reads / (ms_per_step * 1e-3)
+    kf_ms = sum(v for k_, v in stage_ms.items() if k_.startswith(("k4_", "k5_", "k6_", "c2_")))
+    kf_edges = sum(int(kf.edge_index.shape[1]) for kf in built.kf)
+    n_nodes = built.db.num_nodes
+
+    peaks = measured_peaks()
+    local_bytes = (hi - lo) * a.read_len + 4 ** (a.k + 1) * 4
+    rooflines = {}
+    if "k1_count" in stage_ms:
+        ach = local_bytes / (stage_ms["k1_count"] * 1e-3) / 1e9
+        rooflines["k1_count"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms": stage_ms["k1_count"],
+                                 "algorithmic_bytes": local_bytes, "peak_source": peaks["source"]}
+    for s in (int(x) for x in a.small_k.split(",")):
+        d = 4**s
+        key = f"k4_emit_d{d}"
+        if key in stage_ms:
+            flops = d * n_nodes * (n_nodes - 1) / world  # strict upper triangle, this rank's share (balanced shards)
+            ach = flops / (stage_ms[key] * 1e-3) / 1e12
+            rooflines[key] = {"bound": "tensor" if d >= 128 else "alu", "achieved": ach, "peak": peaks["tflops"],
+                              "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "ms": stage_ms[key],
+                              "algorithmic_flops": flops, "peak_source": peaks["source"] + " bf16 burst",
+                              "pairs_per_s": n_nodes * (n_nodes - 1) / 2 / world / (stage_ms[key] * 1e-3)}
+    dominant = max(rooflines, key=lambda k_: rooflines[k_]["ms"]) if rooflines else None
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if dominant and os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            rooflines[dominant]["traffic"] = json.load(fh).get(dominant)
+
+    line = {
+        "metric": f"k={a.k} graph-build reads/sec", "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8 counts, int32/fp32 accumulate, f64 weights",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "parallelism": f"reads and KF row blocks sharded over {world} GPU(s)",
+                   "l2": "256 MiB buffer written between timed iterations", "kf_impl": a.kf_impl},
+        "kf_edges_per_s": kf_edges / (kf_ms * 1e-3) if kf_ms else None,
+        "kf_pairs_per_s": n_small * n_nodes * (n_nodes - 1) / 2 / (kf_ms * 1e-3) if kf_ms else None,
+        "kf_edges": kf_edges, "nodes": n_nodes, "db_edges": built.db.num_edges,
+        "stage_ms": stage_ms,
+        "e2e": {"value": a.reads / (e2e_ms / a.steps * 1e-3), "unit": "reads/s", "ms_per_step": e2e_ms / a.steps,
+                "h2d_bytes_per_step": (hi - lo) * a.read_len, "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": OUR_LAUNCHES_PER_STEP(n_small) * a.steps,
+        "roofline": {"kernel": dominant, **rooflines[dominant]} if dominant else None,
+        "rooflines": rooflines,
+        "clocks": clock_info,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sec, desc, detail = cpu_reference_sample(a, reads_all[:50_000])
+        line["cpu_baseline"] = {"value": a.reads / sec, "unit": "reads/s", "cores": blas_threads(), "kind": "port",
+                                "sample": desc, "host_cpus": os.cpu_count(), "est_seconds_full_workload": sec,
+                                "detail": detail}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a, int(os.environ.get("RANK", "0")))
+        return
+    run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,6 +5,7 @@ Stages: count -> first occurrence -> De Bruijn assembly
 -> sub-k-mer counts / features -> KF edges (threshold, global top-n).
 """
 import ctypes as C
+from contextlib import contextmanager
 from dataclasses import dataclass, field
 from fractions import Fraction
 from functools import lru_cache
@@ -20,6 +21,59 @@ from ._lib import GGError, KfParams, check, ptr
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class StageTimer:
+    """CUDA-event timing of the pipeline stages on the launching stream (bench.py)."""
+
+    def __init__(self):
+        self.ranges = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.ranges:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+
+_TIMER: Optional[StageTimer] = None
+
+
+def set_timer(timer: Optional[StageTimer]):
+    global _TIMER
+    _TIMER = timer
+
+
+@contextmanager
+def _stage(name):
+    if _TIMER is None:
+        yield
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    try:
+        yield
+    finally:
+        b.record()
+        _TIMER.ranges.append((name, a, b))
+
+
+class LocalComm:
+    """Single-process stand-in for the collectives of dist.TorchComm."""
+    world, rank = 1, 0
+
+    def sum_int(self, x):
+        return int(x)
+
+    def sum_tensor_(self, t):
+        return t
+
+    def gather_ints(self, x):
+        return [int(x)]
+
+    def gather_cat(self, t, dim=0):
+        return t
 
 
 def _require_cuda():
@@ -111,11 +165,13 @@ def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, fi
         bridges = torch.empty((max(bridge_capacity, 1), 4), dtype=torch.int32, device=dev)
         st = _stream()
         check(lib.gg_count_reset(k, ptr(hist), ptr(first), ptr(status), st), "gg_count_reset")
-        check(lib.gg_count_kp1mers(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base, ptr(hist),
-                                   ptr(bridges), bridge_capacity, ptr(status), st), "gg_count_kp1mers")
+        with _stage("k1_count"):
+            check(lib.gg_count_kp1mers(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
+                                       ptr(hist), ptr(bridges), bridge_capacity, ptr(status), st), "gg_count_kp1mers")
         if first_occurrence:
-            check(lib.gg_first_occurrence(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
-                                          ptr(hist), ptr(first), ptr(status), st), "gg_first_occurrence")
+            with _stage("k1_first"):
+                check(lib.gg_first_occurrence(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
+                                              ptr(hist), ptr(first), ptr(status), st), "gg_first_occurrence")
         if not sync:
             return CountResult(k, hist, first, bridges, -1, status)
         st_host = status.cpu()
@@ -159,10 +215,11 @@ def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weigh
     thr = -1.0 if edge_weight_threshold is None else float(edge_weight_threshold)
     if edge_weight_threshold is not None and thr < 0:
         thr = 0.0 if thr == 0 else -1.0  # a negative threshold keeps every edge
-    check(lib.gg_db_build(ptr(cr.hist), ptr(cr.first_pos), ptr(cr.bridges), cr.n_bridges, k, int(bool(normalise)),
-                          int(bool(create_all_kmers)), thr, ptr(node_codes), ptr(code_to_node), ptr(edges[0]),
-                          ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes, _stream()),
-          "gg_db_build")
+    with _stage("k2_db"):
+        check(lib.gg_db_build(ptr(cr.hist), ptr(cr.first_pos), ptr(cr.bridges), cr.n_bridges, k, int(bool(normalise)),
+                              int(bool(create_all_kmers)), thr, ptr(node_codes), ptr(code_to_node), ptr(edges[0]),
+                              ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes, _stream()),
+              "gg_db_build")
     n, e = (int(x) for x in ne.cpu())
     return DBGraph(k, n, e, node_codes[:n], code_to_node, edges[:, :e].contiguous(), w32[:e], w64[:e])
 
@@ -189,8 +246,9 @@ def kf_counts(node_codes: torch.Tensor, k: int, s: int) -> KFCounts:
     counts = torch.empty((n, d), dtype=torch.uint8, device=dev)
     sqnorm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     present = torch.empty(d, dtype=torch.int32, device=dev)
-    check(lib.gg_kf_counts(ptr(node_codes), n, k, s, ptr(counts), ptr(sqnorm), ptr(present), _stream()),
-          "gg_kf_counts")
+    with _stage(f"k3_counts_d{d}"):
+        check(lib.gg_kf_counts(ptr(node_codes), n, k, s, ptr(counts), ptr(sqnorm), ptr(present), _stream()),
+              "gg_kf_counts")
     col_keep = torch.nonzero(present, as_tuple=False).reshape(-1).to(torch.int32)
     return KFCounts(k, s, counts, sqnorm[:n], col_keep)
 
@@ -210,8 +268,9 @@ def kf_features_f32(kc: KFCounts) -> torch.Tensor:
     dk = int(kc.col_keep.numel())
     lut = torch.from_numpy(value_lut(kc.m).astype(np.float32)).to(dev)
     x = torch.empty((n, dk), dtype=torch.float32, device=dev)
-    check(lib.gg_kf_features_f32(ptr(kc.counts), n, d, ptr(kc.col_keep), dk, ptr(lut), ptr(x), _stream()),
-          "gg_kf_features_f32")
+    with _stage(f"k3_features_d{d}"):
+        check(lib.gg_kf_features_f32(ptr(kc.counts), n, d, ptr(kc.col_keep), dk, ptr(lut), ptr(x), _stream()),
+              "gg_kf_features_f32")
     return x
 
 
@@ -282,8 +341,9 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
         rec_capacity = 1 << 22
     while True:
         recs = torch.empty((max(rec_capacity, 1), 4), dtype=torch.int32, device=dev)
-        check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
-                             rec_capacity, ptr(rowcnt), ptr(status), _stream()), "gg_kf_emit")
+        with _stage(f"k4_emit_d{d}"):
+            check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
+                                 rec_capacity, ptr(rowcnt), ptr(status), _stream()), "gg_kf_emit")
         found = int(status[0].item())
         if found <= rec_capacity:
             return recs, found, rowcnt, params
@@ -301,9 +361,10 @@ def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=False):
     if n_recs:
         ws_bytes = int(lib.gg_kf_finalize_workspace_bytes(params.n, params.iblock_begin, params.iblock_end))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.gg_kf_finalize(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(sqnorm), ptr(edges[0]),
-                                 ptr(edges[1]), ptr(w64), ptr(w32), ptr(dot), ptr(ws), ws_bytes, _stream()),
-              "gg_kf_finalize")
+        with _stage(f"k6_finalize_d{params.d}"):
+            check(lib.gg_kf_finalize(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(sqnorm), ptr(edges[0]),
+                                     ptr(edges[1]), ptr(w64), ptr(w32), ptr(dot), ptr(ws), ws_bytes, _stream()),
+                  "gg_kf_finalize")
     return edges[:, :n_recs], w64[:n_recs], w32[:n_recs], (dot[:n_recs] if want_dot else None)
 
 
@@ -339,11 +400,18 @@ def choose_cutoff(class_hist: np.ndarray, p_max: int, budget: int):
 
 
 def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
-             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None,
-             n_nodes_for_budget: Optional[int] = None) -> KFEdges:
-    """K4-K6 on one GPU.  Reference: gnn_utils.py:240-322."""
+             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None, comm=None,
+             gather: bool = True) -> KFEdges:
+    """K4-K6.  Reference: gnn_utils.py:240-322.
+
+    With ``comm`` (dist.TorchComm) every rank scores its own row-block shard
+    [iblock_begin, iblock_end); the only exchanges are a candidate-count sum,
+    (when the global top-n binds) a sum of the score-class histogram, and the
+    final all-gather of the per-shard edge lists, which concatenate in rank
+    order to the single-GPU emission order."""
     _require_cuda()
     lib = _lib.load()
+    comm = comm or LocalComm()
     dev = counts.device
     n = int(counts.shape[0])
     empty = KFEdges(torch.zeros((2, 0), dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.float64, device=dev),
@@ -357,33 +425,48 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
     if sq_max == 0:
         return empty
     recs, n_recs, rowcnt, params = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl)
-    budget = top_n_budget(n if n_nodes_for_budget is None else n_nodes_for_budget, keep_top_k, n_recs)
-    need_cut = budget < n_recs
+    n_total = comm.sum_int(n_recs)
+    budget = top_n_budget(n, keep_top_k, n_total)
+    need_cut = budget < n_total
     ei, w64, w32, dot = kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=need_cut)
     del recs, rowcnt
-    if not need_cut:
-        return KFEdges(ei.contiguous(), w64, w32, n_recs, impl=impl)
-    p_max = params.p_max
-    n_classes = (sq_max + 1) * (p_max + 1)
-    hist = torch.zeros(n_classes, dtype=torch.int64, device=dev)
-    src, dst = ei[0].contiguous(), ei[1].contiguous()
-    check(lib.gg_kf_class_hist(ptr(src), ptr(dst), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(hist), _stream()),
-          "gg_kf_class_hist")
-    action, tie_budget, cutoff, tie_total = choose_cutoff(hist.cpu().numpy(), p_max, budget)
-    action_d = torch.from_numpy(action).to(dev)
-    out = torch.empty((2, budget), dtype=torch.int64, device=dev)
-    o64 = torch.empty(budget, dtype=torch.float64, device=dev)
-    o32 = torch.empty(budget, dtype=torch.float32, device=dev)
-    cnt = torch.empty(1, dtype=torch.int64, device=dev)
-    ws_bytes = int(lib.gg_kf_select_workspace_bytes(n_recs))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.gg_kf_select(ptr(src), ptr(dst), ptr(w64), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(action_d),
-                           tie_budget, ptr(out[0]), ptr(out[1]), ptr(o64), ptr(o32), ptr(cnt), ptr(ws), ws_bytes,
-                           _stream()), "gg_kf_select")
-    kept = int(cnt.item())
-    if kept != budget:
-        raise GGError(f"top-n select kept {kept} edges, expected {budget}")
-    return KFEdges(out, o64, o32, n_recs, cutoff, tie_budget, tie_total, impl)
+    cutoff, tie_budget, tie_total = None, 0, 0
+    if need_cut:
+        p_max = params.p_max
+        hist = torch.zeros((sq_max + 1) * (p_max + 1), dtype=torch.int64, device=dev)
+        src, dst = ei[0].contiguous(), ei[1].contiguous()
+        with _stage("k5_class_hist"):
+            check(lib.gg_kf_class_hist(ptr(src), ptr(dst), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(hist), _stream()),
+                  "gg_kf_class_hist")
+        local_hist = hist.cpu().numpy()
+        global_hist = comm.sum_tensor_(hist).cpu().numpy() if comm.world > 1 else local_hist
+        action, tie_budget, cutoff, tie_total = choose_cutoff(global_hist, p_max, budget)
+        # the cut-off class is cut in emission order: lower ranks (earlier row blocks) are served first
+        local_ties = int(local_hist[action == 2].sum())
+        before = sum(comm.gather_ints(local_ties)[: comm.rank])
+        local_tie_budget = min(max(tie_budget - before, 0), local_ties)
+        expect = int(local_hist[action == 1].sum()) + local_tie_budget
+        action_d = torch.from_numpy(action).to(dev)
+        out = torch.empty((2, max(expect, 1)), dtype=torch.int64, device=dev)
+        o64 = torch.empty(max(expect, 1), dtype=torch.float64, device=dev)
+        o32 = torch.empty(max(expect, 1), dtype=torch.float32, device=dev)
+        cnt = torch.empty(1, dtype=torch.int64, device=dev)
+        ws_bytes = int(lib.gg_kf_select_workspace_bytes(n_recs))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with _stage("k5_select"):
+            check(lib.gg_kf_select(ptr(src), ptr(dst), ptr(w64), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(action_d),
+                                   local_tie_budget, ptr(out[0]), ptr(out[1]), ptr(o64), ptr(o32), ptr(cnt), ptr(ws),
+                                   ws_bytes, _stream()), "gg_kf_select")
+        kept = int(cnt.item())
+        if kept != expect:
+            raise GGError(f"top-n select kept {kept} edges, expected {expect}")
+        ei, w64, w32 = out[:, :expect], o64[:expect], o32[:expect]
+    if gather and comm.world > 1:
+        with _stage("c2_gather_edges"):
+            ei = comm.gather_cat(ei.contiguous(), dim=1)
+            w64 = comm.gather_cat(w64.contiguous())
+            w32 = comm.gather_cat(w32.contiguous())
+    return KFEdges(ei.contiguous(), w64, w32, n_total, cutoff, tie_budget, tie_total, impl)
 
 
 # --------------------------------------------------------------------------- whole path on one GPU
@@ -397,10 +480,21 @@ class BuiltGraph:
 
 
 def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_threshold=0.0, edges_keep_top_k=None,
-                kf_impl="auto", with_kf=True) -> BuiltGraph:
-    """kmer_ssgnn.py:162-213 + sampling_task.py:128-161 on one GPU."""
+                kf_impl="auto", with_kf=True, comm=None) -> BuiltGraph:
+    """kmer_ssgnn.py:162-213 + sampling_task.py:128-161.
+
+    Single GPU by default.  With ``comm`` (dist.TorchComm) ``sequences`` is this
+    rank's shard of the reads (a ReadStream whose pos_base is the shard's global
+    stream offset): histograms are summed and first occurrences min-reduced over
+    ranks, the De Bruijn assembly and features run replicated, KF is sharded by
+    row block."""
+    comm = comm or LocalComm()
     stream = upload_reads(sequences)
     cr = count_kp1mers(stream, k)
+    if comm.world > 1:
+        from . import dist
+
+        cr = dist.reduce_counts(cr, comm)
     if cr.n_nonzero == 0 and cr.n_bridges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
@@ -409,7 +503,12 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
     xs = [kf_features_f32(kc) for kc in kcs]
     out = BuiltGraph(k, db, kcs, xs)
     if with_kf:
+        b0, b1 = 0, None
+        if comm.world > 1:
+            from . import dist
+
+            b0, b1 = dist.kf_block_range(_row_blocks(db.num_nodes), comm.world, comm.rank)
         for kc in kcs:
             out.kf.append(kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m,
-                                   impl=kf_impl))
+                                   impl=kf_impl, iblock_begin=b0, iblock_end=b1, comm=comm))
     return out

@@ -22,16 +22,11 @@ def seq_to_kmers(seq, k=3, stride=1, inlcudeUNK=True):
     """src/utils.py:15-31 -- windows seq[i:i+k] for i = 0, stride, ... with
     i+k <= len(seq); windows holding an 'N' become 'N'*k (inlcudeUNK) or are
     dropped."""
-    out = []
-    pad = "N" * k
-    for i in range(0, len(seq) - k + 1, stride):
-        w = seq[i : i + k]
-        if "N" in w:
-            if inlcudeUNK:
-                out.append(pad)
-        else:
-            out.append(w)
-    return out
+    windows = [seq[i : i + k] for i in range(0, len(seq) - k + 1, stride)]
+    if inlcudeUNK:
+        pad = "N" * k
+        return [pad if "N" in w else w for w in windows]
+    return [w for w in windows if "N" not in w]
 
 
 # --------------------------------------------------------------------------- a2
@@ -181,15 +176,17 @@ def node_embedding_initial(graph, method="onehot", k=3, small_k=None, random_siz
 
 
 # --------------------------------------------------------------------------- a6
-def cosine_similarity_to_edge_index_weight(X, chunk_size=1024, threshold=0.0, keep_top_k=None):
+def cosine_similarity_to_edge_index_weight(X, chunk_size=1024, threshold=0.0, keep_top_k=None, row_blocks=None):
     """gnn_utils.py:240-322 -- blocked float64 cosine, strict upper triangle,
     strict ``> threshold``, blocks appended in (i, j>=i) order and row-major
-    inside a block; optional global top-n by np.argpartition (:311-317)."""
+    inside a block; optional global top-n by np.argpartition (:311-317).
+    ``row_blocks`` (not in the reference) limits the outer loop to the first
+    blocks: bench.py times that bounded sample and scales by block pairs."""
     X = np.asarray(X)
     n = X.shape[0]
     nb = (n + chunk_size - 1) // chunk_size
     src, dst, wts = [], [], []
-    for bi in range(nb):
+    for bi in range(nb if row_blocks is None else min(nb, row_blocks)):
         a = X[bi * chunk_size : min((bi + 1) * chunk_size, n)]
         na = np.linalg.norm(a, axis=1).reshape(-1, 1)
         for bj in range(bi, nb):

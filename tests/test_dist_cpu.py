@@ -1,0 +1,129 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo processes (no kernels)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from genomic_gnn_b200 import dist as ggdist
+from genomic_gnn_b200.core import CountResult, choose_cutoff, top_n_budget
+from oracle import fast
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _histogram_of_shard(reads, k, pos_base):
+    """What K1 leaves on a rank, computed by the oracle: (k+1)-mer histogram and
+    first occurrences with global stream offsets (fixed-length rows, no N)."""
+    u, v, cnt, first = fast.count_pairs(reads, k)
+    # oracle stream has one separator per read; the device stream for uint8 [R, L] input has none
+    length = reads.shape[1]
+    first = first - first // (length + 1) + pos_base
+    bins = 4 ** (k + 1)
+    hist = np.zeros(bins, dtype=np.int32)
+    fp = np.full(bins, -1, dtype=np.int64)  # GG_NO_POS viewed as int64
+    e = (u << 2) | (v & 3)
+    hist[e] = cnt
+    fp[e] = first
+    return hist, fp
+
+
+def _worker(rank, world, port, k, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = ggdist.TorchComm()
+        assert comm.world == world and comm.rank == rank and comm.device.type == "cpu"
+        assert comm.sum_int(rank + 1) == world * (world + 1) // 2
+        assert comm.gather_ints(10 * rank) == [10 * r for r in range(world)]
+        # all-gather(v): ragged edge lists concatenate in rank order
+        mine = torch.arange(2 * (rank + 2), dtype=torch.int64).reshape(2, rank + 2) + 100 * rank
+        cat = comm.gather_cat(mine, dim=1)
+        want = torch.cat([torch.arange(2 * (r + 2), dtype=torch.int64).reshape(2, r + 2) + 100 * r for r in range(world)], dim=1)
+        assert torch.equal(cat, want)
+        assert comm.gather_cat(torch.zeros(0), dim=0).numel() == 0
+
+        # C1: sharded counting merges to the single-process result
+        reads = fast.synthetic_reads(600, 50, seed=4)
+        lo, hi = ggdist.shard_bounds(reads.shape[0], world, rank)
+        hist, fp = _histogram_of_shard(reads[lo:hi], k, pos_base=lo * reads.shape[1])
+        cr = CountResult(k, torch.from_numpy(hist), torch.from_numpy(fp), torch.zeros((1, 4), dtype=torch.int32), 0,
+                         torch.zeros(8, dtype=torch.int64))
+        merged = ggdist.reduce_counts(cr, comm)
+        g_hist, g_fp = _histogram_of_shard(reads, k, 0)
+        assert np.array_equal(merged.hist.numpy(), g_hist)
+        occupied = g_hist > 0
+        assert np.array_equal(merged.first_pos.numpy()[occupied], g_fp[occupied])
+        assert merged.n_nonzero == int(occupied.sum())
+
+        # bridges: only rank 1 has some
+        br = torch.tensor([[1, 2, 7, 0], [3, 4, 9, 0]], dtype=torch.int32)
+        cr2 = CountResult(k, torch.from_numpy(hist.copy()), torch.from_numpy(fp.copy()),
+                          br if rank == 1 else torch.zeros((1, 4), dtype=torch.int32), 2 if rank == 1 else 0,
+                          torch.zeros(8, dtype=torch.int64))
+        m2 = ggdist.reduce_counts(cr2, comm)
+        assert m2.n_bridges == 2 and torch.equal(m2.bridges, br)
+        open(os.path.join(tmp, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, 4, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_shard_bounds_cover():
+    for n, w in [(10, 3), (1_000_000, 8), (5, 8), (0, 2)]:
+        b = [ggdist.shard_bounds(n, w, r) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_kf_block_ranges_balanced():
+    for nb, w in [(64, 8), (64, 2), (1024, 8), (16, 4), (3, 8), (1, 1)]:
+        r = ggdist.kf_block_ranges(nb, w)
+        assert r[0][0] == 0 and r[-1][1] == nb and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        work = [sum(nb - i for i in range(a, b)) for a, b in r]
+        assert sum(work) == nb * (nb + 1) // 2
+    work = [sum(64 - i for i in range(a, b)) for a, b in ggdist.kf_block_ranges(64, 8)]
+    assert max(work) <= 1.2 * sum(work) / 8
+
+
+def test_choose_cutoff_matches_oracle_policy():
+    """Host half of K5 against the oracle's statement of the same policy."""
+    rng = np.random.default_rng(0)
+    counts = fast.subkmer_counts(rng.permutation(4**4), 4, 2)      # 256 nodes, m = 3
+    s, t, dot, prod = fast.kf_candidates(counts, 0.0)
+    sq_max = 9
+    p_max = sq_max * sq_max
+    hist = np.bincount(dot * (p_max + 1) + prod, minlength=(sq_max + 1) * (p_max + 1)).astype(np.int64)
+    for frac in (0.01, 0.05, 0.2):
+        budget = top_n_budget(256, frac, s.shape[0])
+        action, tie_budget, cutoff, tie_total = choose_cutoff(hist, p_max, budget)
+        act = action[dot * (p_max + 1) + prod]
+        keep = act == 1
+        ties = np.nonzero(act == 2)[0]
+        keep[ties[:tie_budget]] = True
+        assert int(keep.sum()) == budget
+        ei, w = fast.kf_edges_exact(counts, 0.0, frac)
+        assert np.array_equal(ei, np.stack([s[keep], t[keep]]))
+        if cutoff is not None:
+            assert abs(w.min() - cutoff) < 1e-15 and tie_total == len(ties)
+
+
+def test_top_n_budget_matches_reference_quirks():
+    assert top_n_budget(4096, 0.01, 6_329_598) == 167_772
+    assert top_n_budget(16384, 0.01, 1_206_888) == 1_206_888
+    assert top_n_budget(5, 0.01, 9) == 9
+    assert top_n_budget(100, None, 7) == 7
