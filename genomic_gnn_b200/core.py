@@ -344,7 +344,10 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
         with _stage(f"k4_emit_d{d}"):
             check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
                                  rec_capacity, ptr(rowcnt), ptr(status), _stream()), "gg_kf_emit")
-        found = int(status[0].item())
+        st_host = status.cpu()
+        if int(st_host[2]) != 0:
+            raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
+        found = int(st_host[0])
         if found <= rec_capacity:
             return recs, found, rowcnt, params
         del recs
@@ -424,7 +427,13 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         sq_max = int(sqnorm.max().item())
     if sq_max == 0:
         return empty
-    recs, n_recs, rowcnt, params = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl)
+    # staging capacity: the global top-n budget is the natural first guess (a binding threshold stays below it,
+    # a binding top-n overflows once and is re-run with the exact size)
+    n_pairs = n * (n - 1) // 2
+    guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
+    rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
+    recs, n_recs, rowcnt, params = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
+                                           rec_capacity=rec_capacity)
     n_total = comm.sum_int(n_recs)
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total

@@ -364,7 +364,8 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   a.out.status = reinterpret_cast<unsigned long long*>(kf_status);
 
   int impl = p->impl;
-  if (impl == GG_KF_IMPL_AUTO) impl = p->d <= 64 ? GG_KF_IMPL_DP4A : GG_KF_IMPL_NAIVE;  // TODO tcgen05 once validated
+  if (impl == GG_KF_IMPL_AUTO)
+    impl = p->d <= 64 ? GG_KF_IMPL_DP4A : ((p->d % 128 == 0 && p->d <= 1024) ? GG_KF_IMPL_TCGEN05 : GG_KF_IMPL_NAIVE);
   const long long units = static_cast<long long>(a.ib1 - a.ib0) * a.n_jblocks * kStripsPerBlock;
   GG_REQUIRE(units < (1ll << 31), GG_ERR_ARG, "too many work units for one launch; shard the row blocks");
   switch (impl) {

@@ -1,13 +1,437 @@
-// K4 (tensor path): TMA-fed tcgen05 Gram tiles with the fused exact-threshold epilogue.
+// K4 (tensor path): KF Gram tiles on the 5th-generation tensor cores with the
+// exact-threshold epilogue fused behind them, so the N x N score matrix never
+// leaves the SM.
+//
+// Replaces the blocked X_i @ X_j.T of cosine_similarity_to_edge_index_weight
+// (reference gnn_utils.py:262-279) for feature widths D >= 128 (small_k >= 4).
+//
+//   * operands are the uint8 sub-k-mer count rows as they sit in HBM: A = B =
+//     counts[N, D] (K-major both), fetched by TMA (one tensor map, 128 rows x
+//     128 bytes boxes, 128-byte swizzle), multiplied with
+//     tcgen05.mma.kind::i8 into int32 accumulators in TMEM -- exact integers,
+//     no conversion pass, no rounding;
+//   * a CTA is persistent (one per SM) and walks (128-row strip, column block J)
+//     units of the upper triangle; the strip's A rows (<= 128 KB) stay resident
+//     in shared memory across all its column tiles, B tiles stream through a
+//     multi-stage mbarrier ring;
+//   * warp roles: warps 0-3 epilogue (TMEM -> registers -> integer threshold
+//     test -> staged candidate records), warp 4 TMA producer, warp 5 MMA issuer
+//     and TMEM owner; four 128-column accumulators let the epilogue of tile n
+//     overlap the MMAs of tiles n+1..n+3.
+#include <cuda.h>
+
 #include "gg_kf_emit.cuh"
 
 namespace ggkf {
+namespace {
+
+constexpr int kTileN = 128;           // columns per accumulator tile
+constexpr int kTileM = kStrip;        // 128 rows
+constexpr int kKBlock = 128;          // bytes of K per TMA box / smem stage (= one 128B swizzle row)
+constexpr int kUmmaK = 32;            // K per tcgen05.mma.kind::i8
+constexpr int kStageBytes = kTileN * kKBlock;  // 16 KB
+constexpr int kAccStages = 4;         // 4 x 128 TMEM columns
+constexpr int kTmemCols = 512;
+constexpr int kMaxBStages = 8;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kTilesPerBlock = kBlock / kTileN;  // 8 column tiles per reference block
+constexpr int kMaxD = 1024;           // A strip must fit shared memory next to the B ring
+
+struct __align__(8) Barriers {
+  unsigned long long a_full, a_empty;
+  unsigned long long b_full[kMaxBStages], b_empty[kMaxBStages];
+  unsigned long long acc_full[kAccStages], acc_empty[kAccStages];
+  uint32_t tmem_base;
+  int error;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug must surface as an error, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, int* error_flag) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  *error_flag = 1;
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, unsigned long long* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand, 128-byte swizzle: 8-row groups are 1024 bytes apart (SBO), the
+// leading-dimension field is the canonical 1 for swizzled K-major layouts,
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::i8, uint8 x uint8 -> s32, both operands K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (0u << 10) | ((kTileN >> 3) << 17) | ((kTileM >> 4) << 24);
+
+// ---------------------------------------------------------------- work walk
+// Units (strip, J >= I) of this shard flattened strip-major; every CTA takes a
+// contiguous range so that its A strip changes only a handful of times.
+struct Walk {
+  int strip, i_block, j_block;  // global strip index, its row block, column block
+  long long left;               // units still to do
+};
+
+__device__ __forceinline__ long long units_before_block(int i_local, int ib0, int n_j) {
+  // sum over row blocks ib0 .. ib0+i_local-1 of 8 * (n_j - I)
+  const long long a = i_local;
+  return kStripsPerBlock * (a * (n_j - ib0) - a * (a - 1) / 2);
+}
+
+__device__ Walk walk_begin(const KfArgs& a, long long first_unit, long long n_units) {
+  Walk w;
+  int il = 0;
+  const int n_il = a.ib1 - a.ib0;
+  while (il + 1 < n_il && units_before_block(il + 1, a.ib0, a.n_jblocks) <= first_unit) ++il;
+  long long rem = first_unit - units_before_block(il, a.ib0, a.n_jblocks);
+  w.i_block = a.ib0 + il;
+  const int per_strip = a.n_jblocks - w.i_block;
+  w.strip = w.i_block * kStripsPerBlock + static_cast<int>(rem / per_strip);
+  w.j_block = w.i_block + static_cast<int>(rem % per_strip);
+  w.left = n_units;
+  return w;
+}
+
+__device__ __forceinline__ void walk_next(const KfArgs& a, Walk& w) {
+  --w.left;
+  if (++w.j_block == a.n_jblocks) {
+    ++w.strip;
+    w.i_block = w.strip / kStripsPerBlock;
+    w.j_block = w.i_block;
+  }
+}
+
+// first column tile of block J that can hold a pair s < t for this strip
+__device__ __forceinline__ int first_tile(const Walk& w) {
+  return w.i_block == w.j_block ? (w.strip % kStripsPerBlock) : 0;
+}
+// a strip / column tile that lies entirely beyond the last node has nothing to score
+__device__ __forceinline__ int last_tile(const KfArgs& a, const Walk& w) {
+  const long long cols = a.n - static_cast<long long>(w.j_block) * kBlock;
+  const long long t = (cols + kTileN - 1) / kTileN;
+  return static_cast<int>(t < kTilesPerBlock ? t : kTilesPerBlock);
+}
+
+// ---------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(kThreads, 1)
+kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bstages, long long total_units,
+                  int* error_flag) {
+  extern __shared__ unsigned char smem_raw[];
+  // 128-byte-swizzled TMA boxes and UMMA descriptors assume 1024-byte aligned tiles
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int n_kblocks = a.d / kKBlock;
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
+  uint16_t* sqn = reinterpret_cast<uint16_t*>(smem_b + static_cast<size_t>(n_bstages) * kStageBytes);
+  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kBlock);
+  Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    for (int i = 0; i < n_bstages; ++i) {
+      mbar_init(&bars->b_full[i], 1);
+      mbar_init(&bars->b_empty[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&bars->acc_full[i], 1);
+      mbar_init(&bars->acc_empty[i], kEpiThreads / 32);
+    }
+    bars->error = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // contiguous unit range of this CTA
+  const long long base_units = total_units / gridDim.x, extra = total_units % gridDim.x;
+  const long long u0 = base_units * blockIdx.x + (blockIdx.x < extra ? blockIdx.x : extra);
+  const long long n_units = base_units + (blockIdx.x < extra ? 1 : 0);
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && n_units > 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+      Walk w = walk_begin(a, u0, n_units);
+      int cur_strip = -1;
+      uint32_t a_round = 0, stage = 0, round = 0;
+      for (; w.left > 0; walk_next(a, w)) {
+        if (w.strip != cur_strip) {
+          if (a_round > 0) mbar_wait(&bars->a_empty, (a_round - 1) & 1, &bars->error);  // MMAs on the old strip done
+          mbar_expect_tx(&bars->a_full, static_cast<uint32_t>(n_kblocks) * kStageBytes);
+          for (int kb = 0; kb < n_kblocks; ++kb)
+            tma_load_2d(smem_a + static_cast<size_t>(kb) * kStageBytes, &tmap, &bars->a_full, kb * kKBlock,
+                        w.strip * kTileM);
+          cur_strip = w.strip;
+          ++a_round;
+        }
+        const int t_end = last_tile(a, w);
+        for (int ct = first_tile(w); ct < t_end; ++ct) {
+          const int col = w.j_block * kBlock + ct * kTileN;
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            if (round > 0) mbar_wait(&bars->b_empty[stage], (round - 1) & 1, &bars->error);
+            mbar_expect_tx(&bars->b_full[stage], kStageBytes);
+            tma_load_2d(smem_b + static_cast<size_t>(stage) * kStageBytes, &tmap, &bars->b_full[stage], kb * kKBlock,
+                        col);
+            if (++stage == static_cast<uint32_t>(n_bstages)) {
+              stage = 0;
+              ++round;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && n_units > 0) {
+      Walk w = walk_begin(a, u0, n_units);
+      int cur_strip = -1;
+      uint32_t a_round = 0, stage = 0, round = 0, acc = 0, acc_round = 0;
+      for (; w.left > 0; walk_next(a, w)) {
+        if (w.strip != cur_strip) {
+          if (cur_strip >= 0) tc_commit(&bars->a_empty);  // fires when every MMA issued so far has retired
+          mbar_wait(&bars->a_full, a_round & 1, &bars->error);
+          tc_fence_after();
+          cur_strip = w.strip;
+          ++a_round;
+        }
+        const int t_end = last_tile(a, w);
+        for (int ct = first_tile(w); ct < t_end; ++ct) {
+          if (acc_round > 0) mbar_wait(&bars->acc_empty[acc], (acc_round - 1) & 1, &bars->error);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kTileN;
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            mbar_wait(&bars->b_full[stage], round & 1, &bars->error);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + static_cast<size_t>(kb) * kStageBytes);
+            const uint32_t b_addr = smem_u32(smem_b + static_cast<size_t>(stage) * kStageBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4)
+              tc_mma_i8(tmem_d, umma_desc_sw128(a_addr + k4 * kUmmaK), umma_desc_sw128(b_addr + k4 * kUmmaK), kIdesc,
+                        (kb | k4) != 0);
+            tc_commit(&bars->b_empty[stage]);  // smem slot reusable once these MMAs have read it
+            if (++stage == static_cast<uint32_t>(n_bstages)) {
+              stage = 0;
+              ++round;
+            }
+          }
+          tc_commit(&bars->acc_full[acc]);
+          if (++acc == kAccStages) {
+            acc = 0;
+            ++acc_round;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-3: TMEM lanes 32*warp ..) =====================
+    WarpStage& ws = stages[warp];
+    if (lane == 0) ws.fill = 0;
+    __syncwarp();
+    if (n_units > 0) {
+      Walk w = walk_begin(a, u0, n_units);
+      uint32_t acc = 0, acc_round = 0;
+      for (; w.left > 0; walk_next(a, w)) {
+        const long long col0 = static_cast<long long>(w.j_block) * kBlock;
+        const int cols_in_block = static_cast<int>(min(static_cast<long long>(kBlock), a.n - col0));
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // everyone is done with the old sqn panel
+        for (int c = tid; c < kBlock; c += kEpiThreads)
+          sqn[c] = c < cols_in_block ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+
+        const int r = (w.strip % kStripsPerBlock) * kStrip + tid;  // block-local row
+        const long long s = static_cast<long long>(w.strip) * kStrip + tid;
+        const bool row_ok = s < a.n;
+        uint32_t sq_i = 0, scale_i = 0;
+        if (row_ok) {
+          sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
+          scale_i = __ldg(a.fast_scale + sq_i);
+        }
+        const bool diag = w.i_block == w.j_block;
+        uint32_t row_cnt = 0;
+        const int t_end = last_tile(a, w);
+        for (int ct = first_tile(w); ct < t_end; ++ct) {
+          mbar_wait(&bars->acc_full[acc], acc_round & 1, &bars->error);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * kTileN;
+#pragma unroll 1
+          for (int cc = 0; cc < kTileN; cc += 32) {
+            const int c0 = ct * kTileN + cc;  // block-local column of bit 0
+            uint32_t v[32];
+            tc_ld32(taddr + cc, v);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+              mask |= static_cast<uint32_t>(((v[b] * v[b]) << a.fast_shift) > scale_i * sqn[c0 + b]) << b;
+            mask &= chunk_col_mask(cols_in_block, c0);
+            if (diag) mask &= chunk_diag_mask(r, c0);
+            if (!row_ok) mask = 0;
+            if (__any_sync(0xFFFFFFFFu, mask != 0)) {
+              int n_l = 0;
+#pragma unroll
+              for (int b = 0; b < 32; ++b) {
+                if ((mask >> b) & 1u) {
+                  if (v[b] >= __ldg(a.dmin + sq_i * sqn[c0 + b]))
+                    ws.scratch[n_l++][lane] = static_cast<uint16_t>((v[b] << 5) | b);
+                }
+              }
+              stage_commit(ws, a.out, lane, n_l, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), row_cnt);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+          if (++acc == kAccStages) {
+            acc = 0;
+            ++acc_round;
+          }
+        }
+        stage_flush(ws, a.out, lane);
+        if (row_ok) a.rowcnt[rowcnt_index(w.i_block - a.ib0, a.n_jblocks, w.j_block, r)] = row_cnt;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+  if (tid == 0 && bars->error) *error_flag = 1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
 
 int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
-  (void)a;
-  (void)s;
-  gg::set_error("tcgen05 KF kernel not built yet");
-  return GG_ERR_ARG;
+  GG_REQUIRE(a.d % kKBlock == 0 && a.d >= kKBlock && a.d <= kMaxD, GG_ERR_ARG,
+             "tcgen05 KF kernel needs d in {128, 256, ..., 1024}");
+  EncodeTiledFn encode = encode_tiled();
+  GG_REQUIRE(encode != nullptr, GG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.d), static_cast<cuuint64_t>(a.n)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.d)};  // row pitch in bytes
+  const cuuint32_t box[2] = {kKBlock, kTileM};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(a.counts), dims, strides, box,
+                            elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    gg::set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return GG_ERR_CUDA;
+  }
+
+  const int n_kblocks = a.d / kKBlock;
+  const size_t fixed = static_cast<size_t>(n_kblocks) * kStageBytes + kBlock * sizeof(uint16_t) +
+                       (kEpiThreads / 32) * sizeof(WarpStage) + sizeof(Barriers) + 1024 /* base alignment slack */;
+  int dev = 0, max_smem = 0;
+  GG_CUDA_CHECK(cudaGetDevice(&dev));
+  GG_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int n_bstages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / kStageBytes);
+  if (n_bstages > kMaxBStages) n_bstages = kMaxBStages;
+  GG_REQUIRE(n_bstages >= 2, GG_ERR_ARG, "not enough shared memory for the B ring");
+  const size_t smem_bytes = fixed + static_cast<size_t>(n_bstages) * kStageBytes;
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kf_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem_bytes)));
+
+  // units of this shard: 8 strips per row block, n_j - I column blocks each
+  long long total_units = 0;
+  for (int ib = a.ib0; ib < a.ib1; ++ib) total_units += static_cast<long long>(kStripsPerBlock) * (a.n_jblocks - ib);
+  if (total_units == 0) return GG_OK;
+  const long long sms = gg::sm_count();
+  const unsigned grid = static_cast<unsigned>(total_units < sms ? total_units : sms);
+  int* error_flag = reinterpret_cast<int*>(a.out.status + 2);  // kf_status[2]
+  kf_tcgen05_kernel<<<grid, kThreads, smem_bytes, s>>>(tmap, a, n_bstages, total_units, error_flag);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
 }
 
 }  // namespace ggkf

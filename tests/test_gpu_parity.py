@@ -165,6 +165,33 @@ def test_kf_impls_agree(gg):
     assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
 
 
+@pytest.mark.parametrize("k,s,n_reads,thr", [
+    (6, 4, 4000, 0.5),     # D = 256, N = 4096 (all 6-mers)
+    (6, 5, 4000, 0.4),     # D = 1024, N = 4096
+    (7, 5, 150, 0.3),      # D = 1024, ragged N (not every 7-mer occurs): partial strips, tiles and blocks
+    (6, 4, 12, 0.0),       # tiny N, threshold 0: every pair sharing a 4-mer
+    (8, 5, 3000, 0.7),     # D = 1024, N ~ 65k: many units per CTA, strip changes, deep ring reuse
+])
+def test_kf_tcgen05_matches_generic(gg, k, s, n_reads, thr):
+    """TMA + tcgen05.mma.kind::i8 + TMEM epilogue vs the SIMT slab kernel: identical edges, order and weights."""
+    from genomic_gnn_b200 import core
+
+    reads = fast.synthetic_reads(n_reads, 150, seed=21 + k + s)
+    built = core.build_graph(reads, k, str(s), with_kf=False)
+    kc = built.kf_counts[0]
+    a = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="tcgen05")
+    b = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="naive")
+    assert b.edge_index.shape[1] > 0
+    assert a.edge_index.shape == b.edge_index.shape
+    assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
+    # and a row-block shard of it
+    nb = (built.db.num_nodes + 1023) // 1024
+    if nb >= 3:
+        a1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="tcgen05", iblock_begin=1, iblock_end=3)
+        b1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="naive", iblock_begin=1, iblock_end=3)
+        assert torch.equal(a1.edge_index, b1.edge_index)
+
+
 def test_kf_row_block_shards_concatenate(gg):
     """Row-block shards (the multi-GPU unit) concatenate to the single-GPU result."""
     from genomic_gnn_b200 import core
