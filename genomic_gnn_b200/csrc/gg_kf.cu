@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
   __syncthreads();
 
   const bool diag = un.i_block == un.j_block;
-  uint32_t row_cnt = 0;
-  // diagonal block: columns <= r contribute nothing, skip whole chunks below the strip
-  const int c_begin = diag ? (un.strip * kStrip) & ~31 : 0;
+  uint32_t tile_cnt = 0;
+  // diagonal block: columns <= r contribute nothing, skip whole tiles below the strip
+  const int c_begin = diag ? un.strip * kStrip : 0;
   for (int c0 = c_begin; c0 < cols_in_block; c0 += 32) {
     uint32_t mask = 0;
 #pragma unroll
@@ -105,20 +105,26 @@ __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
     if (diag) mask &= chunk_diag_mask(r, c0);
     if (!row_ok) mask = 0;
     if (__any_sync(0xFFFFFFFFu, mask != 0)) {
-      int n_l = 0;
+      uint32_t exact = 0;
       for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {
         const int b = __ffs(m2) - 1;
         const uint32_t* cw = colw + (c0 + b) * W;
         uint32_t dot = 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) dot = __dp4a(row[w], cw[w], dot);
-        if (dot >= __ldg(a.dmin + sq_i * sqn[c0 + b])) ws.scratch[n_l++][lane] = static_cast<uint16_t>((dot << 5) | b);
+        if (dot >= __ldg(a.dmin + sq_i * sqn[c0 + b])) {
+          exact |= 1u << b;
+          ws.dot[b][lane] = static_cast<uint8_t>(dot);
+        }
       }
-      stage_commit(ws, a.out, lane, n_l, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), row_cnt);
+      stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
+    }
+    if (((c0 + 32) & (kTile - 1)) == 0 || c0 + 32 >= cols_in_block) {  // end of a 128-column tile
+      if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = tile_cnt;
+      tile_cnt = 0;
     }
   }
   stage_flush(ws, a.out, lane);
-  if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r)] = row_cnt;
 }
 
 // ---------------------------------------------------------------------------- any D % 64 == 0
@@ -149,8 +155,8 @@ __global__ void __launch_bounds__(kStrip) kf_generic_kernel(KfArgs a) {
   const uint4* row_ptr = reinterpret_cast<const uint4*>(a.counts + (row_ok ? s : 0) * a.d);
   const int n_slabs = a.d / (4 * kSlabWords);
   const bool diag = un.i_block == un.j_block;
-  uint32_t row_cnt = 0;
-  const int c_begin = diag ? (un.strip * kStrip) & ~31 : 0;
+  uint32_t tile_cnt = 0;
+  const int c_begin = diag ? un.strip * kStrip : 0;
 
   for (int c0 = c_begin; c0 < cols_in_block; c0 += 32) {
     uint32_t acc[32];
@@ -187,18 +193,24 @@ __global__ void __launch_bounds__(kStrip) kf_generic_kernel(KfArgs a) {
     if (diag) mask &= chunk_diag_mask(r, c0);
     if (!row_ok) mask = 0;
     if (__any_sync(0xFFFFFFFFu, mask != 0)) {
-      int n_l = 0;
+      uint32_t exact = 0;
 #pragma unroll
       for (int b = 0; b < 32; ++b) {
         if ((mask >> b) & 1u) {
-          if (acc[b] >= __ldg(a.dmin + sq_i * sqn[b])) ws.scratch[n_l++][lane] = static_cast<uint16_t>((acc[b] << 5) | b);
+          if (acc[b] >= __ldg(a.dmin + sq_i * sqn[b])) {
+            exact |= 1u << b;
+            ws.dot[b][lane] = static_cast<uint8_t>(acc[b]);
+          }
         }
       }
-      stage_commit(ws, a.out, lane, n_l, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), row_cnt);
+      stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
+    }
+    if (((c0 + 32) & (kTile - 1)) == 0 || c0 + 32 >= cols_in_block) {
+      if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = tile_cnt;
+      tile_cnt = 0;
     }
   }
   stage_flush(ws, a.out, lane);
-  if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r)] = row_cnt;
 }
 
 template <int W>
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const gg_kf_rec_t* recs, l
     const uint4 rc = __ldg(reinterpret_cast<const uint4*>(recs) + i);
     const uint32_t s = rc.x, t = rc.y;
     const long long idx = rowcnt_index(static_cast<int>(s / kBlock) - ib0, n_jblocks, static_cast<int>(t / kBlock),
-                                       static_cast<int>(s % kBlock));
+                                       static_cast<int>(s % kBlock), static_cast<int>((t % kBlock) / kTile));
     const unsigned long long pos = offsets[idx] + rc.z;
     src[pos] = s;
     dst[pos] = t;
@@ -329,7 +341,7 @@ int check_params(const gg_kf_params_t* p) {
 extern "C" size_t gg_kf_rowcnt_elems(int64_t n, int iblock_begin, int iblock_end) {
   if (n <= 0 || iblock_end <= iblock_begin) return 0;
   const size_t nj = static_cast<size_t>((n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
-  return static_cast<size_t>(iblock_end - iblock_begin) * nj * GG_KF_BLOCK;
+  return static_cast<size_t>(iblock_end - iblock_begin) * nj * GG_KF_BLOCK * ggkf::kTilesPerBlock;
 }
 
 extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const int32_t* sqnorm, const uint16_t* dmin,

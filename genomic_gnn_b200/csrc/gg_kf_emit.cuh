@@ -1,9 +1,10 @@
 // Candidate emission shared by every KF scoring kernel (SIMT dp4a, SIMT
 // generic, tcgen05).  One thread owns one row s of a 128-row strip and walks
-// the columns of a reference block pair (I, J) in increasing t, so the rank of
-// a candidate inside (row, block pair) is a running per-thread counter; that
-// rank plus a prefix sum over per-row counts reproduces the reference's
-// emission order (gnn_utils.py:262-301) without sorting.
+// the 128 columns of one tile in increasing t, so the rank of a candidate
+// inside (row, column tile) is a running per-thread counter; that rank plus a
+// prefix sum over the per-(block pair, row, tile) counts reproduces the
+// reference's emission order (gnn_utils.py:262-301) without sorting, and lets
+// any warp score any tile independently.
 #pragma once
 #include "gg_common.cuh"
 
@@ -12,7 +13,9 @@ namespace ggkf {
 constexpr int kBlock = GG_KF_BLOCK;  // rows / columns of a reference block
 constexpr int kStrip = 128;          // rows per CTA (one per thread)
 constexpr int kStripsPerBlock = kBlock / kStrip;
-constexpr int kStageCap = 128;       // records staged per warp before a coalesced flush
+constexpr int kTile = 128;           // columns per rank-counting tile
+constexpr int kTilesPerBlock = kBlock / kTile;
+constexpr int kStageCap = 64;        // records staged per warp before a coalesced flush
 
 struct EmitOut {
   gg_kf_rec_t* recs;
@@ -36,7 +39,7 @@ struct KfArgs {
 
 struct WarpStage {
   uint4 rec[kStageCap];
-  uint16_t scratch[32][32];  // [entry][lane]: (dot << 5) | column bit
+  uint8_t dot[32][32];  // [column bit][lane]: dot of the candidates of the current 32-column chunk (dot <= 225)
   int fill;
   int pad[3];
 };
@@ -55,10 +58,12 @@ __device__ __forceinline__ void stage_flush(WarpStage& ws, const EmitOut& out, i
   __syncwarp();
 }
 
-// Every lane has pushed n_l entries into ws.scratch[.][lane]; turn them into
+// Every lane has marked its exact candidates of the current chunk in `exact`
+// (bit b = column t0 + b) and left their dots in ws.dot[b][lane]; turn them into
 // records.  Must be called by the whole warp.
-__device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, int lane, int n_l, uint32_t s,
-                                             uint32_t t0, uint32_t& row_cnt) {
+__device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, int lane, uint32_t exact, uint32_t s,
+                                             uint32_t t0, uint32_t& tile_cnt) {
+  const int n_l = __popc(exact);
   int incl = n_l;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -74,23 +79,25 @@ __device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, 
     if (lane == 0) base = atomicAdd(out.status, static_cast<unsigned long long>(total));
     base = __shfl_sync(0xFFFFFFFFu, base, 0) + off;
     uint4* dst = reinterpret_cast<uint4*>(out.recs);
-    for (int i = 0; i < n_l; ++i) {
-      const uint32_t e = ws.scratch[i][lane];
+    int i = 0;
+    for (uint32_t m = exact; m; m &= m - 1, ++i) {
+      const int b = __ffs(m) - 1;
       if (static_cast<long long>(base + i) < out.capacity)
-        dst[base + i] = make_uint4(s, t0 + (e & 31u), row_cnt + i, e >> 5);
+        dst[base + i] = make_uint4(s, t0 + b, tile_cnt + i, ws.dot[b][lane]);
     }
   } else {
     if (ws.fill + total > kStageCap) stage_flush(ws, out, lane);
     const int fill = ws.fill;
-    for (int i = 0; i < n_l; ++i) {
-      const uint32_t e = ws.scratch[i][lane];
-      ws.rec[fill + off + i] = make_uint4(s, t0 + (e & 31u), row_cnt + i, e >> 5);
+    int i = 0;
+    for (uint32_t m = exact; m; m &= m - 1, ++i) {
+      const int b = __ffs(m) - 1;
+      ws.rec[fill + off + i] = make_uint4(s, t0 + b, tile_cnt + i, ws.dot[b][lane]);
     }
     __syncwarp();
     if (lane == 0) ws.fill = fill + total;
     __syncwarp();
   }
-  row_cnt += n_l;
+  tile_cnt += n_l;
 }
 
 // valid-column bits of the 32-column chunk starting at block-local column c0
@@ -105,8 +112,9 @@ __device__ __forceinline__ uint32_t chunk_diag_mask(int r, int c0) {
   return first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : ~((1u << first) - 1u));
 }
 
-__device__ __forceinline__ long long rowcnt_index(int i_local, int n_jblocks, int j, int r) {
-  return (static_cast<long long>(i_local) * n_jblocks + j) * kBlock + r;
+// counts laid out so that a plain prefix sum walks (I, J, row, tile) = the reference's emission order
+__device__ __forceinline__ long long rowcnt_index(int i_local, int n_jblocks, int j, int r, int tile) {
+  return ((static_cast<long long>(i_local) * n_jblocks + j) * kBlock + r) * kTilesPerBlock + tile;
 }
 
 }  // namespace ggkf

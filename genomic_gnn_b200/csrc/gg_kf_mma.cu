@@ -14,10 +14,12 @@
 //     units of the upper triangle; the strip's A rows (<= 128 KB) stay resident
 //     in shared memory across all its column tiles, B tiles stream through a
 //     multi-stage mbarrier ring;
-//   * warp roles: warps 0-3 epilogue (TMEM -> registers -> integer threshold
-//     test -> staged candidate records), warp 4 TMA producer, warp 5 MMA issuer
-//     and TMEM owner; four 128-column accumulators let the epilogue of tile n
-//     overlap the MMAs of tiles n+1..n+3.
+//   * warp roles: warps 0-11 are three epilogue groups of 128 threads (TMEM ->
+//     registers -> integer threshold test -> staged candidate records) that take
+//     the accumulator tiles round-robin -- one group alone is issue-latency
+//     bound at ~2.6x the MMA time of a tile --, warp 12 is the TMA producer,
+//     warp 13 the MMA issuer and TMEM owner; four 128-column accumulators keep
+//     the tensor pipe ahead of the epilogues.
 #include <cuda.h>
 
 #include "gg_kf_emit.cuh"
@@ -33,9 +35,12 @@ constexpr int kStageBytes = kTileN * kKBlock;  // 16 KB
 constexpr int kAccStages = 4;         // 4 x 128 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kMaxBStages = 8;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
-constexpr int kTilesPerBlock = kBlock / kTileN;  // 8 column tiles per reference block
+constexpr int kEpiGroups = 3;
+constexpr int kGroupThreads = 128;
+constexpr int kEpiThreads = kEpiGroups * kGroupThreads;
+constexpr int kProducerWarp = kEpiThreads / 32, kMmaWarp = kProducerWarp + 1;
+constexpr int kThreads = kEpiThreads + 64;
+static_assert(kTileN == kTile, "rank tiles and accumulator tiles must coincide");
 constexpr int kMaxD = 1024;           // A strip must fit shared memory next to the B ring
 
 struct __align__(8) Barriers {
@@ -58,21 +63,42 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done;
+}
 // bounded spin: a protocol bug must surface as an error, never as a hung GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, int* error_flag) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
   *error_flag = 1;
   __trap();
+}
+// Whole-warp wait whose exit is a warp vote: control flow after it is provably
+// uniform, so loop state, descriptors and addresses stay in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(unsigned long long* bar, uint32_t parity, int* error_flag) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin)
+    if (__all_sync(0xFFFFFFFFu, mbar_try_wait(bar, parity))) return;
+  *error_flag = 1;
+  __trap();
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, unsigned long long* bar, int c0,
                                             int c1) {
@@ -184,7 +210,7 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
   uint16_t* sqn = reinterpret_cast<uint16_t*>(smem_b + static_cast<size_t>(n_bstages) * kStageBytes);
-  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kBlock);
+  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kEpiGroups * kBlock);  // sqn: one panel per epilogue group
   Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -198,12 +224,12 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&bars->acc_full[i], 1);
-      mbar_init(&bars->acc_empty[i], kEpiThreads / 32);
+      mbar_init(&bars->acc_empty[i], kGroupThreads / 32);
     }
     bars->error = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
                  "n"(kTmemCols)
                  : "memory");
@@ -212,27 +238,40 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  // This CTA owns all 512 columns of its SM's tensor memory, so the allocation starts at lane 0 / column 0;
+  // using the literal keeps every TMEM address in uniform registers.
+  if (bars->tmem_base != 0) {
+    if (tid == 0) *error_flag = 2;
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0;
 
   // contiguous unit range of this CTA
   const long long base_units = total_units / gridDim.x, extra = total_units % gridDim.x;
   const long long u0 = base_units * blockIdx.x + (blockIdx.x < extra ? blockIdx.x : extra);
   const long long n_units = base_units + (blockIdx.x < extra ? 1 : 0);
 
-  if (warp == 4) {
+  // The producer and MMA warps run their loops warp-uniformly (all 32 lanes wait and
+  // count; one lane issues): addresses, descriptors and phases then live in
+  // uniform registers.  A lane-0-only loop costs an ELECT + R2UR.BROADCAST per
+  // operand and made the single issuing thread the bottleneck (profiles/r1).
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
-    if (lane == 0 && n_units > 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    if (n_units > 0) {
+      if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
       Walk w = walk_begin(a, u0, n_units);
       int cur_strip = -1;
       uint32_t a_round = 0, stage = 0, round = 0;
       for (; w.left > 0; walk_next(a, w)) {
         if (w.strip != cur_strip) {
-          if (a_round > 0) mbar_wait(&bars->a_empty, (a_round - 1) & 1, &bars->error);  // MMAs on the old strip done
-          mbar_expect_tx(&bars->a_full, static_cast<uint32_t>(n_kblocks) * kStageBytes);
-          for (int kb = 0; kb < n_kblocks; ++kb)
-            tma_load_2d(smem_a + static_cast<size_t>(kb) * kStageBytes, &tmap, &bars->a_full, kb * kKBlock,
-                        w.strip * kTileM);
+          if (a_round > 0) mbar_wait_warp(&bars->a_empty, (a_round - 1) & 1, &bars->error);  // MMAs on the old strip done
+          if (elect_one()) {
+            mbar_expect_tx(&bars->a_full, static_cast<uint32_t>(n_kblocks) * kStageBytes);
+            for (int kb = 0; kb < n_kblocks; ++kb)
+              tma_load_2d(smem_a + static_cast<size_t>(kb) * kStageBytes, &tmap, &bars->a_full, kb * kKBlock,
+                          w.strip * kTileM);
+          }
+          __syncwarp();
           cur_strip = w.strip;
           ++a_round;
         }
@@ -240,10 +279,13 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
         for (int ct = first_tile(w); ct < t_end; ++ct) {
           const int col = w.j_block * kBlock + ct * kTileN;
           for (int kb = 0; kb < n_kblocks; ++kb) {
-            if (round > 0) mbar_wait(&bars->b_empty[stage], (round - 1) & 1, &bars->error);
-            mbar_expect_tx(&bars->b_full[stage], kStageBytes);
-            tma_load_2d(smem_b + static_cast<size_t>(stage) * kStageBytes, &tmap, &bars->b_full[stage], kb * kKBlock,
-                        col);
+            if (round > 0) mbar_wait_warp(&bars->b_empty[stage], (round - 1) & 1, &bars->error);
+            if (elect_one()) {
+              mbar_expect_tx(&bars->b_full[stage], kStageBytes);
+              tma_load_2d(smem_b + static_cast<size_t>(stage) * kStageBytes, &tmap, &bars->b_full[stage],
+                          kb * kKBlock, col);
+            }
+            __syncwarp();
             if (++stage == static_cast<uint32_t>(n_bstages)) {
               stage = 0;
               ++round;
@@ -252,41 +294,51 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && n_units > 0) {
+    if (n_units > 0) {
       Walk w = walk_begin(a, u0, n_units);
       int cur_strip = -1;
       uint32_t a_round = 0, stage = 0, round = 0, acc = 0, acc_round = 0;
+      const uint32_t desc_hi = static_cast<uint32_t>(umma_desc_sw128(0) >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem_a)));
+      const uint32_t b_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem_b)));
       for (; w.left > 0; walk_next(a, w)) {
         if (w.strip != cur_strip) {
-          if (cur_strip >= 0) tc_commit(&bars->a_empty);  // fires when every MMA issued so far has retired
-          mbar_wait(&bars->a_full, a_round & 1, &bars->error);
+          if (cur_strip >= 0 && elect_one()) tc_commit(&bars->a_empty);  // fires when every MMA issued so far retired
+          __syncwarp();
+          mbar_wait_warp(&bars->a_full, a_round & 1, &bars->error);
           tc_fence_after();
           cur_strip = w.strip;
           ++a_round;
         }
         const int t_end = last_tile(a, w);
         for (int ct = first_tile(w); ct < t_end; ++ct) {
-          if (acc_round > 0) mbar_wait(&bars->acc_empty[acc], (acc_round - 1) & 1, &bars->error);
+          if (acc_round > 0) mbar_wait_warp(&bars->acc_empty[acc], (acc_round - 1) & 1, &bars->error);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * kTileN;
           for (int kb = 0; kb < n_kblocks; ++kb) {
-            mbar_wait(&bars->b_full[stage], round & 1, &bars->error);
+            mbar_wait_warp(&bars->b_full[stage], round & 1, &bars->error);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem_a + static_cast<size_t>(kb) * kStageBytes);
-            const uint32_t b_addr = smem_u32(smem_b + static_cast<size_t>(stage) * kStageBytes);
+            // descriptor low words: start address in 16-byte units (the tiles are 1024-byte aligned, < 256 KB)
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(kb) * (kStageBytes >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4)
-              tc_mma_i8(tmem_d, umma_desc_sw128(a_addr + k4 * kUmmaK), umma_desc_sw128(b_addr + k4 * kUmmaK), kIdesc,
-                        (kb | k4) != 0);
-            tc_commit(&bars->b_empty[stage]);  // smem slot reusable once these MMAs have read it
+              for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
+                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k4 * (kUmmaK >> 4));
+                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k4 * (kUmmaK >> 4));
+                tc_mma_i8(tmem_d, da, db, kIdesc, (kb | k4) != 0);
+              }
+              tc_commit(&bars->b_empty[stage]);  // smem slot reusable once these MMAs have read it
+              if (kb == n_kblocks - 1) tc_commit(&bars->acc_full[acc]);
+            }
+            __syncwarp();
             if (++stage == static_cast<uint32_t>(n_bstages)) {
               stage = 0;
               ++round;
             }
           }
-          tc_commit(&bars->acc_full[acc]);
           if (++acc == kAccStages) {
             acc = 0;
             ++acc_round;
@@ -295,36 +347,44 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
       }
     }
   } else {
-    // ===================== epilogue (warps 0-3: TMEM lanes 32*warp ..) =====================
+    // ===================== epilogue groups (warp % 4 selects the TMEM lane quarter) =====================
     WarpStage& ws = stages[warp];
     if (lane == 0) ws.fill = 0;
     __syncwarp();
+    const int group = warp / 4;
+    const int gt = tid % kGroupThreads;  // row of the strip == TMEM lane
+    uint16_t* my_sqn = sqn + group * kBlock;
     if (n_units > 0) {
       Walk w = walk_begin(a, u0, n_units);
-      uint32_t acc = 0, acc_round = 0;
+      uint32_t tile_seq = 0;  // position in this CTA's tile sequence (same enumeration as the MMA warp)
       for (; w.left > 0; walk_next(a, w)) {
         const long long col0 = static_cast<long long>(w.j_block) * kBlock;
         const int cols_in_block = static_cast<int>(min(static_cast<long long>(kBlock), a.n - col0));
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // everyone is done with the old sqn panel
-        for (int c = tid; c < kBlock; c += kEpiThreads)
-          sqn[c] = c < cols_in_block ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-
-        const int r = (w.strip % kStripsPerBlock) * kStrip + tid;  // block-local row
-        const long long s = static_cast<long long>(w.strip) * kStrip + tid;
+        const int r = (w.strip % kStripsPerBlock) * kStrip + gt;  // block-local row
+        const long long s = static_cast<long long>(w.strip) * kStrip + gt;
         const bool row_ok = s < a.n;
-        uint32_t sq_i = 0, scale_i = 0;
-        if (row_ok) {
-          sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
-          scale_i = __ldg(a.fast_scale + sq_i);
-        }
         const bool diag = w.i_block == w.j_block;
-        uint32_t row_cnt = 0;
+        uint32_t sq_i = 0, scale_i = 0;
+        bool panel_loaded = false;
         const int t_end = last_tile(a, w);
-        for (int ct = first_tile(w); ct < t_end; ++ct) {
-          mbar_wait(&bars->acc_full[acc], acc_round & 1, &bars->error);
+        for (int ct = first_tile(w); ct < t_end; ++ct, ++tile_seq) {
+          if (tile_seq % kEpiGroups != static_cast<uint32_t>(group)) continue;
+          if (!panel_loaded) {  // first tile this group takes in the unit: fetch the unit's column norms
+            asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+            for (int c = gt; c < kBlock; c += kGroupThreads)
+              my_sqn[c] = c < cols_in_block ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
+            asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+            if (row_ok) {
+              sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
+              scale_i = __ldg(a.fast_scale + sq_i);
+            }
+            panel_loaded = true;
+          }
+          const uint32_t acc = tile_seq % kAccStages;
+          mbar_wait(&bars->acc_full[acc], (tile_seq / kAccStages) & 1, &bars->error);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * kTileN;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * kTileN;
+          uint32_t tile_cnt = 0;
 #pragma unroll 1
           for (int cc = 0; cc < kTileN; cc += 32) {
             const int c0 = ct * kTileN + cc;  // block-local column of bit 0
@@ -333,39 +393,38 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
             uint32_t mask = 0;
 #pragma unroll
             for (int b = 0; b < 32; ++b)
-              mask |= static_cast<uint32_t>(((v[b] * v[b]) << a.fast_shift) > scale_i * sqn[c0 + b]) << b;
+              mask |= static_cast<uint32_t>(((v[b] * v[b]) << a.fast_shift) > scale_i * my_sqn[c0 + b]) << b;
             mask &= chunk_col_mask(cols_in_block, c0);
             if (diag) mask &= chunk_diag_mask(r, c0);
             if (!row_ok) mask = 0;
             if (__any_sync(0xFFFFFFFFu, mask != 0)) {
-              int n_l = 0;
+              uint32_t exact = 0;
 #pragma unroll
               for (int b = 0; b < 32; ++b) {
                 if ((mask >> b) & 1u) {
-                  if (v[b] >= __ldg(a.dmin + sq_i * sqn[c0 + b]))
-                    ws.scratch[n_l++][lane] = static_cast<uint16_t>((v[b] << 5) | b);
+                  if (v[b] >= __ldg(a.dmin + sq_i * my_sqn[c0 + b])) {
+                    exact |= 1u << b;
+                    ws.dot[b][lane] = static_cast<uint8_t>(v[b]);
+                  }
                 }
               }
-              stage_commit(ws, a.out, lane, n_l, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), row_cnt);
+              stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0),
+                           tile_cnt);
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
-          if (++acc == kAccStages) {
-            acc = 0;
-            ++acc_round;
-          }
+          if (row_ok) a.rowcnt[rowcnt_index(w.i_block - a.ib0, a.n_jblocks, w.j_block, r, ct)] = tile_cnt;
         }
-        stage_flush(ws, a.out, lane);
-        if (row_ok) a.rowcnt[rowcnt_index(w.i_block - a.ib0, a.n_jblocks, w.j_block, r)] = row_cnt;
       }
+      stage_flush(ws, a.out, lane);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
@@ -410,7 +469,7 @@ int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
   }
 
   const int n_kblocks = a.d / kKBlock;
-  const size_t fixed = static_cast<size_t>(n_kblocks) * kStageBytes + kBlock * sizeof(uint16_t) +
+  const size_t fixed = static_cast<size_t>(n_kblocks) * kStageBytes + kEpiGroups * kBlock * sizeof(uint16_t) +
                        (kEpiThreads / 32) * sizeof(WarpStage) + sizeof(Barriers) + 1024 /* base alignment slack */;
   int dev = 0, max_smem = 0;
   GG_CUDA_CHECK(cudaGetDevice(&dev));
