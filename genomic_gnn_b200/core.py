@@ -335,7 +335,7 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
     scale_d = torch.from_numpy(scale.view(np.int32)).to(dev)
     params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl])
     rc_elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
-    rowcnt = torch.empty(max(rc_elems, 1), dtype=torch.int32, device=dev)
+    rowcnt = torch.empty(max(rc_elems, 1), dtype=torch.int64, device=dev)
     status = torch.empty(4, dtype=torch.int64, device=dev)
     if rec_capacity is None:
         rec_capacity = 1 << 22

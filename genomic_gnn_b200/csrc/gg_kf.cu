@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
       stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
     }
     if (((c0 + 32) & (kTile - 1)) == 0 || c0 + 32 >= cols_in_block) {  // end of a 128-column tile
-      if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = tile_cnt;
+      if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = static_cast<uint8_t>(tile_cnt);
       tile_cnt = 0;
     }
   }
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kStrip) kf_generic_kernel(KfArgs a) {
       stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
     }
     if (((c0 + 32) & (kTile - 1)) == 0 || c0 + 32 >= cols_in_block) {
-      if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = tile_cnt;
+      if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = static_cast<uint8_t>(tile_cnt);
       tile_cnt = 0;
     }
   }
@@ -224,21 +224,24 @@ int launch_dp4a(const KfArgs& a, long long units, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------- ordered compaction
-struct ToU64 {
-  __host__ __device__ unsigned long long operator()(uint32_t v) const { return v; }
+struct RowTotal {  // candidates of one (block pair, row): sum of its 8 packed tile counts
+  __host__ __device__ unsigned long long operator()(unsigned long long v) const { return byte_sum(v); }
 };
 
 __global__ void __launch_bounds__(256) scatter_kernel(const gg_kf_rec_t* recs, long long n_recs,
-                                                      const unsigned long long* offsets, const int32_t* sqnorm,
+                                                      const unsigned long long* offsets,
+                                                      const unsigned long long* rowcnt, const int32_t* sqnorm,
                                                       int ib0, int n_jblocks, int64_t* src, int64_t* dst, double* w64,
                                                       float* w32, uint32_t* dot_out) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_recs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 rc = __ldg(reinterpret_cast<const uint4*>(recs) + i);
     const uint32_t s = rc.x, t = rc.y;
-    const long long idx = rowcnt_index(static_cast<int>(s / kBlock) - ib0, n_jblocks, static_cast<int>(t / kBlock),
-                                       static_cast<int>(s % kBlock), static_cast<int>((t % kBlock) / kTile));
-    const unsigned long long pos = offsets[idx] + rc.z;
+    const long long word = rowcnt_word(static_cast<int>(s / kBlock) - ib0, n_jblocks, static_cast<int>(t / kBlock),
+                                       static_cast<int>(s % kBlock));
+    const int tile = static_cast<int>((t % kBlock) / kTile);
+    const unsigned long long earlier_tiles = __ldg(rowcnt + word) & ((1ull << (8 * tile)) - 1ull);
+    const unsigned long long pos = offsets[word] + byte_sum(earlier_tiles) + rc.z;
     src[pos] = s;
     dst[pos] = t;
     const double p = static_cast<double>(static_cast<long long>(sqnorm[s]) * static_cast<long long>(sqnorm[t]));
@@ -341,11 +344,11 @@ int check_params(const gg_kf_params_t* p) {
 extern "C" size_t gg_kf_rowcnt_elems(int64_t n, int iblock_begin, int iblock_end) {
   if (n <= 0 || iblock_end <= iblock_begin) return 0;
   const size_t nj = static_cast<size_t>((n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
-  return static_cast<size_t>(iblock_end - iblock_begin) * nj * GG_KF_BLOCK * ggkf::kTilesPerBlock;
+  return static_cast<size_t>(iblock_end - iblock_begin) * nj * GG_KF_BLOCK;
 }
 
 extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const int32_t* sqnorm, const uint16_t* dmin,
-                          const uint32_t* fast_scale, gg_kf_rec_t* recs, int64_t rec_capacity, uint32_t* rowcnt,
+                          const uint32_t* fast_scale, gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt,
                           int64_t* kf_status, gg_stream_t st) {
   if (int rc = check_params(p)) return rc;
   GG_REQUIRE(kf_status, GG_ERR_ARG, "null status");
@@ -357,7 +360,7 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   GG_REQUIRE(rec_capacity >= 0 && (rec_capacity == 0 || recs), GG_ERR_ARG, "record buffer");
   GG_REQUIRE((reinterpret_cast<uintptr_t>(counts) & 15) == 0 && (reinterpret_cast<uintptr_t>(recs) & 15) == 0,
              GG_ERR_ARG, "counts / recs must be 16-byte aligned");
-  GG_CUDA_CHECK(cudaMemsetAsync(rowcnt, 0, rc_elems * sizeof(uint32_t), s));
+  GG_CUDA_CHECK(cudaMemsetAsync(rowcnt, 0, rc_elems * sizeof(uint64_t), s));
 
   KfArgs a;
   a.counts = counts;
@@ -370,7 +373,7 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   a.ib1 = p->iblock_end;
   a.n_jblocks = static_cast<int>((p->n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
   a.fast_shift = p->fast_shift;
-  a.rowcnt = rowcnt;
+  a.rowcnt = reinterpret_cast<uint8_t*>(rowcnt);
   a.out.recs = recs;
   a.out.capacity = rec_capacity;
   a.out.status = reinterpret_cast<unsigned long long*>(kf_status);
@@ -405,11 +408,11 @@ extern "C" size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, in
   const size_t elems = gg_kf_rowcnt_elems(n, iblock_begin, iblock_end);
   gg::Carver c(nullptr);
   c.take<unsigned long long>(elems ? elems : 1);
-  c.take<char>(scan_temp_bytes<ToU64, uint32_t>(static_cast<long long>(elems ? elems : 1)));
+  c.take<char>(scan_temp_bytes<RowTotal, unsigned long long>(static_cast<long long>(elems ? elems : 1)));
   return c.used();
 }
 
-extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, int64_t n_recs, const uint32_t* rowcnt,
+extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
                               const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64,
                               float* weight32, uint32_t* dot_out, void* workspace, size_t workspace_bytes,
                               gg_stream_t st) {
@@ -423,12 +426,13 @@ extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, 
   const long long elems = static_cast<long long>(gg_kf_rowcnt_elems(p->n, p->iblock_begin, p->iblock_end));
   gg::Carver c(workspace);
   unsigned long long* offsets = c.take<unsigned long long>(elems);
-  size_t tb = scan_temp_bytes<ToU64, uint32_t>(elems);
+  size_t tb = scan_temp_bytes<RowTotal, unsigned long long>(elems);
   void* temp = c.take<char>(tb);
-  cub::TransformInputIterator<unsigned long long, ToU64, const uint32_t*> it(rowcnt, ToU64());
+  const unsigned long long* words = reinterpret_cast<const unsigned long long*>(rowcnt);
+  cub::TransformInputIterator<unsigned long long, RowTotal, const unsigned long long*> it(words, RowTotal());
   GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb, it, offsets, elems, s));
   const int n_jblocks = static_cast<int>((p->n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
-  scatter_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, sqnorm, p->iblock_begin, n_jblocks, edge_src,
+  scatter_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, words, sqnorm, p->iblock_begin, n_jblocks, edge_src,
                                                   edge_dst, weight64, weight32, dot_out);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;

@@ -33,7 +33,7 @@ struct KfArgs {
   int ib0, ib1;
   int n_jblocks;
   int fast_shift;
-  uint32_t* rowcnt;
+  uint8_t* rowcnt;  // one 64-bit word per (block pair, row): byte t = candidates of that row in column tile t
   EmitOut out;
 };
 
@@ -112,9 +112,18 @@ __device__ __forceinline__ uint32_t chunk_diag_mask(int r, int c0) {
   return first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : ~((1u << first) - 1u));
 }
 
-// counts laid out so that a plain prefix sum walks (I, J, row, tile) = the reference's emission order
+// Counts are laid out so that a plain prefix sum walks (I, J, row, tile) = the reference's emission order.
+// A (row, tile) count is <= 128, so the 8 tiles of a row pack into the bytes of one 64-bit word.
+static_assert(kTilesPerBlock == 8 && kTile <= 255, "tile counts are packed as 8 bytes per row");
+__host__ __device__ __forceinline__ long long rowcnt_word(int i_local, int n_jblocks, int j, int r) {
+  return (static_cast<long long>(i_local) * n_jblocks + j) * kBlock + r;
+}
 __device__ __forceinline__ long long rowcnt_index(int i_local, int n_jblocks, int j, int r, int tile) {
-  return ((static_cast<long long>(i_local) * n_jblocks + j) * kBlock + r) * kTilesPerBlock + tile;
+  return rowcnt_word(i_local, n_jblocks, j, r) * kTilesPerBlock + tile;
+}
+__host__ __device__ __forceinline__ unsigned long long byte_sum(unsigned long long x) {
+  const unsigned long long pair = (x & 0x00FF00FF00FF00FFull) + ((x >> 8) & 0x00FF00FF00FF00FFull);
+  return (pair * 0x0001000100010001ull) >> 48;
 }
 
 }  // namespace ggkf

@@ -415,7 +415,7 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
-          if (row_ok) a.rowcnt[rowcnt_index(w.i_block - a.ib0, a.n_jblocks, w.j_block, r, ct)] = tile_cnt;
+          if (row_ok) a.rowcnt[rowcnt_index(w.i_block - a.ib0, a.n_jblocks, w.j_block, r, ct)] = static_cast<uint8_t>(tile_cnt);
         }
       }
       stage_flush(ws, a.out, lane);

@@ -144,13 +144,15 @@ GG_API int gg_kf_features_f32(const uint8_t* counts, int64_t n, int d, const int
  *
  * gg_kf_emit scores every pair s < t with s in the row blocks
  * [iblock_begin, iblock_end) (GG_KF_BLOCK rows each; multi-GPU sharding unit),
- * writes one record per candidate (unordered) and per-(block pair,row) counts.
+ * writes one record per candidate (unordered) and, per (block pair, row), the
+ * candidate counts of its eight 128-column tiles packed as the bytes of one
+ * 64-bit word (rowcnt, gg_kf_rowcnt_elems() words).
  * gg_kf_finalize turns the counts into offsets and scatters the records into
  * the reference's emission order: block (I, J >= I), then row, then column.
  * ------------------------------------------------------------------------ */
 typedef struct {
   uint32_t s, t;
-  uint32_t rank; /* rank of t among the candidates of row s inside block pair (I,J) */
+  uint32_t rank; /* rank of t among the candidates of row s inside its 128-column tile */
   uint32_t dot;
 } gg_kf_rec_t;
 
@@ -171,10 +173,10 @@ typedef struct {
 GG_API size_t gg_kf_rowcnt_elems(int64_t n, int iblock_begin, int iblock_end);
 GG_API int gg_kf_emit(const gg_kf_params_t* h_params, const uint8_t* counts, const int32_t* sqnorm,
                const uint16_t* dmin, const uint32_t* fast_scale /* [max sqnorm + 1] */,
-               gg_kf_rec_t* recs, int64_t rec_capacity, uint32_t* rowcnt, int64_t* kf_status, gg_stream_t st);
+               gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt, int64_t* kf_status, gg_stream_t st);
 
 GG_API size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end);
-GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint32_t* rowcnt,
+GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
                    const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
                    uint32_t* dot_out /* nullable: dot per edge, for top-n */, void* workspace, size_t workspace_bytes,
                    gg_stream_t st);
