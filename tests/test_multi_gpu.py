@@ -1,0 +1,60 @@
+"""N-GPU build == 1-GPU build (NCCL, one process per GPU).  Needs >= 2 GPUs; skipped otherwise."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir, k, small_k, thr, topk, n_reads):
+    import torch.distributed as dist
+
+    from genomic_gnn_b200 import core, dist as ggdist
+    from genomic_gnn_b200.synth import synthetic_reads
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        comm = ggdist.TorchComm()
+        reads = synthetic_reads(n_reads, 150, seed=5)
+        # sprinkle N so that bridge records exist on some ranks
+        reads[::97, 60] = ord("N")
+        lo, hi = ggdist.shard_bounds(n_reads, world, rank)
+        shard = core.upload_reads(reads[lo:hi], pos_base=lo * 150)
+        got = core.build_graph(shard, k, small_k, edges_threshold=thr, edges_keep_top_k=topk, comm=comm)
+        if rank == 0:
+            ref = core.build_graph(reads, k, small_k, edges_threshold=thr, edges_keep_top_k=topk)
+            assert torch.equal(got.db.node_codes, ref.db.node_codes)
+            assert torch.equal(got.db.edge_index, ref.db.edge_index)
+            assert torch.equal(got.db.weight, ref.db.weight)
+            for a, b in zip(got.kf, ref.kf):
+                assert a.n_candidates == b.n_candidates
+                assert torch.equal(a.edge_index, b.edge_index), (a.edge_index.shape, b.edge_index.shape)
+                assert torch.equal(a.weight64, b.weight64)
+            open(os.path.join(out_dir, "ok"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("k,small_k,thr,topk,n_reads", [
+    (7, "2,5", 0.8, 0.01, 40_000),     # threshold-bound, 16 row blocks
+    (6, "2,4", 0.0, 0.01, 20_000),     # global top-n binding: class histogram all-reduce + tie split across ranks
+])
+def test_multi_gpu_equals_single(tmp_path, k, small_k, thr, topk, n_reads):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), k, small_k, thr, topk, n_reads), nprocs=world, join=True)
+    assert os.path.exists(tmp_path / "ok")
