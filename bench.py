@@ -269,7 +269,11 @@ def run_ours(a):
         return core.build_graph(resident, **kw)
 
     def step_e2e():
-        stream = core.upload_reads(reads_host, pos_base=pos_base)     # H2D of this step's reads (pinned source)
+        if world == 1:   # public host-to-host call: chunked H2D under the counting, D2H under the KF kernels
+            g = core.build_graph_to_host(reads_host, a.k, a.small_k, edges_threshold=a.threshold,
+                                         edges_keep_top_k=a.top_k, kf_impl=a.kf_impl)
+            return g, g.d2h_bytes
+        stream = core.upload_reads(reads_host, pos_base=pos_base)     # H2D of this rank's reads (pinned source)
         built = core.build_graph(stream, **kw)
         host, nbytes = to_host_pinned(graph_tensors(built)) if rank == 0 else ([], 0)
         torch.cuda.current_stream().synchronize()                     # results are on the host

@@ -21,6 +21,6 @@ from .builders import (  # noqa: F401
     networkx_to_dataloader_full_batch,
     networkx_to_dataloader_mini_batch,
 )
-from .core import build_graph  # noqa: F401
+from .core import build_graph, build_graph_to_host  # noqa: F401
 
 __version__ = "0.1.0"

@@ -327,6 +327,9 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
     Returns (recs, n_recs, rowcnt, params)."""
     lib = _lib.load()
     dev = counts.device
+    if counts.shape[1] < 32 and impl in ("auto", "tcgen05"):
+        # the tensor path wants >= 32 bytes of K per row (one kind::i8 MMA); zero columns change nothing
+        counts = torch.nn.functional.pad(counts, (0, 32 - counts.shape[1]))
     n, d = int(counts.shape[0]), int(counts.shape[1])
     nb = _row_blocks(n)
     iblock_end = nb if iblock_end is None else iblock_end
@@ -521,3 +524,118 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
             out.kf.append(kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m,
                                    impl=kf_impl, iblock_begin=b0, iblock_end=b1, comm=comm))
     return out
+
+
+# --------------------------------------------------------------------------- host-to-host build with overlapped copies
+@dataclass
+class HostGraph:
+    """Every tensor the reference's builders hand to PyG, in pinned host memory."""
+    k: int
+    num_nodes: int
+    node_codes: torch.Tensor
+    edge_index: torch.Tensor
+    weight: torch.Tensor
+    x: List[torch.Tensor]
+    kf_edge_index: List[torch.Tensor]
+    kf_weight: List[torch.Tensor]
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream():
+    dev = torch.cuda.current_device()
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[dev]
+
+
+def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kmers=False, edges_threshold=0.0,
+                        edges_keep_top_k=None, kf_impl="auto", chunks: int = 8) -> HostGraph:
+    """The whole path from host reads to host graph tensors (what ``create_graphs`` hands to the CPU-side PyG
+    loaders), with the PCIe copies overlapped with the kernels: the reads go up in ``chunks`` pieces that are
+    counted as they land, the DB graph and the features go down while the KF sets are scored, and each KF set
+    goes down while the next one is scored.
+
+    ``reads``: uint8 [n_reads, read_len] ASCII on the host (pinned memory avoids a staging copy)."""
+    _require_cuda()
+    lib = _lib.load()
+    if not (isinstance(reads, torch.Tensor) and reads.dtype == torch.uint8 and reads.dim() == 2 and not reads.is_cuda):
+        raise ValueError("reads must be a host uint8 [n_reads, read_len] tensor")
+    if not (1 <= k <= _lib.GG_MAX_K):
+        raise ValueError(f"k must be in [1, {_lib.GG_MAX_K}]")
+    n_reads, length = int(reads.shape[0]), int(reads.shape[1])
+    n_bytes = n_reads * length
+    dev = torch.device("cuda", torch.cuda.current_device())
+    main, side = torch.cuda.current_stream(), _copy_stream()
+    buf = torch.empty(_padded(n_bytes), dtype=torch.uint8, device=dev)
+    bins = int(lib.gg_hist_bins(k))
+    hist = torch.empty(bins, dtype=torch.int32, device=dev)
+    first = torch.empty(bins, dtype=torch.int64, device=dev)
+    status = torch.empty(_lib.ST_WORDS, dtype=torch.int64, device=dev)
+    cap = 1 << 16
+    bridges = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    st = _stream()
+    check(lib.gg_count_reset(k, ptr(hist), ptr(first), ptr(status), st), "gg_count_reset")
+    side.wait_stream(main)
+    buf.record_stream(side)
+    flat = reads.reshape(-1)
+    per = max(16, -(-n_reads // max(chunks, 1) // 16) * 16)  # reads per piece, multiple of 16: 16-byte aligned offsets
+    for lo in range(0, n_reads, per):
+        hi = min(n_reads, lo + per)
+        with torch.cuda.stream(side):
+            buf[lo * length : hi * length].copy_(flat[lo * length : hi * length], non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(side)
+        main.wait_event(landed)
+        with _stage("k1_count"):
+            check(lib.gg_count_kp1mers(C.c_void_p(buf.data_ptr() + lo * length), (hi - lo) * length, length, k,
+                                       lo * length, ptr(hist), ptr(bridges), cap, ptr(status), st), "gg_count_kp1mers")
+    with _stage("k1_first"):
+        check(lib.gg_first_occurrence(ptr(buf), n_bytes, length, k, 0, ptr(hist), ptr(first), ptr(status), st),
+              "gg_first_occurrence")
+    st_host = status.cpu()
+    if int(st_host[_lib.ST_BAD_BYTES]) > 0:
+        raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN")
+    nb = int(st_host[_lib.ST_BRIDGES])
+    if nb > cap:  # many internal N runs: redo the count in one piece with room for every bridge record
+        cr = count_kp1mers(ReadStream(buf, n_bytes, length, n_reads), k, bridge_capacity=nb)
+    else:
+        cr = CountResult(k, hist, first, bridges, nb, status, int(st_host[_lib.ST_NONZERO]))
+    if cr.n_nonzero == 0 and cr.n_bridges == 0:
+        raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
+    db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
+    kcs = [kf_counts(db.node_codes, k, int(s)) for s in str(small_k).split(",")]
+    xs = [kf_features_f32(kc) for kc in kcs]
+
+    d2h = 0
+    keep_alive = []
+
+    def down(tensors):
+        """Queue device->pinned-host copies on the side stream, ordered after what the main stream has produced."""
+        nonlocal d2h
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        out = []
+        with torch.cuda.stream(side):
+            for t in tensors:
+                t.record_stream(side)
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t, non_blocking=True)
+                out.append(h)
+                d2h += t.numel() * t.element_size()
+        keep_alive.extend(tensors)
+        return out
+
+    h_codes, h_ei, h_w, *h_x = down([db.node_codes, db.edge_index, db.weight, *xs])
+    kf_ei, kf_w = [], []
+    for kc in kcs:
+        kf = kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl)
+        e, w = down([kf.edge_index, kf.weight])
+        kf_ei.append(e)
+        kf_w.append(w)
+    side.synchronize()
+    return HostGraph(k, db.num_nodes, h_codes, h_ei, h_w, h_x, kf_ei, kf_w, n_bytes, d2h)

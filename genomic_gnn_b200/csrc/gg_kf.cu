@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
         for (int w = 0; w < W; ++w) dot = __dp4a(row[w], cw[w], dot);
         if (dot >= __ldg(a.dmin + sq_i * sqn[c0 + b])) {
           exact |= 1u << b;
-          ws.dot[b][lane] = static_cast<uint8_t>(dot);
+          stage_set_dot(ws, b, lane, dot);
         }
       }
       stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kStrip) kf_generic_kernel(KfArgs a) {
         if ((mask >> b) & 1u) {
           if (acc[b] >= __ldg(a.dmin + sq_i * sqn[b])) {
             exact |= 1u << b;
-            ws.dot[b][lane] = static_cast<uint8_t>(acc[b]);
+            stage_set_dot(ws, b, lane, acc[b]);
           }
         }
       }
@@ -379,8 +379,8 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   a.out.status = reinterpret_cast<unsigned long long*>(kf_status);
 
   int impl = p->impl;
-  if (impl == GG_KF_IMPL_AUTO)
-    impl = p->d <= 64 ? GG_KF_IMPL_DP4A : ((p->d % 128 == 0 && p->d <= 1024) ? GG_KF_IMPL_TCGEN05 : GG_KF_IMPL_NAIVE);
+  const bool mma_ok = p->d == 32 || p->d == 64 || (p->d % 128 == 0 && p->d <= 1024);
+  if (impl == GG_KF_IMPL_AUTO) impl = mma_ok ? GG_KF_IMPL_TCGEN05 : (p->d <= 64 ? GG_KF_IMPL_DP4A : GG_KF_IMPL_NAIVE);
   const long long units = static_cast<long long>(a.ib1 - a.ib0) * a.n_jblocks * kStripsPerBlock;
   GG_REQUIRE(units < (1ll << 31), GG_ERR_ARG, "too many work units for one launch; shard the row blocks");
   switch (impl) {
@@ -391,7 +391,6 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
       gg::set_error("dp4a KF kernel supports d in {4, 16, 64}, got %d", p->d);
       return GG_ERR_ARG;
     case GG_KF_IMPL_TCGEN05:
-      GG_REQUIRE(p->d % 128 == 0, GG_ERR_ARG, "tcgen05 KF kernel needs d % 128 == 0");
       return ggkf::emit_tcgen05(a, s);
     case GG_KF_IMPL_NAIVE:
       GG_REQUIRE(p->d % 64 == 0, GG_ERR_ARG, "generic KF kernel needs d % 64 == 0");

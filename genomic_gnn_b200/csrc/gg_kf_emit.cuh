@@ -39,10 +39,17 @@ struct KfArgs {
 
 struct WarpStage {
   uint4 rec[kStageCap];
-  uint8_t dot[32][32];  // [column bit][lane]: dot of the candidates of the current 32-column chunk (dot <= 225)
+  uint32_t dotw[8][32];  // [column bit / 4][lane]: dots of the current 32-column chunk, one byte each (dot <= 225)
   int fill;
   int pad[3];
 };
+
+__device__ __forceinline__ void stage_set_dot(WarpStage& ws, int b, int lane, uint32_t dot) {
+  reinterpret_cast<uint8_t*>(&ws.dotw[b >> 2][lane])[b & 3] = static_cast<uint8_t>(dot);
+}
+__device__ __forceinline__ uint32_t stage_get_dot(const WarpStage& ws, int b, int lane) {
+  return (ws.dotw[b >> 2][lane] >> (8 * (b & 3))) & 0xFFu;
+}
 
 __device__ __forceinline__ void stage_flush(WarpStage& ws, const EmitOut& out, int lane) {
   const int fill = ws.fill;  // warp-uniform
@@ -59,7 +66,7 @@ __device__ __forceinline__ void stage_flush(WarpStage& ws, const EmitOut& out, i
 }
 
 // Every lane has marked its exact candidates of the current chunk in `exact`
-// (bit b = column t0 + b) and left their dots in ws.dot[b][lane]; turn them into
+// (bit b = column t0 + b) and left their dots in ws.dotw (stage_set_dot); turn them into
 // records.  Must be called by the whole warp.
 __device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, int lane, uint32_t exact, uint32_t s,
                                              uint32_t t0, uint32_t& tile_cnt) {
@@ -83,7 +90,7 @@ __device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, 
     for (uint32_t m = exact; m; m &= m - 1, ++i) {
       const int b = __ffs(m) - 1;
       if (static_cast<long long>(base + i) < out.capacity)
-        dst[base + i] = make_uint4(s, t0 + b, tile_cnt + i, ws.dot[b][lane]);
+        dst[base + i] = make_uint4(s, t0 + b, tile_cnt + i, stage_get_dot(ws, b, lane));
     }
   } else {
     if (ws.fill + total > kStageCap) stage_flush(ws, out, lane);
@@ -91,7 +98,7 @@ __device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, 
     int i = 0;
     for (uint32_t m = exact; m; m &= m - 1, ++i) {
       const int b = __ffs(m) - 1;
-      ws.rec[fill + off + i] = make_uint4(s, t0 + b, tile_cnt + i, ws.dot[b][lane]);
+      ws.rec[fill + off + i] = make_uint4(s, t0 + b, tile_cnt + i, stage_get_dot(ws, b, lane));
     }
     __syncwarp();
     if (lane == 0) ws.fill = fill + total;

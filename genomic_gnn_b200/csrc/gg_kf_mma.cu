@@ -29,9 +29,8 @@ namespace {
 
 constexpr int kTileN = 128;           // columns per accumulator tile
 constexpr int kTileM = kStrip;        // 128 rows
-constexpr int kKBlock = 128;          // bytes of K per TMA box / smem stage (= one 128B swizzle row)
 constexpr int kUmmaK = 32;            // K per tcgen05.mma.kind::i8
-constexpr int kStageBytes = kTileN * kKBlock;  // 16 KB
+constexpr int kMaxKBlock = 128;       // widest TMA box / smem stage row: one 128-byte swizzle row
 constexpr int kAccStages = 4;         // 4 x 128 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kMaxBStages = 8;
@@ -136,17 +135,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major operand, 128-byte swizzle: 8-row groups are 1024 bytes apart (SBO), the
-// leading-dimension field is the canonical 1 for swizzled K-major layouts,
-// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
+// Geometry of one K block.  Row pitch in shared memory = kb_bytes (32, 64 or 128) with the matching TMA / UMMA
+// swizzle mode, so that a feature width of 16..64 bytes is a single block and wider rows are split into
+// 128-byte blocks.  K-major operand descriptor: 8-row groups are 8*kb_bytes apart (SBO), the leading-dimension
+// field is the canonical 1 for swizzled K-major layouts, descriptor version 1 (Blackwell).
+struct Geom {
+  int kb_bytes;      // bytes of K per TMA box row / per stage row
+  int n_kblocks;     // row pitch of `counts` / kb_bytes
+  int stage_bytes;   // 128 rows * kb_bytes
+  int mma_per_kb;    // kb_bytes / 32
+  uint32_t desc_hi;  // SBO, version, layout type
+};
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
 }
 // kind::i8, uint8 x uint8 -> s32, both operands K-major, M = 128, N = 128
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (0u << 10) | ((kTileN >> 3) << 17) | ((kTileM >> 4) << 24);
@@ -200,13 +201,16 @@ __device__ __forceinline__ int last_tile(const KfArgs& a, const Walk& w) {
 }
 
 // ---------------------------------------------------------------- kernel
+template <int KB_BYTES>
 __global__ void __launch_bounds__(kThreads, 1)
 kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bstages, long long total_units,
-                  int* error_flag) {
+                  int* error_flag, Geom g) {
   extern __shared__ unsigned char smem_raw[];
-  // 128-byte-swizzled TMA boxes and UMMA descriptors assume 1024-byte aligned tiles
+  // swizzled TMA boxes and UMMA descriptors assume (up to) 1024-byte aligned tiles
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int n_kblocks = a.d / kKBlock;
+  const int n_kblocks = g.n_kblocks;
+  constexpr int kKBlock = KB_BYTES;
+  constexpr int kStageBytes = kTileN * KB_BYTES;
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
   uint16_t* sqn = reinterpret_cast<uint16_t*>(smem_b + static_cast<size_t>(n_bstages) * kStageBytes);
@@ -300,9 +304,10 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
       Walk w = walk_begin(a, u0, n_units);
       int cur_strip = -1;
       uint32_t a_round = 0, stage = 0, round = 0, acc = 0, acc_round = 0;
-      const uint32_t desc_hi = static_cast<uint32_t>(umma_desc_sw128(0) >> 32);
-      const uint32_t a_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem_a)));
-      const uint32_t b_lo0 = static_cast<uint32_t>(umma_desc_sw128(smem_u32(smem_b)));
+      const uint32_t desc_hi = g.desc_hi;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b));
+      constexpr int mma_per_kb = KB_BYTES / kUmmaK;
       for (; w.left > 0; walk_next(a, w)) {
         if (w.strip != cur_strip) {
           if (cur_strip >= 0 && elect_one()) tc_commit(&bars->a_empty);  // fires when every MMA issued so far retired
@@ -325,7 +330,7 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
             const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
             if (elect_one()) {
 #pragma unroll
-              for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
+              for (int k4 = 0; k4 < mma_per_kb; ++k4) {
                 const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k4 * (kUmmaK >> 4));
                 const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k4 * (kUmmaK >> 4));
                 tc_mma_i8(tmem_d, da, db, kIdesc, (kb | k4) != 0);
@@ -398,15 +403,14 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
             if (diag) mask &= chunk_diag_mask(r, c0);
             if (!row_ok) mask = 0;
             if (__any_sync(0xFFFFFFFFu, mask != 0)) {
-              uint32_t exact = 0;
+              // rare path: park the chunk's dots (one byte each) so that the survivors can be indexed dynamically
 #pragma unroll
-              for (int b = 0; b < 32; ++b) {
-                if ((mask >> b) & 1u) {
-                  if (v[b] >= __ldg(a.dmin + sq_i * my_sqn[c0 + b])) {
-                    exact |= 1u << b;
-                    ws.dot[b][lane] = static_cast<uint8_t>(v[b]);
-                  }
-                }
+              for (int j = 0; j < 8; ++j)
+                ws.dotw[j][lane] = v[4 * j] | (v[4 * j + 1] << 8) | (v[4 * j + 2] << 16) | (v[4 * j + 3] << 24);
+              uint32_t exact = 0;
+              for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {
+                const int b = __ffs(m2) - 1;
+                if (stage_get_dot(ws, b, lane) >= __ldg(a.dmin + sq_i * my_sqn[c0 + b])) exact |= 1u << b;
               }
               stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0),
                            tile_cnt);
@@ -450,36 +454,46 @@ EncodeTiledFn encode_tiled() {
 }  // namespace
 
 int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
-  GG_REQUIRE(a.d % kKBlock == 0 && a.d >= kKBlock && a.d <= kMaxD, GG_ERR_ARG,
-             "tcgen05 KF kernel needs d in {128, 256, ..., 1024}");
+  // a.d is the row pitch of `counts` in bytes: 32 or 64 (one K block), or a multiple of 128 up to kMaxD
+  GG_REQUIRE(a.d == 32 || a.d == 64 || (a.d % kMaxKBlock == 0 && a.d >= kMaxKBlock && a.d <= kMaxD), GG_ERR_ARG,
+             "tcgen05 KF kernel needs a row pitch of 32, 64 or a multiple of 128 up to 1024 bytes");
   EncodeTiledFn encode = encode_tiled();
   GG_REQUIRE(encode != nullptr, GG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+
+  Geom g;
+  g.kb_bytes = a.d < kMaxKBlock ? a.d : kMaxKBlock;
+  g.n_kblocks = a.d / g.kb_bytes;
+  g.stage_bytes = kTileN * g.kb_bytes;
+  g.mma_per_kb = g.kb_bytes / kUmmaK;
+  const CUtensorMapSwizzle swz = g.kb_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                 : (g.kb_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+  const uint32_t layout_type = g.kb_bytes == 32 ? 6u : (g.kb_bytes == 64 ? 4u : 2u);  // UMMA SWIZZLE_32B/64B/128B
+  g.desc_hi = static_cast<uint32_t>((8 * g.kb_bytes) >> 4) | (1u << 14) | (layout_type << 29);
 
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.d), static_cast<cuuint64_t>(a.n)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.d)};  // row pitch in bytes
-  const cuuint32_t box[2] = {kKBlock, kTileM};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(g.kb_bytes), kTileM};
   const cuuint32_t elem[2] = {1, 1};
   const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(a.counts), dims, strides, box,
-                            elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            elem, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     gg::set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return GG_ERR_CUDA;
   }
 
-  const int n_kblocks = a.d / kKBlock;
-  const size_t fixed = static_cast<size_t>(n_kblocks) * kStageBytes + kEpiGroups * kBlock * sizeof(uint16_t) +
+  const size_t fixed = static_cast<size_t>(g.n_kblocks) * g.stage_bytes + kEpiGroups * kBlock * sizeof(uint16_t) +
                        (kEpiThreads / 32) * sizeof(WarpStage) + sizeof(Barriers) + 1024 /* base alignment slack */;
   int dev = 0, max_smem = 0;
   GG_CUDA_CHECK(cudaGetDevice(&dev));
   GG_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  int n_bstages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / kStageBytes);
+  int n_bstages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / g.stage_bytes);
   if (n_bstages > kMaxBStages) n_bstages = kMaxBStages;
   GG_REQUIRE(n_bstages >= 2, GG_ERR_ARG, "not enough shared memory for the B ring");
-  const size_t smem_bytes = fixed + static_cast<size_t>(n_bstages) * kStageBytes;
-  GG_CUDA_CHECK(cudaFuncSetAttribute(kf_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem_bytes)));
+  const size_t smem_bytes = fixed + static_cast<size_t>(n_bstages) * g.stage_bytes;
+  auto kernel = g.kb_bytes == 32 ? kf_tcgen05_kernel<32> : (g.kb_bytes == 64 ? kf_tcgen05_kernel<64> : kf_tcgen05_kernel<128>);
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
 
   // units of this shard: 8 strips per row block, n_j - I column blocks each
   long long total_units = 0;
@@ -488,7 +502,7 @@ int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
   const long long sms = gg::sm_count();
   const unsigned grid = static_cast<unsigned>(total_units < sms ? total_units : sms);
   int* error_flag = reinterpret_cast<int*>(a.out.status + 2);  // kf_status[2]
-  kf_tcgen05_kernel<<<grid, kThreads, smem_bytes, s>>>(tmap, a, n_bstages, total_units, error_flag);
+  kernel<<<grid, kThreads, smem_bytes, s>>>(tmap, a, n_bstages, total_units, error_flag, g);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

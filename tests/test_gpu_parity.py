@@ -152,17 +152,22 @@ def test_pipeline_matches_oracle(gg, k, n_reads, small_k, thr, topk):
         assert np.array_equal(got.kf[i].weight64.cpu().numpy(), want[f"edge_weight_KF{i}"])
 
 
-def test_kf_impls_agree(gg):
-    """dp4a (D = 64) and the generic slab kernel must emit identical edges."""
+@pytest.mark.parametrize("k,s,thr", [(6, 3, 0.5), (6, 2, 0.8), (6, 2, 0.0), (5, 1, 0.9), (7, 2, 0.75)])
+def test_kf_impls_agree(gg, k, s, thr):
+    """Narrow rows (D = 4, 16, 64): tensor path (rows padded to >= 32 bytes, 32B/64B swizzle), dp4a kernel and the
+    generic slab kernel must emit identical edges in identical order."""
     from genomic_gnn_b200 import core
 
-    reads = fast.synthetic_reads(4000, 150, seed=11)
-    built = core.build_graph(reads, 6, "3", with_kf=False)
+    reads = fast.synthetic_reads(4000 if k < 7 else 900, 150, seed=11 + k)
+    built = core.build_graph(reads, k, str(s), with_kf=False)
     kc = built.kf_counts[0]
-    a = core.kf_edges(kc.counts, kc.sqnorm, 0.5, None, sq_max=kc.m**2, impl="dp4a")
-    b = core.kf_edges(kc.counts, kc.sqnorm, 0.5, None, sq_max=kc.m**2, impl="naive")
+    a = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="dp4a")
+    b = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="tcgen05")
     assert a.edge_index.shape[1] > 0
     assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
+    if 4**s == 64:
+        c = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="naive")
+        assert torch.equal(a.edge_index, c.edge_index) and torch.equal(a.weight64, c.weight64)
 
 
 @pytest.mark.parametrize("k,s,n_reads,thr", [
@@ -219,6 +224,25 @@ def test_input_forms_agree(gg):
     for o in outs[1:]:
         for x, y in zip(outs[0], o):
             assert np.array_equal(x, y)
+
+
+def test_host_to_host_build_matches_device_build(gg):
+    from genomic_gnn_b200 import core
+
+    arr = fast.synthetic_reads(3001, 150, seed=6)
+    arr[::53, 20] = ord("N")
+    dev = core.build_graph(arr, 6, "2,4", edges_threshold=0.8, edges_keep_top_k=0.01)
+    for chunks in (1, 3, 8):
+        host = core.build_graph_to_host(torch.from_numpy(arr), 6, "2,4", edges_threshold=0.8, edges_keep_top_k=0.01,
+                                        chunks=chunks)
+        assert not host.edge_index.is_cuda and host.edge_index.is_pinned()
+        assert torch.equal(host.node_codes, dev.db.node_codes.cpu())
+        assert torch.equal(host.edge_index, dev.db.edge_index.cpu()) and torch.equal(host.weight, dev.db.weight.cpu())
+        for i in range(2):
+            assert torch.equal(host.x[i], dev.x[i].cpu())
+            assert torch.equal(host.kf_edge_index[i], dev.kf[i].edge_index.cpu())
+            assert torch.equal(host.kf_weight[i], dev.kf[i].weight.cpu())
+        assert host.h2d_bytes == arr.size
 
 
 def test_degenerate_inputs(gg):
