@@ -75,6 +75,9 @@ class LocalComm:
     def gather_cat(self, t, dim=0):
         return t
 
+    def gather_packed(self, tensors, sizes, dim_list):
+        return list(tensors)
+
 
 def _require_cuda():
     if not torch.cuda.is_available():
@@ -437,7 +440,8 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
     rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
     recs, n_recs, rowcnt, params = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
                                            rec_capacity=rec_capacity)
-    n_total = comm.sum_int(n_recs)
+    per_rank = comm.gather_ints(n_recs)
+    n_total = sum(per_rank)
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total
     ei, w64, w32, dot = kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=need_cut)
@@ -473,11 +477,10 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         if kept != expect:
             raise GGError(f"top-n select kept {kept} edges, expected {expect}")
         ei, w64, w32 = out[:, :expect], o64[:expect], o32[:expect]
+        per_rank = comm.gather_ints(expect) if comm.world > 1 else [expect]
     if gather and comm.world > 1:
-        with _stage("c2_gather_edges"):
-            ei = comm.gather_cat(ei.contiguous(), dim=1)
-            w64 = comm.gather_cat(w64.contiguous())
-            w32 = comm.gather_cat(w32.contiguous())
+        with _stage("c2_gather_edges"):  # one collective: edge_index, float64 and float32 weights packed together
+            ei, w64, w32 = comm.gather_packed([ei, w64, w32], per_rank, [1, 0, 0])
     return KFEdges(ei.contiguous(), w64, w32, n_total, cutoff, tie_budget, tie_total, impl)
 
 

@@ -88,6 +88,36 @@ class TorchComm:
         return cat.movedim(0, dim).contiguous()
 
 
+    def gather_packed(self, tensors, sizes, dim_list):
+        """One all-gather for several ragged tensors: ``tensors[i]`` is ragged along ``dim_list[i]`` with
+        ``sizes[r]`` entries on rank r.  Each rank packs its pieces into one byte buffer (padded to the largest
+        rank), a single all_gather_into_tensor moves everything, and the pieces are unpacked in rank order."""
+        mx = max(sizes)
+        if mx == 0:
+            return list(tensors)
+        rows = [t.movedim(d, 0).contiguous() for t, d in zip(tensors, dim_list)]
+        per_item = [r[0].numel() * r.element_size() if r.shape[0] else
+                    (r.element_size() * int(torch.tensor(r.shape[1:]).prod()) if r.dim() > 1 else r.element_size())
+                    for r in rows]
+        offs = [0]
+        for b in per_item:
+            offs.append(offs[-1] + (mx * b + 15) // 16 * 16)
+        mine = torch.zeros(offs[-1], dtype=torch.uint8, device=rows[0].device)
+        for r, b, o in zip(rows, per_item, offs):
+            n = r.shape[0]
+            if n:
+                mine[o : o + n * b] = r.reshape(-1).view(torch.uint8)
+        flat = torch.empty(self.world * offs[-1], dtype=torch.uint8, device=mine.device)
+        dist_.all_gather_into_tensor(flat, mine, group=self.group)
+        everyone = flat.view(self.world, offs[-1])
+        out = []
+        for r, b, o, d in zip(rows, per_item, offs, dim_list):
+            parts = [everyone[k, o : o + sizes[k] * b].view(r.dtype).reshape((sizes[k],) + tuple(r.shape[1:]))
+                     for k in range(self.world)]
+            out.append(torch.cat(parts, dim=0).movedim(0, d).contiguous())
+        return out
+
+
 _I64_MAX = torch.iinfo(torch.int64).max
 
 
@@ -96,16 +126,21 @@ def reduce_counts(cr, comm: TorchComm):
     histogram, the global first occurrences and all bridge records."""
     from .core import CountResult
 
-    hist = comm.sum_tensor_(cr.hist)  # uint32 counts in int32 storage: exact while totals < 2^31
+    # one SUM all-reduce carries the histogram and, in `world` extra slots, every rank's bridge count
+    n_bins = cr.hist.numel()
+    packed = torch.zeros(n_bins + comm.world, dtype=cr.hist.dtype, device=cr.hist.device)
+    packed[:n_bins] = cr.hist      # uint32 counts in int32 storage: exact while totals < 2^31
+    packed[n_bins + comm.rank] = cr.n_bridges
+    comm.sum_tensor_(packed)
+    hist = packed[:n_bins]
     first = cr.first_pos
     first.masked_fill_(first < 0, _I64_MAX)  # GG_NO_POS is -1 as int64: lift it above every real offset
     first = comm.min_tensor_(first)
-    n_br = comm.gather_ints(cr.n_bridges)
+    tail = packed[n_bins:].cpu()
+    n_br = [int(x) for x in tail]
     bridges, n_bridges = cr.bridges, cr.n_bridges
     if sum(n_br) > 0:
-        bridges = comm.gather_cat(cr.bridges[: cr.n_bridges].contiguous(), dim=0)
+        (bridges,) = comm.gather_packed([cr.bridges[: cr.n_bridges]], n_br, [0])
         n_bridges = int(bridges.shape[0])
-        if n_bridges == 0:
-            bridges = cr.bridges
     n_nonzero = int((hist != 0).sum().item())
     return CountResult(cr.k, hist, first, bridges, n_bridges, cr.status, n_nonzero)

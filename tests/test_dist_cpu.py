@@ -49,6 +49,16 @@ def _worker(rank, world, port, k, tmp):
         want = torch.cat([torch.arange(2 * (r + 2), dtype=torch.int64).reshape(2, r + 2) + 100 * r for r in range(world)], dim=1)
         assert torch.equal(cat, want)
         assert comm.gather_cat(torch.zeros(0), dim=0).numel() == 0
+        # packed all-gather(v): several ragged tensors in one collective
+        sizes = [r + 2 for r in range(world)]
+        w32 = torch.arange(rank + 2, dtype=torch.float32) + rank
+        w64 = torch.arange(rank + 2, dtype=torch.float64) * 2 + rank
+        ei, f64, f32 = comm.gather_packed([mine, w64, w32], sizes, [1, 0, 0])
+        assert torch.equal(ei, want)
+        assert torch.equal(f32, torch.cat([torch.arange(r + 2, dtype=torch.float32) + r for r in range(world)]))
+        assert torch.equal(f64, torch.cat([torch.arange(r + 2, dtype=torch.float64) * 2 + r for r in range(world)]))
+        z = comm.gather_packed([torch.zeros((2, 0), dtype=torch.int64)], [0] * world, [1])
+        assert z[0].shape == (2, 0)
 
         # C1: sharded counting merges to the single-process result
         reads = fast.synthetic_reads(600, 50, seed=4)
