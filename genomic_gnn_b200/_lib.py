@@ -15,7 +15,7 @@ GG_MAX_K = 13
 GG_KF_BLOCK = 1024
 GG_NO_POS = 0xFFFFFFFFFFFFFFFF
 ST_BAD_BYTES, ST_BRIDGES, ST_CURSOR, ST_REMAINING, ST_NONZERO, ST_WORDS = 0, 1, 2, 3, 4, 8
-KF_IMPL = {"auto": 0, "dp4a": 1, "tcgen05": 2, "naive": 3}
+KF_IMPL = {"auto": 0, "dp4a": 1, "tcgen05": 2, "naive": 3, "tcgen05x2": 4}
 
 
 class KfParams(C.Structure):

@@ -311,7 +311,7 @@ def top_n_budget(n_nodes: int, keep_top_k: Optional[float], n_candidates: int) -
 @dataclass
 class KFEdges:
     edge_index: torch.Tensor   # int64 [2, E], s < t, reference emission order
-    weight64: torch.Tensor     # float64 [E]
+    weight64: Optional[torch.Tensor]  # float64 [E] (None after a multi-GPU gather)
     weight: torch.Tensor       # float32 [E]
     n_candidates: int          # pairs above the threshold before the top-n cut
     cutoff: Optional[float] = None   # score of the cut-off class when top-n was binding
@@ -330,7 +330,7 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
     Returns (recs, n_recs, rowcnt, params)."""
     lib = _lib.load()
     dev = counts.device
-    if counts.shape[1] < 32 and impl in ("auto", "tcgen05"):
+    if counts.shape[1] < 32 and impl == "tcgen05":
         # the tensor path wants >= 32 bytes of K per row (one kind::i8 MMA); zero columns change nothing
         counts = torch.nn.functional.pad(counts, (0, 32 - counts.shape[1]))
     n, d = int(counts.shape[0]), int(counts.shape[1])
@@ -479,8 +479,9 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         ei, w64, w32 = out[:, :expect], o64[:expect], o32[:expect]
         per_rank = comm.gather_ints(expect) if comm.world > 1 else [expect]
     if gather and comm.world > 1:
-        with _stage("c2_gather_edges"):  # one collective: edge_index, float64 and float32 weights packed together
-            ei, w64, w32 = comm.gather_packed([ei, w64, w32], per_rank, [1, 0, 0])
+        with _stage("c2_gather_edges"):  # one collective: edge_index and float32 weights packed together
+            ei, w32 = comm.gather_packed([ei, w32], per_rank, [1, 0])
+            w64 = None  # the float64 weights stay sharded: only the function-level API wants them
     return KFEdges(ei.contiguous(), w64, w32, n_total, cutoff, tie_budget, tie_total, impl)
 
 

@@ -435,6 +435,351 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
   if (tid == 0 && bars->error) *error_flag = 1;
 }
 
+
+// ======================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster score a 256-row x 256-column tile
+// together.  Each CTA keeps its own 128-row strip of A resident and streams only HALF of
+// every B tile (128 of the 256 rows); the leader CTA's single thread issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 32), which feeds both SMs' tensor cores
+// and writes 128 x 256 accumulators into each CTA's own TMEM.  Operand traffic per MMA and
+// TMA fill traffic per SM are both halved against the single-CTA kernel, whose SS-mode
+// 128x128x32 MMAs saturate the 128 B/clk of shared-memory bandwidth (profiles/r1).
+//
+// Barrier placement: b_full / a_full / acc_empty live in the LEADER (the only waiter is its
+// MMA warp; the peer's TMA transactions and epilogue arrivals reach them through the
+// cluster address space); b_empty / a_empty / acc_full are multicast by tcgen05.commit to
+// the same offset in both CTAs.
+// ======================================================================================
+constexpr int kPairTileN = 256;
+constexpr int kPairAccStages = 2;
+constexpr int kPairsPerBlock = kStripsPerBlock / 2;
+constexpr int kPairTilesPerBlock = kBlock / kPairTileN;
+constexpr uint32_t kIdescPair = (2u << 4) | ((kPairTileN >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(unsigned long long* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_leader_only(unsigned long long* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(1))
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct PairWalk {
+  int pair, i_block, j_block;  // global strip-pair index (strips 2*pair, 2*pair+1), its row block, column block
+  long long left;
+};
+__device__ __forceinline__ long long pair_units_before_block(int i_local, int ib0, int n_j) {
+  const long long a = i_local;
+  return kPairsPerBlock * (a * (n_j - ib0) - a * (a - 1) / 2);
+}
+__device__ PairWalk pair_walk_begin(const KfArgs& a, long long first_unit, long long n_units) {
+  PairWalk w;
+  int il = 0;
+  const int n_il = a.ib1 - a.ib0;
+  while (il + 1 < n_il && pair_units_before_block(il + 1, a.ib0, a.n_jblocks) <= first_unit) ++il;
+  const long long rem = first_unit - pair_units_before_block(il, a.ib0, a.n_jblocks);
+  w.i_block = a.ib0 + il;
+  const int per_pair = a.n_jblocks - w.i_block;
+  w.pair = w.i_block * kPairsPerBlock + static_cast<int>(rem / per_pair);
+  w.j_block = w.i_block + static_cast<int>(rem % per_pair);
+  w.left = n_units;
+  return w;
+}
+__device__ __forceinline__ void pair_walk_next(const KfArgs& a, PairWalk& w) {
+  --w.left;
+  if (++w.j_block == a.n_jblocks) {
+    ++w.pair;
+    w.i_block = w.pair / kPairsPerBlock;
+    w.j_block = w.i_block;
+  }
+}
+__device__ __forceinline__ int pair_first_tile(const PairWalk& w) {
+  return w.i_block == w.j_block ? (w.pair % kPairsPerBlock) : 0;  // 256-column tile holding the pair's diagonal
+}
+__device__ __forceinline__ int pair_last_tile(const KfArgs& a, const PairWalk& w) {
+  const long long cols = a.n - static_cast<long long>(w.j_block) * kBlock;
+  const long long t = (cols + kPairTileN - 1) / kPairTileN;
+  return static_cast<int>(t < kPairTilesPerBlock ? t : kPairTilesPerBlock);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bstages, long long total_units,
+                       int* error_flag, Geom g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kKBlock = 128;
+  constexpr int kStageBytes = kTileM * kKBlock;  // each CTA stages 128 rows of A or of its half of B
+  const int n_kblocks = g.n_kblocks;
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
+  uint16_t* sqn = reinterpret_cast<uint16_t*>(smem_b + static_cast<size_t>(n_bstages) * kStageBytes);
+  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kEpiGroups * kBlock);
+  Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (tid == 0) {
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    for (int i = 0; i < n_bstages; ++i) {
+      mbar_init(&bars->b_full[i], 1);
+      mbar_init(&bars->b_empty[i], 1);
+    }
+    for (int i = 0; i < kPairAccStages; ++i) {
+      mbar_init(&bars->acc_full[i], 1);
+      mbar_init(&bars->acc_empty[i], 2 * 2 * (kGroupThreads / 32));  // 2 CTAs x 2 half tiles x 4 warps
+    }
+    bars->error = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  if (bars->tmem_base != 0) {
+    if (tid == 0) *error_flag = 2;
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0;
+
+  const uint32_t n_pairs_grid = gridDim.x / 2, pair_id = blockIdx.x / 2;
+  const long long base_units = total_units / n_pairs_grid, extra = total_units % n_pairs_grid;
+  const long long u0 = base_units * pair_id + (pair_id < extra ? pair_id : extra);
+  const long long n_units = base_units + (pair_id < extra ? 1 : 0);
+
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer (both CTAs; transactions complete on the leader's barriers) ==========
+    if (n_units > 0) {
+      if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+      const uint32_t a_full_leader = map_to_cta(smem_u32(&bars->a_full), 0);
+      PairWalk w = pair_walk_begin(a, u0, n_units);
+      int cur_pair = -1;
+      uint32_t a_round = 0, stage = 0, round = 0;
+      for (; w.left > 0; pair_walk_next(a, w)) {
+        if (w.pair != cur_pair) {
+          if (a_round > 0) mbar_wait_warp(&bars->a_empty, (a_round - 1) & 1, &bars->error);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&bars->a_full, 2u * static_cast<uint32_t>(n_kblocks) * kStageBytes);
+            for (int kb = 0; kb < n_kblocks; ++kb)
+              tma_load_2d_pair(smem_a + static_cast<size_t>(kb) * kStageBytes, &tmap, a_full_leader, kb * kKBlock,
+                               (2 * w.pair + static_cast<int>(rank)) * kTileM);
+          }
+          __syncwarp();
+          cur_pair = w.pair;
+          ++a_round;
+        }
+        const int t_end = pair_last_tile(a, w);
+        for (int ct = pair_first_tile(w); ct < t_end; ++ct) {
+          const int col = w.j_block * kBlock + ct * kPairTileN + static_cast<int>(rank) * kTileM;  // this CTA's half of B
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            if (round > 0) mbar_wait_warp(&bars->b_empty[stage], (round - 1) & 1, &bars->error);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(&bars->b_full[stage], 2u * kStageBytes);
+              tma_load_2d_pair(smem_b + static_cast<size_t>(stage) * kStageBytes, &tmap,
+                               map_to_cta(smem_u32(&bars->b_full[stage]), 0), kb * kKBlock, col);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(n_bstages)) {
+              stage = 0;
+              ++round;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && n_units > 0) {
+      PairWalk w = pair_walk_begin(a, u0, n_units);
+      int cur_pair = -1;
+      uint32_t a_round = 0, stage = 0, round = 0, acc = 0, acc_round = 0;
+      const uint32_t desc_hi = g.desc_hi;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b));
+      for (; w.left > 0; pair_walk_next(a, w)) {
+        if (w.pair != cur_pair) {
+          if (cur_pair >= 0 && elect_one()) tc_commit_pair(&bars->a_empty);
+          __syncwarp();
+          mbar_wait_warp(&bars->a_full, a_round & 1, &bars->error);
+          tc_fence_after();
+          cur_pair = w.pair;
+          ++a_round;
+        }
+        const int t_end = pair_last_tile(a, w);
+        for (int ct = pair_first_tile(w); ct < t_end; ++ct) {
+          if (acc_round > 0) mbar_wait_warp(&bars->acc_empty[acc], (acc_round - 1) & 1, &bars->error);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kPairTileN;
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            mbar_wait_warp(&bars->b_full[stage], round & 1, &bars->error);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(kb) * (kStageBytes >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
+                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k4 * (kUmmaK >> 4));
+                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k4 * (kUmmaK >> 4));
+                tc_mma_i8_pair(tmem_d, da, db, kIdescPair, (kb | k4) != 0);
+              }
+              tc_commit_pair(&bars->b_empty[stage]);
+              if (kb == n_kblocks - 1) tc_commit_pair(&bars->acc_full[acc]);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(n_bstages)) {
+              stage = 0;
+              ++round;
+            }
+          }
+          if (++acc == kPairAccStages) {
+            acc = 0;
+            ++acc_round;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue groups: 128-column half tiles round-robin =====================
+    WarpStage& ws = stages[warp];
+    if (lane == 0) ws.fill = 0;
+    __syncwarp();
+    const int group = warp / 4;
+    const int gt = tid % kGroupThreads;
+    uint16_t* my_sqn = sqn + group * kBlock;
+    if (n_units > 0) {
+      PairWalk w = pair_walk_begin(a, u0, n_units);
+      uint32_t tile_seq = 0;
+      for (; w.left > 0; pair_walk_next(a, w)) {
+        const long long col0 = static_cast<long long>(w.j_block) * kBlock;
+        const int cols_in_block = static_cast<int>(min(static_cast<long long>(kBlock), a.n - col0));
+        const int strip = 2 * w.pair + static_cast<int>(rank);
+        const int strip_local = strip % kStripsPerBlock;
+        const int r = strip_local * kStrip + gt;
+        const long long s = static_cast<long long>(strip) * kStrip + gt;
+        const bool row_ok = s < a.n;
+        const bool diag = w.i_block == w.j_block;
+        uint32_t sq_i = 0, scale_i = 0;
+        bool panel_loaded = false;
+        const int t_end = pair_last_tile(a, w);
+        for (int ct = pair_first_tile(w); ct < t_end; ++ct, ++tile_seq) {
+          const uint32_t acc = tile_seq % kPairAccStages;
+          const uint32_t acc_parity = (tile_seq / kPairAccStages) & 1;
+          for (int half = 0; half < 2; ++half) {
+            if ((2 * tile_seq + half) % kEpiGroups != static_cast<uint32_t>(group)) continue;
+            const int ct128 = 2 * ct + half;  // rank tile inside the block
+            // nothing to score: the half tile lies below this strip's diagonal or beyond the last node
+            const bool skip = (diag && ct128 < strip_local) || ct128 * kTile >= cols_in_block;
+            mbar_wait(&bars->acc_full[acc], acc_parity, &bars->error);
+            tc_fence_after();
+            if (!skip) {
+              if (!panel_loaded) {
+                asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+                for (int c = gt; c < kBlock; c += kGroupThreads)
+                  my_sqn[c] = c < cols_in_block ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
+                asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+                if (row_ok) {
+                  sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
+                  scale_i = __ldg(a.fast_scale + sq_i);
+                }
+                panel_loaded = true;
+              }
+              const uint32_t taddr =
+                  tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * kPairTileN + half * kTile;
+              uint32_t tile_cnt = 0;
+#pragma unroll 1
+              for (int cc = 0; cc < kTile; cc += 32) {
+                const int c0 = ct128 * kTile + cc;
+                uint32_t v[32];
+                tc_ld32(taddr + cc, v);
+                uint32_t mask = 0;
+#pragma unroll
+                for (int b = 0; b < 32; ++b)
+                  mask |= static_cast<uint32_t>(((v[b] * v[b]) << a.fast_shift) > scale_i * my_sqn[c0 + b]) << b;
+                mask &= chunk_col_mask(cols_in_block, c0);
+                if (diag) mask &= chunk_diag_mask(r, c0);
+                if (!row_ok) mask = 0;
+                if (__any_sync(0xFFFFFFFFu, mask != 0)) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    ws.dotw[j][lane] = v[4 * j] | (v[4 * j + 1] << 8) | (v[4 * j + 2] << 16) | (v[4 * j + 3] << 24);
+                  uint32_t exact = 0;
+                  for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {
+                    const int b = __ffs(m2) - 1;
+                    if (stage_get_dot(ws, b, lane) >= __ldg(a.dmin + sq_i * my_sqn[c0 + b])) exact |= 1u << b;
+                  }
+                  stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0),
+                               tile_cnt);
+                }
+              }
+              if (row_ok) a.rowcnt[rowcnt_index(w.i_block - a.ib0, a.n_jblocks, w.j_block, r, ct128)] =
+                  static_cast<uint8_t>(tile_cnt);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->acc_empty[acc]), 0));
+          }
+        }
+      }
+      stage_flush(ws, a.out, lane);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading the pair's operands
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+  if (tid == 0 && bars->error) *error_flag = 1;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -452,6 +797,8 @@ EncodeTiledFn encode_tiled() {
 }
 
 }  // namespace
+
+int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s);
 
 int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
   // a.d is the row pitch of `counts` in bytes: 32 or 64 (one K block), or a multiple of 128 up to kMaxD
@@ -504,6 +851,62 @@ int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
   int* error_flag = reinterpret_cast<int*>(a.out.status + 2);  // kf_status[2]
   kernel<<<grid, kThreads, smem_bytes, s>>>(tmap, a, n_bstages, total_units, error_flag, g);
   GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
+  GG_REQUIRE(a.d % kMaxKBlock == 0 && a.d >= kMaxKBlock && a.d <= kMaxD, GG_ERR_ARG,
+             "CTA-pair tcgen05 KF kernel needs a row pitch that is a multiple of 128 up to 1024 bytes");
+  EncodeTiledFn encode = encode_tiled();
+  GG_REQUIRE(encode != nullptr, GG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  Geom g;
+  g.kb_bytes = kMaxKBlock;
+  g.n_kblocks = a.d / g.kb_bytes;
+  g.stage_bytes = kTileM * g.kb_bytes;
+  g.mma_per_kb = g.kb_bytes / kUmmaK;
+  g.desc_hi = static_cast<uint32_t>((8 * g.kb_bytes) >> 4) | (1u << 14) | (2u << 29);
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.d), static_cast<cuuint64_t>(a.n)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.d)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(g.kb_bytes), kTileM};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(a.counts), dims, strides, box,
+                            elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    gg::set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return GG_ERR_CUDA;
+  }
+  const size_t fixed = static_cast<size_t>(g.n_kblocks) * g.stage_bytes + kEpiGroups * kBlock * sizeof(uint16_t) +
+                       (kEpiThreads / 32) * sizeof(WarpStage) + sizeof(Barriers) + 1024;
+  int dev = 0, max_smem = 0;
+  GG_CUDA_CHECK(cudaGetDevice(&dev));
+  GG_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int n_bstages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / g.stage_bytes);
+  if (n_bstages > kMaxBStages) n_bstages = kMaxBStages;
+  GG_REQUIRE(n_bstages >= 2, GG_ERR_ARG, "not enough shared memory for the B ring");
+  const size_t smem_bytes = fixed + static_cast<size_t>(n_bstages) * g.stage_bytes;
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kf_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem_bytes)));
+  long long total_units = 0;  // (strip pair, column block) units of this shard
+  for (int ib = a.ib0; ib < a.ib1; ++ib) total_units += static_cast<long long>(kPairsPerBlock) * (a.n_jblocks - ib);
+  if (total_units == 0) return GG_OK;
+  const long long pairs = gg::sm_count() / 2;
+  const unsigned grid = 2u * static_cast<unsigned>(total_units < pairs ? total_units : pairs);
+  int* error_flag = reinterpret_cast<int*>(a.out.status + 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kf_tcgen05_pair_kernel, tmap, a, n_bstages, total_units, error_flag, g));
   return GG_OK;
 }
 

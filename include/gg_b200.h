@@ -156,7 +156,7 @@ typedef struct {
   uint32_t dot;
 } gg_kf_rec_t;
 
-enum { GG_KF_IMPL_AUTO = 0, GG_KF_IMPL_DP4A = 1, GG_KF_IMPL_TCGEN05 = 2, GG_KF_IMPL_NAIVE = 3 };
+enum { GG_KF_IMPL_AUTO = 0, GG_KF_IMPL_DP4A = 1, GG_KF_IMPL_TCGEN05 = 2, GG_KF_IMPL_NAIVE = 3, GG_KF_IMPL_TCGEN05_PAIR = 4 };
 
 typedef struct {
   int64_t n;            /* nodes */

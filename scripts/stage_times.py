@@ -35,7 +35,7 @@ ms, db = timed(lambda: core.build_db(cr)); print(f"db build ms {ms:.3f} N={db.nu
 for s in (2, 5):
     ms, kc = timed(lambda: core.kf_counts(db.node_codes, k, s)); print(f"counts s={s} ms {ms:.3f}")
     ms, x = timed(lambda: core.kf_features_f32(kc)); print(f"features s={s} ms {ms:.3f}")
-    for impl in (["dp4a", "tcgen05"] if s == 2 else ["tcgen05"]):
+    for impl in (["dp4a"] if s == 2 else ["tcgen05", "tcgen05x2"]):
         t0 = time.time()
         ms, kf = timed(lambda: core.kf_edges(kc.counts, kc.sqnorm, 0.8, 0.01, sq_max=kc.m ** 2, impl=impl), n=2)
         print(f"kf s={s} impl={impl} ms {ms:.3f} E={kf.edge_index.shape[1]}  pairs/s {db.num_nodes*(db.num_nodes-1)/2/ms/1e6:.1f} G")

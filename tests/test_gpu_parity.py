@@ -184,17 +184,19 @@ def test_kf_tcgen05_matches_generic(gg, k, s, n_reads, thr):
     reads = fast.synthetic_reads(n_reads, 150, seed=21 + k + s)
     built = core.build_graph(reads, k, str(s), with_kf=False)
     kc = built.kf_counts[0]
-    a = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="tcgen05")
     b = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="naive")
     assert b.edge_index.shape[1] > 0
-    assert a.edge_index.shape == b.edge_index.shape
-    assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
+    for impl in ("tcgen05", "tcgen05x2"):   # single-CTA and CTA-pair (cta_group::2) kernels
+        a = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl=impl)
+        assert a.edge_index.shape == b.edge_index.shape, impl
+        assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64), impl
     # and a row-block shard of it
     nb = (built.db.num_nodes + 1023) // 1024
     if nb >= 3:
-        a1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="tcgen05", iblock_begin=1, iblock_end=3)
         b1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="naive", iblock_begin=1, iblock_end=3)
-        assert torch.equal(a1.edge_index, b1.edge_index)
+        for impl in ("tcgen05", "tcgen05x2"):
+            a1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl=impl, iblock_begin=1, iblock_end=3)
+            assert torch.equal(a1.edge_index, b1.edge_index), impl
 
 
 def test_kf_row_block_shards_concatenate(gg):

@@ -40,7 +40,7 @@ def _worker(rank, world, port, out_dir, k, small_k, thr, topk, n_reads):
             for a, b in zip(got.kf, ref.kf):
                 assert a.n_candidates == b.n_candidates
                 assert torch.equal(a.edge_index, b.edge_index), (a.edge_index.shape, b.edge_index.shape)
-                assert torch.equal(a.weight64, b.weight64)
+                assert torch.equal(a.weight, b.weight)
             open(os.path.join(out_dir, "ok"), "w").close()
     finally:
         dist.destroy_process_group()
