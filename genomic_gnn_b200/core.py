@@ -269,7 +269,7 @@ def kf_features_f32(kc: KFCounts) -> torch.Tensor:
     dev = kc.counts.device
     n, d = kc.counts.shape
     dk = int(kc.col_keep.numel())
-    lut = torch.from_numpy(value_lut(kc.m).astype(np.float32)).to(dev)
+    lut = _device_value_lut(kc.m, dev)
     x = torch.empty((n, dk), dtype=torch.float32, device=dev)
     with _stage(f"k3_features_d{d}"):
         check(lib.gg_kf_features_f32(ptr(kc.counts), n, d, ptr(kc.col_keep), dk, ptr(lut), ptr(x), _stream()),
@@ -298,6 +298,33 @@ def threshold_tables(threshold: float, sq_max: int):
     scale = np.array([(a2 * sq << shift) // b2 for sq in range(sq_max + 1)], dtype=np.uint64)
     assert int(scale.max()) * sq_max < 2**32 and (p_max << shift) < 2**32
     return dmin, scale.astype(np.uint32), shift, p_max
+
+
+_DEVICE_TABLES = {}
+
+
+def _device_threshold_tables(threshold: float, sq_max: int, dev):
+    """Device copies of the threshold tables, cached per (threshold, sq_max, device): the upload is a pageable
+    host-to-device copy that would otherwise synchronise every call."""
+    key = (threshold, sq_max, str(dev))
+    hit = _DEVICE_TABLES.get(key)
+    if hit is None:
+        dmin, scale, shift, p_max = threshold_tables(threshold, sq_max)
+        hit = (torch.from_numpy(dmin.view(np.int16)).to(dev), torch.from_numpy(scale.view(np.int32)).to(dev), shift, p_max)
+        if len(_DEVICE_TABLES) > 256:
+            _DEVICE_TABLES.clear()
+        _DEVICE_TABLES[key] = hit
+    return hit
+
+
+_DEVICE_LUTS = {}
+
+
+def _device_value_lut(m: int, dev):
+    key = (m, str(dev))
+    if key not in _DEVICE_LUTS:
+        _DEVICE_LUTS[key] = torch.from_numpy(value_lut(m).astype(np.float32)).to(dev)
+    return _DEVICE_LUTS[key]
 
 
 def top_n_budget(n_nodes: int, keep_top_k: Optional[float], n_candidates: int) -> int:
@@ -336,9 +363,7 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
     n, d = int(counts.shape[0]), int(counts.shape[1])
     nb = _row_blocks(n)
     iblock_end = nb if iblock_end is None else iblock_end
-    dmin, scale, shift, p_max = threshold_tables(float(threshold), int(sq_max))
-    dmin_d = torch.from_numpy(dmin.view(np.int16)).to(dev)
-    scale_d = torch.from_numpy(scale.view(np.int32)).to(dev)
+    dmin_d, scale_d, shift, p_max = _device_threshold_tables(float(threshold), int(sq_max), dev)
     params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl])
     rc_elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
     rowcnt = torch.empty(max(rc_elems, 1), dtype=torch.int64, device=dev)
