@@ -48,12 +48,16 @@ __device__ __forceinline__ bool fast_pass(uint32_t dot, uint32_t scale_i, uint32
 }
 
 // ---------------------------------------------------------------------------- D <= 64
+// Exact threshold without arithmetic: for the row a thread owns, the smallest passing dot depends only on the
+// column's squared norm, so each CTA tabulates thr_tab[sq][row] = dmin[sq_row * sq] once (<= 226 x 128 bytes) and
+// the per-pair test is one LDS.U8 + one compare -- no conservative pre-filter, no refine pass.
 template <int W>
-__global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
+__global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a, int sq_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* colw = reinterpret_cast<uint32_t*>(smem_raw);                         // [kBlock][W]
-  uint16_t* sqn = reinterpret_cast<uint16_t*>(colw + kBlock * W);                 // [kBlock]
-  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kBlock);                 // [4]
+  uint16_t* sqoff = reinterpret_cast<uint16_t*>(colw + kBlock * W);               // [kBlock] sq_col * kStrip
+  WarpStage* stages = reinterpret_cast<WarpStage*>(sqoff + kBlock);               // [4]
+  uint8_t* thr_tab = reinterpret_cast<uint8_t*>(stages + kStrip / 32);            // [sq_max + 1][kStrip]
 
   const Unit un = decode_unit(a);
   if (!un.active) return;
@@ -69,24 +73,25 @@ __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.counts + (col0 + c) * a.d);
 #pragma unroll
     for (int w = 0; w < W; ++w) colw[c * W + w] = ok ? __ldg(src + w) : 0u;
-    sqn[c] = ok ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
+    sqoff[c] = ok ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c) * kStrip) : 0;
   }
 
   const int r = un.strip * kStrip + tid;  // block-local row
   const long long s = static_cast<long long>(un.i_block) * kBlock + r;
   const bool row_ok = s < a.n;
   uint32_t row[W];
-  uint32_t sq_i = 0, scale_i = 0;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.counts + (row_ok ? s : 0) * a.d);
 #pragma unroll
     for (int w = 0; w < W; ++w) row[w] = row_ok ? __ldg(src + w) : 0u;
-    if (row_ok) {
-      sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
-      scale_i = __ldg(a.fast_scale + sq_i);
+    const uint32_t sq_i = row_ok ? static_cast<uint32_t>(__ldg(a.sqnorm + s)) : 0u;
+    for (int q = 0; q <= sq_max; ++q) {
+      const uint32_t need = row_ok ? __ldg(a.dmin + sq_i * q) : 255u;  // dmin[0] is "never"
+      thr_tab[q * kStrip + tid] = static_cast<uint8_t>(need > 255u ? 255u : need);
     }
   }
   __syncthreads();
+  const uint8_t* my_thr = thr_tab + tid;
 
   const bool diag = un.i_block == un.j_block;
   uint32_t tile_cnt = 0;
@@ -100,25 +105,20 @@ __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a) {
       uint32_t dot = 0;
 #pragma unroll
       for (int w = 0; w < W; ++w) dot = __dp4a(row[w], cw[w], dot);
-      mask |= static_cast<uint32_t>(fast_pass(dot, scale_i, sqn[c0 + b], a.fast_shift)) << b;
+      mask |= static_cast<uint32_t>(dot >= my_thr[sqoff[c0 + b]]) << b;
     }
     mask &= chunk_col_mask(cols_in_block, c0);
     if (diag) mask &= chunk_diag_mask(r, c0);
-    if (!row_ok) mask = 0;
     if (__any_sync(0xFFFFFFFFu, mask != 0)) {
-      uint32_t exact = 0;
-      for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {
+      for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {  // the records carry the dot: recompute it for the few survivors
         const int b = __ffs(m2) - 1;
         const uint32_t* cw = colw + (c0 + b) * W;
         uint32_t dot = 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) dot = __dp4a(row[w], cw[w], dot);
-        if (dot >= __ldg(a.dmin + sq_i * sqn[c0 + b])) {
-          exact |= 1u << b;
-          stage_set_dot(ws, b, lane, dot);
-        }
+        stage_set_dot(ws, b, lane, dot);
       }
-      stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
+      stage_commit(ws, a.out, lane, mask, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
     }
     if (((c0 + 32) & (kTile - 1)) == 0 || c0 + 32 >= cols_in_block) {  // end of a 128-column tile
       if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = static_cast<uint8_t>(tile_cnt);
@@ -215,11 +215,12 @@ __global__ void __launch_bounds__(kStrip) kf_generic_kernel(KfArgs a) {
 }
 
 template <int W>
-int launch_dp4a(const KfArgs& a, long long units, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(kBlock) * W * 4 + kBlock * 2 + (kStrip / 32) * sizeof(WarpStage);
+int launch_dp4a(const KfArgs& a, long long units, int sq_max, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(kBlock) * W * 4 + kBlock * 2 + (kStrip / 32) * sizeof(WarpStage) +
+                      static_cast<size_t>(sq_max + 1) * kStrip;
   GG_CUDA_CHECK(cudaFuncSetAttribute(kf_dp4a_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
-  kf_dp4a_kernel<W><<<static_cast<unsigned>(units), kStrip, smem, s>>>(a);
+  kf_dp4a_kernel<W><<<static_cast<unsigned>(units), kStrip, smem, s>>>(a, sq_max);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }
@@ -391,12 +392,16 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   const long long units = static_cast<long long>(a.ib1 - a.ib0) * a.n_jblocks * kStripsPerBlock;
   GG_REQUIRE(units < (1ll << 31), GG_ERR_ARG, "too many work units for one launch; shard the row blocks");
   switch (impl) {
-    case GG_KF_IMPL_DP4A:
-      if (p->d == 4) return launch_dp4a<1>(a, units, s);
-      if (p->d == 16) return launch_dp4a<4>(a, units, s);
-      if (p->d == 64) return launch_dp4a<16>(a, units, s);
+    case GG_KF_IMPL_DP4A: {
+      int sq_max = 0;  // p_max = sq_max^2 by construction (core.threshold_tables)
+      while ((sq_max + 1) * (sq_max + 1) <= p->p_max) ++sq_max;
+      GG_REQUIRE(sq_max * sq_max == p->p_max && sq_max <= 255, GG_ERR_ARG, "p_max must be a square <= 255^2");
+      if (p->d == 4) return launch_dp4a<1>(a, units, sq_max, s);
+      if (p->d == 16) return launch_dp4a<4>(a, units, sq_max, s);
+      if (p->d == 64) return launch_dp4a<16>(a, units, sq_max, s);
       gg::set_error("dp4a KF kernel supports d in {4, 16, 64}, got %d", p->d);
       return GG_ERR_ARG;
+    }
     case GG_KF_IMPL_TCGEN05:
       return ggkf::emit_tcgen05(a, s);
     case GG_KF_IMPL_TCGEN05_PAIR:
