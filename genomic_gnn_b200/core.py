@@ -393,7 +393,7 @@ def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=False):
     w32 = torch.empty(max(n_recs, 1), dtype=torch.float32, device=dev)
     dot = torch.empty(max(n_recs, 1), dtype=torch.int32, device=dev) if want_dot else None
     if n_recs:
-        ws_bytes = int(lib.gg_kf_finalize_workspace_bytes(params.n, params.iblock_begin, params.iblock_end))
+        ws_bytes = int(lib.gg_kf_finalize_workspace_bytes(params.n, params.iblock_begin, params.iblock_end, n_recs))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with _stage(f"k6_finalize_d{params.d}"):
             check(lib.gg_kf_finalize(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(sqnorm), ptr(edges[0]),

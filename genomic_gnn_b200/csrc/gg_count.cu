@@ -17,7 +17,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kPosPerThread = 16;
 constexpr int kTile = kThreads * kPosPerThread;  // stream positions per CTA iteration
-constexpr int kTilesPerGroup = 8;                // first-occurrence scan: 32 KB of stream per grab
+constexpr int kTilesPerGroup = 4;                // first-occurrence scan: 16 KB of stream per grab
 
 enum Mode { kCount = 0, kFirst = 1 };
 
@@ -323,7 +323,8 @@ extern "C" int gg_first_occurrence(const uint8_t* stream, int64_t n_bytes, int64
   Args a{stream, n_bytes, fixed_len, pos_base, k, const_cast<uint32_t*>(hist), first_pos, nullptr, 0, stw};
   const int64_t n_tiles = (n_bytes + kTile - 1) / kTile;
   const int64_t n_groups = (n_tiles + kTilesPerGroup - 1) / kTilesPerGroup;
-  const int64_t resident = static_cast<int64_t>(gg::sm_count()) * 2;
+  // one CTA per SM: every CTA scans at least one group, so the floor of the early-exit scan is grid x 16 KB
+  const int64_t resident = static_cast<int64_t>(gg::sm_count());
   const int grid = static_cast<int>(n_groups < resident ? n_groups : resident);
   first_kernel<<<grid, kThreads, 0, s>>>(a);
   GG_CUDA_CHECK(cudaGetLastError());

@@ -258,8 +258,9 @@ extern "C" int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, cons
   node_sort_input_kernel<<<grid_for(n_codes), 256, 0, s>>>(l.node_key, n_codes, create_all_kmers, l.key_in, l.val_in);
   {
     size_t tb = l.cub_bytes;
+    // node keys are 2*pos(+1) < 2^41; the all-ones "absent" key still sorts last on the low 42 bits
     GG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(l.cub_temp, tb, l.key_in, l.key_out, l.val_in, l.val_out, n_codes,
-                                                  0, 64, s));
+                                                  0, 42, s));
   }
   node_rank_kernel<<<grid_for(n_codes), 256, 0, s>>>(l.key_out, l.val_out, n_codes, node_codes, code_to_node, out_ne);
 

@@ -230,11 +230,13 @@ struct RowTotal {  // candidates of one (block pair, row): sum of its 8 packed t
   __host__ __device__ unsigned long long operator()(unsigned long long v) const { return byte_sum(v); }
 };
 
-__global__ void __launch_bounds__(256) scatter_kernel(const gg_kf_rec_t* recs, long long n_recs,
-                                                      const unsigned long long* offsets,
-                                                      const unsigned long long* rowcnt, const int32_t* sqnorm,
-                                                      int ib0, int n_jblocks, int64_t* src, int64_t* dst, double* w64,
-                                                      float* w32, uint32_t* dot_out) {
+// Two steps instead of one scatter: a record's five output fields would otherwise be five scattered sector
+// writes.  place_kernel scatters ONE packed 8-byte word per record into emission order, expand_kernel then
+// streams that array and writes every output array fully coalesced.
+__global__ void __launch_bounds__(256) place_kernel(const gg_kf_rec_t* recs, long long n_recs,
+                                                    const unsigned long long* offsets,
+                                                    const unsigned long long* rowcnt, int ib0, int n_jblocks,
+                                                    uint2* ordered) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_recs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 rc = __ldg(reinterpret_cast<const uint4*>(recs) + i);
@@ -243,14 +245,25 @@ __global__ void __launch_bounds__(256) scatter_kernel(const gg_kf_rec_t* recs, l
                                        static_cast<int>(s % kBlock));
     const int tile = static_cast<int>((t % kBlock) / kTile);
     const unsigned long long earlier_tiles = __ldg(rowcnt + word) & ((1ull << (8 * tile)) - 1ull);
-    const unsigned long long pos = offsets[word] + byte_sum(earlier_tiles) + rc.z;
-    src[pos] = s;
-    dst[pos] = t;
-    const double p = static_cast<double>(static_cast<long long>(sqnorm[s]) * static_cast<long long>(sqnorm[t]));
-    const double w = static_cast<double>(rc.w) / sqrt(p);
-    if (w64) w64[pos] = w;
-    if (w32) w32[pos] = static_cast<float>(w);
-    if (dot_out) dot_out[pos] = rc.w;
+    const unsigned long long pos = __ldg(offsets + word) + byte_sum(earlier_tiles) + rc.z;
+    ordered[pos] = make_uint2(s | (rc.w << 24), t);  // s, t < 2^24 (check_params), dot <= 225
+  }
+}
+
+__global__ void __launch_bounds__(256) expand_kernel(const uint2* ordered, long long n_recs, const int32_t* sqnorm,
+                                                     int64_t* src, int64_t* dst, double* w64, float* w32,
+                                                     uint32_t* dot_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_recs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint2 e = __ldg(ordered + i);
+    const uint32_t s = e.x & 0xFFFFFFu, dot = e.x >> 24, t = e.y;
+    src[i] = s;
+    dst[i] = t;
+    const double p = static_cast<double>(static_cast<long long>(__ldg(sqnorm + s)) * static_cast<long long>(__ldg(sqnorm + t)));
+    const double w = static_cast<double>(dot) / sqrt(p);
+    if (w64) w64[i] = w;
+    if (w32) w32[i] = static_cast<float>(w);
+    if (dot_out) dot_out[i] = dot;
   }
 }
 
@@ -417,10 +430,11 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   }
 }
 
-extern "C" size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end) {
+extern "C" size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end, int64_t n_recs) {
   const size_t elems = gg_kf_rowcnt_elems(n, iblock_begin, iblock_end);
   gg::Carver c(nullptr);
   c.take<unsigned long long>(elems ? elems : 1);
+  c.take<uint2>(n_recs > 0 ? n_recs : 1);
   c.take<char>(scan_temp_bytes<RowTotal, unsigned long long>(static_cast<long long>(elems ? elems : 1)));
   return c.used();
 }
@@ -433,20 +447,22 @@ extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, 
   GG_REQUIRE(n_recs >= 0, GG_ERR_ARG, "negative record count");
   if (n_recs == 0) return GG_OK;
   GG_REQUIRE(recs && rowcnt && sqnorm && edge_src && edge_dst && workspace, GG_ERR_ARG, "null buffer");
-  GG_REQUIRE(workspace_bytes >= gg_kf_finalize_workspace_bytes(p->n, p->iblock_begin, p->iblock_end),
+  GG_REQUIRE(workspace_bytes >= gg_kf_finalize_workspace_bytes(p->n, p->iblock_begin, p->iblock_end, n_recs),
              GG_ERR_WORKSPACE, "workspace too small");
   cudaStream_t s = gg::as_stream(st);
   const long long elems = static_cast<long long>(gg_kf_rowcnt_elems(p->n, p->iblock_begin, p->iblock_end));
   gg::Carver c(workspace);
   unsigned long long* offsets = c.take<unsigned long long>(elems);
+  uint2* ordered = c.take<uint2>(n_recs);
   size_t tb = scan_temp_bytes<RowTotal, unsigned long long>(elems);
   void* temp = c.take<char>(tb);
   const unsigned long long* words = reinterpret_cast<const unsigned long long*>(rowcnt);
   cub::TransformInputIterator<unsigned long long, RowTotal, const unsigned long long*> it(words, RowTotal());
   GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb, it, offsets, elems, s));
   const int n_jblocks = static_cast<int>((p->n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
-  scatter_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, words, sqnorm, p->iblock_begin, n_jblocks, edge_src,
-                                                  edge_dst, weight64, weight32, dot_out);
+  place_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, words, p->iblock_begin, n_jblocks, ordered);
+  expand_kernel<<<grid_for(n_recs), 256, 0, s>>>(ordered, n_recs, sqnorm, edge_src, edge_dst, weight64, weight32,
+                                                 dot_out);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

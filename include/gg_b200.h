@@ -175,7 +175,7 @@ GG_API int gg_kf_emit(const gg_kf_params_t* h_params, const uint8_t* counts, con
                const uint16_t* dmin, const uint32_t* fast_scale /* [max sqnorm + 1] */,
                gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt, int64_t* kf_status, gg_stream_t st);
 
-GG_API size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end);
+GG_API size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end, int64_t n_recs);
 GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
                    const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
                    uint32_t* dot_out /* nullable: dot per edge, for top-n */, void* workspace, size_t workspace_bytes,
