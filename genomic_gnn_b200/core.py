@@ -354,17 +354,19 @@ def _row_blocks(n):
 def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max: int, iblock_begin=0,
             iblock_end=None, impl="auto", rec_capacity=None):
     """Score all pairs of the row-block shard and stage the candidates.
-    Returns (recs, n_recs, rowcnt, params)."""
+    Returns (recs, n_recs, rowcnt, params, counts_scored): the last is the matrix the kernel read (zero-padded to a
+    32-byte pitch for the tensor path on narrow rows), which kf_finalize needs to re-multiply narrow rows."""
     lib = _lib.load()
     dev = counts.device
-    if counts.shape[1] < 32 and impl == "tcgen05":
+    d_valid = int(counts.shape[1])
+    if counts.shape[1] < 32 and impl in ("auto", "tcgen05"):
         # the tensor path wants >= 32 bytes of K per row (one kind::i8 MMA); zero columns change nothing
         counts = torch.nn.functional.pad(counts, (0, 32 - counts.shape[1]))
     n, d = int(counts.shape[0]), int(counts.shape[1])
     nb = _row_blocks(n)
     iblock_end = nb if iblock_end is None else iblock_end
     dmin_d, scale_d, shift, p_max = _device_threshold_tables(float(threshold), int(sq_max), dev)
-    params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl])
+    params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl], d_valid)
     rc_elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
     rowcnt = torch.empty(max(rc_elems, 1), dtype=torch.int64, device=dev)
     status = torch.empty(4, dtype=torch.int64, device=dev)
@@ -380,12 +382,12 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
         found = int(st_host[0])
         if found <= rec_capacity:
-            return recs, found, rowcnt, params
+            return recs, found, rowcnt, params, counts
         del recs
         rec_capacity = found
 
 
-def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=False):
+def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, counts, want_dot=False):
     lib = _lib.load()
     dev = sqnorm.device
     edges = torch.empty((2, max(n_recs, 1)), dtype=torch.int64, device=dev)
@@ -396,7 +398,7 @@ def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=False):
         ws_bytes = int(lib.gg_kf_finalize_workspace_bytes(params.n, params.iblock_begin, params.iblock_end, n_recs))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with _stage(f"k6_finalize_d{params.d}"):
-            check(lib.gg_kf_finalize(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(sqnorm), ptr(edges[0]),
+            check(lib.gg_kf_finalize(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(sqnorm), ptr(counts), ptr(edges[0]),
                                      ptr(edges[1]), ptr(w64), ptr(w32), ptr(dot), ptr(ws), ws_bytes, _stream()),
                   "gg_kf_finalize")
     return edges[:, :n_recs], w64[:n_recs], w32[:n_recs], (dot[:n_recs] if want_dot else None)
@@ -463,13 +465,13 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
     n_pairs = n * (n - 1) // 2
     guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
     rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
-    recs, n_recs, rowcnt, params = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
-                                           rec_capacity=rec_capacity)
+    recs, n_recs, rowcnt, params, scored = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
+                                                   rec_capacity=rec_capacity)
     per_rank = comm.gather_ints(n_recs)
     n_total = sum(per_rank)
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total
-    ei, w64, w32, dot = kf_finalize(recs, n_recs, rowcnt, params, sqnorm, want_dot=need_cut)
+    ei, w64, w32, dot = kf_finalize(recs, n_recs, rowcnt, params, sqnorm, scored, want_dot=need_cut)
     del recs, rowcnt
     cutoff, tie_budget, tie_total = None, 0, 0
     if need_cut:

@@ -18,7 +18,7 @@
 #include "gg_kf_emit.cuh"
 
 namespace ggkf {
-int emit_tcgen05(const KfArgs& a, cudaStream_t s);       // gg_kf_mma.cu
+int emit_tcgen05(const KfArgs& a, int p_max, cudaStream_t s);  // gg_kf_mma.cu
 int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s);  // gg_kf_mma.cu (cta_group::2)
 }
 
@@ -51,18 +51,20 @@ __device__ __forceinline__ bool fast_pass(uint32_t dot, uint32_t scale_i, uint32
 // Exact threshold without arithmetic: for the row a thread owns, the smallest passing dot depends only on the
 // column's squared norm, so each CTA tabulates thr_tab[sq][row] = dmin[sq_row * sq] once (<= 226 x 128 bytes) and
 // the per-pair test is one LDS.U8 + one compare -- no conservative pre-filter, no refine pass.
+using DeepStage = WarpStageT<256>;  // ~20 records per (row strip, column block) warp-chunk: flush every ~12 chunks
+
 template <int W>
 __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a, int sq_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* colw = reinterpret_cast<uint32_t*>(smem_raw);                         // [kBlock][W]
   uint16_t* sqoff = reinterpret_cast<uint16_t*>(colw + kBlock * W);               // [kBlock] sq_col * kStrip
-  WarpStage* stages = reinterpret_cast<WarpStage*>(sqoff + kBlock);               // [4]
+  DeepStage* stages = reinterpret_cast<DeepStage*>(sqoff + kBlock);               // [4]
   uint8_t* thr_tab = reinterpret_cast<uint8_t*>(stages + kStrip / 32);            // [sq_max + 1][kStrip]
 
   const Unit un = decode_unit(a);
   if (!un.active) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  WarpStage& ws = stages[warp];
+  DeepStage& ws = stages[warp];
   if (lane == 0) ws.fill = 0;
   __syncwarp();
 
@@ -109,17 +111,9 @@ __global__ void __launch_bounds__(kStrip) kf_dp4a_kernel(KfArgs a, int sq_max) {
     }
     mask &= chunk_col_mask(cols_in_block, c0);
     if (diag) mask &= chunk_diag_mask(r, c0);
-    if (__any_sync(0xFFFFFFFFu, mask != 0)) {
-      for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {  // the records carry the dot: recompute it for the few survivors
-        const int b = __ffs(m2) - 1;
-        const uint32_t* cw = colw + (c0 + b) * W;
-        uint32_t dot = 0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) dot = __dp4a(row[w], cw[w], dot);
-        stage_set_dot(ws, b, lane, dot);
-      }
+    // narrow rows: the records carry no dot, K6 recomputes it from the two short rows
+    if (__any_sync(0xFFFFFFFFu, mask != 0))  // (the dot field of these records is never read)
       stage_commit(ws, a.out, lane, mask, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0), tile_cnt);
-    }
     if (((c0 + 32) & (kTile - 1)) == 0 || c0 + 32 >= cols_in_block) {  // end of a 128-column tile
       if (row_ok) a.rowcnt[rowcnt_index(un.i_local, a.n_jblocks, un.j_block, r, c0 / kTile)] = static_cast<uint8_t>(tile_cnt);
       tile_cnt = 0;
@@ -216,7 +210,7 @@ __global__ void __launch_bounds__(kStrip) kf_generic_kernel(KfArgs a) {
 
 template <int W>
 int launch_dp4a(const KfArgs& a, long long units, int sq_max, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(kBlock) * W * 4 + kBlock * 2 + (kStrip / 32) * sizeof(WarpStage) +
+  const size_t smem = static_cast<size_t>(kBlock) * W * 4 + kBlock * 2 + (kStrip / 32) * sizeof(DeepStage) +
                       static_cast<size_t>(sq_max + 1) * kStrip;
   GG_CUDA_CHECK(cudaFuncSetAttribute(kf_dp4a_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
@@ -236,7 +230,7 @@ struct RowTotal {  // candidates of one (block pair, row): sum of its 8 packed t
 __global__ void __launch_bounds__(256) place_kernel(const gg_kf_rec_t* recs, long long n_recs,
                                                     const unsigned long long* offsets,
                                                     const unsigned long long* rowcnt, int ib0, int n_jblocks,
-                                                    uint2* ordered) {
+                                                    const uint8_t* counts, int pitch, uint2* ordered, int words) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_recs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 rc = __ldg(reinterpret_cast<const uint4*>(recs) + i);
@@ -246,7 +240,14 @@ __global__ void __launch_bounds__(256) place_kernel(const gg_kf_rec_t* recs, lon
     const int tile = static_cast<int>((t % kBlock) / kTile);
     const unsigned long long earlier_tiles = __ldg(rowcnt + word) & ((1ull << (8 * tile)) - 1ull);
     const unsigned long long pos = __ldg(offsets + word) + byte_sum(earlier_tiles) + rc.z;
-    ordered[pos] = make_uint2(s | (rc.w << 24), t);  // s, t < 2^24 (check_params), dot <= 225
+    uint32_t dot = rc.w;
+    if (counts) {  // narrow rows: the scoring kernels do not carry the dot
+      const uint32_t* ra = reinterpret_cast<const uint32_t*>(counts + static_cast<size_t>(s) * pitch);
+      const uint32_t* rb = reinterpret_cast<const uint32_t*>(counts + static_cast<size_t>(t) * pitch);
+      dot = 0;
+      for (int wd = 0; wd < words; ++wd) dot = __dp4a(__ldg(ra + wd), __ldg(rb + wd), dot);
+    }
+    ordered[pos] = make_uint2(s | (dot << 24), t);  // s, t < 2^24 (check_params), dot <= 225
   }
 }
 
@@ -395,13 +396,12 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
 
   int impl = p->impl;
   const bool mma_ok = p->d == 32 || p->d == 64 || (p->d % 128 == 0 && p->d <= 1024);
-  // narrow rows (K <= 64): one MMA per tile cannot hide the epilogue, the dp4a kernel with its 20 resident warps is
-  // faster (1.47 ms vs 1.89 ms at k=8); the tensor path takes over from D = 128
+  // >= 128-byte rows: CTA-pair kernel; 32/64-byte rows: single-CTA kernel with the narrow epilogue (1.12 ms vs
+  // 1.42 ms for the dp4a kernel at k=8, D=16); anything else: SIMT kernels
   const bool dp4a_ok = p->d == 4 || p->d == 16 || p->d == 64;
   if (impl == GG_KF_IMPL_AUTO)
-    impl = dp4a_ok ? GG_KF_IMPL_DP4A
-                   : (p->d % 128 == 0 && p->d <= 1024 ? GG_KF_IMPL_TCGEN05_PAIR
-                                                      : (mma_ok ? GG_KF_IMPL_TCGEN05 : GG_KF_IMPL_NAIVE));
+    impl = (p->d % 128 == 0 && p->d <= 1024) ? GG_KF_IMPL_TCGEN05_PAIR
+           : (mma_ok ? GG_KF_IMPL_TCGEN05 : (dp4a_ok ? GG_KF_IMPL_DP4A : GG_KF_IMPL_NAIVE));
   const long long units = static_cast<long long>(a.ib1 - a.ib0) * a.n_jblocks * kStripsPerBlock;
   GG_REQUIRE(units < (1ll << 31), GG_ERR_ARG, "too many work units for one launch; shard the row blocks");
   switch (impl) {
@@ -416,7 +416,7 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
       return GG_ERR_ARG;
     }
     case GG_KF_IMPL_TCGEN05:
-      return ggkf::emit_tcgen05(a, s);
+      return ggkf::emit_tcgen05(a, p->p_max, s);
     case GG_KF_IMPL_TCGEN05_PAIR:
       return ggkf::emit_tcgen05_pair(a, s);
     case GG_KF_IMPL_NAIVE:
@@ -440,9 +440,9 @@ extern "C" size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, in
 }
 
 extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
-                              const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64,
-                              float* weight32, uint32_t* dot_out, void* workspace, size_t workspace_bytes,
-                              gg_stream_t st) {
+                              const int32_t* sqnorm, const uint8_t* counts, int64_t* edge_src, int64_t* edge_dst,
+                              double* weight64, float* weight32, uint32_t* dot_out, void* workspace,
+                              size_t workspace_bytes, gg_stream_t st) {
   if (int rc = check_params(p)) return rc;
   GG_REQUIRE(n_recs >= 0, GG_ERR_ARG, "negative record count");
   if (n_recs == 0) return GG_OK;
@@ -460,7 +460,12 @@ extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, 
   cub::TransformInputIterator<unsigned long long, RowTotal, const unsigned long long*> it(words, RowTotal());
   GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb, it, offsets, elems, s));
   const int n_jblocks = static_cast<int>((p->n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
-  place_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, words, p->iblock_begin, n_jblocks, ordered);
+  // rows of <= 64 bytes: records carry no dot, recompute it here (counts must be the matrix the emit step scored)
+  const bool recompute = p->d <= 64;
+  GG_REQUIRE(!recompute || counts != nullptr, GG_ERR_ARG, "counts is required to finalise narrow-row records");
+  place_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, words, p->iblock_begin, n_jblocks,
+                                                recompute ? counts : nullptr, p->d, ordered,
+                                                (p->d_valid > 0 && p->d_valid < p->d ? p->d_valid : p->d) / 4);
   expand_kernel<<<grid_for(n_recs), 256, 0, s>>>(ordered, n_recs, sqnorm, edge_src, edge_dst, weight64, weight32,
                                                  dot_out);
   GG_CUDA_CHECK(cudaGetLastError());

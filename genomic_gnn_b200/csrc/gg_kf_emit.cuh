@@ -15,7 +15,7 @@ constexpr int kStrip = 128;          // rows per CTA (one per thread)
 constexpr int kStripsPerBlock = kBlock / kStrip;
 constexpr int kTile = 128;           // columns per rank-counting tile
 constexpr int kTilesPerBlock = kBlock / kTile;
-constexpr int kStageCap = 64;        // records staged per warp before a coalesced flush
+constexpr int kStageCap = 64;        // default: records staged per warp before a coalesced flush
 
 struct EmitOut {
   gg_kf_rec_t* recs;
@@ -37,21 +37,29 @@ struct KfArgs {
   EmitOut out;
 };
 
-struct WarpStage {
-  uint4 rec[kStageCap];
+// CAP trades shared memory for global-cursor traffic: every flush is one returning atomic on a single address,
+// whose round trip (~1 us under load) stalls the warp, so kernels that emit many records use a deep stage.
+template <int CAP>
+struct WarpStageT {
+  static constexpr int kCap = CAP;
+  uint4 rec[CAP];
   uint32_t dotw[8][32];  // [column bit / 4][lane]: dots of the current 32-column chunk, one byte each (dot <= 225)
   int fill;
   int pad[3];
 };
+using WarpStage = WarpStageT<kStageCap>;
 
-__device__ __forceinline__ void stage_set_dot(WarpStage& ws, int b, int lane, uint32_t dot) {
+template <class WS>
+__device__ __forceinline__ void stage_set_dot(WS& ws, int b, int lane, uint32_t dot) {
   reinterpret_cast<uint8_t*>(&ws.dotw[b >> 2][lane])[b & 3] = static_cast<uint8_t>(dot);
 }
-__device__ __forceinline__ uint32_t stage_get_dot(const WarpStage& ws, int b, int lane) {
+template <class WS>
+__device__ __forceinline__ uint32_t stage_get_dot(const WS& ws, int b, int lane) {
   return (ws.dotw[b >> 2][lane] >> (8 * (b & 3))) & 0xFFu;
 }
 
-__device__ __forceinline__ void stage_flush(WarpStage& ws, const EmitOut& out, int lane) {
+template <class WS>
+__device__ __forceinline__ void stage_flush(WS& ws, const EmitOut& out, int lane) {
   const int fill = ws.fill;  // warp-uniform
   if (fill == 0) return;
   unsigned long long base = 0;
@@ -68,7 +76,8 @@ __device__ __forceinline__ void stage_flush(WarpStage& ws, const EmitOut& out, i
 // Every lane has marked its exact candidates of the current chunk in `exact`
 // (bit b = column t0 + b) and left their dots in ws.dotw (stage_set_dot); turn them into
 // records.  Must be called by the whole warp.
-__device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, int lane, uint32_t exact, uint32_t s,
+template <class WS>
+__device__ __forceinline__ void stage_commit(WS& ws, const EmitOut& out, int lane, uint32_t exact, uint32_t s,
                                              uint32_t t0, uint32_t& tile_cnt) {
   const int n_l = __popc(exact);
   int incl = n_l;
@@ -80,7 +89,7 @@ __device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, 
   const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
   if (total == 0) return;
   const int off = incl - n_l;
-  if (total > kStageCap) {  // dense chunk: bypass the stage
+  if (total > WS::kCap) {  // dense chunk: bypass the stage
     stage_flush(ws, out, lane);
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(out.status, static_cast<unsigned long long>(total));
@@ -93,13 +102,58 @@ __device__ __forceinline__ void stage_commit(WarpStage& ws, const EmitOut& out, 
         dst[base + i] = make_uint4(s, t0 + b, tile_cnt + i, stage_get_dot(ws, b, lane));
     }
   } else {
-    if (ws.fill + total > kStageCap) stage_flush(ws, out, lane);
+    if (ws.fill + total > WS::kCap) stage_flush(ws, out, lane);
     const int fill = ws.fill;
     int i = 0;
     for (uint32_t m = exact; m; m &= m - 1, ++i) {
       const int b = __ffs(m) - 1;
       ws.rec[fill + off + i] = make_uint4(s, t0 + b, tile_cnt + i, stage_get_dot(ws, b, lane));
     }
+    __syncwarp();
+    if (lane == 0) ws.fill = fill + total;
+    __syncwarp();
+  }
+  tile_cnt += n_l;
+}
+
+// Whole-tile variant for narrow feature rows: every lane holds the exact candidate masks of the four 32-column
+// chunks of one 128-column tile (m[c] bit b = column t0 + 32 c + b).  One warp scan per tile instead of per chunk;
+// the records carry no dot (the finalize step recomputes it from the two short rows).
+template <class WS>
+__device__ __forceinline__ void stage_commit_tile(WS& ws, const EmitOut& out, int lane, const uint32_t (&m)[4],
+                                                  uint32_t s, uint32_t t0, uint32_t& tile_cnt) {
+  const int n_l = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+  int incl = n_l;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  if (total == 0) return;
+  const int off = incl - n_l;
+  const bool direct = total > WS::kCap;
+  if (direct || ws.fill + total > WS::kCap) stage_flush(ws, out, lane);
+  unsigned long long base = 0;
+  if (direct) {
+    if (lane == 0) base = atomicAdd(out.status, static_cast<unsigned long long>(total));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0) + off;
+  }
+  const int fill = ws.fill;
+  uint4* dst = reinterpret_cast<uint4*>(out.recs);
+  int i = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    for (uint32_t mm = m[c]; mm; mm &= mm - 1, ++i) {
+      const uint4 rec = make_uint4(s, t0 + 32 * c + (__ffs(mm) - 1), tile_cnt + i, 0u);
+      if (direct) {
+        if (static_cast<long long>(base + i) < out.capacity) dst[base + i] = rec;
+      } else {
+        ws.rec[fill + off + i] = rec;
+      }
+    }
+  }
+  if (!direct) {
     __syncwarp();
     if (lane == 0) ws.fill = fill + total;
     __syncwarp();

@@ -40,6 +40,7 @@ constexpr int kEpiThreads = kEpiGroups * kGroupThreads;
 constexpr int kProducerWarp = kEpiThreads / 32, kMmaWarp = kProducerWarp + 1;
 constexpr int kThreads = kEpiThreads + 64;
 static_assert(kTileN == kTile, "rank tiles and accumulator tiles must coincide");
+constexpr int kNarrowStageCap = 512;  // narrow rows emit ~40 records per warp-tile and have shared memory to spare
 constexpr int kMaxD = 1024;           // A strip must fit shared memory next to the B ring
 
 struct __align__(8) Barriers {
@@ -204,7 +205,11 @@ __device__ __forceinline__ int last_tile(const KfArgs& a, const Walk& w) {
 template <int KB_BYTES>
 __global__ void __launch_bounds__(kThreads, 1)
 kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bstages, long long total_units,
-                  int* error_flag, Geom g) {
+                  int* error_flag, Geom g, int sq_max) {
+  // Narrow rows (one K block): a tile is a single MMA, the epilogue is everything.  It then tests dot >= per-row
+  // threshold table (exact, one LDS + one compare per score), keeps only bit masks, and commits once per tile.
+  constexpr bool kNarrow = KB_BYTES < kMaxKBlock;
+  using Stage = WarpStageT<(KB_BYTES < kMaxKBlock) ? kNarrowStageCap : kStageCap>;
   extern __shared__ unsigned char smem_raw[];
   // swizzled TMA boxes and UMMA descriptors assume (up to) 1024-byte aligned tiles
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -214,8 +219,9 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
   uint16_t* sqn = reinterpret_cast<uint16_t*>(smem_b + static_cast<size_t>(n_bstages) * kStageBytes);
-  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kEpiGroups * kBlock);  // sqn: one panel per epilogue group
+  Stage* stages = reinterpret_cast<Stage*>(sqn + kEpiGroups * kBlock);  // sqn: one panel per epilogue group
   Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
+  uint8_t* thr_tabs = reinterpret_cast<uint8_t*>(bars + 1);  // narrow only: [group][sq_max + 1][128]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -353,12 +359,15 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
     }
   } else {
     // ===================== epilogue groups (warp % 4 selects the TMEM lane quarter) =====================
-    WarpStage& ws = stages[warp];
+    Stage& ws = stages[warp];
     if (lane == 0) ws.fill = 0;
     __syncwarp();
     const int group = warp / 4;
     const int gt = tid % kGroupThreads;  // row of the strip == TMEM lane
     uint16_t* my_sqn = sqn + group * kBlock;
+    uint8_t* my_thr_w = thr_tabs + static_cast<size_t>(group) * (sq_max + 1) * kGroupThreads + gt;
+    const uint8_t* my_thr = my_thr_w;
+    int tab_strip = -1;
     if (n_units > 0) {
       Walk w = walk_begin(a, u0, n_units);
       uint32_t tile_seq = 0;  // position in this CTA's tile sequence (same enumeration as the MMA warp)
@@ -376,12 +385,21 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
           if (tile_seq % kEpiGroups != static_cast<uint32_t>(group)) continue;
           if (!panel_loaded) {  // first tile this group takes in the unit: fetch the unit's column norms
             asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
-            for (int c = gt; c < kBlock; c += kGroupThreads)
-              my_sqn[c] = c < cols_in_block ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
+            for (int c = gt; c < kBlock; c += kGroupThreads) {
+              const uint32_t sqc = c < cols_in_block ? static_cast<uint32_t>(__ldg(a.sqnorm + col0 + c)) : 0u;
+              my_sqn[c] = static_cast<uint16_t>(kNarrow ? sqc * kGroupThreads : sqc);  // narrow: offset into thr table
+            }
             asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
             if (row_ok) {
               sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
               scale_i = __ldg(a.fast_scale + sq_i);
+            }
+            if (kNarrow && w.strip != tab_strip) {  // this thread's column of the table: no one else reads it
+              for (int q = 0; q <= sq_max; ++q) {
+                const uint32_t need = row_ok ? __ldg(a.dmin + sq_i * q) : 255u;
+                my_thr_w[q * kGroupThreads] = static_cast<uint8_t>(need > 255u ? 255u : need);
+              }
+              tab_strip = w.strip;
             }
             panel_loaded = true;
           }
@@ -390,6 +408,30 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * kTileN;
           uint32_t tile_cnt = 0;
+          if constexpr (kNarrow) {
+            uint32_t m[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c0 = ct * kTileN + 32 * q;
+              uint32_t v[32];
+              tc_ld32(taddr + 32 * q, v);
+              uint32_t mask = 0;
+#pragma unroll
+              for (int b = 0; b < 32; ++b) mask |= static_cast<uint32_t>(v[b] >= my_thr[my_sqn[c0 + b]]) << b;
+              mask &= chunk_col_mask(cols_in_block, c0);
+              if (diag) mask &= chunk_diag_mask(r, c0);
+              m[q] = mask;
+            }
+            // the accumulator is free as soon as the masks are in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+            stage_commit_tile(ws, a.out, lane, m, static_cast<uint32_t>(s),
+                              static_cast<uint32_t>(col0 + ct * kTileN), tile_cnt);
+            if (row_ok) a.rowcnt[rowcnt_index(w.i_block - a.ib0, a.n_jblocks, w.j_block, r, ct)] =
+                static_cast<uint8_t>(tile_cnt);
+            continue;
+          }
 #pragma unroll 1
           for (int cc = 0; cc < kTileN; cc += 32) {
             const int c0 = ct * kTileN + cc;  // block-local column of bit 0
@@ -800,7 +842,7 @@ EncodeTiledFn encode_tiled() {
 
 int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s);
 
-int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
+int emit_tcgen05(const KfArgs& a, int p_max, cudaStream_t s) {
   // a.d is the row pitch of `counts` in bytes: 32 or 64 (one K block), or a multiple of 128 up to kMaxD
   GG_REQUIRE(a.d == 32 || a.d == 64 || (a.d % kMaxKBlock == 0 && a.d >= kMaxKBlock && a.d <= kMaxD), GG_ERR_ARG,
              "tcgen05 KF kernel needs a row pitch of 32, 64 or a multiple of 128 up to 1024 bytes");
@@ -830,8 +872,15 @@ int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
     return GG_ERR_CUDA;
   }
 
+  int sq_max = 0;  // p_max = sq_max^2 (core.threshold_tables); the narrow epilogue tabulates dmin per row
+  while (static_cast<long long>(sq_max + 1) * (sq_max + 1) <= p_max) ++sq_max;
+  const bool narrow = g.kb_bytes < kMaxKBlock;
+  GG_REQUIRE(!narrow || (static_cast<long long>(sq_max) * sq_max == p_max && sq_max <= 255 && sq_max * kGroupThreads < 65536),
+             GG_ERR_ARG, "p_max must be a square with sq_max <= 255 for narrow rows");
   const size_t fixed = static_cast<size_t>(g.n_kblocks) * g.stage_bytes + kEpiGroups * kBlock * sizeof(uint16_t) +
-                       (kEpiThreads / 32) * sizeof(WarpStage) + sizeof(Barriers) + 1024 /* base alignment slack */;
+                       (kEpiThreads / 32) * (narrow ? sizeof(WarpStageT<kNarrowStageCap>) : sizeof(WarpStage)) +
+                       sizeof(Barriers) + (narrow ? static_cast<size_t>(kEpiGroups) * (sq_max + 1) * kGroupThreads : 0) +
+                       1024 /* base alignment slack */;
   int dev = 0, max_smem = 0;
   GG_CUDA_CHECK(cudaGetDevice(&dev));
   GG_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -849,7 +898,7 @@ int emit_tcgen05(const KfArgs& a, cudaStream_t s) {
   const long long sms = gg::sm_count();
   const unsigned grid = static_cast<unsigned>(total_units < sms ? total_units : sms);
   int* error_flag = reinterpret_cast<int*>(a.out.status + 2);  // kf_status[2]
-  kernel<<<grid, kThreads, smem_bytes, s>>>(tmap, a, n_bstages, total_units, error_flag, g);
+  kernel<<<grid, kThreads, smem_bytes, s>>>(tmap, a, n_bstages, total_units, error_flag, g, sq_max);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

@@ -153,7 +153,7 @@ GG_API int gg_kf_features_f32(const uint8_t* counts, int64_t n, int d, const int
 typedef struct {
   uint32_t s, t;
   uint32_t rank; /* rank of t among the candidates of row s inside its 128-column tile */
-  uint32_t dot;
+  uint32_t dot;  /* only filled for rows wider than 64 bytes; narrower rows are re-multiplied by gg_kf_finalize */
 } gg_kf_rec_t;
 
 enum { GG_KF_IMPL_AUTO = 0, GG_KF_IMPL_DP4A = 1, GG_KF_IMPL_TCGEN05 = 2, GG_KF_IMPL_NAIVE = 3, GG_KF_IMPL_TCGEN05_PAIR = 4 };
@@ -166,6 +166,8 @@ typedef struct {
   int32_t p_max;        /* dmin has p_max + 1 entries */
   int32_t fast_shift;   /* fast pre-filter: (dot*dot) << fast_shift > fast_scale[sqnorm_i] * sqnorm_j */
   int32_t impl;         /* GG_KF_IMPL_* */
+  int32_t d_valid;      /* bytes of a row that can be non-zero (<= d; rows may be zero-padded to the 32-byte pitch
+                           the tensor path needs); 0 means d */
 } gg_kf_params_t;
 
 /* kf_status (device int64[4]): [0] candidates found (may exceed rec_capacity: re-run larger),
@@ -177,7 +179,8 @@ GG_API int gg_kf_emit(const gg_kf_params_t* h_params, const uint8_t* counts, con
 
 GG_API size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end, int64_t n_recs);
 GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
-                   const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
+                   const int32_t* sqnorm, const uint8_t* counts /* the matrix gg_kf_emit scored; used when d <= 64 */,
+                   int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
                    uint32_t* dot_out /* nullable: dot per edge, for top-n */, void* workspace, size_t workspace_bytes,
                    gg_stream_t st);
 

@@ -12,6 +12,6 @@ reads = synthetic_reads(200_000, 150, 0)
 built = core.build_graph(reads, k, str(s), with_kf=False)
 kc = built.kf_counts[0]
 for _ in range(3):
-    recs, n, rowcnt, params = core.kf_emit(kc.counts, kc.sqnorm, 0.8, kc.m ** 2, impl=impl, rec_capacity=1 << 25)
+    recs, n, rowcnt, params, scored = core.kf_emit(kc.counts, kc.sqnorm, 0.8, kc.m ** 2, impl=impl, rec_capacity=1 << 25)
 torch.cuda.synchronize()
 print("candidates", n)

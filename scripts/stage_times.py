@@ -35,12 +35,12 @@ ms, db = timed(lambda: core.build_db(cr)); print(f"db build ms {ms:.3f} N={db.nu
 for s in (2, 5):
     ms, kc = timed(lambda: core.kf_counts(db.node_codes, k, s)); print(f"counts s={s} ms {ms:.3f}")
     ms, x = timed(lambda: core.kf_features_f32(kc)); print(f"features s={s} ms {ms:.3f}")
-    for impl in (["dp4a"] if s == 2 else ["tcgen05", "tcgen05x2"]):
+    for impl in (["dp4a", "tcgen05"] if s == 2 else ["tcgen05x2"]):
         t0 = time.time()
         ms, kf = timed(lambda: core.kf_edges(kc.counts, kc.sqnorm, 0.8, 0.01, sq_max=kc.m ** 2, impl=impl), n=2)
         print(f"kf s={s} impl={impl} ms {ms:.3f} E={kf.edge_index.shape[1]}  pairs/s {db.num_nodes*(db.num_nodes-1)/2/ms/1e6:.1f} G")
-        recs, n_recs, rowcnt, params = core.kf_emit(kc.counts, kc.sqnorm, 0.8, kc.m ** 2, impl=impl, rec_capacity=1 << 25)
+        recs, n_recs, rowcnt, params, scored = core.kf_emit(kc.counts, kc.sqnorm, 0.8, kc.m ** 2, impl=impl, rec_capacity=1 << 25)
         ms, _ = timed(lambda: core.kf_emit(kc.counts, kc.sqnorm, 0.8, kc.m ** 2, impl=impl, rec_capacity=1 << 25), n=3)
         print(f"   emit only ms {ms:.3f}")
-        ms, _ = timed(lambda: core.kf_finalize(recs, n_recs, rowcnt, params, kc.sqnorm), n=3)
+        ms, _ = timed(lambda: core.kf_finalize(recs, n_recs, rowcnt, params, kc.sqnorm, scored), n=3)
         print(f"   finalize only ms {ms:.3f}")
