@@ -262,6 +262,186 @@ __global__ void __launch_bounds__(256) pending_kernel(const uint32_t* hist, cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-memory counting path (k <= 8).
+//
+// Measured on B200 (scripts/micro/atomics.cu): random 32-bit atomic adds run at >= 1600 G/s into shared memory,
+// 183 G/s into an L2-resident table and 51 G/s into a cluster-distributed (DSMEM) table.  The L2 path above is
+// therefore capped at ~0.8 ms for 1.42e8 windows.  The 4^(k+1)-bin table does not fit one SM, so the bin space is
+// cut into `n_ranges` slices of <= kSmemBins bins and the CTAs are dealt round-robin to the slices: CTA b counts
+// only keys of slice b % n_ranges over slab b / n_ranges of the input, in a private shared-memory histogram, and adds
+// its slice to the global table once at the end.  Every key is extracted n_ranges times, so the stream is first
+// packed (pack_kernel: 2-bit codes + two flag bits per base, one pass over the ASCII bytes) and the counting
+// passes only shift and mask.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmemBins = 52432;     // 4^9 / 5 rounded up to a multiple of 16: 209,728 bytes of shared memory
+constexpr int kSmemThreads = 1024;
+constexpr int kMaxRanges = 8;
+
+struct Packed {
+  uint32_t* codes;   // 16 bases per word, first base in the top bits
+  uint16_t* bad;     // N, separator, illegal byte or beyond the end: the base cannot be part of a k-mer
+  uint16_t* hard;    // separator, illegal byte or beyond the end: a k-mer search must stop here
+  int64_t n_words;   // ceil(n_bytes / 16) + 1 all-bad tail word
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len,
+                                                   Packed pk, unsigned long long* status) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= pk.n_words) return;
+  const int64_t b = i * 16;
+  if (b >= n_bytes) {
+    pk.codes[i] = 0;
+    pk.bad[i] = 0xFFFF;
+    pk.hard[i] = 0xFFFF;
+    return;
+  }
+  const uint4 w = __ldg(reinterpret_cast<const uint4*>(stream + b));
+  uint32_t codes, nmask, sepmask, badmask;
+  classify16(w, codes, nmask, sepmask, badmask);
+  const int64_t left = n_bytes - b;
+  const uint32_t beyond = left >= 16 ? 0u : (~((1u << left) - 1u) & 0xFFFFu);
+  nmask &= ~beyond;
+  badmask &= ~beyond;
+  sepmask &= ~beyond;
+  if (fixed_len > 0) {
+    badmask |= sepmask;  // a separator byte is illegal inside fixed-length rows
+    sepmask = 0;
+  }
+  if (badmask) atomicAdd(status + GG_ST_BAD_BYTES, static_cast<unsigned long long>(__popc(badmask)));
+  const uint32_t hard = sepmask | badmask | beyond;
+  pk.codes[i] = codes;
+  pk.bad[i] = static_cast<uint16_t>(nmask | hard);
+  pk.hard[i] = static_cast<uint16_t>(hard);
+}
+
+struct SmemArgs {
+  Packed pk;
+  int64_t n_bytes;
+  int64_t fixed_len;
+  int64_t pos_base;
+  int k;
+  int n_ranges;
+  uint32_t bins_per_range;
+  uint32_t* hist;
+  gg_bridge_t* bridges;
+  int64_t bridge_capacity;
+  unsigned long long* status;
+};
+
+__device__ __forceinline__ uint32_t packed_base(const Packed& pk, int64_t q) {
+  return (pk.codes[q >> 4] >> (30 - 2 * static_cast<int>(q & 15))) & 3u;
+}
+
+// packed-stream version of next_clean_kmer
+__device__ bool next_clean_kmer_packed(const SmemArgs& a, int64_t q, uint32_t& v_out) {
+  const uint32_t kmask = (1u << (2 * a.k)) - 1u;
+  uint32_t v = 0;
+  int run = 0;
+  for (; q < a.n_bytes; ++q) {
+    if (a.fixed_len > 0 && (q % a.fixed_len) == 0) return false;
+    const uint32_t bit = 1u << (q & 15);
+    if (a.pk.hard[q >> 4] & bit) return false;
+    if (a.pk.bad[q >> 4] & bit) {  // an N
+      run = 0;
+      v = 0;
+      continue;
+    }
+    v = ((v << 2) | packed_base(a.pk, q)) & kmask;
+    if (++run == a.k) {
+      v_out = v;
+      return true;
+    }
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kSmemThreads, 1) count_smem_kernel(SmemArgs a) {
+  extern __shared__ uint32_t h[];
+  const int range = blockIdx.x % a.n_ranges;
+  const int slab = blockIdx.x / a.n_ranges, n_slabs = gridDim.x / a.n_ranges;
+  if (slab >= n_slabs) return;  // the few CTAs that do not complete a round of slices stay idle
+  const uint32_t lo = static_cast<uint32_t>(range) * a.bins_per_range;
+  for (uint32_t i = threadIdx.x; i < a.bins_per_range; i += kSmemThreads) h[i] = 0;
+  __syncthreads();
+
+  const int k = a.k;
+  const int key_shift = 32 - 2 * (k + 1);
+  const int64_t n_data_words = a.pk.n_words - 1;  // the tail word is padding
+  const int64_t w_begin = n_data_words * slab / n_slabs, w_end = n_data_words * (slab + 1) / n_slabs;
+  constexpr int kBatch = 4;  // words per thread per iteration: all loads are issued before any is consumed
+  for (int64_t i0 = w_begin + threadIdx.x; i0 < w_end; i0 += static_cast<int64_t>(kSmemThreads) * kBatch) {
+    uint32_t hi_[kBatch], lo_[kBatch], dirty_[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * kSmemThreads;
+      const bool in = i < w_end;
+      hi_[u] = in ? __ldg(a.pk.codes + i) : 0u;
+      lo_[u] = in ? __ldg(a.pk.codes + i + 1) : 0u;
+      dirty_[u] = in ? (static_cast<uint32_t>(__ldg(a.pk.bad + i)) | (static_cast<uint32_t>(__ldg(a.pk.bad + i + 1)) << 16))
+                     : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * kSmemThreads;
+      const uint32_t hi = hi_[u], lo_w = lo_[u], dirty = dirty_[u];
+      if (dirty == 0xFFFFFFFFu) continue;
+      const int64_t b = i * 16;
+      uint32_t brk = 0;
+      if (a.fixed_len > 0) {
+        const int64_t len = a.fixed_len;
+        int64_t j;
+        if (a.n_bytes < (1ll << 31)) {
+          const uint32_t r = static_cast<uint32_t>(b) % static_cast<uint32_t>(len);
+          j = r ? static_cast<int64_t>(len - r) : 0;
+        } else {
+          j = (len - (b % len)) % len;
+        }
+        for (; j < 32; j += len) brk |= 1u << j;
+      }
+      const uint32_t inner = ~(brk >> 1);
+      const uint32_t pair_ok = erode(~dirty, k + 1) & erode(inner, k) & 0xFFFFu;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t idx = (__funnelshift_l(lo_w, hi, 2 * j) >> key_shift) - lo;
+        if (((pair_ok >> j) & 1u) && idx < a.bins_per_range) atomicAdd(&h[idx], 1u);
+      }
+      if (range == 0) {  // one slice owner also handles the rare N bridges of its slab
+        const uint32_t hard = static_cast<uint32_t>(__ldg(a.pk.hard + i)) | (static_cast<uint32_t>(__ldg(a.pk.hard + i + 1)) << 16);
+        const uint32_t nmask = dirty & ~hard;
+        uint32_t cand = erode(~dirty, k) & erode(inner, k - 1) & (nmask >> k) & ~(brk >> k) & 0xFFFFu;
+        while (cand) {
+          const int j = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const uint32_t uu = __funnelshift_l(lo_w, hi, 2 * j) >> (32 - 2 * k);
+          uint32_t v = 0;
+          if (next_clean_kmer_packed(a, b + j + k + 1, v)) {
+            const uint32_t overlap_mask = (1u << (2 * (k - 1))) - 1u;
+            if ((uu & overlap_mask) == (v >> 2)) {
+              atomicAdd(a.hist + ((uu << 2) | (v & 3u)), 1u);
+            } else {
+              const unsigned long long slot = atomicAdd(a.status + GG_ST_BRIDGES, 1ull);
+              if (static_cast<int64_t>(slot) < a.bridge_capacity) {
+                gg_bridge_t r;
+                r.u = uu;
+                r.v = v;
+                r.pos = static_cast<uint64_t>(a.pos_base + b + j);
+                a.bridges[slot] = r;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t total_bins = 1u << (2 * (k + 1));
+  for (uint32_t i = threadIdx.x; i < a.bins_per_range; i += kSmemThreads) {
+    const uint32_t v = h[i];
+    if (v && lo + i < total_bins) atomicAdd(a.hist + lo + i, v);
+  }
+}
+
 int check_stream_args(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len, int k) {
   GG_REQUIRE(k >= 1 && k <= GG_MAX_K, GG_ERR_K, "k outside [1, GG_MAX_K]");
   GG_REQUIRE(n_bytes >= 0 && fixed_len >= 0, GG_ERR_ARG, "negative size");
@@ -327,6 +507,52 @@ extern "C" int gg_first_occurrence(const uint8_t* stream, int64_t n_bytes, int64
   const int64_t resident = static_cast<int64_t>(gg::sm_count());
   const int grid = static_cast<int>(n_groups < resident ? n_groups : resident);
   first_kernel<<<grid, kThreads, 0, s>>>(a);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+extern "C" size_t gg_count_smem_workspace_bytes(int64_t n_bytes, int k) {
+  if (n_bytes < 0 || k < 1 || k > GG_MAX_K) return 0;
+  const size_t bins = static_cast<size_t>(1) << (2 * (k + 1));
+  if ((bins + kSmemBins - 1) / kSmemBins > kMaxRanges) return 0;  // table too large for this path: use gg_count_kp1mers
+  const size_t n_words = (static_cast<size_t>(n_bytes) + 15) / 16 + 1;
+  gg::Carver c(nullptr);
+  c.take<uint32_t>(n_words);
+  c.take<uint16_t>(n_words);
+  c.take<uint16_t>(n_words);
+  return c.used();
+}
+
+extern "C" int gg_count_kp1mers_smem(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len, int k,
+                                     int64_t pos_base, uint32_t* hist, gg_bridge_t* bridges, int64_t bridge_capacity,
+                                     int64_t* status, void* workspace, size_t workspace_bytes, gg_stream_t st) {
+  if (int rc = check_stream_args(stream, n_bytes, fixed_len, k)) return rc;
+  GG_REQUIRE(hist && status, GG_ERR_ARG, "null buffer");
+  GG_REQUIRE(bridge_capacity >= 0 && (bridge_capacity == 0 || bridges), GG_ERR_ARG, "bridge list");
+  const size_t need = gg_count_smem_workspace_bytes(n_bytes, k);
+  GG_REQUIRE(need != 0, GG_ERR_K, "(k+1)-mer table too large for the shared-memory path; use gg_count_kp1mers");
+  GG_REQUIRE(workspace && workspace_bytes >= need, GG_ERR_WORKSPACE, "workspace too small");
+  if (n_bytes == 0) return GG_OK;
+  cudaStream_t s = gg::as_stream(st);
+  const uint32_t bins = 1u << (2 * (k + 1));
+  const int n_ranges = static_cast<int>((bins + kSmemBins - 1) / kSmemBins);
+  const uint32_t bins_per_range = n_ranges == 1 ? bins : (bins + n_ranges - 1) / n_ranges;
+  Packed pk;
+  pk.n_words = (n_bytes + 15) / 16 + 1;
+  gg::Carver c(workspace);
+  pk.codes = c.take<uint32_t>(pk.n_words);
+  pk.bad = c.take<uint16_t>(pk.n_words);
+  pk.hard = c.take<uint16_t>(pk.n_words);
+  unsigned long long* stw = reinterpret_cast<unsigned long long*>(status);
+  pack_kernel<<<static_cast<unsigned>((pk.n_words + 255) / 256), 256, 0, s>>>(stream, n_bytes, fixed_len, pk, stw);
+  GG_CUDA_CHECK(cudaGetLastError());
+  SmemArgs a{pk, n_bytes, fixed_len, pos_base, k, n_ranges, bins_per_range, hist, bridges, bridge_capacity, stw};
+  const size_t smem = static_cast<size_t>(bins_per_range) * sizeof(uint32_t);
+  GG_CUDA_CHECK(cudaFuncSetAttribute(count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  int grid = gg::sm_count();
+  if (grid < n_ranges) grid = n_ranges;
+  count_smem_kernel<<<grid, kSmemThreads, smem, s>>>(a);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

@@ -25,7 +25,14 @@ st = core._stream()
 def f_count():
     lib.gg_count_reset(k, ptr(hist), ptr(first), ptr(status), st)
     lib.gg_count_kp1mers(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, 0, ptr(hist), ptr(br), 1024, ptr(status), st)
-ms, _ = timed(f_count); print(f"count ms {ms:.3f}  -> {stream.n_bytes/ms/1e6:.1f} GB/s")
+ms, _ = timed(f_count); print(f"count (L2 path) ms {ms:.3f}  -> {stream.n_bytes/ms/1e6:.1f} GB/s")
+wsb = int(lib.gg_count_smem_workspace_bytes(stream.n_bytes, k))
+if wsb:
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    def f_count_smem():
+        lib.gg_count_reset(k, ptr(hist), ptr(first), ptr(status), st)
+        lib.gg_count_kp1mers_smem(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, 0, ptr(hist), ptr(br), 1024, ptr(status), ptr(ws), wsb, st)
+    ms, _ = timed(f_count_smem); print(f"count (smem path) ms {ms:.3f}  -> {stream.n_bytes/ms/1e6:.1f} GB/s")
 def f_first():
     first.fill_(-1)
     lib.gg_first_occurrence(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, 0, ptr(hist), ptr(first), ptr(status), st)

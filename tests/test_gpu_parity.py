@@ -228,6 +228,37 @@ def test_input_forms_agree(gg):
             assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("k", [3, 6, 7, 8])
+def test_count_paths_agree(gg, k):
+    """Shared-memory slices (packed stream) and the L2 RED path must give the same histogram, first occurrences and
+    bridge records -- on ragged, N-ridden, separator-delimited input and on fixed-length rows."""
+    from genomic_gnn_b200 import core
+
+    rng = np.random.default_rng(100 + k)
+    reads = []
+    for _ in range(3000):
+        ln = int(rng.integers(0, 200))
+        r = "".join("ACGT"[c] for c in rng.integers(0, 4, ln))
+        r = "".join(("N" if rng.random() < 0.01 else ch) for ch in r) + "N" * int(rng.integers(0, 4))
+        reads.append(r)
+    fixed = fast.synthetic_reads(5000, 151, seed=k)
+    fixed[::41, 77] = ord("N")
+    for inp in (reads, fixed):
+        stream = core.upload_reads(inp)
+        a = core.count_kp1mers(stream, k, impl="smem")
+        b = core.count_kp1mers(stream, k, impl="l2")
+        assert torch.equal(a.hist, b.hist)
+        assert torch.equal(a.first_pos, b.first_pos)
+        assert a.n_bridges == b.n_bridges and a.n_nonzero == b.n_nonzero
+        ka = sorted(map(tuple, a.bridges[: a.n_bridges].cpu().tolist()))
+        kb = sorted(map(tuple, b.bridges[: b.n_bridges].cpu().tolist()))
+        assert ka == kb
+    with pytest.raises(ValueError):
+        core.count_kp1mers(core.upload_reads(["ACGTACGTACGTAAA"]), 10, impl="smem")
+    with pytest.raises(ValueError):
+        core.count_kp1mers(core.upload_reads(["ACGTXCGT"]), 3, impl="smem")
+
+
 def test_host_to_host_build_matches_device_build(gg):
     from genomic_gnn_b200 import core
 
