@@ -205,6 +205,17 @@ GG_API int gg_kf_select(const int64_t* edge_src, const int64_t* edge_dst, const 
                  int64_t tie_budget, int64_t* out_src, int64_t* out_dst, double* out_w64, float* out_w32,
                  int64_t* out_count, void* workspace, size_t workspace_bytes, gg_stream_t st);
 
+/* ------------------------------------------------------------------------
+ * f2  reads -> k-mer index arrays.  Replaces word2index inside KmerSsgnn.transform
+ *     (src/representations/kmer_ssgnn.py:148-158; seq_to_kmers(..., inlcudeUNK=True), src/utils.py:28-30):
+ *     out[out_offsets[r] + w] = code_to_index[code of read r's window w] for windows at 0, stride, 2*stride, ...;
+ *     windows holding an 'N' give unk_index.  status[0] = windows with a byte outside ACGTN (written as -1),
+ *     status[1] = windows whose k-mer has code_to_index < 0 (the caller's "missing k-mers" rebuild trigger).
+ * ------------------------------------------------------------------------ */
+GG_API int gg_kmer_index(const uint8_t* stream, const int64_t* read_start, const int64_t* read_len, int64_t n_reads,
+                  int k, int stride, const int32_t* code_to_index, int64_t unk_index, const int64_t* out_offsets,
+                  int64_t* out, int64_t* status, gg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif
