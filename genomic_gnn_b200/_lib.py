@@ -53,6 +53,9 @@ SIGNATURES = {
     "gg_kf_finalize_workspace_bytes": (_SZ, [_I64, _I32, _I32, _I64]),
     "gg_kf_finalize": (_I32, [C.POINTER(KfParams), _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gg_kf_class_hist": (_I32, [_P, _P, _P, _I64, _P, _I32, _P, _P]),
+    "gg_count_pairs_stride": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I64, _P, _I64, _P, _P]),
+    "gg_db_prune_workspace_bytes": (_SZ, [_I64]),
+    "gg_db_prune_quantile": (_I32, [_P, _P, _P, _I64, _DBL, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gg_kmer_index": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P, _P]),
     "gg_kf_select_workspace_bytes": (_SZ, [_I64]),
     "gg_kf_select": (_I32, [_P, _P, _P, _P, _I64, _P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -129,10 +129,11 @@ def weighted_directed_edges(sequences, k: int = 3, stride: int = 1, inlcudeUNK: 
                             disable_tqdm: bool = True):
     """src/utils.py:52-84.  The GPU path covers what the builders call it with:
     stride 1, inlcudeUNK=False (kmer_ssgnn.py:174-180)."""
-    if stride != 1:
-        raise NotImplementedError("stride > 1 (DB1.. graphs, SURVEY.md row f4) is not on the CUDA path yet")
     if inlcudeUNK:
         raise NotImplementedError("inlcudeUNK=True keeps an 'N'*k node; the builders always pass False")
+    if stride != 1:  # higher-stride graphs (kmer_ssgnn.py:215-226): pairs are no longer (k+1)-mers
+        pairs = PairFrequency(core.count_pairs_stride(sequences, k, int(stride)))
+        return ItemFrequency(pairs), pairs
     stream = core.upload_reads(sequences)
     pairs = PairFrequency(core.count_kp1mers(stream, k))
     return ItemFrequency(pairs), pairs
@@ -239,9 +240,6 @@ def build_deBruijn_graph(pair_frequency, normalise: bool = False, remove_N: bool
                          create_all_kmers: bool = True, disable_tqdm: bool = True) -> KmerGraph:
     """src/utils.py:87-165.  Unlike the reference this does not mutate
     ``pair_frequency``."""
-    if keep_top_k is not None:
-        raise NotImplementedError("quantile pruning of DB edges (higher-stride graphs, SURVEY.md row f4) "
-                                  "is not on the CUDA path yet")
     if isinstance(pair_frequency, PairFrequency):
         cr = pair_frequency.count_result
     else:
@@ -249,7 +247,7 @@ def build_deBruijn_graph(pair_frequency, normalise: bool = False, remove_N: bool
     if cr.n_nonzero == 0 and cr.n_bridges == 0:
         raise IndexError("list index out of range")  # what utils.py:122 raises on an empty dict
     return KmerGraph(core.build_db(cr, normalise=normalise, create_all_kmers=create_all_kmers,
-                                   edge_weight_threshold=edge_weight_threshold))
+                                   edge_weight_threshold=edge_weight_threshold, keep_top_k=keep_top_k))
 
 
 # --------------------------------------------------------------------------- a5

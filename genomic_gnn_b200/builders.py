@@ -126,8 +126,6 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
                                       graphs_strides: Optional[list] = None, faiss_ann: bool = False, device="cpu",
                                       kf_impl="auto", **_faiss_kwargs):
     """gnn_tasks_miniBatch/dataloader.py:21-179 -> (loader, HeteroData)."""
-    if graphs_strides:
-        raise NotImplementedError("higher-stride DB graphs are not on the CUDA path yet (SURVEY.md row f4)")
     if faiss_ann:
         raise NotImplementedError("FAISS ANN KF edges are out of scope; the exact Gram path replaces them")
     if edit_distance_loss_weight != 0:
@@ -136,6 +134,9 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
     data["node"].x = _as_float_tensor(labels, device)
     data["node", "DB", "node"].edge_index = graph.edge_index.to(device)
     data["node", "DB", "node"].edge_attr = graph.weight.to(device)
+    for i, g in enumerate(graphs_strides or []):  # dataloader.py:83-97
+        data["node", f"DB{i + 1}", "node"].edge_index = g.edge_index.to(device)
+        data["node", f"DB{i + 1}", "node"].edge_attr = g.weight.to(device)
     for i, lab in enumerate(labels_to_predict or []):
         data["node"][f"y_{i}"] = _as_float_tensor(lab, device)
     if kmer_frequency_loss_weight != 0:
@@ -167,10 +168,21 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
 
 
 # --------------------------------------------------------------------------- builder methods
+def _stride_graphs(self, k):
+    """kmer_ssgnn.py:215-226 / kmer_ssgnn_miniBatch.py:201-217: one extra DB graph per additional stride, pruned by
+    edge_weight_threshold = 1/4^k and the quantile keep_top_k.  Each has its own node numbering (from_networkx of the
+    new graph), as in the reference."""
+    out = []
+    for stride in list(getattr(self, "strides", [1]))[1:]:
+        _, pf = api.weighted_directed_edges(self.ssgnn_dataset, k=k, stride=int(stride), inlcudeUNK=False)
+        out.append(api.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=self.create_all_kmers,
+                                            edge_weight_threshold=1.0 / float(4**k),
+                                            keep_top_k=getattr(self, "edges_keep_top_k", None)))
+    return out
+
+
 def _common_graph(self, k):
     strides = list(getattr(self, "strides", [1]))
-    if len(strides) > 1:
-        raise NotImplementedError("representation_stride with more than one value is not on the CUDA path yet")
     _, pair_frequency = api.weighted_directed_edges(self.ssgnn_dataset, k=k, stride=int(strides[0]), inlcudeUNK=False,
                                                     disable_tqdm=getattr(self, "disable_tqdm", True))
     self.graph = api.build_deBruijn_graph(pair_frequency, normalise=True, remove_N=True,
@@ -193,6 +205,9 @@ def create_graphs(self, k: int):
         self.dataloader, self.torch_graph = networkx_to_dataloader_full_batch(
             self.graph, self.kf_labels[0], labels_to_predict=self.kf_labels, device=device)
         self.num_features = 4 ** int(str(self.small_k)[0])  # sic: first character (kmer_ssgnn.py:213)
+    for i, g in enumerate(_stride_graphs(self, k)):  # attach_higher_strides_to_torch_graph, gnn_utils.py:496-511
+        self.torch_graph["edge_index_" + str(i + 1)] = g.edge_index.to(device)
+        self.torch_graph["edge_weight_" + str(i + 1)] = g.weight.to(device)
 
 
 def create_graphs_mini_batch(self, k: int):
@@ -207,7 +222,8 @@ def create_graphs_mini_batch(self, k: int):
         edit_distance_loss_weight=self.edit_distance_loss_weight, kmer_freq_labels=self.kf_labels, k=k,
         edges_threshold=self.edges_threshold, edges_keep_top_k=self.edges_keep_top_k,
         layers_config=[*self.layers_config, "1_" + self.representation_ss_last_layer_edge_type],
-        ss_task=self.ss_task, graphs_strides=[], faiss_ann=getattr(self, "faiss_ann", False), device=device)
+        ss_task=self.ss_task, graphs_strides=_stride_graphs(self, k), faiss_ann=getattr(self, "faiss_ann", False),
+        device=device)
     self.num_features = 4**k if one_hot else 4 ** int(str(self.small_k)[0])
 
 

@@ -203,6 +203,49 @@ def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, fi
         bridge_capacity = nb  # rare: many internal N runs -- run again with room for all of them
 
 
+def read_layout(sequences):
+    """Host-side (start offset, length) of every read in the device stream that upload_reads builds."""
+    if isinstance(sequences, (np.ndarray, torch.Tensor)):
+        n, length = int(sequences.shape[0]), int(sequences.shape[1])
+        return np.arange(n, dtype=np.int64) * length, np.full(n, length, dtype=np.int64)
+    seqs = list(sequences)
+    lens = np.fromiter(map(len, seqs), dtype=np.int64, count=len(seqs))
+    starts = np.zeros(len(seqs), dtype=np.int64)
+    if len(seqs):
+        starts[1:] = np.cumsum(lens[:-1] + 1)  # one separator byte after every read
+    return starts, lens
+
+
+def count_pairs_stride(sequences, k: int, stride: int) -> CountResult:
+    """Row f4: weighted_directed_edges(..., stride > 1, inlcudeUNK=False) (src/utils.py:52-84 with the windows of
+    utils.py:28 at 0, stride, 2*stride, ...).  Every pair of consecutive surviving k-mers becomes one record; the
+    (k+1)-mer histogram stays empty and gg_db_build de-duplicates the records."""
+    _require_cuda()
+    lib = _lib.load()
+    if not (1 <= k <= _lib.GG_MAX_K) or stride < 1:
+        raise ValueError("bad k / stride")
+    stream = upload_reads(sequences)
+    dev = stream.data.device
+    starts, lens = read_layout(sequences)
+    n = int(starts.shape[0])
+    n_win = np.where(lens >= k, (lens - k) // stride + 1, 0)
+    capacity = int(np.maximum(n_win - 1, 0).sum())  # upper bound: every window clean
+    bins = int(lib.gg_hist_bins(k))
+    hist = torch.zeros(bins, dtype=torch.int32, device=dev)
+    first = torch.full((bins,), -1, dtype=torch.int64, device=dev)
+    status = torch.zeros(_lib.ST_WORDS, dtype=torch.int64, device=dev)
+    recs = torch.empty((max(capacity, 1), 4), dtype=torch.int32, device=dev)
+    starts_d, lens_d = torch.from_numpy(starts).to(dev), torch.from_numpy(lens).to(dev)
+    with _stage("k1_stride_pairs"):
+        check(lib.gg_count_pairs_stride(ptr(stream.data), ptr(starts_d), ptr(lens_d), n, k, int(stride),
+                                        stream.pos_base, ptr(recs), capacity, ptr(status), _stream()),
+              "gg_count_pairs_stride")
+    st = status.cpu()
+    if int(st[_lib.ST_BAD_BYTES]) > 0:
+        raise ValueError(f"{int(st[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN")
+    return CountResult(k, hist, first, recs, int(st[_lib.ST_BRIDGES]), status, 0)
+
+
 # --------------------------------------------------------------------------- K2
 @dataclass
 class DBGraph:
@@ -216,8 +259,9 @@ class DBGraph:
     weight64: torch.Tensor      # float64 [E]
 
 
-def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weight_threshold=None) -> DBGraph:
-    """K2.  Reference: src/utils.py:87-165 + from_networkx."""
+def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weight_threshold=None,
+             keep_top_k=None) -> DBGraph:
+    """K2.  Reference: src/utils.py:87-165 + from_networkx.  keep_top_k = the quantile pruning of utils.py:151-160."""
     lib = _lib.load()
     dev = cr.hist.device
     k = cr.k
@@ -240,7 +284,19 @@ def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weigh
                               ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes, _stream()),
               "gg_db_build")
     n, e = (int(x) for x in ne.cpu())
-    return DBGraph(k, n, e, node_codes[:n], code_to_node, edges[:, :e].contiguous(), w32[:e], w64[:e])
+    ei, w32, w64 = edges[:, :e].contiguous(), w32[:e], w64[:e]
+    if keep_top_k is not None and e > 0:
+        pw = int(lib.gg_db_prune_workspace_bytes(e))
+        pws = torch.empty(pw, dtype=torch.uint8, device=dev)
+        o_ei = torch.empty((2, e), dtype=torch.int64, device=dev)
+        o64 = torch.empty(e, dtype=torch.float64, device=dev)
+        o32 = torch.empty(e, dtype=torch.float32, device=dev)
+        cnt = torch.empty(1, dtype=torch.int64, device=dev)
+        check(lib.gg_db_prune_quantile(ptr(ei[0]), ptr(ei[1]), ptr(w64), e, 1 - keep_top_k, ptr(o_ei[0]), ptr(o_ei[1]),
+                                       ptr(o64), ptr(o32), ptr(cnt), ptr(pws), pw, _stream()), "gg_db_prune_quantile")
+        e = int(cnt.item())
+        ei, w32, w64 = o_ei[:, :e].contiguous(), o32[:e], o64[:e]
+    return DBGraph(k, n, e, node_codes[:n], code_to_node, ei, w32, w64)
 
 
 # --------------------------------------------------------------------------- K3

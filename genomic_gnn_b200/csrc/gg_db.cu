@@ -275,3 +275,103 @@ extern "C" int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, cons
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Quantile pruning of a built graph (reference src/utils.py:151-160): threshold =
+// np.quantile(weights, 1 - keep_top_k) with numpy's default linear interpolation, edges with
+// weight < threshold are removed, nodes stay.  The interpolation repeats numpy's _lerp without
+// fused multiply-adds so that the threshold is the same float64.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void quantile_kernel(const double* sorted, int64_t n, double q, double* out) {
+  const double vi = static_cast<double>(n - 1) * q;
+  int64_t lo = static_cast<int64_t>(floor(vi));
+  if (lo < 0) lo = 0;
+  if (lo > n - 1) lo = n - 1;
+  const int64_t hi = lo + 1 > n - 1 ? n - 1 : lo + 1;
+  const double t = __dsub_rn(vi, static_cast<double>(lo));
+  const double a = sorted[lo], b = sorted[hi];
+  const double d = __dsub_rn(b, a);
+  *out = t >= 0.5 ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(a, __dmul_rn(d, t));
+}
+
+__global__ void prune_flag_kernel(const double* w, int64_t n, const double* thr, uint8_t* keep) {
+  GRID_STRIDE(i, n) keep[i] = !(w[i] < *thr);
+}
+
+struct KeepToU64 {
+  __host__ __device__ unsigned long long operator()(uint8_t v) const { return v ? 1ull : 0ull; }
+};
+
+__global__ void prune_scatter_kernel(const uint8_t* keep, const unsigned long long* pos, int64_t n, const int64_t* src,
+                                     const int64_t* dst, const double* w, int64_t* o_src, int64_t* o_dst, double* o_w64,
+                                     float* o_w32, int64_t* out_count) {
+  GRID_STRIDE(i, n) {
+    if (keep[i]) {
+      const unsigned long long p = pos[i];
+      o_src[p] = src[i];
+      o_dst[p] = dst[i];
+      if (o_w64) o_w64[p] = w[i];
+      if (o_w32) o_w32[p] = static_cast<float>(w[i]);
+    }
+    if (i == n - 1) *out_count = static_cast<int64_t>(pos[i] + (keep[i] ? 1 : 0));
+  }
+}
+
+struct PruneLayout {
+  double* sorted;
+  double* thr;
+  uint8_t* keep;
+  unsigned long long* pos;
+  void* temp;
+  size_t temp_bytes, total;
+};
+
+PruneLayout prune_carve(void* ws, int64_t n) {
+  gg::Carver c(ws);
+  PruneLayout l;
+  const int64_t m = n > 0 ? n : 1;
+  l.sorted = c.take<double>(m);
+  l.thr = c.take<double>(1);
+  l.keep = c.take<uint8_t>(m);
+  l.pos = c.take<unsigned long long>(m);
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, a, static_cast<const double*>(nullptr), static_cast<double*>(nullptr), m);
+  cub::TransformInputIterator<unsigned long long, KeepToU64, const uint8_t*> it(nullptr, KeepToU64());
+  cub::DeviceScan::ExclusiveSum(nullptr, b, it, static_cast<unsigned long long*>(nullptr), m);
+  l.temp_bytes = a > b ? a : b;
+  l.temp = c.take<char>(l.temp_bytes);
+  l.total = c.used();
+  return l;
+}
+
+}  // namespace
+
+extern "C" size_t gg_db_prune_workspace_bytes(int64_t n_edges) {
+  return n_edges < 0 ? 0 : prune_carve(nullptr, n_edges).total;
+}
+
+extern "C" int gg_db_prune_quantile(const int64_t* edge_src, const int64_t* edge_dst, const double* weight64,
+                                    int64_t n_edges, double quantile, int64_t* out_src, int64_t* out_dst,
+                                    double* out_w64, float* out_w32, int64_t* out_count, void* workspace,
+                                    size_t workspace_bytes, gg_stream_t st) {
+  GG_REQUIRE(n_edges >= 0 && out_count, GG_ERR_ARG, "bad size");
+  cudaStream_t s = gg::as_stream(st);
+  GG_CUDA_CHECK(cudaMemsetAsync(out_count, 0, sizeof(int64_t), s));
+  if (n_edges == 0) return GG_OK;
+  GG_REQUIRE(edge_src && edge_dst && weight64 && out_src && out_dst && workspace, GG_ERR_ARG, "null buffer");
+  PruneLayout l = prune_carve(workspace, n_edges);
+  GG_REQUIRE(workspace_bytes >= l.total, GG_ERR_WORKSPACE, "workspace too small");
+  size_t tb = l.temp_bytes;
+  GG_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(l.temp, tb, weight64, l.sorted, n_edges, 0, 64, s));
+  quantile_kernel<<<1, 1, 0, s>>>(l.sorted, n_edges, quantile, l.thr);
+  prune_flag_kernel<<<grid_for(n_edges), 256, 0, s>>>(weight64, n_edges, l.thr, l.keep);
+  cub::TransformInputIterator<unsigned long long, KeepToU64, const uint8_t*> it(l.keep, KeepToU64());
+  tb = l.temp_bytes;
+  GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(l.temp, tb, it, l.pos, n_edges, s));
+  prune_scatter_kernel<<<grid_for(n_edges), 256, 0, s>>>(l.keep, l.pos, n_edges, edge_src, edge_dst, weight64, out_src,
+                                                         out_dst, out_w64, out_w32, out_count);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}

@@ -216,6 +216,22 @@ GG_API int gg_kmer_index(const uint8_t* stream, const int64_t* read_start, const
                   int k, int stride, const int32_t* code_to_index, int64_t unk_index, const int64_t* out_offsets,
                   int64_t* out, int64_t* status, gg_stream_t st);
 
+/* ------------------------------------------------------------------------
+ * f4  higher-stride De Bruijn graphs (kmer_ssgnn.py:215-226).
+ *     gg_count_pairs_stride: weighted_directed_edges(..., stride = s > 1, inlcudeUNK=False): one (u, v, pos) record
+ *     per pair of consecutive surviving k-mers at offsets 0, s, 2s, ... (status[GG_ST_BRIDGES] = records found);
+ *     feed them to gg_db_build as `bridges` with an all-zero histogram.
+ *     gg_db_prune_quantile: keep_top_k of build_deBruijn_graph (utils.py:151-160): drops edges with weight <
+ *     np.quantile(weights, quantile) (linear interpolation, numpy's _lerp), order kept, out_count[0] = edges left.
+ * ------------------------------------------------------------------------ */
+GG_API int gg_count_pairs_stride(const uint8_t* stream, const int64_t* read_start, const int64_t* read_len,
+                          int64_t n_reads, int k, int stride, int64_t pos_base, gg_bridge_t* records, int64_t capacity,
+                          int64_t* status, gg_stream_t st);
+GG_API size_t gg_db_prune_workspace_bytes(int64_t n_edges);
+GG_API int gg_db_prune_quantile(const int64_t* edge_src, const int64_t* edge_dst, const double* weight64, int64_t n_edges,
+                         double quantile, int64_t* out_src, int64_t* out_dst, double* out_w64, float* out_w32,
+                         int64_t* out_count, void* workspace, size_t workspace_bytes, gg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

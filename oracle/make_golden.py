@@ -87,6 +87,35 @@ def run_reference(ref, reads, k, stride, cak, small_ks, kf_settings, full=True):
     return out
 
 
+def stride_case(ref):
+    """Higher-stride DB graph exactly as the builders make it (kmer_ssgnn.py:215-226): stride 2 and 3,
+    edge_weight_threshold = 1/4^k, quantile keep_top_k."""
+    rng = np.random.default_rng(77)
+    reads = []
+    for _ in range(400):
+        ln = int(rng.integers(0, 70))
+        s = "".join("ACGT"[c] for c in rng.integers(0, 4, ln))
+        reads.append("".join(("N" if rng.random() < 0.02 else ch) for ch in s) + "N" * int(rng.integers(0, 4)))
+    out = {"reads": np.array("\n".join(reads)), "n_reads": len(reads), "k": 4}
+    for stride in (2, 3, 5):
+        for j, (thr, topk) in enumerate([(None, None), (1.0 / 4**4, 0.3), (1.0 / 4**4, None), (None, 0.5)]):
+            with ref_import.quiet():
+                _, pf = ref.weighted_directed_edges(reads, k=4, stride=stride, inlcudeUNK=False)
+                g = ref.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=False,
+                                             edge_weight_threshold=thr, keep_top_k=topk)
+            nodes = list(g.nodes())
+            idx = {n: i for i, n in enumerate(nodes)}
+            edges = list(g.edges(data="weight"))
+            tag = f"s{stride}_{j}"
+            out[f"{tag}_nodes"] = np.array(nodes)
+            out[f"{tag}_edge_index"] = np.array([[idx[u] for u, _, _ in edges], [idx[v] for _, v, _ in edges]],
+                                                dtype=np.int64).reshape(2, -1)
+            out[f"{tag}_weight64"] = np.array([w for _, _, w in edges], dtype=np.float64)
+            out[f"{tag}_thr"] = -1.0 if thr is None else thr
+            out[f"{tag}_topk"] = -1.0 if topk is None else topk
+    return out
+
+
 def large_case(ref, name, n_reads, k, small_ks, thr, topk, seed=0):
     reads_arr = fast.synthetic_reads(n_reads, 150, seed=seed)
     reads = fast.reads_to_strings(reads_arr)
@@ -161,6 +190,9 @@ def main():
             out["kf_settings"] = np.array([(t, -1.0 if p is None else p) for t, p in kfs])
             np.savez_compressed(os.path.join(GOLDEN_DIR, f"small_{name}.npz"), **out)
             print("wrote", name, {kk: getattr(vv, "shape", None) for kk, vv in out.items()})
+    if not args.only or args.only == "stride":
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "stride_k4.npz"), **stride_case(ref))
+        print("wrote stride_k4")
     if args.large:
         cases = [
             ("cfg1_k3_10k", 10_000, 3, (2,), 0.0, None),

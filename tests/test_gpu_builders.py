@@ -82,12 +82,28 @@ def test_mini_batch_create_graphs():
     assert me.num_features == 16
 
 
+def test_higher_stride_graphs_are_attached():
+    """kmer_ssgnn.py:215-230 / dataloader.py:83-97: DB1.. edge sets, each numbered by its own graph."""
+    import genomic_gnn_b200 as gg
+
+    reads = fast.reads_to_strings(fast.synthetic_reads(300, 120, seed=4))
+    k = 4
+    u, v, c, _ = fast.count_pairs(reads, k, 3)
+    _, ei_ref, w_ref = fast.build_db(u, v, c, k, True, False, 1.0 / 4**k, 0.4)
+    me = _self(reads, strides=[1, 3], edges_keep_top_k=0.4, edges_threshold=0.8)
+    gg.create_graphs(me, k)
+    assert np.array_equal(me.torch_graph["edge_index_1"].numpy(), ei_ref)
+    assert np.array_equal(me.torch_graph["edge_weight_1"].numpy(), w_ref.astype(np.float32))
+    mb = _self(reads, strides=[1, 3], edges_keep_top_k=0.4, edges_threshold=0.8)
+    gg.create_graphs_mini_batch(mb, k)
+    assert np.array_equal(mb.torch_graph["node", "DB1", "node"].edge_index.numpy(), ei_ref)
+    assert np.array_equal(mb.torch_graph["node", "DB1", "node"].edge_attr.numpy(), w_ref.astype(np.float32))
+
+
 def test_unsupported_options_fail_loudly():
     import genomic_gnn_b200 as gg
 
     reads = fast.reads_to_strings(fast.synthetic_reads(50, 60, seed=1))
-    with pytest.raises(NotImplementedError):
-        gg.create_graphs(_self(reads, strides=[1, 2]), 3)
     with pytest.raises(NotImplementedError):
         gg.create_graphs_mini_batch(_self(reads, faiss_ann=True), 3)
     with pytest.raises(NotImplementedError):

@@ -42,11 +42,7 @@ def _budget_binds(n_nodes, topk, n_ref_edges):
 def test_api_matches_reference_golden(gg, path):
     g = load_golden(path)
     k = g["k"]
-    if g["stride"] != 1:
-        with pytest.raises(NotImplementedError):
-            gg.weighted_directed_edges(g["reads"], k=k, stride=g["stride"], inlcudeUNK=False)
-        return
-    item, pf = gg.weighted_directed_edges(g["reads"], k=k, stride=1, inlcudeUNK=False)
+    item, pf = gg.weighted_directed_edges(g["reads"], k=k, stride=g["stride"], inlcudeUNK=False)
     assert [p[0] for p in pf] == g["pair_u"].tolist()
     assert [p[1] for p in pf] == g["pair_v"].tolist()
     assert list(pf.values()) == g["pair_count"].tolist()
@@ -77,6 +73,25 @@ def test_api_matches_reference_golden(gg, path):
                     assert_kf_threshold_parity(ei, w, ei_ref, w_ref, thr)
                     if topk is None and thr in (0.0, 0.8):
                         assert np.array_equal(ei, ei_ref)  # same emission order as the reference
+
+
+def test_higher_stride_pruned_graphs_match_reference(gg):
+    """Row f4: stride 2 / 3 / 5 (the last one non-overlapping) with edge_weight_threshold and the quantile
+    keep_top_k, as the builders call it for the DB1.. graphs (kmer_ssgnn.py:215-226)."""
+    z = np.load(os.path.join(GOLDEN, "stride_k4.npz"))
+    reads = str(z["reads"]).split("\n")
+    for stride in (2, 3, 5):
+        _, pf = gg.weighted_directed_edges(reads, k=4, stride=stride, inlcudeUNK=False)
+        for j in range(4):
+            tag = f"s{stride}_{j}"
+            thr = None if float(z[tag + "_thr"]) < 0 else float(z[tag + "_thr"])
+            topk = None if float(z[tag + "_topk"]) < 0 else float(z[tag + "_topk"])
+            g = gg.build_deBruijn_graph(pf, normalise=True, remove_N=True, create_all_kmers=False,
+                                        edge_weight_threshold=thr, keep_top_k=topk)
+            assert g.nodes() == z[tag + "_nodes"].tolist(), tag
+            assert np.array_equal(g.edge_index.cpu().numpy(), z[tag + "_edge_index"]), tag
+            assert np.array_equal(g.db.weight64.cpu().numpy(), z[tag + "_weight64"]), tag
+            assert np.array_equal(g.weight.cpu().numpy(), z[tag + "_weight64"].astype(np.float32)), tag
 
 
 def test_plain_dict_input_to_build(gg):
