@@ -50,6 +50,9 @@ SIGNATURES = {
     "gg_kf_features_f32": (_I32, [_P, _I64, _I32, _P, _I32, _P, _P, _P]),
     "gg_kf_rowcnt_elems": (_SZ, [_I64, _I32, _I32]),
     "gg_kf_emit": (_I32, [C.POINTER(KfParams), _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "gg_kf_place_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "gg_kf_place": (_I32, [C.POINTER(KfParams), _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "gg_kf_expand": (_I32, [_P, _I32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P, _P, _P, _P, _P, _P, _P]),
     "gg_kf_finalize_workspace_bytes": (_SZ, [_I64, _I32, _I32, _I64]),
     "gg_kf_finalize": (_I32, [C.POINTER(KfParams), _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gg_kf_class_hist": (_I32, [_P, _P, _P, _I64, _P, _I32, _P, _P]),

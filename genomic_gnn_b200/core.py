@@ -78,6 +78,12 @@ class LocalComm:
     def gather_packed(self, tensors, sizes, dim_list):
         return list(tensors)
 
+    def exchange_slices(self, tensors, sizes):
+        return []
+
+    def all_gather_padded_(self, buf, stride):
+        return buf
+
 
 def _require_cuda():
     if not torch.cuda.is_available():
@@ -417,6 +423,13 @@ class KFEdges:
     tie_kept: int = 0
     tie_total: int = 0
     impl: str = "auto"
+    pending: list = field(default_factory=list)  # in-flight multi-GPU transfers filling edge_index / weight
+
+    def wait(self):
+        for req in self.pending:
+            req.wait()
+        self.pending = []
+        return self
 
 
 def _row_blocks(n):
@@ -459,12 +472,17 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
         rec_capacity = found
 
 
-def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, counts, want_dot=False):
+def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, counts, want_dot=False, out=None):
+    """K6.  ``out`` = (edge_index [2, >= n_recs] view, weight32 [>= n_recs] view) lets the caller have the edges written
+    straight into its slice of a buffer sized for all ranks (multi-GPU exchange without staging copies)."""
     lib = _lib.load()
     dev = sqnorm.device
-    edges = torch.empty((2, max(n_recs, 1)), dtype=torch.int64, device=dev)
+    if out is None:
+        edges = torch.empty((2, max(n_recs, 1)), dtype=torch.int64, device=dev)
+        w32 = torch.empty(max(n_recs, 1), dtype=torch.float32, device=dev)
+    else:
+        edges, w32 = out
     w64 = torch.empty(max(n_recs, 1), dtype=torch.float64, device=dev)
-    w32 = torch.empty(max(n_recs, 1), dtype=torch.float32, device=dev)
     dot = torch.empty(max(n_recs, 1), dtype=torch.int32, device=dev) if want_dot else None
     if n_recs:
         ws_bytes = int(lib.gg_kf_finalize_workspace_bytes(params.n, params.iblock_begin, params.iblock_end, n_recs))
@@ -543,6 +561,38 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
     n_total = sum(per_rank)
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total
+    exchange = gather and comm.world > 1
+
+    def shared_buffers(sizes):
+        """Output tensors sized for every rank; this rank's slice starts at `lo`."""
+        total, lo = sum(sizes), sum(sizes[: comm.rank])
+        return (torch.empty((2, max(total, 1)), dtype=torch.int64, device=dev),
+                torch.empty(max(total, 1), dtype=torch.float32, device=dev), total, lo)
+
+    full_ei = full_w = None
+    if exchange and not need_cut:
+        # C2 on the packed form: K6a places this rank's edges as 8-byte words into its segment of an all-ranks
+        # buffer, ONE in-place all-gather moves 8 instead of 20 bytes per edge, and K6b expands the gathered words
+        # into edge_index / weight on every rank.  (float64 weights are not produced here: only the function-level
+        # API wants them.)
+        stride = max(max(per_rank), 1)
+        ordered = torch.empty(comm.world * stride, dtype=torch.int64, device=dev)
+        if n_recs:
+            pw = int(lib.gg_kf_place_workspace_bytes(params.n, params.iblock_begin, params.iblock_end))
+            pws = torch.empty(pw, dtype=torch.uint8, device=dev)
+            with _stage(f"k6_place_d{params.d}"):
+                check(lib.gg_kf_place(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(scored),
+                                      C.c_void_p(ordered.data_ptr() + 8 * comm.rank * stride), ptr(pws), pw, _stream()),
+                      "gg_kf_place")
+        with _stage("c2_gather_packed_edges"):
+            comm.all_gather_padded_(ordered, stride)
+        full_ei, full_w, e_total, lo = shared_buffers(per_rank)
+        seg_first = (C.c_int64 * comm.world)(*[r * stride for r in range(comm.world)])
+        seg_size = (C.c_int64 * comm.world)(*per_rank)
+        with _stage(f"k6_expand_d{params.d}"):
+            check(lib.gg_kf_expand(ptr(ordered), comm.world, seg_first, seg_size, ptr(sqnorm), ptr(full_ei[0]),
+                                   ptr(full_ei[1]), None, ptr(full_w), None, _stream()), "gg_kf_expand")
+        return KFEdges(full_ei[:, :e_total], None, full_w[:e_total], n_total, None, 0, 0, impl)
     ei, w64, w32, dot = kf_finalize(recs, n_recs, rowcnt, params, sqnorm, scored, want_dot=need_cut)
     del recs, rowcnt
     cutoff, tie_budget, tie_total = None, 0, 0
@@ -561,10 +611,15 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         before = sum(comm.gather_ints(local_ties)[: comm.rank])
         local_tie_budget = min(max(tie_budget - before, 0), local_ties)
         expect = int(local_hist[action == 1].sum()) + local_tie_budget
+        per_rank = comm.gather_ints(expect) if comm.world > 1 else [expect]
         action_d = torch.from_numpy(action).to(dev)
-        out = torch.empty((2, max(expect, 1)), dtype=torch.int64, device=dev)
+        if exchange:
+            full_ei, full_w, e_total, lo = shared_buffers(per_rank)
+            out, o32 = full_ei[:, lo:], full_w[lo:]
+        else:
+            out = torch.empty((2, max(expect, 1)), dtype=torch.int64, device=dev)
+            o32 = torch.empty(max(expect, 1), dtype=torch.float32, device=dev)
         o64 = torch.empty(max(expect, 1), dtype=torch.float64, device=dev)
-        o32 = torch.empty(max(expect, 1), dtype=torch.float32, device=dev)
         cnt = torch.empty(1, dtype=torch.int64, device=dev)
         ws_bytes = int(lib.gg_kf_select_workspace_bytes(n_recs))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -576,12 +631,22 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         if kept != expect:
             raise GGError(f"top-n select kept {kept} edges, expected {expect}")
         ei, w64, w32 = out[:, :expect], o64[:expect], o32[:expect]
-        per_rank = comm.gather_ints(expect) if comm.world > 1 else [expect]
-    if gather and comm.world > 1:
-        with _stage("c2_gather_edges"):  # one collective: edge_index and float32 weights packed together
-            ei, w32 = comm.gather_packed([ei, w32], per_rank, [1, 0])
-            w64 = None  # the float64 weights stay sharded: only the function-level API wants them
-    return KFEdges(ei.contiguous(), w64, w32, n_total, cutoff, tie_budget, tie_total, impl)
+    pending = []
+    if exchange:
+        # C2: zero-copy all-gather(v) -- every rank's edges already sit in its slice; one batch of point-to-point
+        # transfers fills in the other slices.  The float64 weights stay sharded (only the function-level API wants
+        # them).  The transfers are waited for here: NCCL's send/receive kernels take SMs, and the persistent Gram
+        # kernels (one CTA or CTA pair per SM) lose a whole wave when they cannot all be resident -- measured 2x
+        # on the next set's scoring when the exchange was left in flight underneath it.
+        with _stage("c2_exchange_edges"):
+            pending = comm.exchange_slices([full_ei[0], full_ei[1], full_w], per_rank)
+            for req in pending:
+                req.wait()
+            pending = []
+        ei, w32, w64 = full_ei[:, :e_total], full_w[:e_total], None
+    res = KFEdges(ei if exchange else ei.contiguous(), w64, w32, n_total, cutoff, tie_budget, tie_total, impl)
+    res.pending = pending
+    return res
 
 
 # --------------------------------------------------------------------------- whole path on one GPU
@@ -613,6 +678,8 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
     if cr.n_nonzero == 0 and cr.n_bridges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
+    if db.num_edges == 0:
+        raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     small = [int(s) for s in str(small_k).split(",")]
     kcs = [kf_counts(db.node_codes, k, s) for s in small]
     xs = [kf_features_f32(kc) for kc in kcs]
@@ -626,6 +693,8 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
         for kc in kcs:
             out.kf.append(kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m,
                                    impl=kf_impl, iblock_begin=b0, iblock_end=b1, comm=comm))
+        for kf in out.kf:  # multi-GPU: the edge exchanges of earlier sets ran underneath the scoring of later ones
+            kf.wait()
     return out
 
 

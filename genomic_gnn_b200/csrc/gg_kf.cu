@@ -251,12 +251,24 @@ __global__ void __launch_bounds__(256) place_kernel(const gg_kf_rec_t* recs, lon
   }
 }
 
-__global__ void __launch_bounds__(256) expand_kernel(const uint2* ordered, long long n_recs, const int32_t* sqnorm,
+// Up to kMaxSegs source segments (one per rank after a multi-GPU all-gather of the packed words, each padded to the
+// same stride) are read as one logical array.
+constexpr int kMaxSegs = 16;
+struct Segs {
+  int n;
+  long long src[kMaxSegs];      // first word of segment r in `ordered`
+  long long dst[kMaxSegs + 1];  // first output index of segment r; dst[n] = total
+};
+
+__global__ void __launch_bounds__(256) expand_kernel(const uint2* ordered, Segs segs, const int32_t* sqnorm,
                                                      int64_t* src, int64_t* dst, double* w64, float* w32,
                                                      uint32_t* dot_out) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_recs;
+  const long long n_out = segs.dst[segs.n];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_out;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint2 e = __ldg(ordered + i);
+    int r = 0;
+    while (r + 1 < segs.n && i >= segs.dst[r + 1]) ++r;
+    const uint2 e = __ldg(ordered + segs.src[r] + (i - segs.dst[r]));
     const uint32_t s = e.x & 0xFFFFFFu, dot = e.x >> 24, t = e.y;
     src[i] = s;
     dst[i] = t;
@@ -430,30 +442,27 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   }
 }
 
-extern "C" size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end, int64_t n_recs) {
+extern "C" size_t gg_kf_place_workspace_bytes(int64_t n, int iblock_begin, int iblock_end) {
   const size_t elems = gg_kf_rowcnt_elems(n, iblock_begin, iblock_end);
   gg::Carver c(nullptr);
   c.take<unsigned long long>(elems ? elems : 1);
-  c.take<uint2>(n_recs > 0 ? n_recs : 1);
   c.take<char>(scan_temp_bytes<RowTotal, unsigned long long>(static_cast<long long>(elems ? elems : 1)));
   return c.used();
 }
 
-extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
-                              const int32_t* sqnorm, const uint8_t* counts, int64_t* edge_src, int64_t* edge_dst,
-                              double* weight64, float* weight32, uint32_t* dot_out, void* workspace,
-                              size_t workspace_bytes, gg_stream_t st) {
+extern "C" int gg_kf_place(const gg_kf_params_t* p, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
+                           const uint8_t* counts, uint64_t* ordered, void* workspace, size_t workspace_bytes,
+                           gg_stream_t st) {
   if (int rc = check_params(p)) return rc;
   GG_REQUIRE(n_recs >= 0, GG_ERR_ARG, "negative record count");
   if (n_recs == 0) return GG_OK;
-  GG_REQUIRE(recs && rowcnt && sqnorm && edge_src && edge_dst && workspace, GG_ERR_ARG, "null buffer");
-  GG_REQUIRE(workspace_bytes >= gg_kf_finalize_workspace_bytes(p->n, p->iblock_begin, p->iblock_end, n_recs),
-             GG_ERR_WORKSPACE, "workspace too small");
+  GG_REQUIRE(recs && rowcnt && ordered && workspace, GG_ERR_ARG, "null buffer");
+  GG_REQUIRE(workspace_bytes >= gg_kf_place_workspace_bytes(p->n, p->iblock_begin, p->iblock_end), GG_ERR_WORKSPACE,
+             "workspace too small");
   cudaStream_t s = gg::as_stream(st);
   const long long elems = static_cast<long long>(gg_kf_rowcnt_elems(p->n, p->iblock_begin, p->iblock_end));
   gg::Carver c(workspace);
   unsigned long long* offsets = c.take<unsigned long long>(elems);
-  uint2* ordered = c.take<uint2>(n_recs);
   size_t tb = scan_temp_bytes<RowTotal, unsigned long long>(elems);
   void* temp = c.take<char>(tb);
   const unsigned long long* words = reinterpret_cast<const unsigned long long*>(rowcnt);
@@ -464,12 +473,58 @@ extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, 
   const bool recompute = p->d <= 64;
   GG_REQUIRE(!recompute || counts != nullptr, GG_ERR_ARG, "counts is required to finalise narrow-row records");
   place_kernel<<<grid_for(n_recs), 256, 0, s>>>(recs, n_recs, offsets, words, p->iblock_begin, n_jblocks,
-                                                recompute ? counts : nullptr, p->d, ordered,
+                                                recompute ? counts : nullptr, p->d, reinterpret_cast<uint2*>(ordered),
                                                 (p->d_valid > 0 && p->d_valid < p->d ? p->d_valid : p->d) / 4);
-  expand_kernel<<<grid_for(n_recs), 256, 0, s>>>(ordered, n_recs, sqnorm, edge_src, edge_dst, weight64, weight32,
-                                                 dot_out);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
+}
+
+extern "C" int gg_kf_expand(const uint64_t* ordered, int n_segments, const int64_t* h_seg_first, const int64_t* h_seg_size,
+                            const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64,
+                            float* weight32, uint32_t* dot_out, gg_stream_t st) {
+  GG_REQUIRE(n_segments >= 1 && n_segments <= kMaxSegs && h_seg_first && h_seg_size, GG_ERR_ARG,
+             "1..16 segments expected");
+  Segs segs;
+  segs.n = n_segments;
+  long long total = 0;
+  for (int r = 0; r < n_segments; ++r) {
+    GG_REQUIRE(h_seg_size[r] >= 0 && h_seg_first[r] >= 0, GG_ERR_ARG, "negative segment");
+    segs.src[r] = h_seg_first[r];
+    segs.dst[r] = total;
+    total += h_seg_size[r];
+  }
+  segs.dst[n_segments] = total;
+  if (total == 0) return GG_OK;
+  GG_REQUIRE(ordered && sqnorm && edge_src && edge_dst, GG_ERR_ARG, "null buffer");
+  expand_kernel<<<grid_for(total), 256, 0, gg::as_stream(st)>>>(reinterpret_cast<const uint2*>(ordered), segs, sqnorm,
+                                                               edge_src, edge_dst, weight64, weight32, dot_out);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+extern "C" size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end, int64_t n_recs) {
+  gg::Carver c(nullptr);
+  c.take<char>(gg_kf_place_workspace_bytes(n, iblock_begin, iblock_end));
+  c.take<uint2>(n_recs > 0 ? n_recs : 1);
+  return c.used();
+}
+
+extern "C" int gg_kf_finalize(const gg_kf_params_t* p, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
+                              const int32_t* sqnorm, const uint8_t* counts, int64_t* edge_src, int64_t* edge_dst,
+                              double* weight64, float* weight32, uint32_t* dot_out, void* workspace,
+                              size_t workspace_bytes, gg_stream_t st) {
+  if (int rc = check_params(p)) return rc;
+  GG_REQUIRE(n_recs >= 0, GG_ERR_ARG, "negative record count");
+  if (n_recs == 0) return GG_OK;
+  GG_REQUIRE(workspace && workspace_bytes >= gg_kf_finalize_workspace_bytes(p->n, p->iblock_begin, p->iblock_end, n_recs),
+             GG_ERR_WORKSPACE, "workspace too small");
+  gg::Carver c(workspace);
+  const size_t place_bytes = gg_kf_place_workspace_bytes(p->n, p->iblock_begin, p->iblock_end);
+  void* place_ws = c.take<char>(place_bytes);
+  uint64_t* ordered = reinterpret_cast<uint64_t*>(c.take<uint2>(n_recs));
+  if (int rc = gg_kf_place(p, recs, n_recs, rowcnt, counts, ordered, place_ws, place_bytes, st)) return rc;
+  const int64_t first = 0, size = n_recs;
+  return gg_kf_expand(ordered, 1, &first, &size, sqnorm, edge_src, edge_dst, weight64, weight32, dot_out, st);
 }
 
 extern "C" int gg_kf_class_hist(const int64_t* edge_src, const int64_t* edge_dst, const uint32_t* dot, int64_t n_edges,

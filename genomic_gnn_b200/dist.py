@@ -69,9 +69,9 @@ class TorchComm:
 
     def gather_ints(self, x: int) -> List[int]:
         t = torch.tensor([int(x)], dtype=torch.int64, device=self.device)
-        out = [torch.zeros_like(t) for _ in range(self.world)]
-        dist_.all_gather(out, t, group=self.group)
-        return [int(o.item()) for o in out]
+        out = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        dist_.all_gather_into_tensor(out, t, group=self.group)
+        return [int(v) for v in out.tolist()]  # one device-to-host read for all ranks
 
     def gather_cat(self, t: torch.Tensor, dim: int = 0) -> torch.Tensor:
         """all-gather(v) along ``dim`` and concatenate in rank order."""
@@ -87,6 +87,34 @@ class TorchComm:
         cat = torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
         return cat.movedim(0, dim).contiguous()
 
+
+    def all_gather_padded_(self, buf: torch.Tensor, stride: int):
+        """In-place all-gather: ``buf`` holds world * stride elements and this rank has filled its own segment
+        [rank * stride, (rank + 1) * stride)."""
+        mine = buf[self.rank * stride : (self.rank + 1) * stride]
+        dist_.all_gather_into_tensor(buf, mine, group=self.group)
+        return buf
+
+    def exchange_slices(self, tensors, sizes):
+        """Zero-copy all-gather(v): every tensor in ``tensors`` is 1-D, already sized for ALL ranks, and holds this
+        rank's data in its own slice [offset(rank), offset(rank) + sizes[rank]).  One batched group of point-to-point
+        sends / receives fills the other slices in place.  Returns the request handles (wait on them before use)."""
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        me = self.rank
+        ops = []
+        for t in tensors:
+            mine = t[offs[me] : offs[me + 1]]
+            for r in range(self.world):
+                if r == me:
+                    continue
+                peer = dist_.get_global_rank(self.group, r) if self.group is not None else r
+                if sizes[me] > 0:
+                    ops.append(dist_.P2POp(dist_.isend, mine, peer, group=self.group))
+                if sizes[r] > 0:
+                    ops.append(dist_.P2POp(dist_.irecv, t[offs[r] : offs[r + 1]], peer, group=self.group))
+        return dist_.batch_isend_irecv(ops) if ops else []
 
     def gather_packed(self, tensors, sizes, dim_list):
         """One all-gather for several ragged tensors: ``tensors[i]`` is ragged along ``dim_list[i]`` with
@@ -142,5 +170,5 @@ def reduce_counts(cr, comm: TorchComm):
     if sum(n_br) > 0:
         (bridges,) = comm.gather_packed([cr.bridges[: cr.n_bridges]], n_br, [0])
         n_bridges = int(bridges.shape[0])
-    n_nonzero = int((hist != 0).sum().item())
-    return CountResult(cr.k, hist, first, bridges, n_bridges, cr.status, n_nonzero)
+    # occupied-bin count: not worth a device round trip here; -1 = unknown, build_graph checks the built graph instead
+    return CountResult(cr.k, hist, first, bridges, n_bridges, cr.status, -1)

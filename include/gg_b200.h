@@ -186,6 +186,17 @@ GG_API int gg_kf_emit(const gg_kf_params_t* h_params, const uint8_t* counts, con
                const uint16_t* dmin, const uint32_t* fast_scale /* [max sqnorm + 1] */,
                gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt, int64_t* kf_status, gg_stream_t st);
 
+/* gg_kf_finalize = gg_kf_place (records -> one packed 64-bit word per edge, in emission order: s | dot << 24 in the low
+ * half, t in the high half) followed by gg_kf_expand (packed words -> edge_index / weights, coalesced).  Multi-GPU
+ * builds call the halves separately: the packed words (8 bytes per edge instead of 20) are what is all-gathered, and
+ * gg_kf_expand then reads the gathered buffer as up to 16 segments, segment r holding h_seg_size[r] words from word
+ * h_seg_first[r] on. */
+GG_API size_t gg_kf_place_workspace_bytes(int64_t n, int iblock_begin, int iblock_end);
+GG_API int gg_kf_place(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
+                const uint8_t* counts, uint64_t* ordered, void* workspace, size_t workspace_bytes, gg_stream_t st);
+GG_API int gg_kf_expand(const uint64_t* ordered, int n_segments, const int64_t* h_seg_first, const int64_t* h_seg_size,
+                 const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
+                 uint32_t* dot_out, gg_stream_t st);
 GG_API size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end, int64_t n_recs);
 GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
                    const int32_t* sqnorm, const uint8_t* counts /* the matrix gg_kf_emit scored; used when d <= 64 */,
