@@ -32,8 +32,8 @@ sys.path.insert(0, ROOT)
 
 L2_FLUSH_BYTES = 256 << 20
 # kernels of libgg_b200.so launched by one step (CUB sort/scan kernels and memsets not counted):
-# K1 count+pending+first = 3, K2 = 6, K3 counts+features = 2 per small_k, K4 emit + K6 scatter = 2 per small_k
-OUR_LAUNCHES_PER_STEP = lambda n_small: 3 + 6 + 4 * n_small  # noqa: E731
+# K1 count+pending+first = 3, K2 = 6, per small_k: K3 counts+features = 2, K4 emit = 1, K6 place+expand = 2
+OUR_LAUNCHES_PER_STEP = lambda n_small: 3 + 6 + 5 * n_small  # noqa: E731
 
 
 def parse_args():
