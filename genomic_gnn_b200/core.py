@@ -557,7 +557,8 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
     rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
     recs, n_recs, rowcnt, params, scored = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
                                                    rec_capacity=rec_capacity)
-    per_rank = comm.gather_ints(n_recs)
+    per_rank = comm.gather_ints(n_recs)  # (one more device read per set; folding it into kf_emit's own read would
+    #                                       need the all-gather before the capacity check -- left for the next round)
     n_total = sum(per_rank)
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total
@@ -670,11 +671,18 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
     row block."""
     comm = comm or LocalComm()
     stream = upload_reads(sequences)
-    cr = count_kp1mers(stream, k)
     if comm.world > 1:
         from . import dist
 
-        cr = dist.reduce_counts(cr, comm)
+        capacity = 1 << 16
+        while True:  # K1 without a host round trip; reduce_counts reads every rank's status in its one device read
+            try:
+                cr = dist.reduce_counts(count_kp1mers(stream, k, bridge_capacity=capacity, sync=False), comm)
+                break
+            except OverflowError as exc:  # same decision on every rank: the counts were all-reduced
+                capacity = int(exc.args[0])
+    else:
+        cr = count_kp1mers(stream, k)
     if cr.n_nonzero == 0 and cr.n_bridges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)

@@ -154,21 +154,30 @@ def reduce_counts(cr, comm: TorchComm):
     histogram, the global first occurrences and all bridge records."""
     from .core import CountResult
 
-    # one SUM all-reduce carries the histogram and, in `world` extra slots, every rank's bridge count
+    # One SUM all-reduce carries the histogram and a small tail: every rank's bridge count (one slot per rank) and
+    # the total of illegal bytes.  The tail is filled on the device from K1's status words, so the per-rank count was
+    # launched without a host round trip (count_kp1mers(sync=False)) and this is the only one.
     n_bins = cr.hist.numel()
-    packed = torch.zeros(n_bins + comm.world, dtype=cr.hist.dtype, device=cr.hist.device)
+    world = comm.world
+    packed = torch.zeros(n_bins + world + 1, dtype=cr.hist.dtype, device=cr.hist.device)
     packed[:n_bins] = cr.hist      # uint32 counts in int32 storage: exact while totals < 2^31
-    packed[n_bins + comm.rank] = cr.n_bridges
+    packed[n_bins + comm.rank] = cr.status[1].to(packed.dtype)   # GG_ST_BRIDGES
+    packed[n_bins + world] = cr.status[0].to(packed.dtype)       # GG_ST_BAD_BYTES
     comm.sum_tensor_(packed)
     hist = packed[:n_bins]
     first = cr.first_pos
     first.masked_fill_(first < 0, _I64_MAX)  # GG_NO_POS is -1 as int64: lift it above every real offset
     first = comm.min_tensor_(first)
-    tail = packed[n_bins:].cpu()
-    n_br = [int(x) for x in tail]
-    bridges, n_bridges = cr.bridges, cr.n_bridges
+    tail = packed[n_bins:].cpu().tolist()
+    if tail[world] > 0:
+        raise ValueError(f"{tail[world]} input bytes outside the alphabet ACGTN")
+    n_br = [int(x) for x in tail[:world]]
+    capacity = int(cr.bridges.shape[0])
+    if max(n_br) > capacity:
+        raise OverflowError(max(n_br))  # the caller re-counts with room for every bridge record
+    bridges, n_bridges = cr.bridges, n_br[comm.rank]
     if sum(n_br) > 0:
-        (bridges,) = comm.gather_packed([cr.bridges[: cr.n_bridges]], n_br, [0])
+        (bridges,) = comm.gather_packed([cr.bridges[:n_bridges]], n_br, [0])
         n_bridges = int(bridges.shape[0])
     # occupied-bin count: not worth a device round trip here; -1 = unknown, build_graph checks the built graph instead
     return CountResult(cr.k, hist, first, bridges, n_bridges, cr.status, -1)

@@ -75,7 +75,7 @@ def _worker(rank, world, port, k, tmp):
         reads = fast.synthetic_reads(600, 50, seed=4)
         lo, hi = ggdist.shard_bounds(reads.shape[0], world, rank)
         hist, fp = _histogram_of_shard(reads[lo:hi], k, pos_base=lo * reads.shape[1])
-        cr = CountResult(k, torch.from_numpy(hist), torch.from_numpy(fp), torch.zeros((1, 4), dtype=torch.int32), 0,
+        cr = CountResult(k, torch.from_numpy(hist), torch.from_numpy(fp), torch.zeros((4, 4), dtype=torch.int32), 0,
                          torch.zeros(8, dtype=torch.int64))
         merged = ggdist.reduce_counts(cr, comm)
         g_hist, g_fp = _histogram_of_shard(reads, k, 0)
@@ -86,11 +86,30 @@ def _worker(rank, world, port, k, tmp):
 
         # bridges: only rank 1 has some
         br = torch.tensor([[1, 2, 7, 0], [3, 4, 9, 0]], dtype=torch.int32)
+        st = torch.zeros(8, dtype=torch.int64)
+        st[1] = 2 if rank == 1 else 0                       # GG_ST_BRIDGES as K1 leaves it on the device
         cr2 = CountResult(k, torch.from_numpy(hist.copy()), torch.from_numpy(fp.copy()),
-                          br if rank == 1 else torch.zeros((1, 4), dtype=torch.int32), 2 if rank == 1 else 0,
-                          torch.zeros(8, dtype=torch.int64))
+                          br if rank == 1 else torch.zeros((2, 4), dtype=torch.int32), -1, st)
         m2 = ggdist.reduce_counts(cr2, comm)
         assert m2.n_bridges == 2 and torch.equal(m2.bridges, br)
+        # status words travel with the histogram: illegal bytes on any rank raise on every rank, and a bridge list
+        # that outgrew its buffer asks for a re-count
+        st_bad = torch.zeros(8, dtype=torch.int64)
+        st_bad[0] = 3 if rank == 0 else 0
+        try:
+            ggdist.reduce_counts(CountResult(k, torch.from_numpy(hist.copy()), torch.from_numpy(fp.copy()),
+                                             torch.zeros((2, 4), dtype=torch.int32), -1, st_bad), comm)
+            raise AssertionError("expected ValueError")
+        except ValueError:
+            pass
+        st_big = torch.zeros(8, dtype=torch.int64)
+        st_big[1] = 5 if rank == 1 else 0
+        try:
+            ggdist.reduce_counts(CountResult(k, torch.from_numpy(hist.copy()), torch.from_numpy(fp.copy()),
+                                             torch.zeros((2, 4), dtype=torch.int32), -1, st_big), comm)
+            raise AssertionError("expected OverflowError")
+        except OverflowError as exc:
+            assert exc.args[0] == 5
         open(os.path.join(tmp, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()
