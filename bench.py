@@ -32,8 +32,9 @@ sys.path.insert(0, ROOT)
 
 L2_FLUSH_BYTES = 256 << 20
 # kernels of libgg_b200.so launched by one step (CUB sort/scan kernels and memsets not counted):
-# K1 count+pending+first = 3, K2 = 6, per small_k: K3 counts+features = 2, K4 emit = 1, K6 place+expand = 2
-OUR_LAUNCHES_PER_STEP = lambda n_small: 3 + 6 + 5 * n_small  # noqa: E731
+# K1 partition+bucket count (k = 7, 8; one counting kernel otherwise) + pending + first = 4, K2 = 6,
+# per small_k: K3 counts+features = 2, K4 emit = 1, K6 place+expand = 2
+OUR_LAUNCHES_PER_STEP = lambda n_small, k=8: (4 if k in (7, 8) else 3) + 6 + 5 * n_small  # noqa: E731
 
 
 def parse_args():
@@ -362,7 +363,7 @@ def run_ours(a):
         "stage_ms": stage_ms,
         "e2e": {"value": a.reads / (e2e_ms / a.steps * 1e-3), "unit": "reads/s", "ms_per_step": e2e_ms / a.steps,
                 "h2d_bytes_per_step": (hi - lo) * a.read_len, "d2h_bytes_per_step": d2h_bytes},
-        "gpu_launches": OUR_LAUNCHES_PER_STEP(n_small) * a.steps,
+        "gpu_launches": OUR_LAUNCHES_PER_STEP(n_small, a.k) * a.steps,
         "roofline": {"kernel": dominant, **rooflines[dominant]} if dominant else None,
         "rooflines": rooflines,
         "clocks": clock_info,

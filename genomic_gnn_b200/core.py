@@ -162,37 +162,44 @@ def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, fi
                   sync: bool = True, impl: str = "auto") -> CountResult:
     """K1 (+ first-occurrence scan).  Reference: src/utils.py:15-31,52-84.
 
-    impl: "smem" = packed stream + per-CTA shared-memory histograms over slices of the bin space (k <= 8),
-    "l2" = one RED.ADD per window into the L2-resident table, "auto" = smem when the table is small enough."""
+    impl: "part" = keys partitioned into <= 8 streams of 15-bit keys, each counted with shared-memory atomics (k <= 8;
+    k <= 6 counts in shared memory directly), "smem" = packed stream + per-CTA shared-memory histograms over slices of
+    the bin space (k <= 8; superseded by "part", kept as an independent implementation), "l2" = one RED.ADD per window
+    into the L2-resident table, "auto" = "part" when the table is small enough, else "l2"."""
     _require_cuda()
     lib = _lib.load()
     if not (1 <= k <= _lib.GG_MAX_K):
         raise ValueError(f"k must be in [1, {_lib.GG_MAX_K}] for the dense (k+1)-mer histogram")
+    if impl not in ("auto", "part", "smem", "l2"):
+        raise ValueError(f"unknown counting implementation {impl!r}")
     dev = stream.data.device
     bins = int(lib.gg_hist_bins(k))
     hist = torch.empty(bins, dtype=torch.int32, device=dev)
     first = torch.empty(bins, dtype=torch.int64, device=dev)
     status = torch.empty(_lib.ST_WORDS, dtype=torch.int64, device=dev)
-    # measured on B200 (1M reads): shared-memory slices 0.27 / 0.41 / 0.87 ms at k = 6 / 7 / 8 against 1.59 / 1.03 /
-    # 0.80 ms for the L2 path -- every extra slice of the bin space is one more pass over the packed stream
-    use_smem = impl == "smem" or (impl == "auto" and k <= 7)
-    ws_bytes = int(lib.gg_count_smem_workspace_bytes(stream.n_bytes, k)) if use_smem else 0
-    if impl == "smem" and ws_bytes == 0:
-        raise ValueError(f"k={k}: the (k+1)-mer table is too large for the shared-memory counting path")
+    if impl == "auto":
+        impl = "part" if int(lib.gg_count_part_workspace_bytes(stream.n_bytes, k)) else "l2"
+    ws_bytes = 0
+    if impl == "part":
+        ws_bytes = int(lib.gg_count_part_workspace_bytes(stream.n_bytes, k))
+    elif impl == "smem":
+        ws_bytes = int(lib.gg_count_smem_workspace_bytes(stream.n_bytes, k))
+    if impl != "l2" and ws_bytes == 0:
+        raise ValueError(f"k={k}: the (k+1)-mer table is too large for the shared-memory counting paths")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     while True:
         bridges = torch.empty((max(bridge_capacity, 1), 4), dtype=torch.int32, device=dev)
         st = _stream()
         check(lib.gg_count_reset(k, ptr(hist), ptr(first), ptr(status), st), "gg_count_reset")
         with _stage("k1_count"):
-            if ws is not None:
-                check(lib.gg_count_kp1mers_smem(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
-                                                ptr(hist), ptr(bridges), bridge_capacity, ptr(status), ptr(ws),
-                                                ws_bytes, st), "gg_count_kp1mers_smem")
-            else:
+            if impl == "l2":
                 check(lib.gg_count_kp1mers(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
                                            ptr(hist), ptr(bridges), bridge_capacity, ptr(status), st),
                       "gg_count_kp1mers")
+            else:
+                fn = lib.gg_count_kp1mers_part if impl == "part" else lib.gg_count_kp1mers_smem
+                check(fn(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base, ptr(hist),
+                         ptr(bridges), bridge_capacity, ptr(status), ptr(ws), ws_bytes, st), "gg_count_kp1mers_" + impl)
         if first_occurrence:
             with _stage("k1_first"):
                 check(lib.gg_first_occurrence(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
@@ -763,6 +770,8 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
     buf.record_stream(side)
     flat = reads.reshape(-1)
     per = max(16, -(-n_reads // max(chunks, 1) // 16) * 16)  # reads per piece, multiple of 16: 16-byte aligned offsets
+    ws_bytes = int(lib.gg_count_part_workspace_bytes(per * length, k))  # one workspace serves every piece in turn
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     for lo in range(0, n_reads, per):
         hi = min(n_reads, lo + per)
         with torch.cuda.stream(side):
@@ -770,9 +779,15 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
             landed = torch.cuda.Event()
             landed.record(side)
         main.wait_event(landed)
+        piece = C.c_void_p(buf.data_ptr() + lo * length)
         with _stage("k1_count"):
-            check(lib.gg_count_kp1mers(C.c_void_p(buf.data_ptr() + lo * length), (hi - lo) * length, length, k,
-                                       lo * length, ptr(hist), ptr(bridges), cap, ptr(status), st), "gg_count_kp1mers")
+            if ws is not None:
+                check(lib.gg_count_kp1mers_part(piece, (hi - lo) * length, length, k, lo * length, ptr(hist),
+                                                ptr(bridges), cap, ptr(status), ptr(ws), ws_bytes, st),
+                      "gg_count_kp1mers_part")
+            else:
+                check(lib.gg_count_kp1mers(piece, (hi - lo) * length, length, k, lo * length, ptr(hist), ptr(bridges),
+                                           cap, ptr(status), st), "gg_count_kp1mers")
     with _stage("k1_first"):
         check(lib.gg_first_occurrence(ptr(buf), n_bytes, length, k, 0, ptr(hist), ptr(first), ptr(status), st),
               "gg_first_occurrence")

@@ -107,6 +107,15 @@ GG_API int gg_count_kp1mers_smem(const uint8_t* stream, int64_t n_bytes, int64_t
                           uint32_t* hist, gg_bridge_t* bridges, int64_t bridge_capacity, int64_t* status,
                           void* workspace, size_t workspace_bytes, gg_stream_t st);
 
+/* Same contract and result as gg_count_kp1mers, for tables of up to 8 x 32,768 bins (k <= 8) -- the fastest path:
+ * the keys are partitioned by their top bits into <= 8 streams of 15-bit keys (one pass over the ASCII bytes), then
+ * every stream is counted with full-warp shared-memory atomics; tables of <= 16,384 bins (k <= 6) are counted in
+ * shared memory directly.  gg_count_part_workspace_bytes() returns 0 when k is too large for this path. */
+GG_API size_t gg_count_part_workspace_bytes(int64_t n_bytes, int k);
+GG_API int gg_count_kp1mers_part(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len, int k, int64_t pos_base,
+                          uint32_t* hist, gg_bridge_t* bridges, int64_t bridge_capacity, int64_t* status,
+                          void* workspace, size_t workspace_bytes, gg_stream_t st);
+
 /* first_pos[e] = min global offset at which (k+1)-mer e starts.  Scans the shard
  * in order and stops as soon as every non-zero bin of `hist` has been seen
  * (hist must already hold this shard's counts).  Defines dict insertion order

@@ -65,3 +65,28 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_swar_acgt_formula():
+    """The exact all-ACGT short cut of K1 (csrc/gg_count.cu: acgt_low_bits / all_acgt16), restated on 32-bit words:
+    a byte lane passes iff it is one of A, C, G, T -- for every byte value in every lane, whatever its neighbours."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    m = 0xFFFFFFFF
+
+    def low_bits(x):
+        s1, s2, s4 = x >> 1, x >> 2, x >> 4
+        g1 = x & (~s2 | s1)
+        g2 = s2 & ~s1 & ~x
+        return ((~s4 & g1) | (s4 & g2)) & m
+
+    for lane in range(4):
+        for b in range(256):
+            for _ in range(8):
+                w = [int(v) for v in rng.integers(0, 256, 4)]
+                w[lane] = b
+                x = w[0] | w[1] << 8 | w[2] << 16 | w[3] << 24
+                fixed = ((x & 0xE8E8E8E8) ^ 0x40404040) & m
+                ok = ((fixed >> (8 * lane)) & 0xFF) == 0 and ((low_bits(x) >> (8 * lane)) & 1) == 1
+                assert ok == (b in b"ACGT"), (lane, b)

@@ -245,7 +245,7 @@ def test_input_forms_agree(gg):
 
 @pytest.mark.parametrize("k", [3, 6, 7, 8])
 def test_count_paths_agree(gg, k):
-    """Shared-memory slices (packed stream) and the L2 RED path must give the same histogram, first occurrences and
+    """The partitioned path, the shared-memory slices (packed stream) and the L2 RED path must give the same histogram, first occurrences and
     bridge records -- on ragged, N-ridden, separator-delimited input and on fixed-length rows."""
     from genomic_gnn_b200 import core
 
@@ -258,20 +258,23 @@ def test_count_paths_agree(gg, k):
         reads.append(r)
     fixed = fast.synthetic_reads(5000, 151, seed=k)
     fixed[::41, 77] = ord("N")
-    for inp in (reads, fixed):
+    skewed = ["A" * 150] * 1500 + ["T" * 149] * 700 + ["ACGT" * 40] * 300  # every key of a tile in one bucket
+    for inp in (reads, fixed, skewed):
         stream = core.upload_reads(inp)
-        a = core.count_kp1mers(stream, k, impl="smem")
         b = core.count_kp1mers(stream, k, impl="l2")
-        assert torch.equal(a.hist, b.hist)
-        assert torch.equal(a.first_pos, b.first_pos)
-        assert a.n_bridges == b.n_bridges and a.n_nonzero == b.n_nonzero
-        ka = sorted(map(tuple, a.bridges[: a.n_bridges].cpu().tolist()))
         kb = sorted(map(tuple, b.bridges[: b.n_bridges].cpu().tolist()))
-        assert ka == kb
-    with pytest.raises(ValueError):
-        core.count_kp1mers(core.upload_reads(["ACGTACGTACGTAAA"]), 10, impl="smem")
-    with pytest.raises(ValueError):
-        core.count_kp1mers(core.upload_reads(["ACGTXCGT"]), 3, impl="smem")
+        for impl in ("part", "smem"):
+            a = core.count_kp1mers(stream, k, impl=impl)
+            assert torch.equal(a.hist, b.hist), impl
+            assert torch.equal(a.first_pos, b.first_pos), impl
+            assert a.n_bridges == b.n_bridges and a.n_nonzero == b.n_nonzero
+            ka = sorted(map(tuple, a.bridges[: a.n_bridges].cpu().tolist()))
+            assert ka == kb, impl
+    for impl in ("part", "smem"):
+        with pytest.raises(ValueError):
+            core.count_kp1mers(core.upload_reads(["ACGTACGTACGTAAA"]), 10, impl=impl)
+        with pytest.raises(ValueError):
+            core.count_kp1mers(core.upload_reads(["ACGTXCGT"]), 3, impl=impl)
 
 
 def test_host_to_host_build_matches_device_build(gg):
