@@ -16,6 +16,7 @@ GG_KF_BLOCK = 1024
 GG_NO_POS = 0xFFFFFFFFFFFFFFFF
 ST_BAD_BYTES, ST_BRIDGES, ST_CURSOR, ST_REMAINING, ST_NONZERO, ST_WORDS = 0, 1, 2, 3, 4, 8
 KF_IMPL = {"auto": 0, "dp4a": 1, "tcgen05": 2, "naive": 3, "tcgen05x2": 4}
+KF_DEDUP_MAX_NODES = 1 << 20  # shared-memory bitmap over node space (gg_kf_dedup_*)
 
 
 class KfParams(C.Structure):
@@ -57,6 +58,13 @@ SIGNATURES = {
     "gg_kf_expand": (_I32, [_P, _I32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P, _P, _P, _P, _P, _P, _P]),
     "gg_kf_finalize_workspace_bytes": (_SZ, [_I64, _I32, _I32, _I64]),
     "gg_kf_finalize": (_I32, [C.POINTER(KfParams), _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gg_kf_dedup_classes_workspace_bytes": (_SZ, [_I64]),
+    "gg_kf_dedup_classes": (_I32, [_P, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "gg_kf_dedup_adj_words": (_SZ, [_I64]),
+    "gg_kf_dedup_score": (_I32, [_P, _I32, _I32, _P, _P, _P, _I64, _P, _I32, _P, _P]),
+    "gg_kf_dedup_count_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "gg_kf_dedup_count": (_I32, [_I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "gg_kf_dedup_place": (_I32, [_I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _I32, _I32, _P, _I64, _P, _SZ, _P]),
     "gg_kf_class_hist": (_I32, [_P, _P, _P, _I64, _P, _I32, _P, _P]),
     "gg_count_pairs_stride": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I64, _P, _I64, _P, _P]),
     "gg_db_prune_workspace_bytes": (_SZ, [_I64]),

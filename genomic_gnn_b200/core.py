@@ -479,11 +479,92 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
         rec_capacity = found
 
 
-def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, counts, want_dot=False, out=None):
-    """K6.  ``out`` = (edge_index [2, >= n_recs] view, weight32 [>= n_recs] view) lets the caller have the edges written
-    straight into its slice of a buffer sized for all ranks (multi-GPU exchange without staging copies)."""
+class StagedRecords:
+    """Candidates of a row-block shard as unordered records + per-(block pair, row, tile) counts (gg_kf_emit)."""
+
+    def __init__(self, recs, n_recs, rowcnt, params, scored):
+        self.recs, self.n_recs, self.rowcnt, self.params, self.scored = recs, n_recs, rowcnt, params, scored
+        self.d = params.d
+
+    def place(self, ordered_ptr, capacity=None):
+        """K6a: one packed 8-byte word per edge, in emission order, at ``ordered_ptr`` (room for n_recs words)."""
+        if not self.n_recs:
+            return
+        lib = _lib.load()
+        p = self.params
+        pw = int(lib.gg_kf_place_workspace_bytes(p.n, p.iblock_begin, p.iblock_end))
+        pws = torch.empty(pw, dtype=torch.uint8, device=self.recs.device)
+        with _stage(f"k6_place_d{p.d}"):
+            check(lib.gg_kf_place(C.byref(p), ptr(self.recs), self.n_recs, ptr(self.rowcnt), ptr(self.scored),
+                                  ordered_ptr, ptr(pws), pw, _stream()), "gg_kf_place")
+
+
+class StagedClasses:
+    """Candidates of a row-block shard held as duplicate-row classes + the class-pair bit matrix (gg_kf_dedup_*)."""
+
+    def __init__(self, counts, n, ib0, ib1, members, class_start, n_classes, adj, offsets, n_recs):
+        self.counts, self.n, self.ib0, self.ib1 = counts, n, ib0, ib1
+        self.members, self.class_start, self.n_classes, self.adj, self.offsets = members, class_start, n_classes, adj, offsets
+        self.n_recs = n_recs
+        self.d = int(counts.shape[1])
+
+    def place(self, ordered_ptr, capacity=None):
+        if not self.n_recs:
+            return
+        lib = _lib.load()
+        d = int(self.counts.shape[1])
+        ws = torch.empty(256, dtype=torch.uint8, device=self.counts.device)
+        with _stage(f"k6_place_d{d}"):
+            check(lib.gg_kf_dedup_place(self.n, self.ib0, self.ib1, ptr(self.adj), ptr(self.members),
+                                        ptr(self.class_start), self.n_classes, ptr(self.offsets), ptr(self.counts), d, d,
+                                        ordered_ptr, self.n_recs if capacity is None else capacity, ptr(ws), 256,
+                                        _stream()), "gg_kf_dedup_place")
+
+
+def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max: int, iblock_begin=0,
+                   iblock_end=None) -> StagedClasses:
+    """K4' for narrow rows (<= 16 columns, counts <= 15): group identical rows into classes, score the class pairs,
+    count the shard's edges.  Two small device reads: the number of classes (sizes the bit matrix) and the number
+    of edges (sizes the output)."""
+    lib = _lib.load()
+    dev = counts.device
+    n, d = int(counts.shape[0]), int(counts.shape[1])
+    nb = _row_blocks(n)
+    iblock_end = nb if iblock_end is None else iblock_end
+    dmin_d, _, _, p_max = _device_threshold_tables(float(threshold), int(sq_max), dev)
+    st = _stream()
+    members = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    class_start = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    status = torch.empty(2, dtype=torch.int64, device=dev)
+    wb = int(lib.gg_kf_dedup_classes_workspace_bytes(n))
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    with _stage(f"k4_classes_d{d}"):
+        check(lib.gg_kf_dedup_classes(ptr(counts), d, d, n, ptr(members), ptr(class_start), ptr(status), ptr(ws), wb, st),
+              "gg_kf_dedup_classes")
+    n_classes, n_over = (int(x) for x in status.cpu())
+    if n_over:
+        raise GGError("duplicate-row KF path: a count above 15 does not fit the packed row key")
+    adj = torch.empty(max(int(lib.gg_kf_dedup_adj_words(n_classes)), 1), dtype=torch.int32, device=dev)
+    with _stage(f"k4_score_d{d}"):
+        check(lib.gg_kf_dedup_score(ptr(counts), d, d, ptr(sqnorm), ptr(members), ptr(class_start), n_classes, ptr(dmin_d),
+                                    p_max, ptr(adj), st), "gg_kf_dedup_score")
+    elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
+    offsets = torch.empty(elems + 1, dtype=torch.int64, device=dev)
+    cb = int(lib.gg_kf_dedup_count_workspace_bytes(n, iblock_begin, iblock_end))
+    cws = torch.empty(cb, dtype=torch.uint8, device=dev)
+    with _stage(f"k4_count_d{d}"):
+        check(lib.gg_kf_dedup_count(n, iblock_begin, iblock_end, ptr(adj), ptr(members), ptr(class_start), n_classes,
+                                    ptr(offsets), ptr(cws), cb, st), "gg_kf_dedup_count")
+    n_recs = int(offsets[-1].item())
+    return StagedClasses(counts, n, iblock_begin, iblock_end, members, class_start, n_classes, adj, offsets, n_recs)
+
+
+def kf_finalize(staged, sqnorm, want_dot=False, out=None):
+    """K6: packed placement + coalesced expansion.  ``out`` = (edge_index [2, >= n_recs] view, weight32 [>= n_recs]
+    view) lets the caller have the edges written straight into its slice of a buffer sized for all ranks."""
     lib = _lib.load()
     dev = sqnorm.device
+    n_recs = staged.n_recs
     if out is None:
         edges = torch.empty((2, max(n_recs, 1)), dtype=torch.int64, device=dev)
         w32 = torch.empty(max(n_recs, 1), dtype=torch.float32, device=dev)
@@ -492,12 +573,12 @@ def kf_finalize(recs, n_recs, rowcnt, params, sqnorm, counts, want_dot=False, ou
     w64 = torch.empty(max(n_recs, 1), dtype=torch.float64, device=dev)
     dot = torch.empty(max(n_recs, 1), dtype=torch.int32, device=dev) if want_dot else None
     if n_recs:
-        ws_bytes = int(lib.gg_kf_finalize_workspace_bytes(params.n, params.iblock_begin, params.iblock_end, n_recs))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with _stage(f"k6_finalize_d{params.d}"):
-            check(lib.gg_kf_finalize(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(sqnorm), ptr(counts), ptr(edges[0]),
-                                     ptr(edges[1]), ptr(w64), ptr(w32), ptr(dot), ptr(ws), ws_bytes, _stream()),
-                  "gg_kf_finalize")
+        ordered = torch.empty(n_recs, dtype=torch.int64, device=dev)
+        staged.place(ptr(ordered))
+        first, size = (C.c_int64 * 1)(0), (C.c_int64 * 1)(n_recs)
+        with _stage(f"k6_expand_d{staged.d}"):
+            check(lib.gg_kf_expand(ptr(ordered), 1, first, size, ptr(sqnorm), ptr(edges[0]), ptr(edges[1]), ptr(w64),
+                                   ptr(w32), ptr(dot), _stream()), "gg_kf_expand")
     return edges[:, :n_recs], w64[:n_recs], w32[:n_recs], (dot[:n_recs] if want_dot else None)
 
 
@@ -557,13 +638,25 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         sq_max = int(sqnorm.max().item())
     if sq_max == 0:
         return empty
-    # staging capacity: the global top-n budget is the natural first guess (a binding threshold stays below it,
-    # a binding top-n overflows once and is re-run with the exact size)
-    n_pairs = n * (n - 1) // 2
-    guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
-    rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
-    recs, n_recs, rowcnt, params, scored = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
-                                                   rec_capacity=rec_capacity)
+    d_valid = int(counts.shape[1])
+    # duplicate-row classes pay off once the pair count dwarfs their fixed cost (sort + two class sweeps, ~0.3 ms):
+    # measured 0.96 vs 1.48 ms at N = 65,536 (k=8) but 0.32 vs 0.15 ms at N = 16,384 (k=7)
+    use_dedup = impl == "dedup" or (impl == "auto" and d_valid <= 16 and n >= 32768)
+    if use_dedup and not (d_valid <= 16 and d_valid % 4 == 0 and n <= _lib.KF_DEDUP_MAX_NODES and sq_max <= 225):
+        if impl == "dedup":
+            raise ValueError("the duplicate-row KF path needs <= 16 columns, counts <= 15 and <= 2^20 nodes")
+        use_dedup = False
+    if use_dedup:
+        staged = kf_stage_dedup(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end)
+    else:
+        # staging capacity: the global top-n budget is the natural first guess (a binding threshold stays below it,
+        # a binding top-n overflows once and is re-run with the exact size)
+        n_pairs = n * (n - 1) // 2
+        guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
+        rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
+        staged = StagedRecords(*kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
+                                        rec_capacity=rec_capacity))
+    n_recs = staged.n_recs
     per_rank = comm.gather_ints(n_recs)  # (one more device read per set; folding it into kf_emit's own read would
     #                                       need the all-gather before the capacity check -- left for the next round)
     n_total = sum(per_rank)
@@ -585,27 +678,22 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         # API wants them.)
         stride = max(max(per_rank), 1)
         ordered = torch.empty(comm.world * stride, dtype=torch.int64, device=dev)
-        if n_recs:
-            pw = int(lib.gg_kf_place_workspace_bytes(params.n, params.iblock_begin, params.iblock_end))
-            pws = torch.empty(pw, dtype=torch.uint8, device=dev)
-            with _stage(f"k6_place_d{params.d}"):
-                check(lib.gg_kf_place(C.byref(params), ptr(recs), n_recs, ptr(rowcnt), ptr(scored),
-                                      C.c_void_p(ordered.data_ptr() + 8 * comm.rank * stride), ptr(pws), pw, _stream()),
-                      "gg_kf_place")
+        staged.place(C.c_void_p(ordered.data_ptr() + 8 * comm.rank * stride))
         with _stage("c2_gather_packed_edges"):
             comm.all_gather_padded_(ordered, stride)
         full_ei, full_w, e_total, lo = shared_buffers(per_rank)
         seg_first = (C.c_int64 * comm.world)(*[r * stride for r in range(comm.world)])
         seg_size = (C.c_int64 * comm.world)(*per_rank)
-        with _stage(f"k6_expand_d{params.d}"):
+        with _stage(f"k6_expand_d{staged.d}"):
             check(lib.gg_kf_expand(ptr(ordered), comm.world, seg_first, seg_size, ptr(sqnorm), ptr(full_ei[0]),
                                    ptr(full_ei[1]), None, ptr(full_w), None, _stream()), "gg_kf_expand")
         return KFEdges(full_ei[:, :e_total], None, full_w[:e_total], n_total, None, 0, 0, impl)
-    ei, w64, w32, dot = kf_finalize(recs, n_recs, rowcnt, params, sqnorm, scored, want_dot=need_cut)
-    del recs, rowcnt
+    ei, w64, w32, dot = kf_finalize(staged, sqnorm, want_dot=need_cut)
+    p_max_tables = _device_threshold_tables(float(threshold), int(sq_max), dev)[3]
+    del staged
     cutoff, tie_budget, tie_total = None, 0, 0
     if need_cut:
-        p_max = params.p_max
+        p_max = p_max_tables
         hist = torch.zeros((sq_max + 1) * (p_max + 1), dtype=torch.int64, device=dev)
         src, dst = ei[0].contiguous(), ei[1].contiguous()
         with _stage("k5_class_hist"):

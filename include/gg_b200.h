@@ -206,6 +206,42 @@ GG_API int gg_kf_place(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, 
 GG_API int gg_kf_expand(const uint64_t* ordered, int n_segments, const int64_t* h_seg_first, const int64_t* h_seg_size,
                  const int32_t* sqnorm, int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
                  uint32_t* dot_out, gg_stream_t st);
+/* ------------------------------------------------------------------------
+ * K4'  duplicate-row path for narrow rows (d_valid <= 16 columns, every count <= 15: small_k <= 2).
+ *
+ * Many nodes share one feature row there (k=8, small_k=2: 17,444 distinct rows among 65,536 nodes; k=10: 95,924
+ * among 1,048,576), so the rows are grouped into classes, the CLASS pairs are scored once, and every class expands
+ * its neighbour classes into a bitmap over node space from which its member rows write their edges directly in
+ * emission order.  Produces exactly the packed words gg_kf_emit + gg_kf_place produce; n <= 2^20.
+ *
+ *   gg_kf_dedup_classes  members[n] = node ids grouped by class (ascending inside a class), class_start[n + 1],
+ *                        dd_status (device int64[2]): [0] number of classes, [1] rows holding a count > 15
+ *                        (then this path must not be used).  The host reads [0] to size `adj`.
+ *   gg_kf_dedup_score    adj[c][w]: bit matrix of class pairs whose cosine exceeds the threshold (symmetric; the
+ *                        diagonal is set because two members of one class have cosine 1), gg_kf_dedup_adj_words()
+ *                        uint32 words; same exact test as gg_kf_emit (dmin / p_max of gg_kf_params_t).
+ *   gg_kf_dedup_count    offsets[gg_kf_rowcnt_elems() + 1]: exclusive prefix sum of the candidates per
+ *                        (block pair, row) of the shard; the LAST entry is the shard's number of edges.
+ *   gg_kf_dedup_place    ordered[e] = s | dot << 24, t for every edge of the shard, in emission order
+ *                        (the input of gg_kf_expand).
+ * ------------------------------------------------------------------------ */
+GG_API size_t gg_kf_dedup_classes_workspace_bytes(int64_t n);
+GG_API int gg_kf_dedup_classes(const uint8_t* counts, int pitch, int d_valid, int64_t n, int32_t* members,
+                        int32_t* class_start, int64_t* dd_status, void* workspace, size_t workspace_bytes,
+                        gg_stream_t st);
+GG_API size_t gg_kf_dedup_adj_words(int64_t n_classes);
+GG_API int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, const int32_t* sqnorm, const int32_t* members,
+                      const int32_t* class_start, int64_t n_classes, const uint16_t* dmin, int32_t p_max,
+                      uint32_t* adj, gg_stream_t st);
+GG_API size_t gg_kf_dedup_count_workspace_bytes(int64_t n, int iblock_begin, int iblock_end);
+GG_API int gg_kf_dedup_count(int64_t n, int iblock_begin, int iblock_end, const uint32_t* adj, const int32_t* members,
+                      const int32_t* class_start, int64_t n_classes, uint64_t* offsets, void* workspace,
+                      size_t workspace_bytes, gg_stream_t st);
+GG_API int gg_kf_dedup_place(int64_t n, int iblock_begin, int iblock_end, const uint32_t* adj, const int32_t* members,
+                      const int32_t* class_start, int64_t n_classes, const uint64_t* offsets, const uint8_t* counts,
+                      int pitch, int d_valid, uint64_t* ordered, int64_t capacity, void* workspace /* >= 256 bytes */,
+                      size_t workspace_bytes, gg_stream_t st);
+
 GG_API size_t gg_kf_finalize_workspace_bytes(int64_t n, int iblock_begin, int iblock_end, int64_t n_recs);
 GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* recs, int64_t n_recs, const uint64_t* rowcnt,
                    const int32_t* sqnorm, const uint8_t* counts /* the matrix gg_kf_emit scored; used when d <= 64 */,

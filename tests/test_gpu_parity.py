@@ -167,7 +167,7 @@ def test_pipeline_matches_oracle(gg, k, n_reads, small_k, thr, topk):
         assert np.array_equal(got.kf[i].weight64.cpu().numpy(), want[f"edge_weight_KF{i}"])
 
 
-@pytest.mark.parametrize("k,s,thr", [(6, 3, 0.5), (6, 2, 0.8), (6, 2, 0.0), (5, 1, 0.9), (7, 2, 0.75)])
+@pytest.mark.parametrize("k,s,thr", [(6, 3, 0.5), (6, 2, 0.8), (6, 2, 0.0), (5, 1, 0.9), (7, 2, 0.75), (3, 2, 0.3)])
 def test_kf_impls_agree(gg, k, s, thr):
     """Narrow rows (D = 4, 16, 64): tensor path (rows padded to >= 32 bytes, 32B/64B swizzle), dp4a kernel and the
     generic slab kernel must emit identical edges in identical order."""
@@ -183,6 +183,16 @@ def test_kf_impls_agree(gg, k, s, thr):
     if 4**s == 64:
         c = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="naive")
         assert torch.equal(a.edge_index, c.edge_index) and torch.equal(a.weight64, c.weight64)
+    else:  # duplicate-row classes (the default for <= 16 columns), whole and as a row-block shard
+        c = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="dedup")
+        assert torch.equal(a.edge_index, c.edge_index) and torch.equal(a.weight64, c.weight64)
+        nb = (built.db.num_nodes + 1023) // 1024
+        lo, hi = (1, min(3, nb)) if nb >= 2 else (0, 1)
+        a1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="dp4a", iblock_begin=lo, iblock_end=hi)
+        c1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="dedup", iblock_begin=lo, iblock_end=hi)
+        assert torch.equal(a1.edge_index, c1.edge_index) and torch.equal(a1.weight64, c1.weight64)
+        with pytest.raises(ValueError):
+            core.kf_edges(built.kf_counts[0].counts.repeat(1, 8), kc.sqnorm, thr, None, sq_max=kc.m**2, impl="dedup")
 
 
 @pytest.mark.parametrize("k,s,n_reads,thr", [
