@@ -224,6 +224,26 @@ def test_kf_tcgen05_matches_generic(gg, k, s, n_reads, thr):
             assert torch.equal(a1.edge_index, b1.edge_index), impl
 
 
+@pytest.mark.parametrize("k,s,n_reads,thr", [
+    (9, 2, 400_000, 0.93),   # N ~ 262k: 256 column blocks = four 64-block windows per class, shard across windows
+    (8, 1, 200_000, 0.995),  # 4 columns: a few hundred classes with thousands of members (member sweeps, dense rows)
+])
+def test_kf_duplicate_row_classes_large(gg, k, s, n_reads, thr):
+    """The duplicate-row path beyond one window / one member sweep, against the tensor-core scoring path."""
+    from genomic_gnn_b200 import core
+
+    reads = fast.synthetic_reads(n_reads, 150, seed=5 + k)
+    built = core.build_graph(reads, k, str(s), with_kf=False)
+    kc = built.kf_counts[0]
+    nb = (built.db.num_nodes + 1023) // 1024
+    for lo, hi in ((0, nb), (nb // 3, nb // 3 + max(nb // 4, 1))):
+        a = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="tcgen05", iblock_begin=lo, iblock_end=hi)
+        b = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="dedup", iblock_begin=lo, iblock_end=hi)
+        assert a.edge_index.shape[1] > 0
+        assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
+        del a, b
+
+
 def test_kf_row_block_shards_concatenate(gg):
     """Row-block shards (the multi-GPU unit) concatenate to the single-GPU result."""
     from genomic_gnn_b200 import core
