@@ -72,6 +72,9 @@ class LocalComm:
     def gather_ints(self, x):
         return [int(x)]
 
+    def gather_device_int(self, t):
+        return [int(t.item())]
+
     def gather_cat(self, t, dim=0):
         return t
 
@@ -486,6 +489,9 @@ class StagedRecords:
         self.recs, self.n_recs, self.rowcnt, self.params, self.scored = recs, n_recs, rowcnt, params, scored
         self.d = params.d
 
+    def resolve(self, comm):
+        return comm.gather_ints(self.n_recs)
+
     def place(self, ordered_ptr, capacity=None):
         """K6a: one packed 8-byte word per edge, in emission order, at ``ordered_ptr`` (room for n_recs words)."""
         if not self.n_recs:
@@ -505,8 +511,15 @@ class StagedClasses:
     def __init__(self, counts, n, ib0, ib1, members, class_start, n_classes, adj, offsets, n_recs):
         self.counts, self.n, self.ib0, self.ib1 = counts, n, ib0, ib1
         self.members, self.class_start, self.n_classes, self.adj, self.offsets = members, class_start, n_classes, adj, offsets
-        self.n_recs = n_recs
+        self.n_recs = n_recs                 # None until resolve() has read it
+        self.n_recs_dev = offsets[-1:]       # int64 [1] on the device
         self.d = int(counts.shape[1])
+
+    def resolve(self, comm):
+        """One device read for the edge counts of every rank."""
+        per_rank = comm.gather_device_int(self.n_recs_dev)
+        self.n_recs = per_rank[comm.rank]
+        return per_rank
 
     def place(self, ordered_ptr, capacity=None):
         if not self.n_recs:
@@ -555,8 +568,8 @@ def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float,
     with _stage(f"k4_count_d{d}"):
         check(lib.gg_kf_dedup_count(n, iblock_begin, iblock_end, ptr(adj), ptr(members), ptr(class_start), n_classes,
                                     ptr(offsets), ptr(cws), cb, st), "gg_kf_dedup_count")
-    n_recs = int(offsets[-1].item())
-    return StagedClasses(counts, n, iblock_begin, iblock_end, members, class_start, n_classes, adj, offsets, n_recs)
+    # the shard's edge count stays on the device: the caller reads it together with the other ranks' counts
+    return StagedClasses(counts, n, iblock_begin, iblock_end, members, class_start, n_classes, adj, offsets, None)
 
 
 def kf_finalize(staged, sqnorm, want_dot=False, out=None):
@@ -656,9 +669,8 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
         staged = StagedRecords(*kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
                                         rec_capacity=rec_capacity))
+    per_rank = staged.resolve(comm)
     n_recs = staged.n_recs
-    per_rank = comm.gather_ints(n_recs)  # (one more device read per set; folding it into kf_emit's own read would
-    #                                       need the all-gather before the capacity check -- left for the next round)
     n_total = sum(per_rank)
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total

@@ -494,6 +494,7 @@ kf_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bsta
 // ======================================================================================
 constexpr int kPairTileN = 256;
 constexpr int kPairAccStages = 2;
+constexpr int kPairPanel = kBlock + 16;  // per epilogue group: column norms of a block + per-tile minima
 constexpr int kPairsPerBlock = kStripsPerBlock / 2;
 constexpr int kPairTilesPerBlock = kBlock / kPairTileN;
 constexpr uint32_t kIdescPair = (2u << 4) | ((kPairTileN >> 3) << 17) | ((256u >> 4) << 24);
@@ -593,7 +594,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
   uint16_t* sqn = reinterpret_cast<uint16_t*>(smem_b + static_cast<size_t>(n_bstages) * kStageBytes);
-  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kEpiGroups * kBlock);
+  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kEpiGroups * kPairPanel);
   Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -733,7 +734,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
     __syncwarp();
     const int group = warp / 4;
     const int gt = tid % kGroupThreads;
-    uint16_t* my_sqn = sqn + group * kBlock;
+    uint16_t* my_sqn = sqn + group * kPairPanel;  // [kBlock] column norms + [8] smallest norm per 128-column tile
     if (n_units > 0) {
       PairWalk w = pair_walk_begin(a, u0, n_units);
       uint32_t tile_seq = 0;
@@ -765,6 +766,23 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
                 for (int c = gt; c < kBlock; c += kGroupThreads)
                   my_sqn[c] = c < cols_in_block ? static_cast<uint16_t>(__ldg(a.sqnorm + col0 + c)) : 0;
                 asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+                {  // smallest squared norm per 128-column tile (real columns only): warp q of the group takes tiles 2q, 2q+1
+                  const int q = warp & 3;
+#pragma unroll
+                  for (int t2 = 0; t2 < 2; ++t2) {
+                    const int tile = 2 * q + t2;
+                    uint32_t mn = 0xFFFFu;
+#pragma unroll
+                    for (int e = 0; e < kTile / 32; ++e) {
+                      const int c = tile * kTile + e * 32 + lane;
+                      const uint32_t x = my_sqn[c];
+                      if (c < cols_in_block && x < mn) mn = x;
+                    }
+                    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+                    if (lane == 0) my_sqn[kBlock + tile] = static_cast<uint16_t>(mn);
+                  }
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
                 if (row_ok) {
                   sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
                   scale_i = __ldg(a.fast_scale + sq_i);
@@ -773,12 +791,21 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
               }
               const uint32_t taddr =
                   tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * kPairTileN + half * kTile;
+              // First-level filter, one compare per score: dmin grows with the norm product, so no column of this
+              // tile can pass below dmin[sq_i * smallest column norm of the tile].  (A tile without a real column
+              // keeps the 0xFFFF sentinel and is skipped above.)
+              const uint32_t tile_min_sq = my_sqn[kBlock + ct128];
+              const uint32_t tmin = (row_ok && tile_min_sq != 0xFFFFu) ? __ldg(a.dmin + sq_i * tile_min_sq) : 0xFFFFu;
               uint32_t tile_cnt = 0;
 #pragma unroll 1
               for (int cc = 0; cc < kTile; cc += 32) {
                 const int c0 = ct128 * kTile + cc;
                 uint32_t v[32];
                 tc_ld32(taddr + cc, v);
+                bool hot = false;
+#pragma unroll
+                for (int b = 0; b < 32; ++b) hot |= v[b] >= tmin;
+                if (!__any_sync(0xFFFFFFFFu, hot)) continue;
                 uint32_t mask = 0;
 #pragma unroll
                 for (int b = 0; b < 32; ++b)
@@ -926,7 +953,7 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
     gg::set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return GG_ERR_CUDA;
   }
-  const size_t fixed = static_cast<size_t>(g.n_kblocks) * g.stage_bytes + kEpiGroups * kBlock * sizeof(uint16_t) +
+  const size_t fixed = static_cast<size_t>(g.n_kblocks) * g.stage_bytes + kEpiGroups * kPairPanel * sizeof(uint16_t) +
                        (kEpiThreads / 32) * sizeof(WarpStage) + sizeof(Barriers) + 1024;
   int dev = 0, max_smem = 0;
   GG_CUDA_CHECK(cudaGetDevice(&dev));
