@@ -282,13 +282,25 @@ __device__ __forceinline__ void process_warp(const Args& a, int64_t b, uint32_t 
   prepare_warp<MODE == kCount>(a, b, phase, lane, hi, lo, pair_ok, cand);
   const int key_shift = 32 - 2 * (a.k + 1);
   const uint64_t pos0 = static_cast<uint64_t>(a.pos_base + b);
+  if (MODE == kCount) {
 #pragma unroll
-  for (int j = 0; j < kPosPerThread; ++j) {
-    const uint32_t key = __funnelshift_l(lo, hi, 2 * j) >> key_shift;  // bases j .. j+k, first base on top
-    if (MODE == kCount) {
-      red_global_inc_if(a.hist + key, (pair_ok >> j) & 1u);
-    } else if ((pair_ok >> j) & 1u) {
-      touch<MODE>(a, key, pos0 + j, newly_seen);
+    for (int j = 0; j < kPosPerThread; ++j)  // bases j .. j+k, first base on top
+      red_global_inc_if(a.hist + (__funnelshift_l(lo, hi, 2 * j) >> key_shift), (pair_ok >> j) & 1u);
+  } else {
+    // first-occurrence scan: all 16 slots are read first (independent loads in flight together); an atomic is only
+    // needed where the stored offset is larger, and its return value only where the bin was still unseen
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(a.first_pos);
+    unsigned long long cur[kPosPerThread];
+#pragma unroll
+    for (int j = 0; j < kPosPerThread; ++j)
+      cur[j] = ((pair_ok >> j) & 1u) ? __ldcg(slots + (__funnelshift_l(lo, hi, 2 * j) >> key_shift)) : 0ull;
+#pragma unroll
+    for (int j = 0; j < kPosPerThread; ++j) {
+      if (cur[j] > pos0 + j) {  // never for invalid positions (0)
+        unsigned long long* slot = slots + (__funnelshift_l(lo, hi, 2 * j) >> key_shift);
+        if (cur[j] == GG_NO_POS) newly_seen += (atomicMin(slot, pos0 + j) == GG_NO_POS);
+        else atomicMin(slot, pos0 + j);
+      }
     }
   }
   if (cand) bridge_chunk<MODE>(a, b, hi, lo, cand, newly_seen);
@@ -666,16 +678,16 @@ __global__ void __launch_bounds__(kPartThreads) part_kernel(PartArgs p) {
       stage[valid ? slot : static_cast<uint32_t>(kStageKeys)] = static_cast<uint16_t>((win >> key_shift) & (kBucketBins - 1u));
     }
     __syncthreads();
-    const uint32_t n_groups = bkt_start[kMaxBuckets] >> 3;
-    for (uint32_t g = threadIdx.x; g < n_groups; g += kPartThreads) {
-      const uint32_t slot = g << 3;
-      int q = 0;
-#pragma unroll
-      for (int t = 1; t < kMaxBuckets; ++t) q = (bkt_start[t] <= slot) ? t : q;  // last bucket starting at or before
-      const unsigned long long off = bkt_gbase[q] + (slot - bkt_start[q]);
-      if (off + 8 <= static_cast<unsigned long long>(p.capacity))
-        *reinterpret_cast<uint4*>(p.keys + static_cast<int64_t>(q >> vshift) * p.capacity + off) =
-            *reinterpret_cast<const uint4*>(stage + slot);
+    {  // copy-out: warp q streams virtual bucket q's run (a multiple of 8 keys) as aligned 16-byte groups
+      static_assert(kPartWarps == kMaxBuckets, "one warp per virtual bucket");
+      const uint32_t first = bkt_start[warp], n_groups = (bkt_start[warp + 1] - first) >> 3;
+      const unsigned long long g0 = bkt_gbase[warp];
+      uint16_t* dst = p.keys + static_cast<int64_t>(warp >> vshift) * p.capacity;
+      for (uint32_t g = lane; g < n_groups; g += 32) {
+        const unsigned long long off = g0 + (g << 3);
+        if (off + 8 <= static_cast<unsigned long long>(p.capacity))
+          *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(stage + first + (g << 3));
+      }
     }
     if (cand) {
       int unused = 0;
