@@ -359,9 +359,11 @@ def run_ours(a):
                                            "pairs_per_s": pairs / (ms * 1e-3), "stages": parts}
     dominant = max(rooflines, key=lambda k_: rooflines[k_]["ms"]) if rooflines else None
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if dominant and os.path.exists(traffic_file):
+    if rooflines and os.path.exists(traffic_file):  # per-launch DRAM bytes from the committed ncu --set full capture
         with open(traffic_file) as fh:
-            rooflines[dominant]["traffic"] = json.load(fh).get(dominant)
+            measured = json.load(fh)
+        for key_, r_ in rooflines.items():
+            r_["traffic"] = measured.get(key_)
 
     line = {
         "metric": f"k={a.k} graph-build reads/sec", "value": value, "unit": "reads/s", "n_gpus": world,
