@@ -288,6 +288,23 @@ GG_API int gg_db_prune_quantile(const int64_t* edge_src, const int64_t* edge_dst
                          double quantile, int64_t* out_src, int64_t* out_dst, double* out_w64, float* out_w32,
                          int64_t* out_count, void* workspace, size_t workspace_bytes, gg_stream_t st);
 
+/* ------------------------------------------------------------------------
+ * f3  biased random walks + skip-gram windows -> positive node pairs.  Replaces sample_biased_random_walks
+ *     (gnn_common/gnn_utils.py:514-600; called per epoch / per batch by the sampling tasks).
+ *
+ * Graph: CSR over the directed weighted De Bruijn graph (row_ptr[n + 1], col[E], weight[E]; successors in edge
+ * order).  Walk w = round * n_start + s starts at start_nodes[s]; first step ~ edge weights, later steps node2vec
+ * (weight / p back to the previous node, weight if the successor has an edge to the previous node, weight / q
+ * otherwise); a node without successors ends the walk.  For every position i a half-width ~ U{1..window_size} and the
+ * pairs (walk[i], walk[j]), j != i inside the window.  Every walk owns a Philox stream keyed by (seed, w): mode 0
+ * (pair_counts[w]) and mode 1 (pairs written from pair_offsets[w], the exclusive prefix sum of the counts) replay the
+ * same walks.  walks_out (mode 1, nullable): [n_walks][walk_length + 1], -1 padded.  walk_length <= 32.
+ * ------------------------------------------------------------------------ */
+GG_API int gg_rw_pairs(const int64_t* row_ptr, const int64_t* col, const float* weight, int64_t n,
+                const int64_t* start_nodes, int64_t n_start, int num_walks, int walk_length, int window_size,
+                double p, double q, uint64_t seed, int mode, int64_t* pair_counts, const int64_t* pair_offsets,
+                int64_t* pairs_src, int64_t* pairs_dst, int64_t capacity, int64_t* walks_out, gg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,10 +1,12 @@
 """Pin the CPU oracle against the reference's own outputs (tests/golden made by
 oracle/make_golden.py from /root/reference) -- CPU only."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import faithful, fast, ref_import
-from tests._util import (assert_kf_threshold_parity, edge_keys, load_golden, small_goldens)
+from tests._util import (GOLDEN, assert_kf_threshold_parity, edge_keys, load_golden, small_goldens)
 
 
 @pytest.fixture(params=small_goldens(), ids=lambda p: p.split("small_")[-1][:-4])
@@ -138,3 +140,54 @@ def test_live_reference_random_cross_check():
                 ref_ei = np.array([[idx[a], idx[b]] for a, b in gr.edges()], dtype=np.int64).T.reshape(2, -1)
                 assert np.array_equal(ref_ei, ei)
                 assert np.array_equal(np.array([d for _, _, d in gr.edges(data="weight")]), w)
+
+
+def test_random_walk_law_matches_reference_statistics():
+    """Row f3 oracle pin: the exact walk / window laws of oracle/rw.py against statistics of the REAL reference sampler
+    (gnn_utils.py:514-600) frozen by oracle/make_golden_rw.py -- 32,000 decoded walks with p=0.5, q=2.0 and the
+    pairs-per-walk histogram of 20,000 single walks."""
+    from oracle import rw
+
+    z = np.load(os.path.join(GOLDEN, "rw_reference.npz"))
+    n = int(z["num_nodes"])
+    nbrs = rw.successors(z["edge_index"], z["weight"], n)
+    counts = {tuple(int(x) for x in k): int(c) for k, c in zip(z["walk_keys"], z["walk_counts"])}
+    per_start = {}
+    for (a, _, _), c in counts.items():
+        per_start[a] = per_start.get(a, 0) + c
+    assert len(per_start) == n
+    chi2, dof = 0.0, 0
+    for a in range(n):
+        law = rw.walk_law(nbrs, a, 2, p=float(z["p"]), q=float(z["q"]))
+        assert abs(sum(law.values()) - 1.0) < 1e-12
+        assert set(k for k in counts if k[0] == a) <= set(law)       # the reference never takes an impossible walk
+        for walk, pr in law.items():
+            exp = per_start[a] * pr
+            got = counts.get(walk, 0)
+            assert abs(got - exp) <= 5.0 * np.sqrt(exp * (1 - pr)) + 1.0, (walk, got, exp)
+            if exp >= 5:
+                chi2 += (got - exp) ** 2 / exp
+                dof += 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
+    hist = {int(k): int(c) for k, c in z["pairs_per_walk"]}
+    total = sum(hist.values())
+    law = rw.pairs_per_walk_law(5, 3)
+    assert set(hist) <= set(law)
+    for k, pr in law.items():
+        exp = total * pr
+        assert abs(hist.get(k, 0) - exp) <= 5.0 * np.sqrt(exp * (1 - pr)) + 1.0, (k, hist.get(k, 0), exp)
+    # the line-by-line restatement follows the same law
+    import random
+
+    r = random.Random(3)
+    seen = {}
+    for _ in range(300):
+        _, walks = rw.sample(z["edge_index"], z["weight"], n, n, num_walks=2, walk_length=2, window_size=1,
+                             p=float(z["p"]), q=float(z["q"]), rng=r)
+        for w in walks:
+            seen[tuple(w)] = seen.get(tuple(w), 0) + 1
+    for a in range(n):
+        law = rw.walk_law(nbrs, a, 2, p=float(z["p"]), q=float(z["q"]))
+        for walk, pr in law.items():
+            exp = 600 * pr
+            assert abs(seen.get(walk, 0) - exp) <= 5.0 * np.sqrt(exp * (1 - pr)) + 1.0
