@@ -22,7 +22,7 @@ from .builders import (  # noqa: F401
     networkx_to_dataloader_mini_batch,
 )
 from .core import build_graph, build_graph_to_host  # noqa: F401
-from .sampler import sample_biased_random_walks  # noqa: F401
+from .sampler import sample_biased_random_walks, sample_biased_random_walks_miniBatch  # noqa: F401
 from .transform import kmers_to_index, transform  # noqa: F401
 
 __version__ = "0.1.0"

@@ -73,3 +73,17 @@ def sample_biased_random_walks(data, num_nodes_to_sample: int, num_walks: int = 
           "gg_rw_pairs(write)")
     out = pairs[:, :total].to(home) if total else empty
     return (out, walks.to(home), counts.to(home)) if return_walks else out
+
+
+def sample_biased_random_walks_miniBatch(data, num_nodes_to_sample: int, num_walks: int = 5, walk_length: int = 2,
+                                         window_size: int = 3, p: float = 1.0, q: float = 1.0, seed=None):
+    """Mini-batch flavour (reference gnn_tasks_miniBatch/utils.py:10-45): the walks run on the ("node", "DB", "node")
+    edges of the sampled HeteroData batch.  The reference forwards its arguments POSITIONALLY as
+    ``(graph, num_nodes_to_sample, walk_length, window_size, p, q)`` (utils.py:43-45), so the callee receives
+    num_walks=walk_length, walk_length=window_size, window_size=p and p=q while ``num_walks`` and ``q`` of this
+    wrapper are dropped; that behaviour is reproduced, not corrected."""
+    store = data["node", "DB", "node"]
+    graph = {"edge_index": store.edge_index if hasattr(store, "edge_index") else store["edge_index"],
+             "weight": store.edge_attr if hasattr(store, "edge_attr") else store["edge_attr"],
+             "num_nodes": int((data["node"].x if hasattr(data["node"], "x") else data["node"]["x"]).shape[0])}
+    return sample_biased_random_walks(graph, num_nodes_to_sample, walk_length, window_size, int(p), q, seed=seed)

@@ -289,7 +289,10 @@ def test_count_paths_agree(gg, k):
     fixed = fast.synthetic_reads(5000, 151, seed=k)
     fixed[::41, 77] = ord("N")
     skewed = ["A" * 150] * 1500 + ["T" * 149] * 700 + ["ACGT" * 40] * 300  # every key of a tile in one bucket
-    for inp in (reads, fixed, skewed):
+    short_rows = fast.synthetic_reads(6000, 20, seed=k + 1)   # several read starts per 32 positions: general window path
+    short_rows[::17, 9] = ord("N")
+    odd_rows = fast.synthetic_reads(4000, 33, seed=k + 2)
+    for inp in (reads, fixed, skewed, short_rows, odd_rows):
         stream = core.upload_reads(inp)
         b = core.count_kp1mers(stream, k, impl="l2")
         kb = sorted(map(tuple, b.bridges[: b.n_bridges].cpu().tolist()))

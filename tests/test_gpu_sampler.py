@@ -120,3 +120,16 @@ def test_sampler_on_a_built_graph():
     assert all((int(a), int(b)) in edges for a, b in zip(w[:, 0], w[:, 1]))
     assert all((int(a), int(b)) in edges for a, b in zip(w[:, 1], w[:, 2]))
     assert 4 * 5000 <= pairs.shape[1] <= 6 * 5000          # 3-node walks: 4 pairs at shrink 1, 6 when every window covers the walk
+
+
+def test_mini_batch_wrapper_forwards_like_the_reference():
+    """gnn_tasks_miniBatch/utils.py:43-45 forwards positionally: (walk_length, window_size, p, q) land in
+    (num_walks, walk_length, window_size, p)."""
+    import genomic_gnn_b200 as gg
+
+    z, n, data = _graph()
+    hetero = {("node", "DB", "node"): types.SimpleNamespace(edge_index=data.edge_index, edge_attr=data.weight),
+              "node": types.SimpleNamespace(x=torch.zeros((n, 4)))}
+    a = gg.sample_biased_random_walks_miniBatch(hetero, n, num_walks=7, walk_length=3, window_size=2, p=1.0, q=0.25, seed=4)
+    b = gg.sample_biased_random_walks(data, n, num_walks=3, walk_length=2, window_size=1, p=0.25, q=1.0, seed=4)
+    assert torch.equal(a, b) and a.shape == (2, 4 * 3 * n)

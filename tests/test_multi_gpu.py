@@ -49,6 +49,8 @@ def _worker(rank, world, port, out_dir, k, small_k, thr, topk, n_reads):
 @pytest.mark.parametrize("k,small_k,thr,topk,n_reads", [
     (7, "2,5", 0.8, 0.01, 40_000),     # threshold-bound, 16 row blocks
     (6, "2,4", 0.0, 0.01, 20_000),     # global top-n binding: class histogram all-reduce + tie split across ranks
+    (8, "2", 0.8, 0.01, 120_000),      # 65,536 nodes: duplicate-row KF path sharded by row block, device-side count gather
+    (8, "2", 0.8, 0.001, 120_000),     # ... with the global top-n binding (4.3M of 20.6M candidates kept)
 ])
 def test_multi_gpu_equals_single(tmp_path, k, small_k, thr, topk, n_reads):
     world = min(torch.cuda.device_count(), 4)
