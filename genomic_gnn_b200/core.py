@@ -72,8 +72,8 @@ class LocalComm:
     def gather_ints(self, x):
         return [int(x)]
 
-    def gather_device_int(self, t):
-        return [int(t.item())]
+    def gather_device_ints(self, t):
+        return [t.cpu().tolist()]
 
     def gather_cat(self, t, dim=0):
         return t
@@ -447,10 +447,12 @@ def _row_blocks(n):
 
 
 def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max: int, iblock_begin=0,
-            iblock_end=None, impl="auto", rec_capacity=None):
+            iblock_end=None, impl="auto", rec_capacity=None, sync=True):
     """Score all pairs of the row-block shard and stage the candidates.
     Returns (recs, n_recs, rowcnt, params, counts_scored): the last is the matrix the kernel read (zero-padded to a
-    32-byte pitch for the tensor path on narrow rows), which kf_finalize needs to re-multiply narrow rows."""
+    32-byte pitch for the tensor path on narrow rows), which kf_finalize needs to re-multiply narrow rows.
+    With ``sync=False`` nothing is read back: n_recs is None and a sixth element, the device status words
+    (gg_kf_emit: [0] candidates found, [2] pipeline error), is returned for the caller to read later."""
     lib = _lib.load()
     dev = counts.device
     d_valid = int(counts.shape[1])
@@ -472,6 +474,8 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
         with _stage(f"k4_emit_d{d}"):
             check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
                                  rec_capacity, ptr(rowcnt), ptr(status), _stream()), "gg_kf_emit")
+        if not sync:
+            return recs, None, rowcnt, params, counts, status
         st_host = status.cpu()
         if int(st_host[2]) != 0:
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
@@ -485,12 +489,22 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
 class StagedRecords:
     """Candidates of a row-block shard as unordered records + per-(block pair, row, tile) counts (gg_kf_emit)."""
 
-    def __init__(self, recs, n_recs, rowcnt, params, scored):
+    def __init__(self, recs, n_recs, rowcnt, params, scored, status=None, redo=None):
         self.recs, self.n_recs, self.rowcnt, self.params, self.scored = recs, n_recs, rowcnt, params, scored
         self.d = params.d
+        self.status4 = status      # device int64[4] while n_recs has not been read: [0] found, [2] pipeline error
+        self.redo = redo           # re-scores the shard with room for a given number of records
 
-    def resolve(self, comm):
-        return comm.gather_ints(self.n_recs)
+    def after_counts(self, mine):
+        """``mine`` = this rank's status words as read by kf_resolve."""
+        if int(mine[2]) != 0:
+            raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
+        found = int(mine[0])
+        if found > int(self.recs.shape[0]):   # staging buffer too small (rare): score again with the exact size
+            self.recs, self.n_recs, self.rowcnt, self.params, self.scored = self.redo(found)
+        else:
+            self.n_recs = found
+        self.status4 = None
 
     def place(self, ordered_ptr, capacity=None):
         """K6a: one packed 8-byte word per edge, in emission order, at ``ordered_ptr`` (room for n_recs words)."""
@@ -511,15 +525,14 @@ class StagedClasses:
     def __init__(self, counts, n, ib0, ib1, members, class_start, n_classes, adj, offsets, n_recs):
         self.counts, self.n, self.ib0, self.ib1 = counts, n, ib0, ib1
         self.members, self.class_start, self.n_classes, self.adj, self.offsets = members, class_start, n_classes, adj, offsets
-        self.n_recs = n_recs                 # None until resolve() has read it
-        self.n_recs_dev = offsets[-1:]       # int64 [1] on the device
+        self.n_recs = n_recs                 # None until kf_resolve has read it
         self.d = int(counts.shape[1])
+        self.status4 = torch.zeros(4, dtype=torch.int64, device=counts.device)
+        self.status4[0:1].copy_(offsets[-1:], non_blocking=True)   # the shard's edge count, still on the device
 
-    def resolve(self, comm):
-        """One device read for the edge counts of every rank."""
-        per_rank = comm.gather_device_int(self.n_recs_dev)
-        self.n_recs = per_rank[comm.rank]
-        return per_rank
+    def after_counts(self, mine):
+        self.n_recs = int(mine[0])
+        self.status4 = None
 
     def place(self, ordered_ptr, capacity=None):
         if not self.n_recs:
@@ -626,31 +639,32 @@ def choose_cutoff(class_hist: np.ndarray, p_max: int, budget: int):
     return action, tie_budget, cutoff, tie_total
 
 
-def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
-             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None, comm=None,
-             gather: bool = True) -> KFEdges:
-    """K4-K6.  Reference: gnn_utils.py:240-322.
+@dataclass
+class KFStage:
+    """One KF set between scoring and the read of its candidate count (kf_stage -> kf_resolve -> kf_finish)."""
+    counts: torch.Tensor
+    sqnorm: torch.Tensor
+    threshold: float
+    keep_top_k: Optional[float]
+    sq_max: int
+    impl: str
+    staged: object = None          # StagedRecords / StagedClasses; None: no pair can be an edge
+    per_rank: Optional[list] = None
 
-    With ``comm`` (dist.TorchComm) every rank scores its own row-block shard
-    [iblock_begin, iblock_end); the only exchanges are a candidate-count sum,
-    (when the global top-n binds) a sum of the score-class histogram, and the
-    final all-gather of the per-shard edge lists, which concatenate in rank
-    order to the single-GPU emission order."""
+
+def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
+             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None) -> KFStage:
+    """K4: score this rank's row-block shard; the candidate count stays on the device (kf_resolve reads the counts of
+    any number of staged sets, on every rank, with one device read)."""
     _require_cuda()
-    lib = _lib.load()
-    comm = comm or LocalComm()
-    dev = counts.device
     n = int(counts.shape[0])
-    empty = KFEdges(torch.zeros((2, 0), dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.float64, device=dev),
-                    torch.zeros(0, dtype=torch.float32, device=dev), 0, impl=impl)
     if threshold < 0:
         raise ValueError("negative KF threshold is not supported")
-    if n < 2 or threshold >= 1.0:
-        return empty
     if sq_max is None:
-        sq_max = int(sqnorm.max().item())
-    if sq_max == 0:
-        return empty
+        sq_max = int(sqnorm.max().item()) if n else 0
+    st = KFStage(counts, sqnorm, float(threshold), keep_top_k, int(sq_max), impl)
+    if n < 2 or threshold >= 1.0 or sq_max == 0:
+        return st
     d_valid = int(counts.shape[1])
     # duplicate-row classes pay off once the pair count dwarfs their fixed cost (sort + two class sweeps, ~0.3 ms):
     # measured 0.96 vs 1.48 ms at N = 65,536 (k=8) but 0.32 vs 0.15 ms at N = 16,384 (k=7)
@@ -660,16 +674,62 @@ def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
             raise ValueError("the duplicate-row KF path needs <= 16 columns, counts <= 15 and <= 2^20 nodes")
         use_dedup = False
     if use_dedup:
-        staged = kf_stage_dedup(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end)
+        st.staged = kf_stage_dedup(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end)
     else:
         # staging capacity: the global top-n budget is the natural first guess (a binding threshold stays below it,
         # a binding top-n overflows once and is re-run with the exact size)
         n_pairs = n * (n - 1) // 2
         guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
         rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
-        staged = StagedRecords(*kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl,
-                                        rec_capacity=rec_capacity))
-    per_rank = staged.resolve(comm)
+        recs, _, rowcnt, params, scored, status = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end,
+                                                          impl, rec_capacity=rec_capacity, sync=False)
+
+        def redo(found):
+            return kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl, rec_capacity=found)
+
+        st.staged = StagedRecords(recs, None, rowcnt, params, scored, status, redo)
+    return st
+
+
+def kf_resolve(stages: List[KFStage], comm=None):
+    """One exchange + one device read for the candidate counts (and kernel status words) of all staged KF sets."""
+    comm = comm or LocalComm()
+    live = [st for st in stages if st.staged is not None]
+    if not live:
+        return
+    flat = live[0].staged.status4 if len(live) == 1 else torch.cat([st.staged.status4 for st in live])
+    table = comm.gather_device_ints(flat)          # [rank][4 * set + word]
+    for i, st in enumerate(live):
+        st.staged.after_counts(table[comm.rank][4 * i: 4 * i + 4])
+        st.per_rank = [int(table[r][4 * i]) for r in range(comm.world)]
+
+
+def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
+             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None, comm=None,
+             gather: bool = True) -> KFEdges:
+    """K4-K6.  Reference: gnn_utils.py:240-322.
+
+    With ``comm`` (dist.TorchComm) every rank scores its own row-block shard
+    [iblock_begin, iblock_end); the only exchanges are an all-gather of the candidate counts,
+    (when the global top-n binds) a sum of the score-class histogram, and the
+    final all-gather of the per-shard edge lists, which concatenate in rank
+    order to the single-GPU emission order."""
+    st = kf_stage(counts, sqnorm, threshold, keep_top_k, sq_max, impl, iblock_begin, iblock_end)
+    kf_resolve([st], comm)
+    return kf_finish(st, comm, gather)
+
+
+def kf_finish(st: KFStage, comm=None, gather: bool = True) -> KFEdges:
+    """K5/K6 (+ the multi-GPU exchange) of a staged and resolved KF set."""
+    lib = _lib.load()
+    comm = comm or LocalComm()
+    counts, sqnorm, threshold, keep_top_k, sq_max, impl = st.counts, st.sqnorm, st.threshold, st.keep_top_k, st.sq_max, st.impl
+    dev = counts.device
+    n = int(counts.shape[0])
+    if st.staged is None:
+        return KFEdges(torch.zeros((2, 0), dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.float64, device=dev),
+                       torch.zeros(0, dtype=torch.float32, device=dev), 0, impl=impl)
+    staged, per_rank = st.staged, st.per_rank
     n_recs = staged.n_recs
     n_total = sum(per_rank)
     budget = top_n_budget(n, keep_top_k, n_total)
@@ -805,9 +865,11 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
             from . import dist
 
             b0, b1 = dist.kf_block_range(_row_blocks(db.num_nodes), comm.world, comm.rank)
-        for kc in kcs:
-            out.kf.append(kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m,
-                                   impl=kf_impl, iblock_begin=b0, iblock_end=b1, comm=comm))
+        # every set is scored first; ONE exchange / device read then brings the candidate counts of all of them
+        stages = [kf_stage(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl,
+                           iblock_begin=b0, iblock_end=b1) for kc in kcs]
+        kf_resolve(stages, comm)
+        out.kf = [kf_finish(st, comm) for st in stages]
         for kf in out.kf:  # multi-GPU: the edge exchanges of earlier sets ran underneath the scoring of later ones
             kf.wait()
     return out
@@ -927,6 +989,8 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
 
     h_codes, h_ei, h_w, *h_x = down([db.node_codes, db.edge_index, db.weight, *xs])
     kf_ei, kf_w = [], []
+    # one set at a time here (not stage-all-first as in build_graph): the first set's edges, the largest transfer of
+    # the step, start going down while the second set is still being scored -- measured 17.2 vs 18.5 ms end to end
     for kc in kcs:
         kf = kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl)
         e, w = down([kf.edge_index, kf.weight])

@@ -73,11 +73,13 @@ class TorchComm:
         dist_.all_gather_into_tensor(out, t, group=self.group)
         return [int(v) for v in out.tolist()]  # one device-to-host read for all ranks
 
-    def gather_device_int(self, t: torch.Tensor) -> List[int]:
-        """all-gather of an int64 [1] tensor that already lives on the device: no upload, one read for all ranks."""
-        out = torch.empty(self.world, dtype=torch.int64, device=t.device)
-        dist_.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return [int(v) for v in out.tolist()]
+    def gather_device_ints(self, t: torch.Tensor) -> List[List[int]]:
+        """all-gather of a small int64 vector that already lives on the device: no upload, one read for all ranks.
+        Returns one list per rank."""
+        t = t.contiguous()
+        out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=t.device)
+        dist_.all_gather_into_tensor(out, t, group=self.group)
+        return out.view(self.world, t.numel()).tolist()
 
     def gather_cat(self, t: torch.Tensor, dim: int = 0) -> torch.Tensor:
         """all-gather(v) along ``dim`` and concatenate in rank order."""

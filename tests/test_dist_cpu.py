@@ -85,7 +85,7 @@ def _worker(rank, world, port, k, tmp):
         assert merged.n_nonzero == -1   # left unknown on purpose (saves a device round trip)
 
         # a scalar that already lives on the "device": gathered without an upload
-        assert comm.gather_device_int(torch.tensor([10 + rank], dtype=torch.int64)) == [10 + r for r in range(world)]
+        assert comm.gather_device_ints(torch.tensor([10 + rank, 7], dtype=torch.int64)) == [[10 + r, 7] for r in range(world)]
 
         # bridges: only rank 1 has some
         br = torch.tensor([[1, 2, 7, 0], [3, 4, 9, 0]], dtype=torch.int32)
