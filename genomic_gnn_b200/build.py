@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgg_b200.so")
-SOURCES = ["gg_common.cu", "gg_count.cu", "gg_db.cu", "gg_feat.cu", "gg_kf.cu", "gg_kf_mma.cu", "gg_kf_dedup.cu", "gg_index.cu", "gg_rw.cu"]
+SOURCES = ["gg_common.cu", "gg_count.cu", "gg_db.cu", "gg_feat.cu", "gg_kf.cu", "gg_kf_mma.cu", "gg_kf_dedup.cu", "gg_index.cu", "gg_rw.cu", "gg_host.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
         fh.write(log)
     if verbose:
         print(log)
-    cmd = [NVCC, "-shared", "-o", LIB, *[o for o, _ in results], "-Xcompiler", "-fPIC", "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", LIB, *[o for o, _ in results], "-Xcompiler", "-fPIC", "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

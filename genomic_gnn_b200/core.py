@@ -5,6 +5,8 @@ Stages: count -> first occurrence -> De Bruijn assembly
 -> sub-k-mer counts / features -> KF edges (threshold, global top-n).
 """
 import ctypes as C
+import os
+import threading
 from contextlib import contextmanager
 from dataclasses import dataclass, field
 from fractions import Fraction
@@ -901,8 +903,11 @@ def _copy_stream():
     return _COPY_STREAMS[dev]
 
 
+_HOST_THREADS = max(1, min(16, os.cpu_count() or 1))
+
+
 def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kmers=False, edges_threshold=0.0,
-                        edges_keep_top_k=None, kf_impl="auto", chunks: int = 8) -> HostGraph:
+                        edges_keep_top_k=None, kf_impl="auto", chunks: int = 8, host_expand: bool = True) -> HostGraph:
     """The whole path from host reads to host graph tensors (what ``create_graphs`` hands to the CPU-side PyG
     loaders), with the PCIe copies overlapped with the kernels: the reads go up in ``chunks`` pieces that are
     counted as they land, the DB graph and the features go down while the KF sets are scored, and each KF set
@@ -965,7 +970,10 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
     kcs = [kf_counts(db.node_codes, k, int(s)) for s in str(small_k).split(",")]
-    xs = [kf_features_f32(kc) for kc in kcs]
+    # Wide feature matrices cross PCIe as their uint8 counts and are expanded by the host cores while the edge lists are
+    # still on the wire (gg_host_features_f32); narrow ones, and matrices with dropped columns, come down as float32.
+    via_host = [host_expand and kc.counts.shape[1] >= 256 and int(kc.col_keep.numel()) == kc.counts.shape[1] for kc in kcs]
+    xs = [None if h else kf_features_f32(kc) for kc, h in zip(kcs, via_host)]
 
     d2h = 0
     keep_alive = []
@@ -987,7 +995,32 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
         keep_alive.extend(tensors)
         return out
 
-    h_codes, h_ei, h_w, *h_x = down([db.node_codes, db.edge_index, db.weight, *xs])
+    h_codes, h_ei, h_w, *h_small = down([db.node_codes, db.edge_index, db.weight, *[x for x in xs if x is not None]])
+    h_small = iter(h_small)
+    h_x, workers, worker_errors = [], [], []
+    for kc, h in zip(kcs, via_host):
+        if not h:
+            h_x.append(next(h_small))
+            continue
+        (h_counts,) = down([kc.counts])
+        landed = torch.cuda.Event()
+        landed.record(side)
+        out = torch.empty(kc.counts.shape, dtype=torch.float32, pin_memory=True)
+        lut = value_lut(kc.m).astype(np.float32)
+
+        def expand(h_counts=h_counts, landed=landed, out=out, lut=lut):
+            try:
+                landed.synchronize()
+                check(lib.gg_host_features_f32(C.c_void_p(h_counts.data_ptr()), h_counts.numel(),
+                                               C.c_void_p(lut.ctypes.data), C.c_void_p(out.data_ptr()), _HOST_THREADS),
+                      "gg_host_features_f32")
+            except BaseException as exc:  # noqa: BLE001 -- re-raised on the calling thread below
+                worker_errors.append(exc)
+
+        th = threading.Thread(target=expand)
+        th.start()
+        workers.append(th)
+        h_x.append(out)
     kf_ei, kf_w = [], []
     # one set at a time here (not stage-all-first as in build_graph): the first set's edges, the largest transfer of
     # the step, start going down while the second set is still being scored -- measured 17.2 vs 18.5 ms end to end
@@ -997,4 +1030,8 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
         kf_ei.append(e)
         kf_w.append(w)
     side.synchronize()
+    for th in workers:
+        th.join()
+    if worker_errors:
+        raise worker_errors[0]
     return HostGraph(k, db.num_nodes, h_codes, h_ei, h_w, h_x, kf_ei, kf_w, n_bytes, d2h)

@@ -288,6 +288,12 @@ GG_API int gg_db_prune_quantile(const int64_t* edge_src, const int64_t* edge_dst
                          double quantile, int64_t* out_src, int64_t* out_dst, double* out_w64, float* out_w32,
                          int64_t* out_count, void* workspace, size_t workspace_bytes, gg_stream_t st);
 
+/* Host-side half of gg_kf_features_f32 for the host-to-host build: h_x[i] = h_value_lut[h_counts[i]] on n_threads host
+ * threads (HOST pointers).  Lets the counts cross PCIe instead of the four times larger float32 features; valid when
+ * every column is kept (d_keep == d). */
+GG_API int gg_host_features_f32(const uint8_t* h_counts, int64_t n_elems, const float* h_value_lut, float* h_x,
+                         int n_threads);
+
 /* ------------------------------------------------------------------------
  * f3  biased random walks + skip-gram windows -> positive node pairs.  Replaces sample_biased_random_walks
  *     (gnn_common/gnn_utils.py:514-600; called per epoch / per batch by the sampling tasks).
