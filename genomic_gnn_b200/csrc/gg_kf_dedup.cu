@@ -368,8 +368,12 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
             wd[0] = x.x; wd[1] = x.y; wd[2] = x.z; wd[3] = x.w; wd[4] = y.x; wd[5] = y.y; wd[6] = y.z; wd[7] = y.w;
           }
           int mine = 0;
+          uint32_t nzq = 0;  // which of the 8 words hold a bit at all (most do not)
 #pragma unroll
-          for (int q = 0; q < kWordsPerThread; ++q) mine += __popc(wd[q]);
+          for (int q = 0; q < kWordsPerThread; ++q) {
+            mine += __popc(wd[q]);
+            nzq |= static_cast<uint32_t>(wd[q] != 0u) << q;
+          }
           int incl = mine;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
@@ -399,11 +403,11 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
             if (mine && pre < lo + n_ent && pre + mine > lo) {  // few lanes are busy here: keep the loop body tiny
               unsigned int idx = pre;
               uint32_t rank = rank0;
-#pragma unroll
-              for (int q = 0; q < kWordsPerThread; ++q) {
-                for (uint32_t word = wd[q]; word; word &= word - 1, ++idx, ++rank)
+              for (uint32_t nz = nzq; nz; nz &= nz - 1) {  // ascending words, empty ones skipped
+                const int wq = w + __ffs(nz) - 1;
+                for (uint32_t word = bm[wq]; word; word &= word - 1, ++idx, ++rank)
                   if (idx >= lo && idx < lo + n_ent)
-                    list[idx - lo] = make_uint2(static_cast<uint32_t>((w + q) * 32 + __ffs(word) - 1), rank);
+                    list[idx - lo] = make_uint2(static_cast<uint32_t>(wq * 32 + __ffs(word) - 1), rank);
               }
             }
             __syncthreads();
