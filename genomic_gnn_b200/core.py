@@ -161,6 +161,7 @@ class CountResult:
     n_bridges: int
     status: torch.Tensor      # int64 [8]
     n_nonzero: int = -1
+    pos_limit: int = 1 << 40  # every first-occurrence / bridge position is below this (bounds K2's radix sorts)
 
 
 def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, first_occurrence: bool = True,
@@ -210,14 +211,15 @@ def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, fi
                 check(lib.gg_first_occurrence(ptr(stream.data), stream.n_bytes, stream.fixed_len, k, stream.pos_base,
                                               ptr(hist), ptr(first), ptr(status), st), "gg_first_occurrence")
         if not sync:
-            return CountResult(k, hist, first, bridges, -1, status)
+            return CountResult(k, hist, first, bridges, -1, status, pos_limit=stream.pos_base + stream.n_bytes)
         st_host = status.cpu()
         if int(st_host[_lib.ST_BAD_BYTES]) > 0:
             raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN "
                              "(the reference fails on these at gnn_utils.py:471)")
         nb = int(st_host[_lib.ST_BRIDGES])
         if nb <= bridge_capacity:
-            return CountResult(k, hist, first, bridges, nb, status, int(st_host[_lib.ST_NONZERO]))
+            return CountResult(k, hist, first, bridges, nb, status, int(st_host[_lib.ST_NONZERO]),
+                               pos_limit=stream.pos_base + stream.n_bytes)
         bridge_capacity = nb  # rare: many internal N runs -- run again with room for all of them
 
 
@@ -261,7 +263,8 @@ def count_pairs_stride(sequences, k: int, stride: int) -> CountResult:
     st = status.cpu()
     if int(st[_lib.ST_BAD_BYTES]) > 0:
         raise ValueError(f"{int(st[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN")
-    return CountResult(k, hist, first, recs, int(st[_lib.ST_BRIDGES]), status, 0)
+    return CountResult(k, hist, first, recs, int(st[_lib.ST_BRIDGES]), status, 0,
+                       pos_limit=stream.pos_base + stream.n_bytes)
 
 
 # --------------------------------------------------------------------------- K2
@@ -299,8 +302,8 @@ def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weigh
     with _stage("k2_db"):
         check(lib.gg_db_build(ptr(cr.hist), ptr(cr.first_pos), ptr(cr.bridges), cr.n_bridges, k, int(bool(normalise)),
                               int(bool(create_all_kmers)), thr, ptr(node_codes), ptr(code_to_node), ptr(edges[0]),
-                              ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes, _stream()),
-              "gg_db_build")
+                              ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes,
+                              max(1, min(40, int(cr.pos_limit - 1).bit_length())), _stream()), "gg_db_build")
     n, e = (int(x) for x in ne.cpu())
     ei, w32, w64 = edges[:, :e].contiguous(), w32[:e], w64[:e]
     if keep_top_k is not None and e > 0:
@@ -965,7 +968,7 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
     if nb > cap:  # many internal N runs: redo the count in one piece with room for every bridge record
         cr = count_kp1mers(ReadStream(buf, n_bytes, length, n_reads), k, bridge_capacity=nb)
     else:
-        cr = CountResult(k, hist, first, bridges, nb, status, int(st_host[_lib.ST_NONZERO]))
+        cr = CountResult(k, hist, first, bridges, nb, status, int(st_host[_lib.ST_NONZERO]), pos_limit=n_bytes)
     if cr.n_nonzero == 0 and cr.n_bridges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)

@@ -124,15 +124,15 @@ __global__ void node_rank_kernel(const uint64_t* key, const uint32_t* val, int64
   }
 }
 
-__global__ void edge_sort_input_kernel(Universe un, const uint8_t* kept, const int32_t* code_to_node, uint64_t* key,
-                                       uint32_t* val) {
+__global__ void edge_sort_input_kernel(Universe un, const uint8_t* kept, const int32_t* code_to_node, int pos_bits,
+                                       uint64_t* key, uint32_t* val) {
   GRID_STRIDE(e, un.size()) {
     uint64_t kk = kInf;
     if (kept[e]) {
       uint32_t u, v;
       uint64_t cnt, pos;
       un.get(e, u, v, cnt, pos);
-      kk = (static_cast<uint64_t>(code_to_node[u]) << 40) | pos;
+      kk = (static_cast<uint64_t>(code_to_node[u]) << pos_bits) | pos;
     }
     key[e] = kk;
     val[e] = static_cast<uint32_t>(e);
@@ -225,9 +225,10 @@ extern "C" int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, cons
                            int64_t n_bridges, int k, int normalise, int create_all_kmers,
                            double edge_weight_threshold, int64_t* node_codes, int32_t* code_to_node,
                            int64_t* edge_src, int64_t* edge_dst, double* weight64, float* weight32,
-                           int64_t edge_capacity, int64_t* out_ne, void* workspace, size_t workspace_bytes,
+                           int64_t edge_capacity, int64_t* out_ne, void* workspace, size_t workspace_bytes, int pos_bits,
                            gg_stream_t st) {
   GG_REQUIRE(k >= 1 && k <= GG_MAX_K, GG_ERR_K, "k outside [1, GG_MAX_K]");
+  GG_REQUIRE(pos_bits >= 1 && pos_bits <= 40, GG_ERR_ARG, "pos_bits outside [1, 40]");
   GG_REQUIRE(hist && first_pos && node_codes && code_to_node && edge_src && edge_dst && out_ne && workspace,
              GG_ERR_ARG, "null buffer");
   GG_REQUIRE(n_bridges >= 0 && (n_bridges == 0 || bridges), GG_ERR_ARG, "bridge list");
@@ -258,17 +259,20 @@ extern "C" int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, cons
   node_sort_input_kernel<<<grid_for(n_codes), 256, 0, s>>>(l.node_key, n_codes, create_all_kmers, l.key_in, l.val_in);
   {
     size_t tb = l.cub_bytes;
-    // node keys are 2*pos(+1) < 2^41; the all-ones "absent" key still sorts last on the low 42 bits
+    // node keys are 2*pos(+1) < 2^(pos_bits + 1) (or the code < 4^k); the all-ones "absent" key still sorts last on
+    // one more bit than any real key has
+    const int node_bits = create_all_kmers ? 2 * k + 1 : pos_bits + 2;
     GG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(l.cub_temp, tb, l.key_in, l.key_out, l.val_in, l.val_out, n_codes,
-                                                  0, 42, s));
+                                                  0, node_bits, s));
   }
   node_rank_kernel<<<grid_for(n_codes), 256, 0, s>>>(l.key_out, l.val_out, n_codes, node_codes, code_to_node, out_ne);
 
-  edge_sort_input_kernel<<<grid_for(uni), 256, 0, s>>>(un, l.kept, code_to_node, l.key_in, l.val_in);
+  edge_sort_input_kernel<<<grid_for(uni), 256, 0, s>>>(un, l.kept, code_to_node, pos_bits, l.key_in, l.val_in);
   {
     size_t tb = l.cub_bytes;
-    GG_CUDA_CHECK(
-        cub::DeviceRadixSort::SortPairs(l.cub_temp, tb, l.key_in, l.key_out, l.val_in, l.val_out, uni, 0, 64, s));
+    // key = node rank (< 4^k) above pos_bits of first position; one more bit keeps the all-ones key of dropped edges last
+    GG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(l.cub_temp, tb, l.key_in, l.key_out, l.val_in, l.val_out, uni, 0,
+                                                  pos_bits + 2 * k + 1, s));
   }
   edge_write_kernel<<<grid_for(uni), 256, 0, s>>>(un, l.key_out, l.val_out, l.out_count, code_to_node, normalise,
                                                   edge_src, edge_dst, weight64, weight32, out_ne + 1);

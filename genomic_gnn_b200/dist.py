@@ -167,10 +167,14 @@ def reduce_counts(cr, comm: TorchComm):
     # launched without a host round trip (count_kp1mers(sync=False)) and this is the only one.
     n_bins = cr.hist.numel()
     world = comm.world
-    packed = torch.zeros(n_bins + world + 1, dtype=cr.hist.dtype, device=cr.hist.device)
+    packed = torch.zeros(n_bins + 3 * world + 1, dtype=cr.hist.dtype, device=cr.hist.device)
     packed[:n_bins] = cr.hist      # uint32 counts in int32 storage: exact while totals < 2^31
     packed[n_bins + comm.rank] = cr.status[1].to(packed.dtype)   # GG_ST_BRIDGES
     packed[n_bins + world] = cr.status[0].to(packed.dtype)       # GG_ST_BAD_BYTES
+    # end of this rank's piece of the global stream (bounds K2's sort keys), as two 30-bit halves in its own slots
+    limit = int(getattr(cr, "pos_limit", 1 << 40))
+    packed[n_bins + world + 1 + 2 * comm.rank] = limit & 0x3FFFFFFF
+    packed[n_bins + world + 2 + 2 * comm.rank] = limit >> 30
     comm.sum_tensor_(packed)
     hist = packed[:n_bins]
     first = cr.first_pos
@@ -188,4 +192,5 @@ def reduce_counts(cr, comm: TorchComm):
         (bridges,) = comm.gather_packed([cr.bridges[:n_bridges]], n_br, [0])
         n_bridges = int(bridges.shape[0])
     # occupied-bin count: not worth a device round trip here; -1 = unknown, build_graph checks the built graph instead
-    return CountResult(cr.k, hist, first, bridges, n_bridges, cr.status, -1)
+    pos_limit = max(int(tail[world + 1 + 2 * r]) | (int(tail[world + 2 + 2 * r]) << 30) for r in range(world))
+    return CountResult(cr.k, hist, first, bridges, n_bridges, cr.status, -1, pos_limit=pos_limit)

@@ -131,14 +131,15 @@ GG_API int gg_first_occurrence(const uint8_t* stream, int64_t n_bytes, int64_t f
  * edges grouped by source in node order, inside a source by first occurrence
  * of the pair; weight = count / out-count(source) in float64 (normalise) or
  * the raw count.  edge_weight_threshold < 0 disables the strict `>` filter
- * of utils.py:139-141.  out_ne[0] = N, out_ne[1] = E.
+ * of utils.py:139-141.  out_ne[0] = N, out_ne[1] = E.  pos_bits: every first_pos / bridge position is < 2^pos_bits
+ * (bounds the radix sorts; 40 is always safe).
  * ------------------------------------------------------------------------ */
 GG_API size_t gg_db_workspace_bytes(int k, int64_t n_bridges);
 GG_API int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, const gg_bridge_t* bridges, int64_t n_bridges,
                 int k, int normalise, int create_all_kmers, double edge_weight_threshold,
                 int64_t* node_codes, int32_t* code_to_node, int64_t* edge_src, int64_t* edge_dst,
                 double* weight64, float* weight32, int64_t edge_capacity, int64_t* out_ne,
-                void* workspace, size_t workspace_bytes, gg_stream_t st);
+                void* workspace, size_t workspace_bytes, int pos_bits, gg_stream_t st);
 
 /* ------------------------------------------------------------------------
  * K3  node features.  Replaces node_embedding_initial(method="kmer_frequency")
