@@ -333,20 +333,48 @@ class KFCounts:
         return self.k - self.s + 1
 
 
-def kf_counts(node_codes: torch.Tensor, k: int, s: int) -> KFCounts:
-    """K3.  Reference: gnn_utils.py:454-481."""
+_ARANGE = {}
+
+
+def _col_keep_from_host(present_host: np.ndarray, dev) -> torch.Tensor:
+    """int32 indices of the columns that occur (gnn_utils.py:474-481 drops the others); the usual all-present case
+    reuses a cached identity."""
+    d = int(present_host.shape[0])
+    if present_host.all():
+        key = (d, str(dev))
+        if key not in _ARANGE:
+            _ARANGE[key] = torch.arange(d, dtype=torch.int32, device=dev)
+        return _ARANGE[key]
+    return torch.from_numpy(np.nonzero(present_host)[0].astype(np.int32)).to(dev)
+
+
+def kf_counts_many(node_codes: torch.Tensor, k: int, small_ks) -> List[KFCounts]:
+    """K3 for several small_k with ONE device read for all their column-presence flags."""
     lib = _lib.load()
     dev = node_codes.device
     n = int(node_codes.numel())
-    d = 4**s
-    counts = torch.empty((n, d), dtype=torch.uint8, device=dev)
-    sqnorm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    present = torch.empty(d, dtype=torch.int32, device=dev)
-    with _stage(f"k3_counts_d{d}"):
-        check(lib.gg_kf_counts(ptr(node_codes), n, k, s, ptr(counts), ptr(sqnorm), ptr(present), _stream()),
-              "gg_kf_counts")
-    col_keep = torch.nonzero(present, as_tuple=False).reshape(-1).to(torch.int32)
-    return KFCounts(k, s, counts, sqnorm[:n], col_keep)
+    ds = [4**int(s) for s in small_ks]
+    present = torch.empty(sum(ds), dtype=torch.int32, device=dev)
+    out, lo = [], 0
+    for s, d in zip(small_ks, ds):
+        counts = torch.empty((n, d), dtype=torch.uint8, device=dev)
+        sqnorm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        with _stage(f"k3_counts_d{d}"):
+            check(lib.gg_kf_counts(ptr(node_codes), n, k, int(s), ptr(counts), ptr(sqnorm),
+                                   C.c_void_p(present.data_ptr() + 4 * lo), _stream()), "gg_kf_counts")
+        out.append(KFCounts(k, int(s), counts, sqnorm[:n], None))
+        lo += d
+    host = present.cpu().numpy()
+    lo = 0
+    for kc, d in zip(out, ds):
+        kc.col_keep = _col_keep_from_host(host[lo:lo + d], dev)
+        lo += d
+    return out
+
+
+def kf_counts(node_codes: torch.Tensor, k: int, s: int) -> KFCounts:
+    """K3.  Reference: gnn_utils.py:454-481."""
+    return kf_counts_many(node_codes, k, [int(s)])[0]
 
 
 def value_lut(m: int) -> np.ndarray:
@@ -861,7 +889,7 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
     if db.num_edges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     small = [int(s) for s in str(small_k).split(",")]
-    kcs = [kf_counts(db.node_codes, k, s) for s in small]
+    kcs = kf_counts_many(db.node_codes, k, small)
     xs = [kf_features_f32(kc) for kc in kcs]
     out = BuiltGraph(k, db, kcs, xs)
     if with_kf:
@@ -972,7 +1000,7 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
     if cr.n_nonzero == 0 and cr.n_bridges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
-    kcs = [kf_counts(db.node_codes, k, int(s)) for s in str(small_k).split(",")]
+    kcs = kf_counts_many(db.node_codes, k, [int(s) for s in str(small_k).split(",")])
     # Wide feature matrices cross PCIe as their uint8 counts and are expanded by the host cores while the edge lists are
     # still on the wire (gg_host_features_f32); narrow ones, and matrices with dropped columns, come down as float32.
     via_host = [host_expand and kc.counts.shape[1] >= 256 and int(kc.col_keep.numel()) == kc.counts.shape[1] for kc in kcs]
