@@ -33,8 +33,13 @@ sys.path.insert(0, ROOT)
 L2_FLUSH_BYTES = 256 << 20
 # kernels of libgg_b200.so launched by one step (CUB sort/scan kernels and memsets not counted):
 # K1 partition+bucket count (k = 7, 8; one counting kernel otherwise) + pending + first = 4, K2 = 6,
-# per small_k: K3 counts+features = 2, K4 emit = 1, K6 place+expand = 2
-OUR_LAUNCHES_PER_STEP = lambda n_small, k=8: (4 if k in (7, 8) else 3) + 6 + 5 * n_small  # noqa: E731
+# per small_k: K3 counts+features = 2 and either emit + place + expand = 3 or, for rows of <= 16 counts on >= 32768 nodes
+# (duplicate-row path), row keys + heads + class starts + class scoring + count sweep + place sweep + expand = 7
+def our_launches_per_step(small_ks, k, n_nodes):
+    total = (4 if k in (7, 8) else 3) + 6
+    for s in small_ks:
+        total += 2 + (7 if (4**s <= 16 and n_nodes >= 32768) else 3)
+    return total
 
 
 def parse_args():
@@ -378,7 +383,7 @@ def run_ours(a):
         "stage_ms": stage_ms,
         "e2e": {"value": a.reads / (e2e_ms / a.steps * 1e-3), "unit": "reads/s", "ms_per_step": e2e_ms / a.steps,
                 "h2d_bytes_per_step": (hi - lo) * a.read_len, "d2h_bytes_per_step": d2h_bytes},
-        "gpu_launches": OUR_LAUNCHES_PER_STEP(n_small, a.k) * a.steps,
+        "gpu_launches": our_launches_per_step([int(x) for x in a.small_k.split(",")], a.k, n_nodes) * a.steps,
         "roofline": {"kernel": dominant, **rooflines[dominant]} if dominant else None,
         "rooflines": rooflines,
         "clocks": clock_info,
