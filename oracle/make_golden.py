@@ -176,6 +176,7 @@ def large_case(ref, name, n_reads, k, small_ks, thr, topk, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--large", action="store_true")
+    ap.add_argument("--full", action="store_true", help="BASELINE configs 3 and 4 at their full 1M reads (minutes each)")
     ap.add_argument("--only", default=None)
     args = ap.parse_args()
     ref = ref_import.load()
@@ -200,6 +201,8 @@ def main():
             ("cfg3_k7_100k", 100_000, 7, (2, 5), 0.8, 0.01),
             ("cfg4_k8_100k", 100_000, 8, (2, 5), 0.8, 0.01),
         ]
+        if args.full:
+            cases += [("cfg3_k7_1m", 1_000_000, 7, (2, 5), 0.8, 0.01), ("cfg4_k8_1m", 1_000_000, 8, (2, 5), 0.8, 0.01)]
         for name, r, k, sks, thr, topk in cases:
             if args.only and args.only != name:
                 continue
