@@ -71,6 +71,8 @@ SIGNATURES = {
     "gg_db_prune_quantile": (_I32, [_P, _P, _P, _I64, _DBL, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gg_kmer_index": (_I32, [_P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P, _P]),
     "gg_host_features_f32": (_I32, [_P, _I64, _P, _P, _I32]),
+    "gg_host_features_f32_start": (_P, [_P, _I64, _P, _P, _I32, _I32, _P]),
+    "gg_host_job_wait": (_I32, [_P]),
     "gg_rw_pairs": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _DBL, _DBL, C.c_uint64, _I32, _P, _P, _P, _P, _I64,
                            _P, _P]),
     "gg_kf_select_workspace_bytes": (_SZ, [_I64]),

@@ -6,7 +6,6 @@ Stages: count -> first occurrence -> De Bruijn assembly
 """
 import ctypes as C
 import os
-import threading
 from contextlib import contextmanager
 from dataclasses import dataclass, field
 from fractions import Fraction
@@ -75,7 +74,7 @@ class LocalComm:
         return [int(x)]
 
     def gather_device_ints(self, t):
-        return [t.cpu().tolist()]
+        return [read_small(t).tolist()]
 
     def gather_cat(self, t, dim=0):
         return t
@@ -88,6 +87,26 @@ class LocalComm:
 
     def all_gather_padded_(self, buf, stride):
         return buf
+
+
+_MAILBOX = {}
+
+
+def read_small(t: torch.Tensor) -> torch.Tensor:
+    """Small device tensor -> host tensor through a persistent pinned mailbox (an async copy + one stream sync; a
+    plain .cpu() stages through pageable memory and costs ~10 us more per read, and a build does five of them).
+    The result is a view of the mailbox: consume it before the next read of the same dtype."""
+    if not t.is_cuda:
+        return t
+    n = int(t.numel())
+    key = (t.device, t.dtype)
+    box = _MAILBOX.get(key)
+    if box is None or box.numel() < n:
+        box = torch.empty(max(n, 4096), dtype=t.dtype, pin_memory=True)
+        _MAILBOX[key] = box
+    box[:n].copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return box[:n].view(t.shape)
 
 
 def _require_cuda():
@@ -212,7 +231,7 @@ def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, fi
                                               ptr(hist), ptr(first), ptr(status), st), "gg_first_occurrence")
         if not sync:
             return CountResult(k, hist, first, bridges, -1, status, pos_limit=stream.pos_base + stream.n_bytes)
-        st_host = status.cpu()
+        st_host = read_small(status).tolist()
         if int(st_host[_lib.ST_BAD_BYTES]) > 0:
             raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN "
                              "(the reference fails on these at gnn_utils.py:471)")
@@ -304,7 +323,7 @@ def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weigh
                               int(bool(create_all_kmers)), thr, ptr(node_codes), ptr(code_to_node), ptr(edges[0]),
                               ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes,
                               max(1, min(40, int(cr.pos_limit - 1).bit_length())), _stream()), "gg_db_build")
-    n, e = (int(x) for x in ne.cpu())
+    n, e = (int(x) for x in read_small(ne).tolist())
     ei, w32, w64 = edges[:, :e].contiguous(), w32[:e], w64[:e]
     if keep_top_k is not None and e > 0:
         pw = int(lib.gg_db_prune_workspace_bytes(e))
@@ -364,7 +383,7 @@ def kf_counts_many(node_codes: torch.Tensor, k: int, small_ks) -> List[KFCounts]
                                    C.c_void_p(present.data_ptr() + 4 * lo), _stream()), "gg_kf_counts")
         out.append(KFCounts(k, int(s), counts, sqnorm[:n], None))
         lo += d
-    host = present.cpu().numpy()
+    host = read_small(present).numpy().copy()
     lo = 0
     for kc, d in zip(out, ds):
         kc.col_keep = _col_keep_from_host(host[lo:lo + d], dev)
@@ -600,7 +619,7 @@ def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float,
     with _stage(f"k4_classes_d{d}"):
         check(lib.gg_kf_dedup_classes(ptr(counts), d, d, n, ptr(members), ptr(class_start), ptr(status), ptr(ws), wb, st),
               "gg_kf_dedup_classes")
-    n_classes, n_over = (int(x) for x in status.cpu())
+    n_classes, n_over = (int(x) for x in read_small(status).tolist())
     if n_over:
         raise GGError("duplicate-row KF path: a count above 15 does not fit the packed row key")
     adj = torch.empty(max(int(lib.gg_kf_dedup_adj_words(n_classes)), 1), dtype=torch.int32, device=dev)
@@ -990,7 +1009,7 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
     with _stage("k1_first"):
         check(lib.gg_first_occurrence(ptr(buf), n_bytes, length, k, 0, ptr(hist), ptr(first), ptr(status), st),
               "gg_first_occurrence")
-    st_host = status.cpu()
+    st_host = read_small(status).tolist()
     if int(st_host[_lib.ST_BAD_BYTES]) > 0:
         raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN")
     nb = int(st_host[_lib.ST_BRIDGES])
@@ -1029,7 +1048,7 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
 
     h_codes, h_ei, h_w, *h_small = down([db.node_codes, db.edge_index, db.weight, *[x for x in xs if x is not None]])
     h_small = iter(h_small)
-    h_x, workers, worker_errors = [], [], []
+    h_x, workers = [], []
     for kc, h in zip(kcs, via_host):
         if not h:
             h_x.append(next(h_small))
@@ -1040,30 +1059,26 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
         out = torch.empty(kc.counts.shape, dtype=torch.float32, pin_memory=True)
         lut = value_lut(kc.m).astype(np.float32)
 
-        def expand(h_counts=h_counts, landed=landed, out=out, lut=lut):
-            try:
-                landed.synchronize()
-                check(lib.gg_host_features_f32(C.c_void_p(h_counts.data_ptr()), h_counts.numel(),
-                                               C.c_void_p(lut.ctypes.data), C.c_void_p(out.data_ptr()), _HOST_THREADS),
-                      "gg_host_features_f32")
-            except BaseException as exc:  # noqa: BLE001 -- re-raised on the calling thread below
-                worker_errors.append(exc)
-
-        th = threading.Thread(target=expand)
-        th.start()
-        workers.append(th)
+        # a native thread waits for the event and expands (no interpreter scheduling on the path)
+        job = lib.gg_host_features_f32_start(C.c_void_p(h_counts.data_ptr()), h_counts.numel(),
+                                             C.c_void_p(lut.ctypes.data), C.c_void_p(out.data_ptr()), _HOST_THREADS,
+                                             dev.index, C.c_void_p(landed.cuda_event))
+        if not job:
+            raise GGError("gg_host_features_f32_start failed: " + lib.gg_last_error().decode("utf-8", "replace"))
+        workers.append((job, h_counts, out, lut, landed))
         h_x.append(out)
     kf_ei, kf_w = [], []
-    # one set at a time here (not stage-all-first as in build_graph): the first set's edges, the largest transfer of
-    # the step, start going down while the second set is still being scored -- measured 17.2 vs 18.5 ms end to end
-    for kc in kcs:
-        kf = kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl)
-        e, w = down([kf.edge_index, kf.weight])
-        kf_ei.append(e)
-        kf_w.append(w)
-    side.synchronize()
-    for th in workers:
-        th.join()
-    if worker_errors:
-        raise worker_errors[0]
+    try:
+        # one set at a time here (not stage-all-first as in build_graph): the first set's edges, the largest transfer
+        # of the step, start going down while the second set is still being scored -- measured 17.2 vs 18.5 ms
+        for kc in kcs:
+            kf = kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl)
+            e, w = down([kf.edge_index, kf.weight])
+            kf_ei.append(e)
+            kf_w.append(w)
+        side.synchronize()
+    finally:  # the native expansion jobs hold pointers into h_counts / out: always join them
+        rcs = [lib.gg_host_job_wait(C.c_void_p(job[0])) for job in workers]
+    for rc in rcs:
+        check(rc, "gg_host_job_wait")
     return HostGraph(k, db.num_nodes, h_codes, h_ei, h_w, h_x, kf_ei, kf_w, n_bytes, d2h)

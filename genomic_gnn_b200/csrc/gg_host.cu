@@ -35,3 +35,43 @@ extern "C" int gg_host_features_f32(const uint8_t* h_counts, int64_t n_elems, co
   for (auto& th : pool) th.join();
   return GG_OK;
 }
+
+// Asynchronous flavour: a native thread waits for the CUDA event that marks the arrival of the counts on the host and
+// then runs the expansion, so that nothing depends on the caller's interpreter getting scheduled (a Python worker
+// thread can wait up to a GIL switch interval, 5 ms, before it even starts).
+namespace {
+struct HostJob {
+  std::thread th;
+  int rc = GG_OK;
+};
+}  // namespace
+
+extern "C" void* gg_host_features_f32_start(const uint8_t* h_counts, int64_t n_elems, const float* h_value_lut,
+                                            float* h_x, int n_threads, int device, void* cuda_event) {
+  if (n_elems < 0 || n_threads < 1 || n_threads > 256 || (n_elems > 0 && (!h_counts || !h_value_lut || !h_x))) {
+    gg::set_error("gg_host_features_f32_start: bad argument");
+    return nullptr;
+  }
+  HostJob* job = new HostJob();
+  std::vector<float> lut(h_value_lut, h_value_lut + 256);
+  job->th = std::thread([=]() {
+    if (cuda_event) {
+      if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(static_cast<cudaEvent_t>(cuda_event)) != cudaSuccess) {
+        job->rc = GG_ERR_CUDA;
+        return;
+      }
+    }
+    job->rc = gg_host_features_f32(h_counts, n_elems, lut.data(), h_x, n_threads);
+  });
+  return job;
+}
+
+extern "C" int gg_host_job_wait(void* handle) {
+  GG_REQUIRE(handle != nullptr, GG_ERR_ARG, "null job");
+  HostJob* job = static_cast<HostJob*>(handle);
+  job->th.join();
+  const int rc = job->rc;
+  delete job;
+  if (rc != GG_OK) gg::set_error("host feature expansion failed (status %d)", rc);
+  return rc;
+}

@@ -79,7 +79,9 @@ class TorchComm:
         t = t.contiguous()
         out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=t.device)
         dist_.all_gather_into_tensor(out, t, group=self.group)
-        return out.view(self.world, t.numel()).tolist()
+        from .core import read_small
+
+        return read_small(out).view(self.world, t.numel()).tolist()
 
     def gather_cat(self, t: torch.Tensor, dim: int = 0) -> torch.Tensor:
         """all-gather(v) along ``dim`` and concatenate in rank order."""
@@ -180,7 +182,9 @@ def reduce_counts(cr, comm: TorchComm):
     first = cr.first_pos
     first.masked_fill_(first < 0, _I64_MAX)  # GG_NO_POS is -1 as int64: lift it above every real offset
     first = comm.min_tensor_(first)
-    tail = packed[n_bins:].cpu().tolist()
+    from .core import read_small
+
+    tail = read_small(packed[n_bins:]).tolist()
     if tail[world] > 0:
         raise ValueError(f"{tail[world]} input bytes outside the alphabet ACGTN")
     n_br = [int(x) for x in tail[:world]]

@@ -294,6 +294,12 @@ GG_API int gg_db_prune_quantile(const int64_t* edge_src, const int64_t* edge_dst
  * every column is kept (d_keep == d). */
 GG_API int gg_host_features_f32(const uint8_t* h_counts, int64_t n_elems, const float* h_value_lut, float* h_x,
                          int n_threads);
+/* Asynchronous flavour: returns a job handle (null on a bad argument) at once; a native thread first waits for
+ * `cuda_event` (a cudaEvent_t of device `device` marking the arrival of h_counts on the host; may be null) and then
+ * expands.  The buffers must stay valid until gg_host_job_wait(handle), which joins and returns the job's status. */
+GG_API void* gg_host_features_f32_start(const uint8_t* h_counts, int64_t n_elems, const float* h_value_lut, float* h_x,
+                                 int n_threads, int device, void* cuda_event);
+GG_API int gg_host_job_wait(void* handle);
 
 /* ------------------------------------------------------------------------
  * f3  biased random walks + skip-gram windows -> positive node pairs.  Replaces sample_biased_random_walks
