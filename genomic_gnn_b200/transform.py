@@ -4,8 +4,7 @@
                                                      src/representations/kmer_ssgnn_miniBatch.py:98-158
     word2index                                       kmer_ssgnn.py:148-153  (seq_to_kmers(seq, k, stride, inlcudeUNK=True))
 """
-import ctypes as C
-from typing import Dict, List, Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 import torch
