@@ -215,11 +215,20 @@ __device__ __forceinline__ uint32_t diag_mask(int r, int c0) {
   return first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : ~((1u << first) - 1u));
 }
 
-constexpr int kMemberChunk = 256;   // members of one class handled per sweep (per-member scratch in shared memory)
-constexpr int kListCap = 2048;      // entries of the shared-memory work list
-constexpr int kWinBlocks = 64;      // column blocks per window: 2048 bitmap words = 8 per thread
-constexpr int kWordsPerThread = kWinBlocks * kSegWords / kThreads;
-static_assert(kWordsPerThread == 8 && kSegWords % kWordsPerThread == 0, "a thread's words lie inside one column block");
+// The per-class kernels are latency-bound (dependent global loads, block barriers, phases in which few threads have
+// work).  The counting pass does little per class, so classes in flight matter most: 128-thread CTAs (0.17 -> 0.15 ms);
+// the placing pass has an edge copy-out that wants wide CTAs: 256 threads (128: 0.29 -> 0.33 ms).
+constexpr int kWinBlocks = 64;      // column blocks per window: 2048 bitmap words
+template <bool PLACE>
+struct RowsCfg {
+  static constexpr int kRowThreads = PLACE ? 256 : 128;
+  static constexpr int kMemberChunk = PLACE ? 256 : 128;  // members of one class per sweep (scratch in shared memory)
+  static constexpr int kListCap = PLACE ? 2048 : 1024;    // work-list entries (>= 1024: one column block always fits)
+  static constexpr int kWordsPerThread = kWinBlocks * kSegWords / kRowThreads;
+  static constexpr int kLanesPerBlock = kSegWords / kWordsPerThread;  // neighbouring lanes that share a column block
+  static_assert(kWordsPerThread % 4 == 0 && kSegWords % kWordsPerThread == 0 && kWordsPerThread <= 32,
+                "a thread's words lie inside one column block and load as uint4");
+};
 
 // One class per CTA iteration (classes are handed out through an atomic cursor: their sizes vary widely).
 //   bm    bitmap over node space: bit j set iff node j belongs to a neighbour class of this class
@@ -232,10 +241,13 @@ static_assert(kWordsPerThread == 8 && kSegWords % kWordsPerThread == 0, "a threa
 //         of that block, so a kept bit's rank is its rank inside the block minus dcnt; index of (block row, column
 //         block 0, row) in `offsets`
 template <bool PLACE>
-__global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsigned int* cursor) {
+__global__ void __launch_bounds__(RowsCfg<PLACE>::kRowThreads) class_rows_kernel(RowsArgs a, unsigned int* cursor) {
+  constexpr int kRowThreads = RowsCfg<PLACE>::kRowThreads, kMemberChunk = RowsCfg<PLACE>::kMemberChunk,
+                kListCap = RowsCfg<PLACE>::kListCap, kWordsPerThread = RowsCfg<PLACE>::kWordsPerThread,
+                kLanesPerBlock = RowsCfg<PLACE>::kLanesPerBlock;
   extern __shared__ __align__(16) uint32_t sm[];
   __shared__ int s_class;
-  __shared__ unsigned int s_n, s_warp[kThreads / 32];
+  __shared__ unsigned int s_n, s_warp[kRowThreads / 32];
   const int bm_words = a.n_jblocks * kSegWords;
   uint32_t* bm = sm;  // padded to whole windows
   const int bm_padded = (a.n_jblocks + kWinBlocks - 1) / kWinBlocks * kWinBlocks * kSegWords;
@@ -262,12 +274,12 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
       __syncthreads();  // s_class is rewritten at the top of the loop
       continue;
     }
-    for (int w = threadIdx.x; w < bm_padded / 4; w += kThreads) reinterpret_cast<uint4*>(bm)[w] = make_uint4(0u, 0u, 0u, 0u);
+    for (int w = threadIdx.x; w < bm_padded / 4; w += kRowThreads) reinterpret_cast<uint4*>(bm)[w] = make_uint4(0u, 0u, 0u, 0u);
     // neighbour classes of this class: compact the set bits of its adjacency row into the work list ...
     const uint32_t* arow = a.adj + static_cast<size_t>(c) * a.adj_words;
     uint32_t spill[2] = {0u, 0u};  // a word whose bits did not fit the list (dense adjacency rows)
     int spill_w[2] = {0, 0}, n_spill = 0;
-    for (int w = threadIdx.x; w < a.adj_words; w += kThreads) {
+    for (int w = threadIdx.x; w < a.adj_words; w += kRowThreads) {
       uint32_t bits = __ldg(arow + w);
       if (!bits) continue;
       unsigned int pos = atomicAdd(&s_n, static_cast<unsigned int>(__popc(bits)));
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
     // ... and set the bits of their members
     {
       const unsigned int n_nb = s_n < kNbCap ? s_n : kNbCap;
-      for (unsigned int e = threadIdx.x; e < n_nb; e += kThreads) {
+      for (unsigned int e = threadIdx.x; e < n_nb; e += kRowThreads) {
         const int b = static_cast<int>(nlist[e]);
         const int end = __ldg(a.class_start + b + 1);
         for (int m = __ldg(a.class_start + b); m < end; ++m) {
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
         }
       }
       if (n_spill == 3) {  // re-walk this thread's words: idempotent, bits already listed are simply set twice
-        for (int w = threadIdx.x; w < a.adj_words; w += kThreads) {
+        for (int w = threadIdx.x; w < a.adj_words; w += kRowThreads) {
           for (uint32_t bits = __ldg(arow + w); bits; bits &= bits - 1) {
             const int b = w * 32 + __ffs(bits) - 1;
             const int end = __ldg(a.class_start + b + 1);
@@ -320,21 +332,25 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
     }
     __syncthreads();
     if (!PLACE) {
-      // set bits per column block: a thread sums 8 consecutive words, 4 neighbouring lanes make one block
-      for (int w0 = 0; w0 < bm_padded; w0 += kThreads * kWordsPerThread) {
+      // set bits per column block: a thread sums its consecutive words, neighbouring lanes make one block
+      for (int w0 = 0; w0 < bm_padded; w0 += kRowThreads * kWordsPerThread) {
         const int w = w0 + threadIdx.x * kWordsPerThread;
-        const uint4 x = *reinterpret_cast<const uint4*>(bm + w), y = *reinterpret_cast<const uint4*>(bm + w + 4);
-        int t = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w) + __popc(y.x) + __popc(y.y) + __popc(y.z) + __popc(y.w);
-        t += __shfl_xor_sync(0xFFFFFFFFu, t, 1);
-        t += __shfl_xor_sync(0xFFFFFFFFu, t, 2);
+        int t = 0;
+#pragma unroll
+        for (int q = 0; q < kWordsPerThread; q += 4) {
+          const uint4 x = *reinterpret_cast<const uint4*>(bm + w + q);
+          t += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+        }
+#pragma unroll
+        for (int o = 1; o < kLanesPerBlock; o <<= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
         const int jb = w >> 5;
-        if ((lane & 3) == 0 && jb < a.n_jblocks) cj[jb] = static_cast<uint32_t>(t);
+        if ((lane & (kLanesPerBlock - 1)) == 0 && jb < a.n_jblocks) cj[jb] = static_cast<uint32_t>(t);
       }
     }
     const uint4 rc = load_row(a.counts, a.pitch, a.words, __ldg(a.members + m0));  // the row all members share
     for (int mc = m0; mc < m1; mc += kMemberChunk) {
       const int mcount = (m1 - mc) < kMemberChunk ? (m1 - mc) : kMemberChunk;
-      for (int mi = warp; mi < mcount; mi += kThreads / 32) {  // one warp per member: lane <-> word of its block
+      for (int mi = warp; mi < mcount; mi += kRowThreads / 32) {  // one warp per member: lane <-> word of its block
         const int i = __ldg(a.members + mc + mi), ib = i >> 10, r = i & (kBlock - 1);
         const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, __popc(bm[ib * kSegWords + lane] & ~diag_mask(r, lane * 32)));
         if (lane == 0) {
@@ -347,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
       __syncthreads();
       if (!PLACE) {
         const int n_tasks = mcount * a.n_jblocks;
-        for (int t = threadIdx.x; t < n_tasks; t += kThreads) {
+        for (int t = threadIdx.x; t < n_tasks; t += kRowThreads) {
           const int mi = t / a.n_jblocks, jb = t - mi * a.n_jblocks;
           const int i = memi[mi];
           if (i < 0) continue;
@@ -360,19 +376,16 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
       } else {
         // members ascend: column blocks before the first member's block hold no edge of this sweep
         for (int jw = (__ldg(a.members + mc) >> 10) / kWinBlocks * kWinBlocks; jw < a.n_jblocks; jw += kWinBlocks) {
-          // window of 64 column blocks: every thread owns 8 consecutive bitmap words (all inside one block)
+          // window of 64 column blocks: every thread owns 8 or 16 consecutive bitmap words (all inside one block)
           const int w = jw * kSegWords + threadIdx.x * kWordsPerThread;
-          uint32_t wd[kWordsPerThread];
-          {
-            const uint4 x = *reinterpret_cast<const uint4*>(bm + w), y = *reinterpret_cast<const uint4*>(bm + w + 4);
-            wd[0] = x.x; wd[1] = x.y; wd[2] = x.z; wd[3] = x.w; wd[4] = y.x; wd[5] = y.y; wd[6] = y.z; wd[7] = y.w;
-          }
           int mine = 0;
-          uint32_t nzq = 0;  // which of the 8 words hold a bit at all (most do not)
+          uint32_t nzq = 0;  // which of its words hold a bit at all (most do not)
 #pragma unroll
-          for (int q = 0; q < kWordsPerThread; ++q) {
-            mine += __popc(wd[q]);
-            nzq |= static_cast<uint32_t>(wd[q] != 0u) << q;
+          for (int q = 0; q < kWordsPerThread; q += 4) {
+            const uint4 x = *reinterpret_cast<const uint4*>(bm + w + q);
+            mine += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+            nzq |= (static_cast<uint32_t>(x.x != 0u) | (static_cast<uint32_t>(x.y != 0u) << 1) |
+                    (static_cast<uint32_t>(x.z != 0u) << 2) | (static_cast<uint32_t>(x.w != 0u) << 3)) << q;
           }
           int incl = mine;
 #pragma unroll
@@ -381,20 +394,20 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
             if (lane >= o) incl += v;
           }
           if (lane == 31) s_warp[warp] = static_cast<unsigned int>(incl);
-          // rank inside the column block: the 4 lanes of a block are neighbours
+          // rank inside the column block: the lanes of a block are neighbours
           const int excl_warp = incl - mine;
-          const uint32_t rank0 = static_cast<uint32_t>(excl_warp - __shfl_sync(0xFFFFFFFFu, excl_warp, lane & ~3));
+          const uint32_t rank0 = static_cast<uint32_t>(excl_warp - __shfl_sync(0xFFFFFFFFu, excl_warp, lane & ~(kLanesPerBlock - 1)));
           __syncthreads();
           unsigned int pre = static_cast<unsigned int>(excl_warp), total = 0;
 #pragma unroll
-          for (int q = 0; q < kThreads / 32; ++q) {
+          for (int q = 0; q < kRowThreads / 32; ++q) {
             const unsigned int t = s_warp[q];
             if (q < warp) pre += t;
             total += t;
           }
           // members whose block lies inside or before this window (ascending order: a prefix of the sweep)
           int n_mem = 0;
-          for (int q0 = 0; q0 < mcount; q0 += kThreads) {
+          for (int q0 = 0; q0 < mcount; q0 += kRowThreads) {
             const int mi = q0 + threadIdx.x;
             n_mem += __syncthreads_count(mi < mcount && (__ldg(a.members + mc + mi) >> 10) < jw + kWinBlocks);
           }
@@ -411,11 +424,11 @@ __global__ void __launch_bounds__(kThreads) class_rows_kernel(RowsArgs a, unsign
               }
             }
             __syncthreads();
-            for (unsigned int e = threadIdx.x; e < n_ent; e += kThreads)  // all lanes busy: the dots
+            for (unsigned int e = threadIdx.x; e < n_ent; e += kRowThreads)  // all lanes busy: the dots
               list[e].x |= dot16(rc, load_row(a.counts, a.pitch, a.words, static_cast<int>(list[e].x))) << 24;
             __syncthreads();
             // every thread takes one candidate column and walks the member rows (uniform loop, broadcast reads)
-            for (unsigned int e = threadIdx.x; e < n_ent; e += kThreads) {
+            for (unsigned int e = threadIdx.x; e < n_ent; e += kRowThreads) {
               const uint2 ent = list[e];
               const int j = static_cast<int>(ent.x & 0xFFFFFFu), jb = j >> 10;
               const uint32_t hi = ent.x & 0xFF000000u;
@@ -471,17 +484,16 @@ size_t esum_temp_bytes(long long n) {
 }
 
 size_t rows_smem(int n_jblocks, bool place) {
-  const size_t bm_words = static_cast<size_t>(n_jblocks) * kSegWords;
-  (void)place;
-  (void)bm_words;
   const size_t padded = (static_cast<size_t>(n_jblocks) + kWinBlocks - 1) / kWinBlocks * kWinBlocks * kSegWords;
+  const size_t list_cap = place ? RowsCfg<true>::kListCap : RowsCfg<false>::kListCap;
+  const size_t chunk = place ? RowsCfg<true>::kMemberChunk : RowsCfg<false>::kMemberChunk;
   return (padded + ((static_cast<size_t>(n_jblocks) + 3) & ~static_cast<size_t>(3))) * sizeof(uint32_t) +
-         kListCap * sizeof(uint2) + kMemberChunk * (sizeof(long long) + sizeof(int) + sizeof(uint32_t));
+         list_cap * sizeof(uint2) + chunk * (sizeof(long long) + sizeof(int) + sizeof(uint32_t));
 }
 
 int rows_grid(int n_classes, size_t smem) {
-  size_t per_sm = (200u << 10) / (smem + 1024);
-  if (per_sm > 8) per_sm = 8;
+  size_t per_sm = (220u << 10) / (smem + 1024);
+  if (per_sm > 12) per_sm = 12;
   if (per_sm < 1) per_sm = 1;
   const int cap = gg::sm_count() * static_cast<int>(per_sm);
   return n_classes < cap ? (n_classes < 1 ? 1 : n_classes) : cap;
@@ -624,7 +636,7 @@ extern "C" int gg_kf_dedup_count(int64_t n, int iblock_begin, int iblock_end, co
     GG_CUDA_CHECK(cudaMemsetAsync(cursor, 0, 4 * sizeof(unsigned int), s));
     GG_CUDA_CHECK(cudaFuncSetAttribute(class_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    class_rows_kernel<false><<<rows_grid(a.n_classes, smem), kThreads, smem, s>>>(a, cursor);
+    class_rows_kernel<false><<<rows_grid(a.n_classes, smem), RowsCfg<false>::kRowThreads, smem, s>>>(a, cursor);
     GG_CUDA_CHECK(cudaGetLastError());
   }
   cub::TransformInputIterator<unsigned long long, ToU64, const uint32_t*> it(a.rowtot, ToU64());
@@ -655,7 +667,7 @@ extern "C" int gg_kf_dedup_place(int64_t n, int iblock_begin, int iblock_end, co
   const size_t smem = rows_smem(a.n_jblocks, true);
   GG_CUDA_CHECK(cudaFuncSetAttribute(class_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
-  class_rows_kernel<true><<<rows_grid(a.n_classes, smem), kThreads, smem, gg::as_stream(st)>>>(a, cursor);
+  class_rows_kernel<true><<<rows_grid(a.n_classes, smem), RowsCfg<true>::kRowThreads, smem, gg::as_stream(st)>>>(a, cursor);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }
