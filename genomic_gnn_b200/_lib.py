@@ -46,6 +46,7 @@ SIGNATURES = {
     "gg_count_kp1mers_smem": (_I32, [_P, _I64, _I64, _I32, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
     "gg_count_part_workspace_bytes": (_SZ, [_I64, _I32]),
     "gg_count_kp1mers_part": (_I32, [_P, _I64, _I64, _I32, _I64, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "gg_count_merge": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P]),
     "gg_first_occurrence": (_I32, [_P, _I64, _I64, _I32, _I64, _P, _P, _P, _P]),
     "gg_db_workspace_bytes": (_SZ, [_I32, _I64]),
     "gg_db_build": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _DBL, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _I32, _P]),

@@ -183,8 +183,15 @@ class CountResult:
     pos_limit: int = 1 << 40  # every first-occurrence / bridge position is below this (bounds K2's radix sorts)
 
 
+def count_piece(k: int, dev) -> torch.Tensor:
+    """One contiguous int64 buffer holding a rank's K1 outputs -- [hist: bins int32][first_pos: bins int64]
+    [status: 8 int64][pos_limit] -- so that a multi-GPU build exchanges them with ONE all-gather (dist.reduce_counts)."""
+    bins = int(_lib.load().gg_hist_bins(k))
+    return torch.empty(bins // 2 + bins + _lib.ST_WORDS + 1, dtype=torch.int64, device=dev)
+
+
 def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, first_occurrence: bool = True,
-                  sync: bool = True, impl: str = "auto") -> CountResult:
+                  sync: bool = True, impl: str = "auto", piece: Optional[torch.Tensor] = None) -> CountResult:
     """K1 (+ first-occurrence scan).  Reference: src/utils.py:15-31,52-84.
 
     impl: "part" = keys partitioned into <= 8 streams of 15-bit keys, each counted with shared-memory atomics (k <= 8;
@@ -199,9 +206,15 @@ def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, fi
         raise ValueError(f"unknown counting implementation {impl!r}")
     dev = stream.data.device
     bins = int(lib.gg_hist_bins(k))
-    hist = torch.empty(bins, dtype=torch.int32, device=dev)
-    first = torch.empty(bins, dtype=torch.int64, device=dev)
-    status = torch.empty(_lib.ST_WORDS, dtype=torch.int64, device=dev)
+    if piece is None:
+        hist = torch.empty(bins, dtype=torch.int32, device=dev)
+        first = torch.empty(bins, dtype=torch.int64, device=dev)
+        status = torch.empty(_lib.ST_WORDS, dtype=torch.int64, device=dev)
+    else:  # views into the caller's exchange buffer (count_piece)
+        hist = piece[: bins // 2].view(torch.int32)
+        first = piece[bins // 2: bins // 2 + bins]
+        status = piece[bins // 2 + bins: bins // 2 + bins + _lib.ST_WORDS]
+        piece[-1:].fill_(stream.pos_base + stream.n_bytes)
     if impl == "auto":
         impl = "part" if int(lib.gg_count_part_workspace_bytes(stream.n_bytes, k)) else "l2"
     ws_bytes = 0
@@ -750,7 +763,8 @@ def kf_resolve(stages: List[KFStage], comm=None):
     if not live:
         return
     flat = live[0].staged.status4 if len(live) == 1 else torch.cat([st.staged.status4 for st in live])
-    table = comm.gather_device_ints(flat)          # [rank][4 * set + word]
+    with _stage("c3_gather_counts"):
+        table = comm.gather_device_ints(flat)      # [rank][4 * set + word]
     for i, st in enumerate(live):
         st.staged.after_counts(table[comm.rank][4 * i: 4 * i + 4])
         st.per_rank = [int(table[r][4 * i]) for r in range(comm.world)]
@@ -896,7 +910,10 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
         capacity = 1 << 16
         while True:  # K1 without a host round trip; reduce_counts reads every rank's status in its one device read
             try:
-                cr = dist.reduce_counts(count_kp1mers(stream, k, bridge_capacity=capacity, sync=False), comm)
+                piece = count_piece(k, stream.data.device)
+                local = count_kp1mers(stream, k, bridge_capacity=capacity, sync=False, piece=piece)
+                with _stage("c1_reduce_counts"):
+                    cr = dist.reduce_counts(local, comm, piece=piece)
                 break
             except OverflowError as exc:  # same decision on every rank: the counts were all-reduced
                 capacity = int(exc.args[0])

@@ -771,6 +771,25 @@ __global__ void __launch_bounds__(kBucketThreads, 1) count_direct_kernel(Args a,
   }
 }
 
+// Multi-GPU: every rank's (hist, first_pos) piece has been all-gathered; sum the histograms and take the earliest
+// first occurrence (GG_NO_POS is the largest unsigned value).
+__global__ void __launch_bounds__(256) merge_kernel(const unsigned long long* pieces, int world, long long stride,
+                                                    long long bins, uint32_t* hist_out, unsigned long long* first_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < bins;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint32_t sum = 0;
+    unsigned long long first = GG_NO_POS;
+    for (int r = 0; r < world; ++r) {
+      const unsigned long long* piece = pieces + r * stride;
+      sum += reinterpret_cast<const uint32_t*>(piece)[i];
+      const unsigned long long f = piece[bins / 2 + i];
+      first = f < first ? f : first;
+    }
+    hist_out[i] = sum;
+    first_out[i] = first;
+  }
+}
+
 int check_stream_args(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len, int k) {
   GG_REQUIRE(k >= 1 && k <= GG_MAX_K, GG_ERR_K, "k outside [1, GG_MAX_K]");
   GG_REQUIRE(n_bytes >= 0 && fixed_len >= 0 && fixed_len < (1ll << 31), GG_ERR_ARG, "negative size / row too long");
@@ -948,6 +967,23 @@ extern "C" int gg_count_kp1mers_part(const uint8_t* stream, int64_t n_bytes, int
   int grid = sms / nb * nb;
   if (grid < nb) grid = nb;
   count_bucket_kernel<<<grid, kBucketThreads, smem, s>>>(p.keys, p.capacity, p.cursor, nb, hist);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+/* pieces: `world` buffers of piece_stride 64-bit words each, laid out [hist: bins uint32][first_pos: bins uint64][...] */
+extern "C" int gg_count_merge(const uint64_t* pieces, int world, int64_t piece_stride, int k, uint32_t* hist_out,
+                              uint64_t* first_out, gg_stream_t st) {
+  GG_REQUIRE(k >= 1 && k <= GG_MAX_K, GG_ERR_K, "k outside [1, GG_MAX_K]");
+  const long long bins = static_cast<long long>(gg_hist_bins(k));
+  GG_REQUIRE(world >= 1 && piece_stride >= bins / 2 + bins, GG_ERR_ARG, "bad piece layout");
+  GG_REQUIRE(pieces && hist_out && first_out, GG_ERR_ARG, "null buffer");
+  long long grid = (bins + 255) / 256;
+  const long long cap = static_cast<long long>(gg::sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  merge_kernel<<<static_cast<unsigned>(grid), 256, 0, gg::as_stream(st)>>>(
+      reinterpret_cast<const unsigned long long*>(pieces), world, piece_stride, bins, hist_out,
+      reinterpret_cast<unsigned long long*>(first_out));
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

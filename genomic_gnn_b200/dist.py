@@ -159,10 +159,49 @@ class TorchComm:
 _I64_MAX = torch.iinfo(torch.int64).max
 
 
-def reduce_counts(cr, comm: TorchComm):
+def _reduce_counts_gathered(cr, comm: TorchComm, piece: torch.Tensor):
+    """C1 on the GPU: ONE all-gather of every rank's (hist, first_pos, status, pos_limit) piece, a merge kernel
+    (gg_count_merge) and one device read of the status words -- instead of two all-reduces and a dozen small tensor
+    ops (0.31 ms of a 2.3 ms step at 4 GPUs)."""
+    import ctypes as C
+
+    from . import _lib
+    from .core import CountResult, _stream, check, ptr, read_small
+
+    lib = _lib.load()
+    world, length = comm.world, int(piece.numel())
+    bins = int(cr.hist.numel())
+    everyone = torch.empty(world * length, dtype=torch.int64, device=piece.device)
+    dist_.all_gather_into_tensor(everyone, piece, group=comm.group)
+    hist = torch.empty(bins, dtype=torch.int32, device=piece.device)
+    first = torch.empty(bins, dtype=torch.int64, device=piece.device)
+    check(lib.gg_count_merge(ptr(everyone), world, length, cr.k, ptr(hist), ptr(first), _stream()), "gg_count_merge")
+    n_tail = _lib.ST_WORDS + 1
+    tails = read_small(everyone.view(world, length)[:, length - n_tail:].contiguous()).tolist()
+    bad = sum(int(t[_lib.ST_BAD_BYTES]) for t in tails)
+    if bad > 0:
+        raise ValueError(f"{bad} input bytes outside the alphabet ACGTN")
+    n_br = [int(t[_lib.ST_BRIDGES]) for t in tails]
+    capacity = int(cr.bridges.shape[0])
+    if max(n_br) > capacity:
+        raise OverflowError(max(n_br))  # the caller re-counts with room for every bridge record
+    bridges, n_bridges = cr.bridges, n_br[comm.rank]
+    if sum(n_br) > 0:
+        (bridges,) = comm.gather_packed([cr.bridges[:n_bridges]], n_br, [0])
+        n_bridges = int(bridges.shape[0])
+    pos_limit = max(int(t[-1]) for t in tails)
+    return CountResult(cr.k, hist, first, bridges, n_bridges, cr.status, -1, pos_limit=pos_limit)
+
+
+def reduce_counts(cr, comm: TorchComm, piece: torch.Tensor = None):
     """C1: merge the per-rank K1 results so that every rank holds the global
-    histogram, the global first occurrences and all bridge records."""
+    histogram, the global first occurrences and all bridge records.  With ``piece`` (core.count_piece, the buffer
+    the rank's K1 outputs live in) the exchange is a single all-gather + merge kernel; without it (host-logic tests
+    on gloo) it is two all-reduces."""
     from .core import CountResult
+
+    if piece is not None and piece.is_cuda:
+        return _reduce_counts_gathered(cr, comm, piece)
 
     # One SUM all-reduce carries the histogram and a small tail: every rank's bridge count (one slot per rank) and
     # the total of illegal bytes.  The tail is filled on the device from K1's status words, so the per-rank count was

@@ -123,6 +123,12 @@ GG_API int gg_count_kp1mers_part(const uint8_t* stream, int64_t n_bytes, int64_t
 GG_API int gg_first_occurrence(const uint8_t* stream, int64_t n_bytes, int64_t fixed_len, int k, int64_t pos_base,
                         const uint32_t* hist, uint64_t* first_pos, int64_t* status, gg_stream_t st);
 
+/* Multi-GPU merge of per-rank K1 results after ONE all-gather: pieces holds `world` buffers of piece_stride 64-bit
+ * words, each laid out [hist: 4^(k+1) uint32][first_pos: 4^(k+1) uint64][anything]; hist_out = sum of the histograms,
+ * first_out = earliest first occurrence. */
+GG_API int gg_count_merge(const uint64_t* pieces, int world, int64_t piece_stride, int k, uint32_t* hist_out,
+                   uint64_t* first_out, gg_stream_t st);
+
 /* ------------------------------------------------------------------------
  * K2  De Bruijn graph.  Replaces build_deBruijn_graph (src/utils.py:87-165)
  *     + torch_geometric.utils.from_networkx (gnn_tasks/utils.py:37).
