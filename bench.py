@@ -210,27 +210,6 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- our arm
-def to_host_pinned(tensors):
-    """Async D2H of every tensor into pinned memory; returns (host tensors, bytes)."""
-    import torch
-
-    out, nbytes = [], 0
-    for t in tensors:
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        h.copy_(t, non_blocking=True)
-        out.append(h)
-        nbytes += t.numel() * t.element_size()
-    return out, nbytes
-
-
-def graph_tensors(built):
-    ts = [built.db.node_codes, built.db.edge_index, built.db.weight]
-    ts += list(built.x)
-    for kf in built.kf:
-        ts += [kf.edge_index, kf.weight]
-    return ts
-
-
 def run_ours(a):
     import torch
 
@@ -279,8 +258,8 @@ def run_ours(a):
             return g, g.d2h_bytes
         stream = core.upload_reads(reads_host, pos_base=pos_base)     # H2D of this rank's reads (pinned source)
         built = core.build_graph(stream, **kw)
-        host, nbytes = to_host_pinned(graph_tensors(built)) if rank == 0 else ([], 0)
-        torch.cuda.current_stream().synchronize()                     # results are on the host
+        nbytes = core.graph_to_host(built).d2h_bytes if rank == 0 else 0   # rank 0 delivers the graph to the host
+        torch.cuda.current_stream().synchronize()
         return built, nbytes
 
     def timed_loop(fn, steps, warmup, timer=None):

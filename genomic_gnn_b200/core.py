@@ -960,6 +960,50 @@ class HostGraph:
     d2h_bytes: int = 0
 
 
+def graph_to_host(built: "BuiltGraph", host_expand: bool = True) -> "HostGraph":
+    """Every tensor of a device-resident graph in pinned host memory (what the CPU-side loaders want).  Large
+    transfers first; wide feature matrices cross PCIe as their uint8 counts and are expanded by host threads while the
+    edge lists follow (gg_host_features_f32), exactly as in build_graph_to_host."""
+    lib = _lib.load()
+    dev = built.db.node_codes.device
+    d2h = 0
+
+    def down(t):
+        nonlocal d2h
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        d2h += t.numel() * t.element_size()
+        return h
+
+    jobs, h_x = [], []
+    for kc, x in zip(built.kf_counts, built.x):
+        if not (host_expand and kc.counts.shape[1] >= 256 and int(kc.col_keep.numel()) == kc.counts.shape[1]):
+            h_x.append(down(x))
+            continue
+        h_counts = down(kc.counts)
+        landed = torch.cuda.Event()
+        landed.record()
+        out = torch.empty(kc.counts.shape, dtype=torch.float32, pin_memory=True)
+        lut = value_lut(kc.m).astype(np.float32)
+        job = lib.gg_host_features_f32_start(C.c_void_p(h_counts.data_ptr()), h_counts.numel(),
+                                             C.c_void_p(lut.ctypes.data), C.c_void_p(out.data_ptr()), _HOST_THREADS,
+                                             dev.index, C.c_void_p(landed.cuda_event))
+        if not job:
+            raise GGError("gg_host_features_f32_start failed: " + lib.gg_last_error().decode("utf-8", "replace"))
+        jobs.append((job, h_counts, out, lut, landed))
+        h_x.append(out)
+    try:
+        h_codes, h_ei, h_w = down(built.db.node_codes), down(built.db.edge_index), down(built.db.weight)
+        kf_ei = [down(kf.edge_index) for kf in built.kf]
+        kf_w = [down(kf.weight) for kf in built.kf]
+        torch.cuda.current_stream().synchronize()
+    finally:
+        rcs = [lib.gg_host_job_wait(C.c_void_p(job[0])) for job in jobs]
+    for rc in rcs:
+        check(rc, "gg_host_job_wait")
+    return HostGraph(built.k, built.db.num_nodes, h_codes, h_ei, h_w, h_x, kf_ei, kf_w, 0, d2h)
+
+
 _COPY_STREAMS = {}
 
 

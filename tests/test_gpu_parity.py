@@ -327,6 +327,14 @@ def test_host_to_host_build_matches_device_build(gg):
             assert torch.equal(host.kf_edge_index[i], dev.kf[i].edge_index.cpu())
             assert torch.equal(host.kf_weight[i], dev.kf[i].weight.cpu())
         assert host.h2d_bytes == arr.size
+    # the download half on its own (what a multi-GPU build calls on the rank that owns the host copy)
+    for expand in (True, False):
+        host = core.graph_to_host(dev, host_expand=expand)
+        assert host.x[1].is_pinned() and torch.equal(host.edge_index, dev.db.edge_index.cpu())
+        for i in range(2):
+            assert torch.equal(host.x[i], dev.x[i].cpu())
+            assert torch.equal(host.kf_edge_index[i], dev.kf[i].edge_index.cpu())
+            assert torch.equal(host.kf_weight[i], dev.kf[i].weight.cpu())
 
 
 def test_degenerate_inputs(gg):
