@@ -248,7 +248,6 @@ __global__ void __launch_bounds__(RowsCfg<PLACE>::kRowThreads) class_rows_kernel
   extern __shared__ __align__(16) uint32_t sm[];
   __shared__ int s_class;
   __shared__ unsigned int s_n, s_warp[kRowThreads / 32];
-  const int bm_words = a.n_jblocks * kSegWords;
   uint32_t* bm = sm;  // padded to whole windows
   const int bm_padded = (a.n_jblocks + kWinBlocks - 1) / kWinBlocks * kWinBlocks * kSegWords;
   uint32_t* cj = bm + bm_padded;
