@@ -310,6 +310,36 @@ def test_count_paths_agree(gg, k):
             core.count_kp1mers(core.upload_reads(["ACGTXCGT"]), 3, impl=impl)
 
 
+def test_count_pieces_merge_like_a_multi_gpu_build(gg):
+    """gg_count_merge on one GPU: two shards counted into two exchange pieces (core.count_piece), laid side by side as
+    an all-gather would, merged -- equals the count of the whole stream."""
+    import ctypes as C
+
+    from genomic_gnn_b200 import _lib, core
+
+    lib = _lib.load()
+    k = 7
+    reads = fast.synthetic_reads(6000, 150, seed=12)
+    reads[::29, 60] = ord("N")
+    whole = core.count_kp1mers(core.upload_reads(reads), k)
+    half = 3000
+    pieces = []
+    for lo, hi in ((0, half), (half, 6000)):
+        piece = core.count_piece(k, torch.device("cuda"))
+        core.count_kp1mers(core.upload_reads(reads[lo:hi], pos_base=lo * 150), k, sync=False, piece=piece)
+        pieces.append(piece)
+    everyone = torch.cat(pieces)
+    bins = whole.hist.numel()
+    hist = torch.empty(bins, dtype=torch.int32, device="cuda")
+    first = torch.empty(bins, dtype=torch.int64, device="cuda")
+    assert lib.gg_count_merge(C.c_void_p(everyone.data_ptr()), 2, pieces[0].numel(), k, C.c_void_p(hist.data_ptr()),
+                              C.c_void_p(first.data_ptr()), None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(hist, whole.hist) and torch.equal(first, whole.first_pos)
+    tails = everyone.view(2, -1)[:, -(_lib.ST_WORDS + 1):].cpu()
+    assert int(tails[:, _lib.ST_BRIDGES].sum()) == whole.n_bridges and tails[:, -1].tolist() == [half * 150, 6000 * 150]
+
+
 def test_host_to_host_build_matches_device_build(gg):
     from genomic_gnn_b200 import core
 
