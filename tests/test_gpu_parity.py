@@ -258,6 +258,41 @@ def test_kf_row_block_shards_concatenate(gg):
     assert torch.equal(torch.cat([p.weight64 for p in parts]), full.weight64)
 
 
+def test_packed_shards_expand_like_a_multi_gpu_exchange(gg):
+    """The multi-GPU KF exchange on one GPU: every row-block shard places its packed words into its segment of a
+    padded all-ranks buffer, gg_kf_expand reads the segments as one array -- equals the unsharded edge list.  Both
+    staging flavours (records from the tensor path, duplicate-row classes)."""
+    import ctypes as C
+
+    from genomic_gnn_b200 import _lib, core
+
+    lib = _lib.load()
+    reads = fast.synthetic_reads(5000, 150, seed=3)
+    built = core.build_graph(reads, 6, "2", with_kf=False)   # N = 4096 -> 4 row blocks
+    kc = built.kf_counts[0]
+    full = core.kf_edges(kc.counts, kc.sqnorm, 0.8, None, sq_max=kc.m**2)
+    for impl in ("tcgen05", "dedup"):
+        shards = [(0, 1), (1, 3), (3, 4)]
+        stages = [core.kf_stage(kc.counts, kc.sqnorm, 0.8, None, sq_max=kc.m**2, impl=impl, iblock_begin=a, iblock_end=b)
+                  for a, b in shards]
+        core.kf_resolve(stages)
+        sizes = [st.staged.n_recs for st in stages]
+        stride = max(sizes)
+        ordered = torch.zeros(len(shards) * stride, dtype=torch.int64, device="cuda")
+        for r, st in enumerate(stages):
+            st.staged.place(C.c_void_p(ordered.data_ptr() + 8 * r * stride))
+        total = sum(sizes)
+        ei = torch.empty((2, total), dtype=torch.int64, device="cuda")
+        w = torch.empty(total, dtype=torch.float32, device="cuda")
+        seg_first = (C.c_int64 * len(shards))(*[r * stride for r in range(len(shards))])
+        seg_size = (C.c_int64 * len(shards))(*sizes)
+        assert lib.gg_kf_expand(C.c_void_p(ordered.data_ptr()), len(shards), seg_first, seg_size,
+                                C.c_void_p(kc.sqnorm.data_ptr()), C.c_void_p(ei[0].data_ptr()),
+                                C.c_void_p(ei[1].data_ptr()), None, C.c_void_p(w.data_ptr()), None, None) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(ei, full.edge_index) and torch.equal(w, full.weight), impl
+
+
 # --------------------------------------------------------------------------- edge cases
 def test_input_forms_agree(gg):
     from genomic_gnn_b200 import core
