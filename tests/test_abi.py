@@ -45,6 +45,56 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.gg_kf_emit(None, None, None, None, None, None, 0, None, None, None) == -1  # GG_ERR_ARG
 
 
+def test_newer_entry_points_validate_their_arguments_without_a_gpu():
+    from genomic_gnn_b200 import _lib
+
+    lib = _lib.load()
+    ERR_ARG, ERR_K = -1, -2
+    assert lib.gg_count_part_workspace_bytes(150_000_000, 8) > 2 * 8 * 150_000_000   # 8 buckets of 16-bit keys
+    assert lib.gg_count_part_workspace_bytes(150_000_000, 9) == 0                     # table too large: L2 path
+    assert lib.gg_count_kp1mers_part(None, 16, 0, 9, 0, None, None, 0, None, None, 0, None) != 0
+    assert lib.gg_count_merge(None, 2, 10, 8, None, None, None) == ERR_ARG
+    assert lib.gg_count_merge(None, 2, 10, 99, None, None, None) == ERR_K
+    assert lib.gg_kf_dedup_classes(None, 16, 64, 100, None, None, None, None, 0, None) == ERR_ARG    # > 16 columns
+    assert lib.gg_kf_dedup_classes(None, 16, 16, (1 << 20) + 1, None, None, None, None, 0, None) == ERR_ARG
+    assert lib.gg_kf_dedup_adj_words(17444) == 17444 * 546
+    assert lib.gg_kf_dedup_score(None, 16, 16, None, None, None, 10, None, 50, None, None) == ERR_ARG  # p_max not a square
+    assert lib.gg_kf_dedup_count(100, 0, 5, None, None, None, 10, None, None, 0, None) == ERR_ARG    # shard past the end
+    assert lib.gg_db_build(None, None, None, 0, 8, 1, 0, -1.0, None, None, None, None, None, None, 0, None, None, 0, 41,
+                           None) == ERR_ARG
+    assert lib.gg_rw_pairs(None, None, None, 10, None, 10, 1, 64, 3, 1.0, 1.0, 0, 0, None, None, None, None, 0, None,
+                           None) == ERR_ARG                                                     # walk_length > 32
+    assert b"walk_length" in lib.gg_last_error()
+    assert lib.gg_rw_pairs(None, None, None, 10, None, 10, 1, 2, 3, 0.0, 1.0, 0, 0, None, None, None, None, 0, None,
+                           None) == ERR_ARG                                                     # p must be positive
+    assert lib.gg_host_job_wait(None) == ERR_ARG
+    assert not lib.gg_host_features_f32_start(None, 10, None, None, 4, 0, None)
+
+
+def test_host_feature_expansion_is_the_table_lookup():
+    """gg_host_features_f32 is host code: the CPU suite can run it.  Same 256-entry value table as the device kernel
+    (core.value_lut), any thread count, sizes that do not divide evenly."""
+    import ctypes as C
+
+    import numpy as np
+
+    from genomic_gnn_b200 import _lib
+    from genomic_gnn_b200.core import value_lut
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    lut = value_lut(4).astype(np.float32)
+    for n, threads in ((0, 1), (17, 1), (100_003, 3), (1 << 20, 8)):
+        counts = rng.integers(0, 5, size=n, dtype=np.uint8)
+        out = np.full(n, -1.0, dtype=np.float32)
+        rc = lib.gg_host_features_f32(C.c_void_p(counts.ctypes.data), n, C.c_void_p(lut.ctypes.data),
+                                      C.c_void_p(out.ctypes.data), threads)
+        assert rc == 0 and np.array_equal(out, lut[counts])
+    job = lib.gg_host_features_f32_start(C.c_void_p(counts.ctypes.data), n, C.c_void_p(lut.ctypes.data),
+                                         C.c_void_p(out.ctypes.data), 4, 0, None)   # no CUDA event: starts at once
+    assert job and lib.gg_host_job_wait(C.c_void_p(job)) == 0 and np.array_equal(out, lut[counts])
+
+
 def test_product_fails_loudly_without_cuda():
     import torch
 
