@@ -167,6 +167,52 @@ def test_pipeline_matches_oracle(gg, k, n_reads, small_k, thr, topk):
         assert np.array_equal(got.kf[i].weight64.cpu().numpy(), want[f"edge_weight_KF{i}"])
 
 
+def test_randomised_ragged_inputs_match_oracle(gg):
+    """Forty seeded random inputs in the awkward corner of the input space -- reads of 0..45 bases, N runs, k from 2
+    to 8 (reads shorter than k+1, windows bridged over N, single-pair graphs), string lists and fixed-length rows --
+    through the whole device pipeline against the oracle: node order, De Bruijn edges, float32 weights, features,
+    KF edges and float64 KF weights, all exact."""
+    from genomic_gnn_b200 import core
+
+    rng = np.random.default_rng(2024)
+    done = 0
+    for case in range(60):
+        k = int(rng.integers(2, 9))
+        n_reads = int(rng.integers(1, 70))
+        p_n = float(rng.choice([0.0, 0.02, 0.15]))
+        if case % 3 == 0:   # fixed-length rows (uint8 matrix input)
+            length = int(rng.integers(k + 1, 46))
+            arr = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n_reads, length))].copy()
+            arr[rng.random(arr.shape) < p_n] = ord("N")
+            reads, oracle_reads = arr, fast.reads_to_strings(arr)
+        else:
+            oracle_reads = []
+            for _ in range(n_reads):
+                ln = int(rng.integers(0, 46))
+                r = "".join("ACGT"[c] for c in rng.integers(0, 4, ln))
+                oracle_reads.append("".join("N" if rng.random() < p_n else ch for ch in r))
+            reads = oracle_reads
+        s = int(rng.integers(1, min(k, 3) + 1))
+        thr = float(rng.choice([0.0, 0.5, 0.8]))
+        topk = [None, 0.05][int(rng.integers(0, 2))]
+        try:
+            want = fast.build_graph(oracle_reads, k, str(s), edges_threshold=thr, edges_keep_top_k=topk)
+        except (ValueError, IndexError):
+            with pytest.raises((ValueError, IndexError)):      # no k-mer pair at all: both sides refuse
+                core.build_graph(reads, k, str(s), edges_threshold=thr, edges_keep_top_k=topk)
+            continue
+        got = core.build_graph(reads, k, str(s), edges_threshold=thr, edges_keep_top_k=topk)
+        tag = (case, k, s, thr, topk)
+        assert np.array_equal(got.db.node_codes.cpu().numpy(), want["node_codes"]), tag
+        assert np.array_equal(got.db.edge_index.cpu().numpy(), want["edge_index"]), tag
+        assert np.array_equal(got.db.weight.cpu().numpy().view(np.int32), want["weight"].view(np.int32)), tag
+        assert np.array_equal(got.x[0].cpu().numpy(), want["y_0"]), tag
+        assert np.array_equal(got.kf[0].edge_index.cpu().numpy(), want["edge_index_KF0"]), tag
+        assert np.array_equal(got.kf[0].weight64.cpu().numpy(), want["edge_weight_KF0"]), tag
+        done += 1
+    assert done >= 40
+
+
 @pytest.mark.parametrize("k,s,thr", [(6, 3, 0.5), (6, 2, 0.8), (6, 2, 0.0), (5, 1, 0.9), (7, 2, 0.75), (3, 2, 0.3)])
 def test_kf_impls_agree(gg, k, s, thr):
     """Narrow rows (D = 4, 16, 64): tensor path (rows padded to >= 32 bytes, 32B/64B swizzle), dp4a kernel and the
