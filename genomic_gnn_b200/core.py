@@ -615,8 +615,8 @@ class StagedClasses:
 def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max: int, iblock_begin=0,
                    iblock_end=None) -> StagedClasses:
     """K4' for narrow rows (<= 16 columns, counts <= 15): group identical rows into classes, score the class pairs,
-    count the shard's edges.  Two small device reads: the number of classes (sizes the bit matrix) and the number
-    of edges (sizes the output)."""
+    count the shard's edges.  One small device read here (the number of classes sizes the bit matrix); the number of
+    edges stays on the device for kf_resolve."""
     lib = _lib.load()
     dev = counts.device
     n, d = int(counts.shape[0]), int(counts.shape[1])
