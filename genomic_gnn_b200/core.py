@@ -745,7 +745,8 @@ def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         # a binding top-n overflows once and is re-run with the exact size)
         n_pairs = n * (n - 1) // 2
         guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
-        rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20)))
+        # ... capped at 2 GB of records: at k=10 the budget alone would be 1.1e10 records (176 GB)
+        rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20), 1 << 27))
         recs, _, rowcnt, params, scored, status = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end,
                                                           impl, rec_capacity=rec_capacity, sync=False)
 

@@ -339,6 +339,34 @@ def test_packed_shards_expand_like_a_multi_gpu_exchange(gg):
         assert torch.equal(ei, full.edge_index) and torch.equal(w, full.weight), impl
 
 
+def test_k10_million_nodes(gg):
+    """BASELINE config 5's node count (k=10: 1,048,576 nodes, the most the KF kernels take) with thresholds that keep the
+    edge lists in memory: the duplicate-row path and the tensor path agree edge for edge on the small_k=2 set
+    (5.5e11 pairs), and sampled rows of the small_k=5 set (1.1e15 MACs through tcgen05) match numpy."""
+    from genomic_gnn_b200 import core
+
+    reads = fast.synthetic_reads(2_000_000, 150, seed=0)
+    built = core.build_graph(reads, 10, "2,5", with_kf=False)
+    n = built.db.num_nodes
+    assert n == 4**10 and built.db.num_edges == 4**11
+    kc2, kc5 = built.kf_counts
+    a = core.kf_edges(kc2.counts, kc2.sqnorm, 0.95, None, sq_max=kc2.m**2, impl="dedup")
+    b = core.kf_edges(kc2.counts, kc2.sqnorm, 0.95, None, sq_max=kc2.m**2, impl="tcgen05")
+    assert a.edge_index.shape[1] > 10_000_000
+    assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
+    del a, b
+    kf5 = core.kf_edges(kc5.counts, kc5.sqnorm, 0.8, None, sq_max=kc5.m**2)
+    rng = np.random.default_rng(0)
+    rows = np.sort(rng.choice(n, 16, replace=False))
+    c = kc5.counts.cpu().numpy()
+    sq = kc5.sqnorm.cpu().numpy().astype(np.int64)
+    cos = (c[rows].astype(np.int32) @ c.T.astype(np.int32)) / np.sqrt(sq[rows][:, None] * sq[None, :])
+    ei = kf5.edge_index.cpu().numpy()
+    assert np.all(ei[0] < ei[1])
+    for r, row in zip(rows, cos):
+        assert np.array_equal(np.nonzero((row > 0.8) & (np.arange(n) > r))[0], np.sort(ei[1][ei[0] == r])), r
+
+
 # --------------------------------------------------------------------------- edge cases
 def test_input_forms_agree(gg):
     from genomic_gnn_b200 import core
