@@ -218,17 +218,20 @@ __device__ __forceinline__ uint32_t diag_mask(int r, int c0) {
 // The per-class kernels are latency-bound (dependent global loads, block barriers, phases in which few threads have
 // work).  The counting pass does little per class, so classes in flight matter most: 128-thread CTAs (0.17 -> 0.15 ms);
 // the placing pass has an edge copy-out that wants wide CTAs: 256 threads (128: 0.29 -> 0.33 ms).
-constexpr int kWinBlocks = 64;      // column blocks per window: 2048 bitmap words
-template <bool PLACE>
+// BIG: bitmaps of more than 64 KB (k >= 10) leave room for one CTA per SM only, which then wants all the threads it can
+// get and wide windows (k=10: 16 windows of 64 blocks per class became 4 of 256; count 23 -> 10 ms, place 37 -> 18 ms).
+template <bool PLACE, bool BIG>
 struct RowsCfg {
-  static constexpr int kRowThreads = PLACE ? 256 : 128;
-  static constexpr int kMemberChunk = PLACE ? 256 : 128;  // members of one class per sweep (scratch in shared memory)
-  static constexpr int kListCap = PLACE ? 2048 : 1024;    // work-list entries (>= 1024: one column block always fits)
+  static constexpr int kRowThreads = BIG ? 1024 : (PLACE ? 256 : 128);
+  static constexpr int kWinBlocks = BIG ? 256 : 64;       // column blocks per window
+  static constexpr int kMemberChunk = PLACE || BIG ? 256 : 128;  // members of one class per sweep (shared-memory scratch)
+  static constexpr int kListCap = PLACE || BIG ? 2048 : 1024;    // work-list entries (>= 1024: a column block always fits)
   static constexpr int kWordsPerThread = kWinBlocks * kSegWords / kRowThreads;
   static constexpr int kLanesPerBlock = kSegWords / kWordsPerThread;  // neighbouring lanes that share a column block
   static_assert(kWordsPerThread % 4 == 0 && kSegWords % kWordsPerThread == 0 && kWordsPerThread <= 32,
                 "a thread's words lie inside one column block and load as uint4");
 };
+constexpr size_t kBigBitmapBytes = 64 << 10;
 
 // One class per CTA iteration (classes are handed out through an atomic cursor: their sizes vary widely).
 //   bm    bitmap over node space: bit j set iff node j belongs to a neighbour class of this class
@@ -240,11 +243,12 @@ struct RowsCfg {
 //         at columns <= i, i.e. the candidates the strict upper triangle drops -- all of them precede every kept bit
 //         of that block, so a kept bit's rank is its rank inside the block minus dcnt; index of (block row, column
 //         block 0, row) in `offsets`
-template <bool PLACE>
-__global__ void __launch_bounds__(RowsCfg<PLACE>::kRowThreads) class_rows_kernel(RowsArgs a, unsigned int* cursor) {
-  constexpr int kRowThreads = RowsCfg<PLACE>::kRowThreads, kMemberChunk = RowsCfg<PLACE>::kMemberChunk,
-                kListCap = RowsCfg<PLACE>::kListCap, kWordsPerThread = RowsCfg<PLACE>::kWordsPerThread,
-                kLanesPerBlock = RowsCfg<PLACE>::kLanesPerBlock;
+template <bool PLACE, bool BIG>
+__global__ void __launch_bounds__(RowsCfg<PLACE, BIG>::kRowThreads) class_rows_kernel(RowsArgs a, unsigned int* cursor) {
+  using Cfg = RowsCfg<PLACE, BIG>;
+  constexpr int kRowThreads = Cfg::kRowThreads, kMemberChunk = Cfg::kMemberChunk, kListCap = Cfg::kListCap,
+                kWordsPerThread = Cfg::kWordsPerThread, kLanesPerBlock = Cfg::kLanesPerBlock,
+                kWinBlocks = Cfg::kWinBlocks;
   extern __shared__ __align__(16) uint32_t sm[];
   __shared__ int s_class;
   __shared__ unsigned int s_n, s_warp[kRowThreads / 32];
@@ -482,12 +486,26 @@ size_t esum_temp_bytes(long long n) {
   return bytes;
 }
 
-size_t rows_smem(int n_jblocks, bool place) {
-  const size_t padded = (static_cast<size_t>(n_jblocks) + kWinBlocks - 1) / kWinBlocks * kWinBlocks * kSegWords;
-  const size_t list_cap = place ? RowsCfg<true>::kListCap : RowsCfg<false>::kListCap;
-  const size_t chunk = place ? RowsCfg<true>::kMemberChunk : RowsCfg<false>::kMemberChunk;
+int rows_grid(int n_classes, size_t smem);
+
+bool rows_big(int n_jblocks) { return static_cast<size_t>(n_jblocks) * kSegWords * sizeof(uint32_t) > kBigBitmapBytes; }
+
+template <bool PLACE, bool BIG>
+size_t rows_smem_of(int n_jblocks) {
+  using Cfg = RowsCfg<PLACE, BIG>;
+  const size_t padded = (static_cast<size_t>(n_jblocks) + Cfg::kWinBlocks - 1) / Cfg::kWinBlocks * Cfg::kWinBlocks * kSegWords;
   return (padded + ((static_cast<size_t>(n_jblocks) + 3) & ~static_cast<size_t>(3))) * sizeof(uint32_t) +
-         list_cap * sizeof(uint2) + chunk * (sizeof(long long) + sizeof(int) + sizeof(uint32_t));
+         Cfg::kListCap * sizeof(uint2) + Cfg::kMemberChunk * (sizeof(long long) + sizeof(int) + sizeof(uint32_t));
+}
+
+template <bool PLACE, bool BIG>
+int launch_rows(const RowsArgs& a, unsigned int* cursor, cudaStream_t s) {
+  const size_t smem = rows_smem_of<PLACE, BIG>(a.n_jblocks);
+  GG_CUDA_CHECK(cudaFuncSetAttribute(class_rows_kernel<PLACE, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  class_rows_kernel<PLACE, BIG><<<rows_grid(a.n_classes, smem), RowsCfg<PLACE, BIG>::kRowThreads, smem, s>>>(a, cursor);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
 }
 
 int rows_grid(int n_classes, size_t smem) {
@@ -631,12 +649,9 @@ extern "C" int gg_kf_dedup_count(int64_t n, int iblock_begin, int iblock_end, co
   GG_CUDA_CHECK(cudaMemsetAsync(a.rowtot, 0, elems * sizeof(uint32_t), s));
   if (n_classes > 0 && elems > 1) {
     GG_REQUIRE(adj && members && class_start, GG_ERR_ARG, "null buffer");
-    const size_t smem = rows_smem(a.n_jblocks, false);
     GG_CUDA_CHECK(cudaMemsetAsync(cursor, 0, 4 * sizeof(unsigned int), s));
-    GG_CUDA_CHECK(cudaFuncSetAttribute(class_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    class_rows_kernel<false><<<rows_grid(a.n_classes, smem), RowsCfg<false>::kRowThreads, smem, s>>>(a, cursor);
-    GG_CUDA_CHECK(cudaGetLastError());
+    if (int rc = rows_big(a.n_jblocks) ? launch_rows<false, true>(a, cursor, s) : launch_rows<false, false>(a, cursor, s))
+      return rc;
   }
   cub::TransformInputIterator<unsigned long long, ToU64, const uint32_t*> it(a.rowtot, ToU64());
   GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, reinterpret_cast<unsigned long long*>(offsets),
@@ -663,10 +678,8 @@ extern "C" int gg_kf_dedup_place(int64_t n, int iblock_begin, int iblock_end, co
   a.words = row_words(counts, pitch, d_valid);
   a.ordered = reinterpret_cast<uint2*>(ordered);
   a.capacity = capacity;
-  const size_t smem = rows_smem(a.n_jblocks, true);
-  GG_CUDA_CHECK(cudaFuncSetAttribute(class_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-  class_rows_kernel<true><<<rows_grid(a.n_classes, smem), RowsCfg<true>::kRowThreads, smem, gg::as_stream(st)>>>(a, cursor);
-  GG_CUDA_CHECK(cudaGetLastError());
+  if (int rc = rows_big(a.n_jblocks) ? launch_rows<true, true>(a, cursor, gg::as_stream(st))
+                                     : launch_rows<true, false>(a, cursor, gg::as_stream(st)))
+    return rc;
   return GG_OK;
 }
