@@ -62,7 +62,8 @@ def parse_args():
 
 
 def workload_name(a):
-    return (f"config4: k={a.k}, small_k={a.small_k}, KF threshold={a.threshold}, top_k={a.top_k}, "
+    name = {8: "config4", 7: "config3", 6: "config2", 3: "config1"}.get(a.k, "custom")  # BASELINE.json configs by k
+    return (f"{name}: k={a.k}, small_k={a.small_k}, KF threshold={a.threshold}, top_k={a.top_k}, "
             f"{a.reads} synthetic {a.read_len}-bp reads (uniform ACGT, seed 0)")
 
 
