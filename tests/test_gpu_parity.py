@@ -360,7 +360,9 @@ def test_k10_million_nodes(gg):
     rows = np.sort(rng.choice(n, 16, replace=False))
     c = kc5.counts.cpu().numpy()
     sq = kc5.sqnorm.cpu().numpy().astype(np.int64)
-    cos = (c[rows].astype(np.int32) @ c.T.astype(np.int32)) / np.sqrt(sq[rows][:, None] * sq[None, :])
+    a_rows = c[rows].astype(np.float32)                       # counts <= 6: float32 dots are exact
+    dots = np.concatenate([a_rows @ c[lo:lo + 131072].T.astype(np.float32) for lo in range(0, n, 131072)], axis=1)
+    cos = dots.astype(np.float64) / np.sqrt(sq[rows][:, None] * sq[None, :])
     ei = kf5.edge_index.cpu().numpy()
     assert np.all(ei[0] < ei[1])
     for r, row in zip(rows, cos):
