@@ -21,7 +21,8 @@ from .builders import (  # noqa: F401
     networkx_to_dataloader_full_batch,
     networkx_to_dataloader_mini_batch,
 )
-from .core import build_graph, build_graph_to_host  # noqa: F401
+from .core import build_graph, build_graph_to_host, graph_to_host  # noqa: F401
+from . import gnn  # noqa: F401  (row f1: GCN encoder, contrastive trainer, edit-distance regressor)
 from .sampler import sample_biased_random_walks, sample_biased_random_walks_miniBatch  # noqa: F401
 from .transform import kmers_to_index, transform  # noqa: F401
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "gg_host_features_f32": (_I32, [_P, _I64, _P, _P, _I32]),
     "gg_host_features_f32_start": (_P, [_P, _I64, _P, _P, _I32, _I32, _P]),
     "gg_host_job_wait": (_I32, [_P]),
+    "gg_spmm_csr_f32": (_I32, [_P, _P, _P, _I64, _P, _I32, _P, _P]),
     "gg_rw_pairs": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _DBL, _DBL, C.c_uint64, _I32, _P, _P, _P, _P, _I64,
                            _P, _P]),
     "gg_kf_select_workspace_bytes": (_SZ, [_I64]),

@@ -324,6 +324,14 @@ GG_API int gg_rw_pairs(const int64_t* row_ptr, const int64_t* col, const float* 
                 double p, double q, uint64_t seed, int mode, int64_t* pair_counts, const int64_t* pair_offsets,
                 int64_t* pairs_src, int64_t* pairs_dst, int64_t capacity, int64_t* walks_out, gg_stream_t st);
 
+/* ------------------------------------------------------------------------
+ * f1  sparse aggregation of the GCN layers trained on the graph (gnn_common/gnn_models.py:58-100 uses PyG's GCNConv:
+ *     out[i] = sum over edges (j -> i) of norm_ji * h[j]).  y = A x, A in CSR by target node (col = source node,
+ *     val = normalised weight), x / y dense float32 [n_rows, d], d <= 128.  Fixed summation order (reproducible).
+ * ------------------------------------------------------------------------ */
+GG_API int gg_spmm_csr_f32(const int64_t* row_ptr, const int32_t* col, const float* val, int64_t n_rows, const float* x,
+                    int d, float* y, gg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif
