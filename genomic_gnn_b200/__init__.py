@@ -11,6 +11,7 @@ from .api import (  # noqa: F401
     PairFrequency,
     build_deBruijn_graph,
     cosine_similarity_to_edge_index_weight,
+    kf_faiss_to_edge_index_weight,
     node_embedding_initial,
     weighted_directed_edges,
 )

@@ -365,7 +365,30 @@ def cosine_similarity_to_edge_index_weight(X, chunk_size: int = 1024, threshold:
     return res.edge_index.cpu().numpy(), res.weight64.cpu().numpy()
 
 
+def kf_faiss_to_edge_index_weight(X, k: int, index_type: str = "IVFFlat", distance: str = "L2", nlist=None, nprobe=None,
+                                  m=None, nbits=None, useFloat16: bool = True):
+    """gnn_utils.py:122-237 -> (int64 ndarray [2, E], float32 ndarray [E]): every node's k nearest nodes.
+
+    The reference searches an approximate FAISS index; this is the exact search that index approximates, so
+    ``index_type`` and its tuning knobs are accepted and ignored.  Edges are grouped by source node, most similar
+    first (the order of ``index.search``), ties by ascending target; the query node itself is excluded explicitly
+    (the reference drops column 0 of the result, which with duplicate rows may be a duplicate instead)."""
+    del index_type, nlist, nprobe, m, nbits, useFloat16
+    core._require_cuda()
+    if isinstance(X, KFLabels):
+        counts, sqnorm = X.kc.counts, X.kc.sqnorm
+    else:
+        counts_np, sq_max = _counts_from_matrix(X)
+        if sq_max == 0 or counts_np.shape[0] < 2:
+            return np.zeros((2, 0), dtype=np.int64), np.zeros(0, dtype=np.float32)
+        counts_np = _pad_columns(counts_np)
+        counts = torch.from_numpy(counts_np).cuda()
+        sqnorm = torch.from_numpy((counts_np.astype(np.int64) ** 2).sum(axis=1).astype(np.int32)).cuda()
+    res = core.kf_knn_edges(counts, sqnorm, int(k), distance)
+    return res.edge_index.cpu().numpy(), res.weight.cpu().numpy()
+
+
 __all__ = [
     "weighted_directed_edges", "build_deBruijn_graph", "node_embedding_initial",
-    "cosine_similarity_to_edge_index_weight", "PairFrequency", "ItemFrequency", "KmerGraph", "KFLabels", "GGError",
+    "cosine_similarity_to_edge_index_weight", "kf_faiss_to_edge_index_weight", "PairFrequency", "ItemFrequency", "KmerGraph", "KFLabels", "GGError",
 ]

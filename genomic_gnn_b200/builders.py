@@ -124,10 +124,10 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
                                       edges_threshold: float = 0.0, edges_keep_top_k: Optional[float] = None,
                                       layers_config: Optional[list] = None, ss_task: Optional[str] = None,
                                       graphs_strides: Optional[list] = None, faiss_ann: bool = False, device="cpu",
-                                      kf_impl="auto", **_faiss_kwargs):
-    """gnn_tasks_miniBatch/dataloader.py:21-179 -> (loader, HeteroData)."""
-    if faiss_ann:
-        raise NotImplementedError("FAISS ANN KF edges are out of scope; the exact Gram path replaces them")
+                                      kf_impl="auto", faiss_distance: str = "L2", **_faiss_kwargs):
+    """gnn_tasks_miniBatch/dataloader.py:21-179 -> (loader, HeteroData).  With ``faiss_ann`` the KF edges are every
+    node's int(edges_keep_top_k * N) nearest nodes (dataloader.py:108-121), found exactly instead of through an
+    approximate FAISS index (index type / nlist / nprobe / m / nbits are accepted and ignored)."""
     if edit_distance_loss_weight != 0:
         raise NotImplementedError("edit-distance (ED) edges are out of scope (SURVEY.md section 2, row 8)")
     data = _PygHetero() if HAVE_PYG else HeteroGraphData()
@@ -141,7 +141,15 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
         data["node"][f"y_{i}"] = _as_float_tensor(lab, device)
     if kmer_frequency_loss_weight != 0:
         for i, lab in enumerate(kmer_freq_labels or []):
-            if isinstance(lab, api.KFLabels):
+            if faiss_ann:
+                k_nn = int(edges_keep_top_k * len(lab))
+                if isinstance(lab, api.KFLabels):
+                    res = core.kf_knn_edges(lab.kc.counts, lab.kc.sqnorm, k_nn, faiss_distance)
+                    ei, w = res.edge_index, res.weight
+                else:
+                    ei_np, w_np = api.kf_faiss_to_edge_index_weight(np.vstack(lab), k=k_nn, distance=faiss_distance)
+                    ei, w = torch.tensor(ei_np, dtype=torch.long), torch.tensor(w_np, dtype=torch.float)
+            elif isinstance(lab, api.KFLabels):
                 kc = lab.kc
                 res = core.kf_edges(kc.counts, kc.sqnorm, float(edges_threshold), edges_keep_top_k,
                                     sq_max=kc.m * kc.m, impl=kf_impl)
@@ -223,7 +231,7 @@ def create_graphs_mini_batch(self, k: int):
         edges_threshold=self.edges_threshold, edges_keep_top_k=self.edges_keep_top_k,
         layers_config=[*self.layers_config, "1_" + self.representation_ss_last_layer_edge_type],
         ss_task=self.ss_task, graphs_strides=_stride_graphs(self, k), faiss_ann=getattr(self, "faiss_ann", False),
-        device=device)
+        faiss_distance=getattr(self, "faiss_distance", "L2"), device=device)
     self.num_features = 4**k if one_hot else 4 ** int(str(self.small_k)[0])
 
 

@@ -885,6 +885,108 @@ def kf_finish(st: KFStage, comm=None, gather: bool = True) -> KFEdges:
 
 
 # --------------------------------------------------------------------------- whole path on one GPU
+# --------------------------------------------------------------------------- f4b per-row kNN (faiss_ann mode)
+KNN_METRICS = {"IP": 0, "L2": 1}
+_KNN_NO_RANK = 0xFFFF
+
+
+@lru_cache(maxsize=64)
+def knn_tables(sq_values: tuple, metric: str):
+    """Host tables of gg_knn_*: ``sq_values`` = the distinct squared norms present (sorted).  Returns
+    (sqid uint8[sq_max + 1], rank_tab uint16[n_sq, dot_max + 1], rank_q int32[n_ranks], n_ranks).
+    rank 0 = most similar; equal similarity <=> equal rank.  "IP": cosine order of a row = order of dot / sqrt(sq_j),
+    compared exactly as the rational dot^2 / sq_j; zero dots are never neighbours (similarity 0 is filtered,
+    gnn_utils.py:221).  "L2": order of sq_j - 2 dot (ascending)."""
+    sq_max = int(sq_values[-1])
+    dot_max = sq_max
+    sqid = np.full(sq_max + 1, 0xFF, dtype=np.uint8)
+    keys = {}
+    for ci, sq in enumerate(sq_values):
+        sqid[sq] = ci
+        for dot in range(dot_max + 1):
+            if dot * dot > sq * sq_max:       # Cauchy-Schwarz: no such pair exists
+                continue
+            if metric == "IP":
+                if dot == 0 or sq == 0:
+                    continue
+                keys[(ci, dot)] = -Fraction(dot * dot, sq)
+            else:
+                keys[(ci, dot)] = sq - 2 * dot
+    ordered = sorted(set(keys.values()))
+    rank_of = {v: r for r, v in enumerate(ordered)}
+    tab = np.full((len(sq_values), dot_max + 1), _KNN_NO_RANK, dtype=np.uint16)
+    for (ci, dot), v in keys.items():
+        tab[ci, dot] = rank_of[v]
+    rank_q = np.array([int(v) for v in ordered], dtype=np.int32) if metric == "L2" else np.zeros(max(len(ordered), 1), np.int32)
+    return sqid, tab, rank_q, max(len(ordered), 1)
+
+
+@dataclass
+class KnnEdges:
+    edge_index: torch.Tensor   # int64 [2, E]: source row, neighbour; grouped by source, most similar first
+    weight: torch.Tensor       # float32 [E]
+    k: int
+    metric: str
+
+
+def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance: str = "L2",
+                 hist_mode: int = -1) -> KnnEdges:
+    """Exact per-row k-nearest-neighbour KF edges: what kf_faiss_to_edge_index_weight (gnn_utils.py:122-237)
+    approximates through FAISS.  Two passes over the Gram matrix (gg_knn_count / gg_knn_write), no sort by value.
+    ``hist_mode`` forces where pass 1 accumulates (tests): 0 global atomics, 1 / 2 shared memory 16- / 32-bit."""
+    if distance not in KNN_METRICS:
+        raise ValueError("distance must be 'IP' or 'L2'")
+    lib = _lib.load()
+    dev = counts.device
+    n, pitch = int(counts.shape[0]), int(counts.shape[1])
+    empty = KnnEdges(torch.zeros((2, 0), dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.float32, device=dev),
+                     int(k_nn), distance)
+    if k_nn < 1 or n < 2:
+        return empty
+    if k_nn > n - 1:
+        raise ValueError("k must be at most N - 1 (the reference searches k + 1 <= N entries)")
+    sqnorm = sqnorm[:n].contiguous()
+    sq_values = tuple(int(v) for v in torch.unique(sqnorm).cpu().tolist())
+    if sq_values[-1] == 0:
+        return empty
+    if sq_values[-1] > 254:
+        raise GGError("kNN KF path: squared row norms above 254 are outside the k-mer count range")
+    metric = KNN_METRICS[distance]
+    sqid, tab, rank_q, n_ranks = knn_tables(sq_values, distance)
+    n_sq, dot_max, sq_max = int(tab.shape[0]), int(tab.shape[1]) - 1, int(sq_values[-1])
+    sqid_d = torch.from_numpy(sqid).to(dev)
+    tab_d = torch.from_numpy(tab.view(np.int16)).to(dev)
+    rank_q_d = torch.from_numpy(rank_q).to(dev)
+    hist = torch.empty(n * n_ranks, dtype=torch.int32, device=dev)
+    st = _stream()
+    with _stage(f"knn_count_d{pitch}"):
+        check(lib.gg_knn_count(ptr(counts), pitch, n, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq, dot_max,
+                               n_ranks, int(hist_mode), ptr(hist), st), "gg_knn_count")
+    cut = torch.empty(n, dtype=torch.int32, device=dev)
+    tie_left = torch.empty(n, dtype=torch.int32, device=dev)
+    row_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    qmax = torch.empty(1, dtype=torch.int32, device=dev)
+    wb = int(lib.gg_knn_plan_workspace_bytes(n))
+    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+    with _stage("knn_plan"):
+        check(lib.gg_knn_plan(n, n_ranks, int(k_nn), metric, ptr(sqnorm), ptr(rank_q_d), ptr(hist), ptr(cut),
+                              ptr(tie_left), ptr(row_off), ptr(qmax), ptr(ws), wb, st), "gg_knn_plan")
+    n_edges = int(read_small(row_off[n:n + 1])[0])
+    if metric == 1 and int(read_small(qmax.to(torch.int64))[0]) == 0:
+        raise GGError("kNN KF path (L2): every kept distance is zero, the reference's 1 - d / max(d) is undefined")
+    edge_index = torch.empty((2, n_edges), dtype=torch.int64, device=dev)
+    weight = torch.empty(n_edges, dtype=torch.float32, device=dev)
+    if n_edges:
+        recs = torch.empty(n_edges, dtype=torch.int64, device=dev)
+        with _stage(f"knn_write_d{pitch}"):
+            check(lib.gg_knn_write(ptr(counts), pitch, n, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq, dot_max,
+                                   n_ranks, metric, ptr(hist), ptr(cut), ptr(tie_left), ptr(row_off), ptr(qmax),
+                                   ptr(recs), C.c_void_p(edge_index.data_ptr()),
+                                   C.c_void_p(edge_index.data_ptr() + 8 * n_edges), ptr(weight), n_edges, st),
+                  "gg_knn_write")
+    return KnnEdges(edge_index, weight, int(k_nn), distance)
+
+
 @dataclass
 class BuiltGraph:
     k: int

@@ -1,0 +1,585 @@
+// f4b: per-row k-nearest-neighbour KF edges (the --representation_ss_faiss_ann mode).
+//
+// Replaces kf_faiss_to_edge_index_weight (reference gnn_common/gnn_utils.py:122-237): every node keeps its k most
+// similar nodes (k = int(edges_keep_top_k * N), gnn_tasks_miniBatch/dataloader.py:113), by inner product of the
+// L2-normalised rows ("IP" = cosine) or by squared Euclidean distance of the raw frequency rows ("L2", turned into
+// 1 - d / d_max afterwards), self matches and similarities <= 1e-4 removed.  The reference searches an approximate
+// FAISS index (IVFFlat by default); this is the exact search that index approximates.
+//
+// Rows are small non-negative integer counts, so both orders depend on (dot, sqnorm_j) only and take few distinct
+// values per row.  The host ranks the (sqnorm class, dot) pairs once (rank 0 = most similar); the device then needs
+// two passes over the Gram matrix and never sorts by value:
+//   pass 1  hist[i][rank] = number of columns j != i of that rank (per-CTA shared-memory histograms when they fit),
+//   plan    per row: the rank where the k-th neighbour falls, how many of that tie class fit, the row's first
+//           output slot (exclusive scan) and one cursor per (row, rank),
+//   pass 2  the selected (i, j) of every row, in column order: a warp owns its 16 rows for all columns, so the slot of
+//           a pair is a running per-row count plus a ballot prefix -- no atomics,
+//   order   a warp per row moves its (at most k) pairs to the (row, rank) cursors: grouped by source row, sorted by
+//           similarity, ties by ascending column -- deterministic.
+// The Gram tiles come from mma.sync m16n8k32 (u8 x u8 -> s32): a CTA keeps 128 rows in shared memory and streams
+// all columns past them in 128-column tiles (register-prefetched).  This is the first correct path for this mode;
+// folding the per-row selection into the tcgen05 kernel of gg_kf_mma.cu is the next step.
+#include <cub/cub.cuh>
+
+#include "gg_common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;     // rows per CTA: 8 warps x 16
+constexpr int kCols = 128;     // columns per tile
+constexpr int kThreads = 256;
+constexpr int kChunk = 128;    // bytes of a row staged per column-tile load
+constexpr int kMaxPitch = 1024;
+constexpr unsigned kNoRank = 0xFFFFu;
+constexpr size_t kSmemLimit = 227 * 1024;
+
+enum { kHistGlobal = 0, kHistSmem16 = 1, kHistSmem32 = 2 };
+
+struct KnnArgs {
+  const uint8_t* counts;
+  int pitch;                 // bytes per row
+  int kpad;                  // pitch rounded up to a multiple of 32 (one MMA k-step)
+  int chunk;                 // min(kpad, kChunk)
+  int64_t n;
+  const int32_t* sqnorm;
+  const uint8_t* sqid;       // [sq_max + 1] sqnorm -> class index, 0xFF when no row has it
+  int sq_max;
+  const uint16_t* rank_tab;  // [n_sq][dot_max + 1] -> rank, 0xFFFF = never a neighbour
+  int n_sq, dot_max, n_ranks;
+  int hist_mode;             // pass 1: where the histograms are accumulated
+  uint32_t* hist;            // [n][n_ranks] pass 1 output
+  const int32_t* cut;        // [n] rank of the class the k-th neighbour falls in (n_ranks: fewer than k candidates)
+  const int32_t* tie_left;   // [n] members of the cut class to take (the first in column order)
+  const int64_t* row_off;    // [n + 1]
+  uint64_t* recs;            // pass 2 output: column | dot << 32 | rank << 48, rows at row_off, column order
+};
+
+__device__ __forceinline__ void mma_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// 128 rows x `kbytes` bytes of the count matrix, as per-thread registers (loaded early, stored to shared memory late)
+struct Prefetch {
+  uint4 v[4];
+  int32_t sq;
+};
+
+__device__ __forceinline__ void prefetch_rows(const KnnArgs& a, Prefetch& p, int64_t row0, int kb0, int kbytes) {
+  if (a.pitch >= 16) {
+    const int segs = kbytes >> 4;  // 2, 4 or 8 -> at most 4 units per thread
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * kThreads;
+      p.v[j] = make_uint4(0, 0, 0, 0);
+      if (i < kRows * segs) {
+        const int r = i / segs, sg = i - r * segs;
+        const int64_t row = row0 + r;
+        const int b = kb0 + (sg << 4);
+        if (row < a.n && b < a.pitch) p.v[j] = __ldg(reinterpret_cast<const uint4*>(a.counts + row * a.pitch + b));
+      }
+    }
+  } else {  // pitch 4 or 8: one 32-byte k-step, word loads (128 x 8 words = 4 per thread)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * kThreads;
+      const int r = i >> 3, wd = i & 7;
+      const int64_t row = row0 + r;
+      const int b = kb0 + (wd << 2);
+      p.v[j].x = 0;
+      if (row < a.n && b < a.pitch) p.v[j].x = __ldg(reinterpret_cast<const uint32_t*>(a.counts + row * a.pitch + b));
+    }
+  }
+}
+
+__device__ __forceinline__ void store_rows(const KnnArgs& a, const Prefetch& p, uint8_t* dst, int stride, int kbytes) {
+  if (a.pitch >= 16) {
+    const int segs = kbytes >> 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * kThreads;
+      if (i < kRows * segs) {
+        const int r = i / segs, sg = i - r * segs;
+        *reinterpret_cast<uint4*>(dst + r * stride + (sg << 4)) = p.v[j];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + j * kThreads;
+      *reinterpret_cast<uint32_t*>(dst + (i >> 3) * stride + ((i & 7) << 2)) = p.v[j].x;
+    }
+  }
+}
+
+// the CTA's 128 rows, all kpad bytes (once per CTA: plain loop)
+__device__ __forceinline__ void stage_panel(const KnnArgs& a, uint8_t* dst, int stride, int64_t row0) {
+  const int words = a.kpad >> 2;
+  for (int i = threadIdx.x; i < kRows * words; i += kThreads) {
+    const int r = i / words, wd = i - r * words;
+    const int64_t row = row0 + r;
+    const int b = wd << 2;
+    uint32_t v = 0;
+    if (row < a.n && b < a.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(a.counts + row * a.pitch + b));
+    *reinterpret_cast<uint32_t*>(dst + r * stride + b) = v;
+  }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int pstride = a.kpad + 16, cstride = a.chunk + 16;
+  uint8_t* panel = smem;                                        // [128][kpad + 16]
+  uint8_t* stage = panel + kRows * pstride;                     // [128][chunk + 16]
+  uint16_t* rank_tab = reinterpret_cast<uint16_t*>(stage + kCols * cstride);
+  const int tab_elems = a.n_sq * (a.dot_max + 1);
+  int32_t* rowstate = reinterpret_cast<int32_t*>(rank_tab + ((tab_elems + 1) & ~1));  // [2][128] pass 2
+  uint8_t* sqid = reinterpret_cast<uint8_t*>(rowstate + 2 * kRows);                   // [256]
+  uint8_t* colcls = sqid + 256;                                                       // [128]
+  uint32_t* shist = reinterpret_cast<uint32_t*>(colcls + kCols);                      // pass 1, smem modes
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRows;
+
+  for (int i = threadIdx.x; i < tab_elems; i += kThreads) rank_tab[i] = a.rank_tab[i];
+  for (int i = threadIdx.x; i < 256; i += kThreads) sqid[i] = i <= a.sq_max ? a.sqid[i] : 0xFF;
+  if (PASS == 2)
+    for (int i = threadIdx.x; i < 2 * kRows; i += kThreads) rowstate[i] = 0;
+  int hist_words = 0;
+  if (PASS == 1 && a.hist_mode != kHistGlobal) {
+    hist_words = a.hist_mode == kHistSmem16 ? kRows * ((a.n_ranks + 1) >> 1) : kRows * a.n_ranks;
+    for (int i = threadIdx.x; i < hist_words; i += kThreads) shist[i] = 0;
+  }
+  stage_panel(a, panel, pstride, row0);
+
+  // the two rows this lane sees in every accumulator fragment
+  const int lrow[2] = {warp * 16 + g, warp * 16 + g + 8};
+  const int64_t grow[2] = {row0 + lrow[0], row0 + lrow[1]};
+  int32_t cut[2] = {-1, -1}, budget[2] = {0, 0};
+  int64_t rbase[2] = {0, 0};
+  if (PASS == 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (grow[h] < a.n) {
+        cut[h] = a.cut[grow[h]];
+        budget[h] = a.tie_left[grow[h]];
+        rbase[h] = a.row_off[grow[h]];
+      }
+  }
+  const unsigned lower = (0xFu << (4 * g)) & ((1u << lane) - 1u);  // lanes of my row group with a smaller q
+  const unsigned group = 0xFu << (4 * g);
+
+  const uint8_t* arow0 = panel + lrow[0] * pstride + 4 * q;
+  const uint8_t* arow1 = arow0 + 8 * pstride;
+  const int n_chunks = a.kpad / a.chunk;
+  const int64_t n_tiles = (a.n + kCols - 1) / kCols;
+
+  Prefetch pre;
+  prefetch_rows(a, pre, 0, 0, a.chunk);
+  pre.sq = (threadIdx.x < kCols && threadIdx.x < a.n) ? a.sqnorm[threadIdx.x] : -1;
+
+  for (int64_t tile = 0; tile < n_tiles; ++tile) {
+    const int64_t col0 = tile * kCols;
+    int acc[16][4];
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0;
+
+    for (int c = 0; c < n_chunks; ++c) {
+      __syncthreads();  // the previous stage (and colcls) has been consumed
+      store_rows(a, pre, stage, cstride, a.chunk);
+      if (c == 0 && threadIdx.x < kCols) colcls[threadIdx.x] = pre.sq >= 0 ? sqid[pre.sq] : 0xFF;
+      __syncthreads();
+      {  // next stage's global loads fly during this stage's MMAs
+        const bool last_chunk = c + 1 == n_chunks;
+        const int64_t ncol0 = last_chunk ? col0 + kCols : col0;
+        if (ncol0 < a.n) {
+          prefetch_rows(a, pre, ncol0, last_chunk ? 0 : (c + 1) * a.chunk, a.chunk);
+          if (last_chunk && threadIdx.x < kCols)
+            pre.sq = ncol0 + threadIdx.x < a.n ? a.sqnorm[ncol0 + threadIdx.x] : -1;
+        }
+      }
+      for (int ks = 0; ks < a.chunk; ks += 32) {
+        const int kb = c * a.chunk + ks;
+        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(arow0 + kb);
+        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(arow1 + kb);
+        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(arow0 + kb + 16);
+        const uint32_t a3 = *reinterpret_cast<const uint32_t*>(arow1 + kb + 16);
+        const uint8_t* bp = stage + g * cstride + ks + 4 * q;
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bp + nt * 8 * cstride);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(bp + nt * 8 * cstride + 16);
+          mma_u8(acc[nt], a0, a1, a2, a3, b0, b1);
+        }
+      }
+    }
+
+    // epilogue: fragment element e of n-tile nt is (row grow[e >> 1], column col0 + nt * 8 + 2 q + (e & 1))
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const int lc0 = nt * 8 + 2 * q;
+      const unsigned cls2[2] = {colcls[lc0], colcls[lc0 + 1]};
+      unsigned rk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned cls = cls2[e & 1];
+        unsigned r = kNoRank;
+        if (cls != 0xFF && grow[e >> 1] < a.n && col0 + lc0 + (e & 1) != grow[e >> 1])
+          r = rank_tab[cls * (a.dot_max + 1) + min(acc[nt][e], a.dot_max)];
+        rk[e] = r;
+      }
+      if (PASS == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (rk[e] == kNoRank) continue;
+          if (a.hist_mode == kHistSmem32)
+            atomicAdd(shist + lrow[e >> 1] * a.n_ranks + rk[e], 1u);
+          else if (a.hist_mode == kHistSmem16)
+            atomicAdd(shist + lrow[e >> 1] * ((a.n_ranks + 1) >> 1) + (rk[e] >> 1), 1u << ((rk[e] & 1) * 16));
+          else
+            atomicAdd(a.hist + grow[e >> 1] * a.n_ranks + rk[e], 1u);
+        }
+      } else {
+        bool sel[4], tie[4];
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sel[e] = rk[e] != kNoRank && static_cast<int>(rk[e]) <= cut[e >> 1];
+          tie[e] = sel[e] && static_cast<int>(rk[e]) == cut[e >> 1];
+          any |= sel[e];
+        }
+        if (!__any_sync(0xFFFFFFFFu, any)) continue;
+        unsigned bt[4], ba[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bt[e] = __ballot_sync(0xFFFFFFFFu, tie[e]);
+        int pos[2], seen[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          pos[h] = rowstate[lrow[h]];
+          seen[h] = rowstate[kRows + lrow[h]];
+        }
+        // members of the cut class are taken in column order while the row's tie budget lasts
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = e >> 1;
+          const int before = __popc(bt[2 * h] & lower) + __popc(bt[2 * h + 1] & lower) + ((e & 1) && tie[e - (e & 1)]);
+          if (tie[e] && seen[h] + before >= budget[h]) sel[e] = false;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ba[e] = __ballot_sync(0xFFFFFFFFu, sel[e]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!sel[e]) continue;
+          const int h = e >> 1;
+          const int before = __popc(ba[2 * h] & lower) + __popc(ba[2 * h + 1] & lower) + ((e & 1) && sel[e - (e & 1)]);
+          a.recs[rbase[h] + pos[h] + before] = static_cast<uint64_t>(col0 + lc0 + (e & 1)) |
+                                               static_cast<uint64_t>(acc[nt][e]) << 32 |
+                                               static_cast<uint64_t>(rk[e]) << 48;
+        }
+        __syncwarp();  // every lane of the group has read the row state
+        if (q == 0) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            rowstate[lrow[h]] = pos[h] + __popc(ba[2 * h] & group) + __popc(ba[2 * h + 1] & group);
+            rowstate[kRows + lrow[h]] = seen[h] + __popc(bt[2 * h] & group) + __popc(bt[2 * h + 1] & group);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  if (PASS == 1 && a.hist_mode != kHistGlobal) {
+    __syncthreads();
+    const int rows_here = a.n - row0 < kRows ? static_cast<int>(a.n - row0) : kRows;
+    const int total = rows_here * a.n_ranks;
+    uint32_t* out = a.hist + row0 * a.n_ranks;
+    if (a.hist_mode == kHistSmem32) {
+      for (int i = threadIdx.x; i < total; i += kThreads) out[i] = shist[i];
+    } else {
+      const int wpr = (a.n_ranks + 1) >> 1;
+      for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int r = i / a.n_ranks, j = i - r * a.n_ranks;
+        out[i] = (shist[r * wpr + (j >> 1)] >> ((j & 1) * 16)) & 0xFFFFu;
+      }
+    }
+  }
+}
+
+// ---- order: column-ordered pairs of a row -> (row, rank) cursors ------------------------------------------------------
+struct OrderArgs {
+  const uint64_t* recs;
+  const int64_t* row_off;
+  int64_t n;
+  int n_ranks;
+  uint32_t* cursors;  // [n][n_ranks] first output slot of every (row, rank); advanced here
+  const int32_t* sqnorm;
+  int metric;
+  const int32_t* qmax;
+  int64_t* src;
+  int64_t* dst;
+  float* w;
+};
+
+__global__ void __launch_bounds__(256) order_kernel(OrderArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= a.n) return;
+  const int64_t base = a.row_off[row];
+  const int cnt = static_cast<int>(a.row_off[row + 1] - base);
+  if (cnt == 0) return;
+  const int sqi = a.sqnorm[row];
+  const float qmax_f = a.metric == 1 ? static_cast<float>(*a.qmax) : 1.0f;
+  uint32_t* cur = a.cursors + row * a.n_ranks;
+  for (int i0 = 0; i0 < cnt; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < cnt;
+    const uint64_t rec = valid ? a.recs[base + i] : ~0ull;
+    const unsigned rank = static_cast<unsigned>(rec >> 48);  // 0xFFFF on idle lanes: a group of its own
+    const unsigned same = __match_any_sync(0xFFFFFFFFu, rank);
+    const int leader = __ffs(same) - 1;
+    unsigned first = 0;
+    if (valid && lane == leader) first = atomicAdd(cur + rank, static_cast<unsigned>(__popc(same)));
+    first = __shfl_sync(0xFFFFFFFFu, first, leader);
+    if (valid) {
+      const int64_t slot = static_cast<int64_t>(first) + __popc(same & ((1u << lane) - 1u));
+      const int64_t col = static_cast<int64_t>(rec & 0xFFFFFFFFull);
+      const int dot = static_cast<int>((rec >> 32) & 0xFFFFu);
+      const int sqj = a.sqnorm[col];
+      float wv;
+      if (a.metric == 0) {
+        wv = fminf(static_cast<float>(static_cast<double>(dot) / sqrt(static_cast<double>(sqi) * sqj)), 1.0f);
+      } else {
+        wv = 1.0f - static_cast<float>(sqi + sqj - 2 * dot) / qmax_f;
+      }
+      a.src[slot] = row;
+      a.dst[slot] = col;
+      a.w[slot] = wv;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- plan: cut rank, tie budget, rows' output counts -------------------------------------------------------------
+__global__ void cut_kernel(const uint32_t* hist, int64_t n, int n_ranks, int k_nn, int metric, const int32_t* sqnorm,
+                           const int32_t* rank_q, int32_t* cut, int32_t* tie_left, uint32_t* before, int32_t* qmax) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (row >= n) return;
+  const uint32_t* h = hist + row * n_ranks;
+  uint32_t cum = 0;
+  int c = n_ranks, left = 0, last = -1;
+  for (int r = 0; r < n_ranks; ++r) {
+    const uint32_t x = h[r];
+    if (x == 0) continue;
+    last = r;
+    if (cum + x >= static_cast<uint32_t>(k_nn)) {
+      c = r;
+      left = k_nn - static_cast<int>(cum);
+      break;
+    }
+    cum += x;
+  }
+  cut[row] = c;
+  tie_left[row] = left;
+  before[row] = cum;
+  if (metric == 1 && last >= 0) atomicMax(qmax, sqnorm[row] + rank_q[last]);  // `last` is the worst class kept
+}
+
+// L2: neighbours at the largest kept distance get similarity 0 and are dropped (gnn_utils.py:214-224); in integer
+// units 1 - d / d_max > 1e-4 is d < d_max.  They can only sit in the row's worst kept class.
+__global__ void rows_kernel(int64_t n, int n_ranks, int metric, const int32_t* sqnorm, const int32_t* rank_q,
+                            const int32_t* qmax, int32_t* cut, int32_t* tie_left, const uint32_t* before,
+                            const uint32_t* hist, uint32_t* rowcnt) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (row >= n) return;
+  int c = cut[row];
+  uint32_t cnt = before[row] + static_cast<uint32_t>(tie_left[row]);
+  if (metric == 1) {
+    if (c < n_ranks) {
+      if (sqnorm[row] + rank_q[c] >= *qmax) {  // the whole cut class is at the global maximum
+        cnt = before[row];
+        tie_left[row] = 0;
+      }
+    } else {
+      // fewer than k candidates: every class was kept; drop a last class sitting at the maximum
+      int last = -1;
+      for (int r = n_ranks - 1; r >= 0; --r)
+        if (hist[row * n_ranks + r]) {
+          last = r;
+          break;
+        }
+      if (last >= 0 && sqnorm[row] + rank_q[last] >= *qmax) {
+        cnt = before[row] - hist[row * n_ranks + last];
+        cut[row] = last;
+        tie_left[row] = 0;
+      }
+    }
+  }
+  rowcnt[row] = cnt;
+}
+
+struct ToI64 {
+  __host__ __device__ int64_t operator()(uint32_t x) const { return static_cast<int64_t>(x); }
+};
+
+// hist[row][r] := first output slot of rank r in row `row`
+__global__ void cursor_kernel(int64_t n, int n_ranks, const int64_t* row_off, uint32_t* hist) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (row >= n) return;
+  uint32_t* h = hist + row * n_ranks;
+  uint32_t at = static_cast<uint32_t>(row_off[row]);
+  for (int r = 0; r < n_ranks; ++r) {
+    const uint32_t x = h[r];
+    h[r] = at;
+    at += x;
+  }
+}
+
+size_t knn_base_smem(int kpad, int chunk, int n_sq, int dot_max) {
+  const int tab_elems = n_sq * (dot_max + 1);
+  return static_cast<size_t>(kRows) * (kpad + 16) + static_cast<size_t>(kCols) * (chunk + 16) +
+         2 * static_cast<size_t>((tab_elems + 1) & ~1) + 4 * 2 * kRows + 256 + kCols;
+}
+
+size_t hist_smem(int mode, int n_ranks) {
+  if (mode == kHistSmem32) return static_cast<size_t>(kRows) * n_ranks * 4;
+  if (mode == kHistSmem16) return static_cast<size_t>(kRows) * ((n_ranks + 1) / 2) * 4;
+  return 0;
+}
+
+int fill_args(KnnArgs& a, const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
+              int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks) {
+  GG_REQUIRE(n >= 1 && n < (int64_t(1) << 31), GG_ERR_ARG, "n outside [1, 2^31)");
+  GG_REQUIRE(pitch == 4 || pitch == 8 || (pitch >= 16 && pitch % 16 == 0 && pitch <= kMaxPitch), GG_ERR_ARG,
+             "pitch must be 4, 8 or a multiple of 16 up to 1024");
+  GG_REQUIRE(counts && sqnorm && sqid && rank_tab, GG_ERR_ARG, "null argument");
+  GG_REQUIRE(n_sq >= 1 && n_sq <= 254 && sq_max >= 0 && sq_max <= 254 && dot_max >= 0, GG_ERR_ARG, "bad class table");
+  GG_REQUIRE(n_ranks >= 1 && n_ranks < 0xFFFF, GG_ERR_ARG, "n_ranks outside [1, 65535)");
+  GG_REQUIRE(static_cast<uint64_t>(n) * static_cast<uint64_t>(n_ranks) < (uint64_t(1) << 40), GG_ERR_ARG,
+             "histogram too large");
+  a = KnnArgs{};
+  a.counts = counts;
+  a.pitch = pitch;
+  a.kpad = (pitch + 31) / 32 * 32;
+  a.chunk = a.kpad < kChunk ? a.kpad : kChunk;
+  GG_REQUIRE(a.kpad % a.chunk == 0, GG_ERR_ARG, "row pitch above 128 must be a multiple of 128");
+  a.n = n;
+  a.sqnorm = sqnorm;
+  a.sqid = sqid;
+  a.sq_max = sq_max;
+  a.rank_tab = rank_tab;
+  a.n_sq = n_sq;
+  a.dot_max = dot_max;
+  a.n_ranks = n_ranks;
+  GG_REQUIRE(knn_base_smem(a.kpad, a.chunk, n_sq, dot_max) <= kSmemLimit, GG_ERR_ARG,
+             "tables do not fit shared memory");
+  return GG_OK;
+}
+
+template <int PASS>
+int launch_knn(const KnnArgs& a, size_t smem, cudaStream_t s) {
+  GG_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  const unsigned grid = static_cast<unsigned>((a.n + kRows - 1) / kRows);
+  knn_kernel<PASS><<<grid, kThreads, smem, s>>>(a);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+}  // namespace
+
+/* pass 1: hist[n][n_ranks].  hist_mode: -1 auto, 0 global atomics, 1 shared memory 16-bit (n <= 65536), 2 shared
+ * memory 32-bit; a forced shared-memory mode that does not fit is an error. */
+extern "C" int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
+                            int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, int hist_mode,
+                            uint32_t* hist, gg_stream_t st) {
+  KnnArgs a;
+  const int rc = fill_args(a, counts, pitch, n, sqnorm, sqid, sq_max, rank_tab, n_sq, dot_max, n_ranks);
+  if (rc != GG_OK) return rc;
+  GG_REQUIRE(hist, GG_ERR_ARG, "null histogram");
+  GG_REQUIRE(hist_mode >= -1 && hist_mode <= 2, GG_ERR_ARG, "hist_mode must be -1, 0, 1 or 2");
+  const size_t base = knn_base_smem(a.kpad, a.chunk, n_sq, dot_max);
+  const bool fits32 = base + hist_smem(kHistSmem32, n_ranks) <= kSmemLimit;
+  const bool fits16 = n <= 65536 && base + hist_smem(kHistSmem16, n_ranks) <= kSmemLimit;
+  if (hist_mode < 0) hist_mode = fits32 ? kHistSmem32 : fits16 ? kHistSmem16 : kHistGlobal;
+  GG_REQUIRE(hist_mode != kHistSmem32 || fits32, GG_ERR_ARG, "32-bit shared-memory histograms do not fit");
+  GG_REQUIRE(hist_mode != kHistSmem16 || fits16, GG_ERR_ARG, "16-bit shared-memory histograms do not fit");
+  a.hist_mode = hist_mode;
+  a.hist = hist;
+  cudaStream_t s = gg::as_stream(st);
+  if (hist_mode == kHistGlobal)
+    GG_CUDA_CHECK(cudaMemsetAsync(hist, 0, static_cast<size_t>(n) * n_ranks * sizeof(uint32_t), s));
+  return launch_knn<1>(a, base + hist_smem(hist_mode, n_ranks), s);
+}
+
+extern "C" size_t gg_knn_plan_workspace_bytes(int64_t n) {
+  size_t scan = 0;
+  cub::TransformInputIterator<int64_t, ToI64, const uint32_t*> it(nullptr, ToI64());
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, it, static_cast<int64_t*>(nullptr), static_cast<int>(n + 1));
+  return gg::align_up(scan, 256) + 2 * gg::align_up(static_cast<size_t>(n + 1) * 4, 256) + 256;
+}
+
+/* plan: cut[n], tie_left[n], row_offsets[n + 1] (the last entry = number of edges), qmax (device int32[1], L2 only:
+ * the largest kept squared distance in integer units); turns hist into the per-(row, rank) cursors of gg_knn_write. */
+extern "C" int gg_knn_plan(int64_t n, int n_ranks, int k_nn, int metric, const int32_t* sqnorm, const int32_t* rank_q,
+                           uint32_t* hist, int32_t* cut, int32_t* tie_left, int64_t* row_offsets, int32_t* qmax,
+                           void* workspace, size_t workspace_bytes, gg_stream_t st) {
+  GG_REQUIRE(n >= 1 && n < (int64_t(1) << 31), GG_ERR_ARG, "n outside [1, 2^31)");
+  GG_REQUIRE(n_ranks >= 1 && n_ranks < 0xFFFF, GG_ERR_ARG, "n_ranks outside [1, 65535)");
+  GG_REQUIRE(k_nn >= 1 && k_nn < n, GG_ERR_ARG, "k must be in [1, n - 1]");
+  GG_REQUIRE(metric == 0 || metric == 1, GG_ERR_ARG, "metric must be 0 (IP) or 1 (L2)");
+  GG_REQUIRE(hist && cut && tie_left && row_offsets && qmax && sqnorm && workspace, GG_ERR_ARG, "null argument");
+  GG_REQUIRE(metric == 0 || rank_q, GG_ERR_ARG, "L2 needs rank_q");
+  GG_REQUIRE(workspace_bytes >= gg_knn_plan_workspace_bytes(n), GG_ERR_ARG, "workspace too small");
+  cudaStream_t s = gg::as_stream(st);
+  gg::Carver cv(workspace);
+  uint32_t* before = cv.take<uint32_t>(n + 1);
+  uint32_t* rowcnt = cv.take<uint32_t>(n + 1);
+  void* temp = cv.take<char>(0);
+  size_t temp_bytes = workspace_bytes - cv.used();
+  const unsigned grid = static_cast<unsigned>((n + 127) / 128);
+  GG_CUDA_CHECK(cudaMemsetAsync(qmax, 0, sizeof(int32_t), s));
+  GG_CUDA_CHECK(cudaMemsetAsync(rowcnt + n, 0, sizeof(uint32_t), s));
+  cut_kernel<<<grid, 128, 0, s>>>(hist, n, n_ranks, k_nn, metric, sqnorm, rank_q, cut, tie_left, before, qmax);
+  GG_CUDA_CHECK(cudaGetLastError());
+  rows_kernel<<<grid, 128, 0, s>>>(n, n_ranks, metric, sqnorm, rank_q, qmax, cut, tie_left, before, hist, rowcnt);
+  GG_CUDA_CHECK(cudaGetLastError());
+  cub::TransformInputIterator<int64_t, ToI64, const uint32_t*> it(rowcnt, ToI64());
+  GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, row_offsets, static_cast<int>(n + 1), s));
+  cursor_kernel<<<grid, 128, 0, s>>>(n, n_ranks, row_offsets, hist);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+/* pass 2 + order: edge_src / edge_dst / weight[row_offsets[n]], grouped by source row, most similar first.
+ * recs: scratch of row_offsets[n] 64-bit words (`capacity` of them). */
+extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
+                            int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, int metric,
+                            uint32_t* cursors, const int32_t* cut, const int32_t* tie_left,
+                            const int64_t* row_offsets, const int32_t* qmax, uint64_t* recs, int64_t* edge_src,
+                            int64_t* edge_dst, float* weight, int64_t capacity, gg_stream_t st) {
+  KnnArgs a;
+  const int rc = fill_args(a, counts, pitch, n, sqnorm, sqid, sq_max, rank_tab, n_sq, dot_max, n_ranks);
+  if (rc != GG_OK) return rc;
+  GG_REQUIRE(metric == 0 || metric == 1, GG_ERR_ARG, "metric must be 0 (IP) or 1 (L2)");
+  GG_REQUIRE(cursors && cut && tie_left && row_offsets && qmax, GG_ERR_ARG, "null plan");
+  GG_REQUIRE(capacity >= 0 && (capacity == 0 || (recs && edge_src && edge_dst && weight)), GG_ERR_ARG, "null output");
+  GG_REQUIRE(capacity < (int64_t(1) << 32), GG_ERR_ARG, "more than 2^32 - 1 edges");
+  if (capacity == 0) return GG_OK;
+  a.cut = cut;
+  a.tie_left = tie_left;
+  a.row_off = row_offsets;
+  a.recs = recs;
+  cudaStream_t s = gg::as_stream(st);
+  const int rc2 = launch_knn<2>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s);
+  if (rc2 != GG_OK) return rc2;
+  OrderArgs o{recs, row_offsets, n, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
+  const unsigned grid = static_cast<unsigned>((n * 32 + 255) / 256);
+  order_kernel<<<grid, 256, 0, s>>>(o);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}

@@ -332,6 +332,38 @@ GG_API int gg_rw_pairs(const int64_t* row_ptr, const int64_t* col, const float* 
 GG_API int gg_spmm_csr_f32(const int64_t* row_ptr, const int32_t* col, const float* val, int64_t n_rows, const float* x,
                     int d, float* y, gg_stream_t st);
 
+/* ------------------------------------------------------------------------
+ * f4b  per-row k-nearest-neighbour KF edges: the --representation_ss_faiss_ann mode.  Replaces
+ *      kf_faiss_to_edge_index_weight (gnn_common/gnn_utils.py:122-237; k = int(edges_keep_top_k * N),
+ *      gnn_tasks_miniBatch/dataloader.py:108-121) by the EXACT search its FAISS index approximates.
+ *
+ * metric 0 ("IP"): cosine of the count rows; metric 1 ("L2"): squared Euclidean distance, returned as
+ * 1 - d / (largest kept d) with the neighbours at that largest distance dropped (similarity <= 1e-4).  Self matches
+ * are excluded; "IP" neighbours with a zero dot are never returned.
+ * Tables from the host: sqid[sq_max + 1] maps a squared norm to its class (0xFF: no such row), rank_tab[n_sq]
+ * [dot_max + 1] ranks the (class of column j, dot) pairs by similarity (0 = most similar, 0xFFFF = never a
+ * neighbour; equal similarity <=> equal rank), rank_q[n_ranks] (L2) = sqnorm_j - 2 dot of a rank.
+ *   gg_knn_count  hist[n][n_ranks] = columns j != i of every rank, per row
+ *   gg_knn_plan   cut[n] (rank holding the k-th neighbour), tie_left[n] (members of that rank that still fit),
+ *                 row_offsets[n + 1] (LAST entry = number of edges), qmax; hist becomes the cursors of gg_knn_write
+ *   gg_knn_write  second pass (the selected pairs of every row, in column order, into `recs`) + reorder: edges
+ *                 grouped by source row, most similar first, ties by ascending column.
+ * pitch: bytes per row of counts: 4, 8, or a multiple of 16 (of 128 above 128) up to 1024.
+ * ------------------------------------------------------------------------ */
+GG_API int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
+                 int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks,
+                 int hist_mode /* -1 auto; 0 global atomics, 1 / 2 per-CTA shared memory, 16- / 32-bit bins */,
+                 uint32_t* hist, gg_stream_t st);
+GG_API size_t gg_knn_plan_workspace_bytes(int64_t n);
+GG_API int gg_knn_plan(int64_t n, int n_ranks, int k_nn, int metric, const int32_t* sqnorm, const int32_t* rank_q,
+                uint32_t* hist, int32_t* cut, int32_t* tie_left, int64_t* row_offsets, int32_t* qmax, void* workspace,
+                size_t workspace_bytes, gg_stream_t st);
+GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
+                 int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, int metric, uint32_t* cursors,
+                 const int32_t* cut, const int32_t* tie_left, const int64_t* row_offsets, const int32_t* qmax,
+                 uint64_t* recs /* scratch: `capacity` words */, int64_t* edge_src, int64_t* edge_dst, float* weight,
+                 int64_t capacity /* = row_offsets[n] */, gg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

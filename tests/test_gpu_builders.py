@@ -105,6 +105,4 @@ def test_unsupported_options_fail_loudly():
 
     reads = fast.reads_to_strings(fast.synthetic_reads(50, 60, seed=1))
     with pytest.raises(NotImplementedError):
-        gg.create_graphs_mini_batch(_self(reads, faiss_ann=True), 3)
-    with pytest.raises(NotImplementedError):
         gg.create_graphs_mini_batch(_self(reads, edit_distance_loss_weight=1.0), 3)

@@ -191,3 +191,34 @@ def test_random_walk_law_matches_reference_statistics():
         for walk, pr in law.items():
             exp = 600 * pr
             assert abs(seen.get(walk, 0) - exp) <= 5.0 * np.sqrt(exp * (1 - pr)) + 1.0
+
+
+def test_knn_tables_rank_like_the_exact_search():
+    """Host tables of the kNN KF path (core.knn_tables) against oracle/knn.py's order on a small graph: sorting every
+    row by (rank, column) must reproduce the oracle's neighbour lists for both metrics."""
+    from genomic_gnn_b200.core import knn_tables
+    from oracle import knn
+
+    k, s = 4, 2
+    n, d = 4**k, 4**s
+    codes = np.arange(n)
+    counts = np.zeros((n, d), dtype=np.int64)
+    for j in range(k - s + 1):
+        np.add.at(counts, (codes, (codes >> (2 * (k - s - j))) & (d - 1)), 1)
+    sq = (counts * counts).sum(axis=1)
+    G = counts @ counts.T
+    k_nn = 12
+    for metric in ("IP", "L2"):
+        sqid, tab, rank_q, n_ranks = knn_tables(tuple(int(v) for v in np.unique(sq)), metric)
+        ranks = tab[sqid[sq][None, :].repeat(n, 0), G].astype(np.int64)
+        ranks[codes, codes] = 0xFFFF
+        assert ranks[ranks != 0xFFFF].max() < n_ranks
+        order = np.lexsort((np.broadcast_to(codes, (n, n)), ranks), axis=1)[:, :k_nn]
+        keep = np.take_along_axis(ranks, order, axis=1) != 0xFFFF
+        if metric == "L2":
+            dist = sq[:, None] + np.take_along_axis(np.broadcast_to(sq, (n, n)), order, axis=1) - 2 * np.take_along_axis(G, order, axis=1)
+            assert np.array_equal(dist, sq[:, None] + rank_q[np.take_along_axis(ranks, order, axis=1)])
+            keep &= dist < dist.max()
+        want_ei, _ = knn.knn_edges(counts, k - s + 1, k_nn, metric)
+        assert np.array_equal(np.repeat(codes, k_nn)[keep.ravel()], want_ei[0])
+        assert np.array_equal(order.ravel()[keep.ravel()], want_ei[1])
