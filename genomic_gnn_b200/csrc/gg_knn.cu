@@ -40,6 +40,7 @@ struct KnnArgs {
   int pitch;                 // bytes per row
   int kpad;                  // pitch rounded up to a multiple of 32 (one MMA k-step)
   int chunk;                 // min(kpad, kChunk)
+  int seg_shift;             // log2 of the load units per staged row
   int64_t n;
   const int32_t* sqnorm;
   const uint8_t* sqid;       // [sq_max + 1] sqnorm -> class index, 0xFF when no row has it
@@ -62,57 +63,49 @@ __device__ __forceinline__ void mma_u8(int (&c)[4], uint32_t a0, uint32_t a1, ui
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// 128 rows x `kbytes` bytes of the count matrix, as per-thread registers (loaded early, stored to shared memory late)
+// 128 rows x `chunk` bytes of the count matrix, as per-thread registers (loaded early, stored to shared memory late).
+// Unit = 16 bytes (pitch >= 16) or one word (pitch 4 / 8); a row holds 1 << seg_shift units, a thread at most 4.
 struct Prefetch {
   uint4 v[4];
   int32_t sq;
 };
 
-__device__ __forceinline__ void prefetch_rows(const KnnArgs& a, Prefetch& p, int64_t row0, int kb0, int kbytes) {
-  if (a.pitch >= 16) {
-    const int segs = kbytes >> 4;  // 2, 4 or 8 -> at most 4 units per thread
+__device__ __forceinline__ void prefetch_rows(const KnnArgs& a, Prefetch& p, int64_t row0, int kb0) {
+  const bool wide = a.pitch >= 16;
+  const int ub = wide ? 4 : 2;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = threadIdx.x + j * kThreads;
-      p.v[j] = make_uint4(0, 0, 0, 0);
-      if (i < kRows * segs) {
-        const int r = i / segs, sg = i - r * segs;
-        const int64_t row = row0 + r;
-        const int b = kb0 + (sg << 4);
-        if (row < a.n && b < a.pitch) p.v[j] = __ldg(reinterpret_cast<const uint4*>(a.counts + row * a.pitch + b));
-      }
-    }
-  } else {  // pitch 4 or 8: one 32-byte k-step, word loads (128 x 8 words = 4 per thread)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = threadIdx.x + j * kThreads;
-      const int r = i >> 3, wd = i & 7;
-      const int64_t row = row0 + r;
-      const int b = kb0 + (wd << 2);
-      p.v[j].x = 0;
-      if (row < a.n && b < a.pitch) p.v[j].x = __ldg(reinterpret_cast<const uint32_t*>(a.counts + row * a.pitch + b));
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + j * kThreads;
+    const int r = i >> a.seg_shift, b = kb0 + ((i & ((1 << a.seg_shift) - 1)) << ub);
+    const int64_t row = row0 + r;
+    p.v[j] = make_uint4(0, 0, 0, 0);
+    if (r < kRows && row < a.n && b < a.pitch) {
+      const uint8_t* src = a.counts + row * a.pitch + b;
+      if (wide) p.v[j] = __ldg(reinterpret_cast<const uint4*>(src));
+      else p.v[j].x = __ldg(reinterpret_cast<const uint32_t*>(src));
     }
   }
 }
 
-__device__ __forceinline__ void store_rows(const KnnArgs& a, const Prefetch& p, uint8_t* dst, int stride, int kbytes) {
-  if (a.pitch >= 16) {
-    const int segs = kbytes >> 4;
+__device__ __forceinline__ void store_rows(const KnnArgs& a, const Prefetch& p, uint8_t* dst, int stride) {
+  const bool wide = a.pitch >= 16;
+  const int ub = wide ? 4 : 2;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = threadIdx.x + j * kThreads;
-      if (i < kRows * segs) {
-        const int r = i / segs, sg = i - r * segs;
-        *reinterpret_cast<uint4*>(dst + r * stride + (sg << 4)) = p.v[j];
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = threadIdx.x + j * kThreads;
-      *reinterpret_cast<uint32_t*>(dst + (i >> 3) * stride + ((i & 7) << 2)) = p.v[j].x;
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + j * kThreads;
+    const int r = i >> a.seg_shift, b = (i & ((1 << a.seg_shift) - 1)) << ub;
+    if (r < kRows) {
+      if (wide) *reinterpret_cast<uint4*>(dst + r * stride + b) = p.v[j];
+      else *reinterpret_cast<uint32_t*>(dst + r * stride + b) = p.v[j].x;
     }
   }
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const uint8_t* p) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
 }
 
 // the CTA's 128 rows, all kpad bytes (once per CTA: plain loop)
@@ -173,13 +166,17 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
   const unsigned lower = (0xFu << (4 * g)) & ((1u << lane) - 1u);  // lanes of my row group with a smaller q
   const unsigned group = 0xFu << (4 * g);
 
-  const uint8_t* arow0 = panel + lrow[0] * pstride + 4 * q;
-  const uint8_t* arow1 = arow0 + 8 * pstride;
+  // ldmatrix addresses: lane l supplies row (l & 7) of 8x16-byte matrix (l >> 3).
+  // A: matrices (rows 0-7, k 0-15), (rows 8-15, k 0-15), (rows 0-7, k 16-31), (rows 8-15, k 16-31) = a0..a3.
+  // B: (n-tile nt, k 0-15), (nt, k 16-31), (nt + 1, k 0-15), (nt + 1, k 16-31) = b0, b1 of two n-tiles.
+  const int mi = lane >> 3, mr = lane & 7;
+  const uint8_t* a_ld = panel + (warp * 16 + mr + (mi & 1) * 8) * pstride + (mi >> 1) * 16;
+  const uint8_t* b_ld = stage + ((mi >> 1) * 8 + mr) * cstride + (mi & 1) * 16;
   const int n_chunks = a.kpad / a.chunk;
   const int64_t n_tiles = (a.n + kCols - 1) / kCols;
 
   Prefetch pre;
-  prefetch_rows(a, pre, 0, 0, a.chunk);
+  prefetch_rows(a, pre, 0, 0);
   pre.sq = (threadIdx.x < kCols && threadIdx.x < a.n) ? a.sqnorm[threadIdx.x] : -1;
 
   for (int64_t tile = 0; tile < n_tiles; ++tile) {
@@ -190,30 +187,27 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
 
     for (int c = 0; c < n_chunks; ++c) {
       __syncthreads();  // the previous stage (and colcls) has been consumed
-      store_rows(a, pre, stage, cstride, a.chunk);
+      store_rows(a, pre, stage, cstride);
       if (c == 0 && threadIdx.x < kCols) colcls[threadIdx.x] = pre.sq >= 0 ? sqid[pre.sq] : 0xFF;
       __syncthreads();
       {  // next stage's global loads fly during this stage's MMAs
         const bool last_chunk = c + 1 == n_chunks;
         const int64_t ncol0 = last_chunk ? col0 + kCols : col0;
         if (ncol0 < a.n) {
-          prefetch_rows(a, pre, ncol0, last_chunk ? 0 : (c + 1) * a.chunk, a.chunk);
+          prefetch_rows(a, pre, ncol0, last_chunk ? 0 : (c + 1) * a.chunk);
           if (last_chunk && threadIdx.x < kCols)
             pre.sq = ncol0 + threadIdx.x < a.n ? a.sqnorm[ncol0 + threadIdx.x] : -1;
         }
       }
       for (int ks = 0; ks < a.chunk; ks += 32) {
-        const int kb = c * a.chunk + ks;
-        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(arow0 + kb);
-        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(arow1 + kb);
-        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(arow0 + kb + 16);
-        const uint32_t a3 = *reinterpret_cast<const uint32_t*>(arow1 + kb + 16);
-        const uint8_t* bp = stage + g * cstride + ks + 4 * q;
+        uint32_t af[4];
+        ldsm_x4(af, a_ld + c * a.chunk + ks);
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt) {
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bp + nt * 8 * cstride);
-          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(bp + nt * 8 * cstride + 16);
-          mma_u8(acc[nt], a0, a1, a2, a3, b0, b1);
+        for (int nt = 0; nt < 16; nt += 2) {
+          uint32_t bf[4];
+          ldsm_x4(bf, b_ld + nt * 8 * cstride + ks);
+          mma_u8(acc[nt], af[0], af[1], af[2], af[3], bf[0], bf[1]);
+          mma_u8(acc[nt + 1], af[0], af[1], af[2], af[3], bf[2], bf[3]);
         }
       }
     }
@@ -467,6 +461,9 @@ int fill_args(KnnArgs& a, const uint8_t* counts, int pitch, int64_t n, const int
   a.kpad = (pitch + 31) / 32 * 32;
   a.chunk = a.kpad < kChunk ? a.kpad : kChunk;
   GG_REQUIRE(a.kpad % a.chunk == 0, GG_ERR_ARG, "row pitch above 128 must be a multiple of 128");
+  GG_REQUIRE(a.chunk == 32 || a.chunk == 64 || a.chunk == 128, GG_ERR_ARG, "row pitch of 65..127 bytes");
+  const int units = pitch >= 16 ? a.chunk / 16 : a.chunk / 4;  // 2, 4 or 8 per staged row
+  a.seg_shift = units == 2 ? 1 : units == 4 ? 2 : 3;
   a.n = n;
   a.sqnorm = sqnorm;
   a.sqid = sqid;
