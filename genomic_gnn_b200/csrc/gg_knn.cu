@@ -13,7 +13,7 @@
 //   plan    per row: the rank where the k-th neighbour falls, how many of that tie class fit, the row's first
 //           output slot (exclusive scan) and one cursor per (row, rank),
 //   pass 2  the selected (i, j) of every row, in column order: a warp owns its 16 rows for all columns, so the slot of
-//           a pair is a running per-row count plus a ballot prefix -- no atomics,
+//           a pair is a running per-row count (kept in registers) plus a ballot prefix -- no atomics,
 //   order   a warp per row moves its (at most k) pairs to the (row, rank) cursors: grouped by source row, sorted by
 //           similarity, ties by ascending column -- deterministic.
 // The Gram tiles come from mma.sync m16n8k32 (u8 x u8 -> s32): a CTA keeps 128 rows in shared memory and streams
@@ -121,16 +121,15 @@ __device__ __forceinline__ void stage_panel(const KnnArgs& a, uint8_t* dst, int 
   }
 }
 
-template <int PASS>
+template <int PASS, int HIST>
 __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int pstride = a.kpad + 16, cstride = a.chunk + 16;
   uint8_t* panel = smem;                                        // [128][kpad + 16]
   uint8_t* stage = panel + kRows * pstride;                     // [128][chunk + 16]
   uint16_t* rank_tab = reinterpret_cast<uint16_t*>(stage + kCols * cstride);
-  const int tab_elems = a.n_sq * (a.dot_max + 1);
-  int32_t* rowstate = reinterpret_cast<int32_t*>(rank_tab + ((tab_elems + 1) & ~1));  // [2][128] pass 2
-  uint8_t* sqid = reinterpret_cast<uint8_t*>(rowstate + 2 * kRows);                   // [256]
+  const int tab_elems = (a.n_sq + 1) * (a.dot_max + 1);  // + one all-"never" row for columns past the end
+  uint8_t* sqid = reinterpret_cast<uint8_t*>(rank_tab + ((tab_elems + 1) & ~1));     // [256]
   uint8_t* colcls = sqid + 256;                                                       // [128]
   uint32_t* shist = reinterpret_cast<uint32_t*>(colcls + kCols);                      // pass 1, smem modes
 
@@ -138,13 +137,12 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
   const int g = lane >> 2, q = lane & 3;
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRows;
 
-  for (int i = threadIdx.x; i < tab_elems; i += kThreads) rank_tab[i] = a.rank_tab[i];
+  for (int i = threadIdx.x; i < tab_elems; i += kThreads)
+    rank_tab[i] = i < a.n_sq * (a.dot_max + 1) ? a.rank_tab[i] : static_cast<uint16_t>(kNoRank);
   for (int i = threadIdx.x; i < 256; i += kThreads) sqid[i] = i <= a.sq_max ? a.sqid[i] : 0xFF;
-  if (PASS == 2)
-    for (int i = threadIdx.x; i < 2 * kRows; i += kThreads) rowstate[i] = 0;
   int hist_words = 0;
-  if (PASS == 1 && a.hist_mode != kHistGlobal) {
-    hist_words = a.hist_mode == kHistSmem16 ? kRows * ((a.n_ranks + 1) >> 1) : kRows * a.n_ranks;
+  if (PASS == 1 && HIST != kHistGlobal) {
+    hist_words = HIST == kHistSmem16 ? kRows * ((a.n_ranks + 1) >> 1) : kRows * a.n_ranks;
     for (int i = threadIdx.x; i < hist_words; i += kThreads) shist[i] = 0;
   }
   stage_panel(a, panel, pstride, row0);
@@ -154,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
   const int64_t grow[2] = {row0 + lrow[0], row0 + lrow[1]};
   int32_t cut[2] = {-1, -1}, budget[2] = {0, 0};
   int64_t rbase[2] = {0, 0};
+  int pos[2] = {0, 0}, seen[2] = {0, 0};
   if (PASS == 2) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -163,6 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
         rbase[h] = a.row_off[grow[h]];
       }
   }
+  const bool rowok[2] = {grow[0] < a.n, grow[1] < a.n};
+  const int hwords = HIST == kHistSmem16 ? (a.n_ranks + 1) >> 1 : a.n_ranks;
+  const int hbase[2] = {lrow[0] * hwords, lrow[1] * hwords};
   const unsigned lower = (0xFu << (4 * g)) & ((1u << lane) - 1u);  // lanes of my row group with a smaller q
   const unsigned group = 0xFu << (4 * g);
 
@@ -188,7 +190,10 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
     for (int c = 0; c < n_chunks; ++c) {
       __syncthreads();  // the previous stage (and colcls) has been consumed
       store_rows(a, pre, stage, cstride);
-      if (c == 0 && threadIdx.x < kCols) colcls[threadIdx.x] = pre.sq >= 0 ? sqid[pre.sq] : 0xFF;
+      if (c == 0 && threadIdx.x < kCols) {
+        const unsigned cls = pre.sq >= 0 ? sqid[pre.sq] : 0xFFu;
+        colcls[threadIdx.x] = cls == 0xFFu ? a.n_sq : cls;  // the all-"never" row of rank_tab
+      }
       __syncthreads();
       {  // next stage's global loads fly during this stage's MMAs
         const bool last_chunk = c + 1 == n_chunks;
@@ -212,57 +217,61 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
       }
     }
 
-    // epilogue: fragment element e of n-tile nt is (row grow[e >> 1], column col0 + nt * 8 + 2 q + (e & 1))
+    // epilogue: fragment element e of n-tile nt is (row grow[e >> 1], column col0 + nt * 8 + 2 q + (e & 1)).
+    // Branch-free rank lookup: columns past the end sit in an all-"never" class; the self pair only exists in the
+    // diagonal tile (row block = column tile).
+    const bool diag = tile == blockIdx.x;
+    const int tstride = a.dot_max + 1;
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) {
       const int lc0 = nt * 8 + 2 * q;
-      const unsigned cls2[2] = {colcls[lc0], colcls[lc0 + 1]};
+      const int cb[2] = {colcls[lc0] * tstride, colcls[lc0 + 1] * tstride};
       unsigned rk[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const unsigned cls = cls2[e & 1];
-        unsigned r = kNoRank;
-        if (cls != 0xFF && grow[e >> 1] < a.n && col0 + lc0 + (e & 1) != grow[e >> 1])
-          r = rank_tab[cls * (a.dot_max + 1) + min(acc[nt][e], a.dot_max)];
-        rk[e] = r;
+        const unsigned r = rank_tab[cb[e & 1] + min(acc[nt][e], a.dot_max)];
+        const bool dead = !rowok[e >> 1] || (diag && lc0 + (e & 1) == lrow[e >> 1]);
+        rk[e] = dead ? kNoRank : r;
       }
       if (PASS == 1) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (rk[e] == kNoRank) continue;
-          if (a.hist_mode == kHistSmem32)
-            atomicAdd(shist + lrow[e >> 1] * a.n_ranks + rk[e], 1u);
-          else if (a.hist_mode == kHistSmem16)
-            atomicAdd(shist + lrow[e >> 1] * ((a.n_ranks + 1) >> 1) + (rk[e] >> 1), 1u << ((rk[e] & 1) * 16));
+          if (HIST == kHistSmem32)
+            atomicAdd(shist + hbase[e >> 1] + rk[e], 1u);
+          else if (HIST == kHistSmem16)
+            atomicAdd(shist + hbase[e >> 1] + (rk[e] >> 1), 1u << ((rk[e] & 1) * 16));
           else
             atomicAdd(a.hist + grow[e >> 1] * a.n_ranks + rk[e], 1u);
         }
       } else {
+        // every lane of a row group keeps the same running state of its two rows (pos: pairs written, seen: members
+        // of the cut class met), advanced by ballot totals -- no shared state, no atomics
         bool sel[4], tie[4];
-        bool any = false;
+        bool any = false, anytie = false;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          sel[e] = rk[e] != kNoRank && static_cast<int>(rk[e]) <= cut[e >> 1];
-          tie[e] = sel[e] && static_cast<int>(rk[e]) == cut[e >> 1];
+          sel[e] = static_cast<int>(rk[e]) <= cut[e >> 1];  // 0xFFFF is above every cut
+          tie[e] = static_cast<int>(rk[e]) == cut[e >> 1];
           any |= sel[e];
+          anytie |= tie[e];
         }
         if (!__any_sync(0xFFFFFFFFu, any)) continue;
-        unsigned bt[4], ba[4];
+        if (__any_sync(0xFFFFFFFFu, anytie)) {
+          // members of the cut class are taken in column order while the row's tie budget lasts
+          unsigned bt[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) bt[e] = __ballot_sync(0xFFFFFFFFu, tie[e]);
-        int pos[2], seen[2];
+          for (int e = 0; e < 4; ++e) bt[e] = __ballot_sync(0xFFFFFFFFu, tie[e]);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          pos[h] = rowstate[lrow[h]];
-          seen[h] = rowstate[kRows + lrow[h]];
+          for (int e = 0; e < 4; ++e) {
+            const int h = e >> 1;
+            const int before = __popc(bt[2 * h] & lower) + __popc(bt[2 * h + 1] & lower) + ((e & 1) && tie[e - (e & 1)]);
+            if (tie[e] && seen[h] + before >= budget[h]) sel[e] = false;
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) seen[h] += __popc(bt[2 * h] & group) + __popc(bt[2 * h + 1] & group);
         }
-        // members of the cut class are taken in column order while the row's tie budget lasts
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int h = e >> 1;
-          const int before = __popc(bt[2 * h] & lower) + __popc(bt[2 * h + 1] & lower) + ((e & 1) && tie[e - (e & 1)]);
-          if (tie[e] && seen[h] + before >= budget[h]) sel[e] = false;
-        }
+        unsigned ba[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) ba[e] = __ballot_sync(0xFFFFFFFFu, sel[e]);
 #pragma unroll
@@ -274,25 +283,18 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
                                                static_cast<uint64_t>(acc[nt][e]) << 32 |
                                                static_cast<uint64_t>(rk[e]) << 48;
         }
-        __syncwarp();  // every lane of the group has read the row state
-        if (q == 0) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            rowstate[lrow[h]] = pos[h] + __popc(ba[2 * h] & group) + __popc(ba[2 * h + 1] & group);
-            rowstate[kRows + lrow[h]] = seen[h] + __popc(bt[2 * h] & group) + __popc(bt[2 * h + 1] & group);
-          }
-        }
-        __syncwarp();
+        for (int h = 0; h < 2; ++h) pos[h] += __popc(ba[2 * h] & group) + __popc(ba[2 * h + 1] & group);
       }
     }
   }
 
-  if (PASS == 1 && a.hist_mode != kHistGlobal) {
+  if (PASS == 1 && HIST != kHistGlobal) {
     __syncthreads();
     const int rows_here = a.n - row0 < kRows ? static_cast<int>(a.n - row0) : kRows;
     const int total = rows_here * a.n_ranks;
     uint32_t* out = a.hist + row0 * a.n_ranks;
-    if (a.hist_mode == kHistSmem32) {
+    if (HIST == kHistSmem32) {
       for (int i = threadIdx.x; i < total; i += kThreads) out[i] = shist[i];
     } else {
       const int wpr = (a.n_ranks + 1) >> 1;
@@ -434,9 +436,9 @@ __global__ void cursor_kernel(int64_t n, int n_ranks, const int64_t* row_off, ui
 }
 
 size_t knn_base_smem(int kpad, int chunk, int n_sq, int dot_max) {
-  const int tab_elems = n_sq * (dot_max + 1);
+  const int tab_elems = (n_sq + 1) * (dot_max + 1);
   return static_cast<size_t>(kRows) * (kpad + 16) + static_cast<size_t>(kCols) * (chunk + 16) +
-         2 * static_cast<size_t>((tab_elems + 1) & ~1) + 4 * 2 * kRows + 256 + kCols;
+         2 * static_cast<size_t>((tab_elems + 1) & ~1) + 256 + kCols;
 }
 
 size_t hist_smem(int mode, int n_ranks) {
@@ -477,12 +479,12 @@ int fill_args(KnnArgs& a, const uint8_t* counts, int pitch, int64_t n, const int
   return GG_OK;
 }
 
-template <int PASS>
+template <int PASS, int HIST>
 int launch_knn(const KnnArgs& a, size_t smem, cudaStream_t s) {
-  GG_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  GG_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<PASS, HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
   const unsigned grid = static_cast<unsigned>((a.n + kRows - 1) / kRows);
-  knn_kernel<PASS><<<grid, kThreads, smem, s>>>(a);
+  knn_kernel<PASS, HIST><<<grid, kThreads, smem, s>>>(a);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }
@@ -510,7 +512,10 @@ extern "C" int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, const i
   cudaStream_t s = gg::as_stream(st);
   if (hist_mode == kHistGlobal)
     GG_CUDA_CHECK(cudaMemsetAsync(hist, 0, static_cast<size_t>(n) * n_ranks * sizeof(uint32_t), s));
-  return launch_knn<1>(a, base + hist_smem(hist_mode, n_ranks), s);
+  const size_t smem = base + hist_smem(hist_mode, n_ranks);
+  if (hist_mode == kHistSmem32) return launch_knn<1, kHistSmem32>(a, smem, s);
+  if (hist_mode == kHistSmem16) return launch_knn<1, kHistSmem16>(a, smem, s);
+  return launch_knn<1, kHistGlobal>(a, smem, s);
 }
 
 extern "C" size_t gg_knn_plan_workspace_bytes(int64_t n) {
@@ -572,7 +577,7 @@ extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, const i
   a.row_off = row_offsets;
   a.recs = recs;
   cudaStream_t s = gg::as_stream(st);
-  const int rc2 = launch_knn<2>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s);
+  const int rc2 = launch_knn<2, kHistGlobal>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s);
   if (rc2 != GG_OK) return rc2;
   OrderArgs o{recs, row_offsets, n, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
   const unsigned grid = static_cast<unsigned>((n * 32 + 255) / 256);
