@@ -929,11 +929,28 @@ class KnnEdges:
     metric: str
 
 
-def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance: str = "L2",
-                 hist_mode: int = -1) -> KnnEdges:
+KNN_ROW_BLOCK = 128   # gg_knn_* row-shard granularity
+
+
+def knn_row_shard(n: int, world: int, rank: int):
+    """Contiguous, 128-aligned row range of ``rank``: every row costs the same (it meets all n columns)."""
+    blocks = (n + KNN_ROW_BLOCK - 1) // KNN_ROW_BLOCK
+    lo = blocks * rank // world * KNN_ROW_BLOCK
+    hi = min(blocks * (rank + 1) // world * KNN_ROW_BLOCK, n)
+    return min(lo, n), hi
+
+
+def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance: str = "L2", hist_mode: int = -1,
+                 rows=None, qmax_reduce=None, comm=None, gather: bool = True) -> KnnEdges:
     """Exact per-row k-nearest-neighbour KF edges: what kf_faiss_to_edge_index_weight (gnn_utils.py:122-237)
     approximates through FAISS.  Two passes over the Gram matrix (gg_knn_count / gg_knn_write), no sort by value.
-    ``hist_mode`` forces where pass 1 accumulates (tests): 0 global atomics, 1 / 2 shared memory 16- / 32-bit."""
+
+    Rows are independent, so the work shards by row range: with ``comm`` (dist.TorchComm) every rank takes
+    knn_row_shard() of the rows against all columns, the ranks agree on the "L2" normaliser (max over ranks of one
+    integer) and, unless ``gather=False``, all-gather their edge lists in rank order = the single-GPU result.
+    ``rows=(lo, hi)`` computes one shard explicitly (``qmax_reduce``: callable mapping the shard's integer
+    maximum distance to the global one).  ``hist_mode`` forces where pass 1 accumulates (tests): 0 global atomics,
+    1 / 2 shared memory 16- / 32-bit."""
     if distance not in KNN_METRICS:
         raise ValueError("distance must be 'IP' or 'L2'")
     lib = _lib.load()
@@ -951,39 +968,67 @@ def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance
         return empty
     if sq_values[-1] > 254:
         raise GGError("kNN KF path: squared row norms above 254 are outside the k-mer count range")
+    sharded = comm is not None and comm.world > 1
+    if rows is None:
+        rows = knn_row_shard(n, comm.world, comm.rank) if sharded else (0, n)
+    lo, hi = int(rows[0]), int(rows[1])
+    m = hi - lo
     metric = KNN_METRICS[distance]
     sqid, tab, rank_q, n_ranks = knn_tables(sq_values, distance)
     n_sq, dot_max, sq_max = int(tab.shape[0]), int(tab.shape[1]) - 1, int(sq_values[-1])
     sqid_d = torch.from_numpy(sqid).to(dev)
     tab_d = torch.from_numpy(tab.view(np.int16)).to(dev)
     rank_q_d = torch.from_numpy(rank_q).to(dev)
-    hist = torch.empty(n * n_ranks, dtype=torch.int32, device=dev)
     st = _stream()
-    with _stage(f"knn_count_d{pitch}"):
-        check(lib.gg_knn_count(ptr(counts), pitch, n, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq, dot_max,
-                               n_ranks, int(hist_mode), ptr(hist), st), "gg_knn_count")
-    cut = torch.empty(n, dtype=torch.int32, device=dev)
-    tie_left = torch.empty(n, dtype=torch.int32, device=dev)
-    row_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    qmax = torch.empty(1, dtype=torch.int32, device=dev)
-    wb = int(lib.gg_knn_plan_workspace_bytes(n))
-    ws = torch.empty(wb, dtype=torch.uint8, device=dev)
-    with _stage("knn_plan"):
-        check(lib.gg_knn_plan(n, n_ranks, int(k_nn), metric, ptr(sqnorm), ptr(rank_q_d), ptr(hist), ptr(cut),
-                              ptr(tie_left), ptr(row_off), ptr(qmax), ptr(ws), wb, st), "gg_knn_plan")
-    n_edges = int(read_small(row_off[n:n + 1])[0])
-    if metric == 1 and int(read_small(qmax.to(torch.int64))[0]) == 0:
+    n_edges, qmax_v = 0, 0
+    qmax = torch.zeros(1, dtype=torch.int32, device=dev)
+    if m > 0:
+        hist = torch.empty(m * n_ranks, dtype=torch.int32, device=dev)
+        with _stage(f"knn_count_d{pitch}"):
+            check(lib.gg_knn_count(ptr(counts), pitch, n, lo, hi, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq,
+                                   dot_max, n_ranks, int(hist_mode), ptr(hist), st), "gg_knn_count")
+        cut = torch.empty(m, dtype=torch.int32, device=dev)
+        tie_left = torch.empty(m, dtype=torch.int32, device=dev)
+        row_off = torch.empty(m + 1, dtype=torch.int64, device=dev)
+        wb = int(lib.gg_knn_plan_workspace_bytes(m))
+        ws = torch.empty(wb, dtype=torch.uint8, device=dev)
+
+        def plan(phase):
+            with _stage("knn_plan"):
+                check(lib.gg_knn_plan(n, lo, hi, n_ranks, int(k_nn), metric, ptr(sqnorm), ptr(rank_q_d), ptr(hist),
+                                      ptr(cut), ptr(tie_left), ptr(row_off), ptr(qmax), phase, ptr(ws), wb, st),
+                      "gg_knn_plan")
+    two_phase = metric == 1 and (sharded or qmax_reduce is not None)
+    if two_phase:   # the "L2" normaliser is global: max over the shards of one integer
+        if m > 0:
+            plan(1)
+        mine = int(read_small(qmax.to(torch.int64))[0])
+        qmax_v = max(comm.gather_ints(mine)) if sharded else int(qmax_reduce(mine))
+        qmax.fill_(qmax_v)
+        if m > 0:
+            plan(2)
+    elif m > 0:
+        plan(0)
+        if metric == 1:
+            qmax_v = int(read_small(qmax.to(torch.int64))[0])
+    if metric == 1 and qmax_v == 0:
         raise GGError("kNN KF path (L2): every kept distance is zero, the reference's 1 - d / max(d) is undefined")
+    if m > 0:
+        n_edges = int(read_small(row_off[m:m + 1])[0])
     edge_index = torch.empty((2, n_edges), dtype=torch.int64, device=dev)
     weight = torch.empty(n_edges, dtype=torch.float32, device=dev)
     if n_edges:
         recs = torch.empty(n_edges, dtype=torch.int64, device=dev)
         with _stage(f"knn_write_d{pitch}"):
-            check(lib.gg_knn_write(ptr(counts), pitch, n, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq, dot_max,
-                                   n_ranks, metric, ptr(hist), ptr(cut), ptr(tie_left), ptr(row_off), ptr(qmax),
+            check(lib.gg_knn_write(ptr(counts), pitch, n, lo, hi, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq,
+                                   dot_max, n_ranks, metric, ptr(hist), ptr(cut), ptr(tie_left), ptr(row_off), ptr(qmax),
                                    ptr(recs), C.c_void_p(edge_index.data_ptr()),
                                    C.c_void_p(edge_index.data_ptr() + 8 * n_edges), ptr(weight), n_edges, st),
                   "gg_knn_write")
+    if sharded and gather:
+        with _stage("c4_gather_knn_edges"):
+            edge_index = comm.gather_cat(edge_index, dim=1)
+            weight = comm.gather_cat(weight, dim=0)
     return KnnEdges(edge_index, weight, int(k_nn), distance)
 
 

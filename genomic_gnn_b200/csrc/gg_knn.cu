@@ -42,6 +42,7 @@ struct KnnArgs {
   int chunk;                 // min(kpad, kChunk)
   int seg_shift;             // log2 of the load units per staged row
   int64_t n;
+  int64_t row_begin, row_end;  // the shard's rows (row_begin is a multiple of 128); per-row arrays are shard-local
   const int32_t* sqnorm;
   const uint8_t* sqid;       // [sq_max + 1] sqnorm -> class index, 0xFF when no row has it
   int sq_max;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void stage_panel(const KnnArgs& a, uint8_t* dst, int 
     const int64_t row = row0 + r;
     const int b = wd << 2;
     uint32_t v = 0;
-    if (row < a.n && b < a.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(a.counts + row * a.pitch + b));
+    if (row < a.row_end && b < a.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(a.counts + row * a.pitch + b));
     *reinterpret_cast<uint32_t*>(dst + r * stride + b) = v;
   }
 }
@@ -135,7 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
-  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kRows;
+  const int64_t row0 = a.row_begin + static_cast<int64_t>(blockIdx.x) * kRows;
+  const int64_t loc0 = static_cast<int64_t>(blockIdx.x) * kRows;  // shard-local index of the CTA's first row
 
   for (int i = threadIdx.x; i < tab_elems; i += kThreads)
     rank_tab[i] = i < a.n_sq * (a.dot_max + 1) ? a.rank_tab[i] : static_cast<uint16_t>(kNoRank);
@@ -150,19 +152,20 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
   // the two rows this lane sees in every accumulator fragment
   const int lrow[2] = {warp * 16 + g, warp * 16 + g + 8};
   const int64_t grow[2] = {row0 + lrow[0], row0 + lrow[1]};
+  const int64_t loc[2] = {loc0 + lrow[0], loc0 + lrow[1]};
   int32_t cut[2] = {-1, -1}, budget[2] = {0, 0};
   int64_t rbase[2] = {0, 0};
   int pos[2] = {0, 0}, seen[2] = {0, 0};
   if (PASS == 2) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
-      if (grow[h] < a.n) {
-        cut[h] = a.cut[grow[h]];
-        budget[h] = a.tie_left[grow[h]];
-        rbase[h] = a.row_off[grow[h]];
+      if (grow[h] < a.row_end) {
+        cut[h] = a.cut[loc[h]];
+        budget[h] = a.tie_left[loc[h]];
+        rbase[h] = a.row_off[loc[h]];
       }
   }
-  const bool rowok[2] = {grow[0] < a.n, grow[1] < a.n};
+  const bool rowok[2] = {grow[0] < a.row_end, grow[1] < a.row_end};
   const int hwords = HIST == kHistSmem16 ? (a.n_ranks + 1) >> 1 : a.n_ranks;
   const int hbase[2] = {lrow[0] * hwords, lrow[1] * hwords};
   const unsigned lower = (0xFu << (4 * g)) & ((1u << lane) - 1u);  // lanes of my row group with a smaller q
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
     // epilogue: fragment element e of n-tile nt is (row grow[e >> 1], column col0 + nt * 8 + 2 q + (e & 1)).
     // Branch-free rank lookup: columns past the end sit in an all-"never" class; the self pair only exists in the
     // diagonal tile (row block = column tile).
-    const bool diag = tile == blockIdx.x;
+    const bool diag = col0 == row0;
     const int tstride = a.dot_max + 1;
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) {
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
           else if (HIST == kHistSmem16)
             atomicAdd(shist + hbase[e >> 1] + (rk[e] >> 1), 1u << ((rk[e] & 1) * 16));
           else
-            atomicAdd(a.hist + grow[e >> 1] * a.n_ranks + rk[e], 1u);
+            atomicAdd(a.hist + loc[e >> 1] * a.n_ranks + rk[e], 1u);
         }
       } else {
         // every lane of a row group keeps the same running state of its two rows (pos: pairs written, seen: members
@@ -291,9 +294,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
 
   if (PASS == 1 && HIST != kHistGlobal) {
     __syncthreads();
-    const int rows_here = a.n - row0 < kRows ? static_cast<int>(a.n - row0) : kRows;
+    const int rows_here = a.row_end - row0 < kRows ? static_cast<int>(a.row_end - row0) : kRows;
     const int total = rows_here * a.n_ranks;
-    uint32_t* out = a.hist + row0 * a.n_ranks;
+    uint32_t* out = a.hist + loc0 * a.n_ranks;
     if (HIST == kHistSmem32) {
       for (int i = threadIdx.x; i < total; i += kThreads) out[i] = shist[i];
     } else {
@@ -310,7 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn_kernel(KnnArgs a) {
 struct OrderArgs {
   const uint64_t* recs;
   const int64_t* row_off;
-  int64_t n;
+  int64_t n;          // rows of the shard
+  int64_t row_begin;
   int n_ranks;
   uint32_t* cursors;  // [n][n_ranks] first output slot of every (row, rank); advanced here
   const int32_t* sqnorm;
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(256) order_kernel(OrderArgs a) {
   const int64_t base = a.row_off[row];
   const int cnt = static_cast<int>(a.row_off[row + 1] - base);
   if (cnt == 0) return;
-  const int sqi = a.sqnorm[row];
+  const int sqi = a.sqnorm[a.row_begin + row];
   const float qmax_f = a.metric == 1 ? static_cast<float>(*a.qmax) : 1.0f;
   uint32_t* cur = a.cursors + row * a.n_ranks;
   for (int i0 = 0; i0 < cnt; i0 += 32) {
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(256) order_kernel(OrderArgs a) {
       } else {
         wv = 1.0f - static_cast<float>(sqi + sqj - 2 * dot) / qmax_f;
       }
-      a.src[slot] = row;
+      a.src[slot] = a.row_begin + row;
       a.dst[slot] = col;
       a.w[slot] = wv;
     }
@@ -447,16 +451,19 @@ size_t hist_smem(int mode, int n_ranks) {
   return 0;
 }
 
-int fill_args(KnnArgs& a, const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
-              int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks) {
+int fill_args(KnnArgs& a, const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
+              const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max,
+              int n_ranks) {
   GG_REQUIRE(n >= 1 && n < (int64_t(1) << 31), GG_ERR_ARG, "n outside [1, 2^31)");
+  GG_REQUIRE(row_begin >= 0 && row_begin < row_end && row_end <= n && row_begin % kRows == 0, GG_ERR_ARG,
+             "row shard must be a non-empty [multiple of 128, <= n) range");
   GG_REQUIRE(pitch == 4 || pitch == 8 || (pitch >= 16 && pitch % 16 == 0 && pitch <= kMaxPitch), GG_ERR_ARG,
              "pitch must be 4, 8 or a multiple of 16 up to 1024");
   GG_REQUIRE(counts && sqnorm && sqid && rank_tab, GG_ERR_ARG, "null argument");
   GG_REQUIRE(n_sq >= 1 && n_sq <= 254 && sq_max >= 0 && sq_max <= 254 && dot_max >= 0, GG_ERR_ARG, "bad class table");
   GG_REQUIRE(n_ranks >= 1 && n_ranks < 0xFFFF, GG_ERR_ARG, "n_ranks outside [1, 65535)");
-  GG_REQUIRE(static_cast<uint64_t>(n) * static_cast<uint64_t>(n_ranks) < (uint64_t(1) << 40), GG_ERR_ARG,
-             "histogram too large");
+  GG_REQUIRE(static_cast<uint64_t>(row_end - row_begin) * static_cast<uint64_t>(n_ranks) < (uint64_t(1) << 40),
+             GG_ERR_ARG, "histogram too large");
   a = KnnArgs{};
   a.counts = counts;
   a.pitch = pitch;
@@ -467,6 +474,8 @@ int fill_args(KnnArgs& a, const uint8_t* counts, int pitch, int64_t n, const int
   const int units = pitch >= 16 ? a.chunk / 16 : a.chunk / 4;  // 2, 4 or 8 per staged row
   a.seg_shift = units == 2 ? 1 : units == 4 ? 2 : 3;
   a.n = n;
+  a.row_begin = row_begin;
+  a.row_end = row_end;
   a.sqnorm = sqnorm;
   a.sqid = sqid;
   a.sq_max = sq_max;
@@ -483,7 +492,7 @@ template <int PASS, int HIST>
 int launch_knn(const KnnArgs& a, size_t smem, cudaStream_t s) {
   GG_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<PASS, HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
-  const unsigned grid = static_cast<unsigned>((a.n + kRows - 1) / kRows);
+  const unsigned grid = static_cast<unsigned>((a.row_end - a.row_begin + kRows - 1) / kRows);
   knn_kernel<PASS, HIST><<<grid, kThreads, smem, s>>>(a);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
@@ -491,13 +500,14 @@ int launch_knn(const KnnArgs& a, size_t smem, cudaStream_t s) {
 
 }  // namespace
 
-/* pass 1: hist[n][n_ranks].  hist_mode: -1 auto, 0 global atomics, 1 shared memory 16-bit (n <= 65536), 2 shared
- * memory 32-bit; a forced shared-memory mode that does not fit is an error. */
-extern "C" int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
-                            int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, int hist_mode,
-                            uint32_t* hist, gg_stream_t st) {
+/* pass 1: hist[row_end - row_begin][n_ranks] of the row shard.  hist_mode: -1 auto, 0 global atomics, 1 shared memory
+ * 16-bit (n <= 65536), 2 shared memory 32-bit; a forced shared-memory mode that does not fit is an error. */
+extern "C" int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
+                            const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq,
+                            int dot_max, int n_ranks, int hist_mode, uint32_t* hist, gg_stream_t st) {
   KnnArgs a;
-  const int rc = fill_args(a, counts, pitch, n, sqnorm, sqid, sq_max, rank_tab, n_sq, dot_max, n_ranks);
+  const int rc =
+      fill_args(a, counts, pitch, n, row_begin, row_end, sqnorm, sqid, sq_max, rank_tab, n_sq, dot_max, n_ranks);
   if (rc != GG_OK) return rc;
   GG_REQUIRE(hist, GG_ERR_ARG, "null histogram");
   GG_REQUIRE(hist_mode >= -1 && hist_mode <= 2, GG_ERR_ARG, "hist_mode must be -1, 0, 1 or 2");
@@ -511,7 +521,7 @@ extern "C" int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, const i
   a.hist = hist;
   cudaStream_t s = gg::as_stream(st);
   if (hist_mode == kHistGlobal)
-    GG_CUDA_CHECK(cudaMemsetAsync(hist, 0, static_cast<size_t>(n) * n_ranks * sizeof(uint32_t), s));
+    GG_CUDA_CHECK(cudaMemsetAsync(hist, 0, static_cast<size_t>(row_end - row_begin) * n_ranks * sizeof(uint32_t), s));
   const size_t smem = base + hist_smem(hist_mode, n_ranks);
   if (hist_mode == kHistSmem32) return launch_knn<1, kHistSmem32>(a, smem, s);
   if (hist_mode == kHistSmem16) return launch_knn<1, kHistSmem16>(a, smem, s);
@@ -525,47 +535,61 @@ extern "C" size_t gg_knn_plan_workspace_bytes(int64_t n) {
   return gg::align_up(scan, 256) + 2 * gg::align_up(static_cast<size_t>(n + 1) * 4, 256) + 256;
 }
 
-/* plan: cut[n], tie_left[n], row_offsets[n + 1] (the last entry = number of edges), qmax (device int32[1], L2 only:
- * the largest kept squared distance in integer units); turns hist into the per-(row, rank) cursors of gg_knn_write. */
-extern "C" int gg_knn_plan(int64_t n, int n_ranks, int k_nn, int metric, const int32_t* sqnorm, const int32_t* rank_q,
-                           uint32_t* hist, int32_t* cut, int32_t* tie_left, int64_t* row_offsets, int32_t* qmax,
-                           void* workspace, size_t workspace_bytes, gg_stream_t st) {
+/* plan for the rows [row_begin, row_end) (per-row arrays are shard-local, m = row_end - row_begin entries): cut[m],
+ * tie_left[m], row_offsets[m + 1] (the last entry = number of edges of the shard), qmax (device int32[1], L2 only: the
+ * largest kept squared distance in integer units); turns hist into the per-(row, rank) cursors of gg_knn_write.
+ * phase 0: everything.  Row-sharded builds need the GLOBAL qmax: phase 1 stops after the cut ranks and the shard's
+ * qmax, the caller maximises qmax over the shards, phase 2 finishes (same workspace, untouched in between). */
+extern "C" int gg_knn_plan(int64_t n, int64_t row_begin, int64_t row_end, int n_ranks, int k_nn, int metric,
+                           const int32_t* sqnorm, const int32_t* rank_q, uint32_t* hist, int32_t* cut, int32_t* tie_left,
+                           int64_t* row_offsets, int32_t* qmax, int phase, void* workspace, size_t workspace_bytes,
+                           gg_stream_t st) {
   GG_REQUIRE(n >= 1 && n < (int64_t(1) << 31), GG_ERR_ARG, "n outside [1, 2^31)");
+  GG_REQUIRE(row_begin >= 0 && row_begin < row_end && row_end <= n, GG_ERR_ARG, "empty or out-of-range row shard");
   GG_REQUIRE(n_ranks >= 1 && n_ranks < 0xFFFF, GG_ERR_ARG, "n_ranks outside [1, 65535)");
   GG_REQUIRE(k_nn >= 1 && k_nn < n, GG_ERR_ARG, "k must be in [1, n - 1]");
   GG_REQUIRE(metric == 0 || metric == 1, GG_ERR_ARG, "metric must be 0 (IP) or 1 (L2)");
+  GG_REQUIRE(phase >= 0 && phase <= 2, GG_ERR_ARG, "phase must be 0, 1 or 2");
   GG_REQUIRE(hist && cut && tie_left && row_offsets && qmax && sqnorm && workspace, GG_ERR_ARG, "null argument");
   GG_REQUIRE(metric == 0 || rank_q, GG_ERR_ARG, "L2 needs rank_q");
-  GG_REQUIRE(workspace_bytes >= gg_knn_plan_workspace_bytes(n), GG_ERR_ARG, "workspace too small");
+  const int64_t m = row_end - row_begin;
+  GG_REQUIRE(workspace_bytes >= gg_knn_plan_workspace_bytes(m), GG_ERR_ARG, "workspace too small");
   cudaStream_t s = gg::as_stream(st);
   gg::Carver cv(workspace);
-  uint32_t* before = cv.take<uint32_t>(n + 1);
-  uint32_t* rowcnt = cv.take<uint32_t>(n + 1);
+  uint32_t* before = cv.take<uint32_t>(m + 1);
+  uint32_t* rowcnt = cv.take<uint32_t>(m + 1);
   void* temp = cv.take<char>(0);
   size_t temp_bytes = workspace_bytes - cv.used();
-  const unsigned grid = static_cast<unsigned>((n + 127) / 128);
-  GG_CUDA_CHECK(cudaMemsetAsync(qmax, 0, sizeof(int32_t), s));
-  GG_CUDA_CHECK(cudaMemsetAsync(rowcnt + n, 0, sizeof(uint32_t), s));
-  cut_kernel<<<grid, 128, 0, s>>>(hist, n, n_ranks, k_nn, metric, sqnorm, rank_q, cut, tie_left, before, qmax);
-  GG_CUDA_CHECK(cudaGetLastError());
-  rows_kernel<<<grid, 128, 0, s>>>(n, n_ranks, metric, sqnorm, rank_q, qmax, cut, tie_left, before, hist, rowcnt);
-  GG_CUDA_CHECK(cudaGetLastError());
-  cub::TransformInputIterator<int64_t, ToI64, const uint32_t*> it(rowcnt, ToI64());
-  GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, row_offsets, static_cast<int>(n + 1), s));
-  cursor_kernel<<<grid, 128, 0, s>>>(n, n_ranks, row_offsets, hist);
-  GG_CUDA_CHECK(cudaGetLastError());
+  const unsigned grid = static_cast<unsigned>((m + 127) / 128);
+  const int32_t* sq = sqnorm + row_begin;
+  if (phase != 2) {
+    GG_CUDA_CHECK(cudaMemsetAsync(qmax, 0, sizeof(int32_t), s));
+    cut_kernel<<<grid, 128, 0, s>>>(hist, m, n_ranks, k_nn, metric, sq, rank_q, cut, tie_left, before, qmax);
+    GG_CUDA_CHECK(cudaGetLastError());
+  }
+  if (phase != 1) {
+    GG_CUDA_CHECK(cudaMemsetAsync(rowcnt + m, 0, sizeof(uint32_t), s));
+    rows_kernel<<<grid, 128, 0, s>>>(m, n_ranks, metric, sq, rank_q, qmax, cut, tie_left, before, hist, rowcnt);
+    GG_CUDA_CHECK(cudaGetLastError());
+    cub::TransformInputIterator<int64_t, ToI64, const uint32_t*> it(rowcnt, ToI64());
+    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, row_offsets, static_cast<int>(m + 1), s));
+    cursor_kernel<<<grid, 128, 0, s>>>(m, n_ranks, row_offsets, hist);
+    GG_CUDA_CHECK(cudaGetLastError());
+  }
   return GG_OK;
 }
 
-/* pass 2 + order: edge_src / edge_dst / weight[row_offsets[n]], grouped by source row, most similar first.
- * recs: scratch of row_offsets[n] 64-bit words (`capacity` of them). */
-extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
-                            int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, int metric,
+/* pass 2 + order for the row shard: edge_src / edge_dst / weight[row_offsets[m]], grouped by source row, most similar
+ * first.  recs: scratch of row_offsets[m] 64-bit words (`capacity` of them). */
+extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
+                            const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq,
+                            int dot_max, int n_ranks, int metric,
                             uint32_t* cursors, const int32_t* cut, const int32_t* tie_left,
                             const int64_t* row_offsets, const int32_t* qmax, uint64_t* recs, int64_t* edge_src,
                             int64_t* edge_dst, float* weight, int64_t capacity, gg_stream_t st) {
   KnnArgs a;
-  const int rc = fill_args(a, counts, pitch, n, sqnorm, sqid, sq_max, rank_tab, n_sq, dot_max, n_ranks);
+  const int rc =
+      fill_args(a, counts, pitch, n, row_begin, row_end, sqnorm, sqid, sq_max, rank_tab, n_sq, dot_max, n_ranks);
   if (rc != GG_OK) return rc;
   GG_REQUIRE(metric == 0 || metric == 1, GG_ERR_ARG, "metric must be 0 (IP) or 1 (L2)");
   GG_REQUIRE(cursors && cut && tie_left && row_offsets && qmax, GG_ERR_ARG, "null plan");
@@ -579,8 +603,9 @@ extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, const i
   cudaStream_t s = gg::as_stream(st);
   const int rc2 = launch_knn<2, kHistGlobal>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s);
   if (rc2 != GG_OK) return rc2;
-  OrderArgs o{recs, row_offsets, n, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
-  const unsigned grid = static_cast<unsigned>((n * 32 + 255) / 256);
+  const int64_t m = row_end - row_begin;
+  OrderArgs o{recs, row_offsets, m, row_begin, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
+  const unsigned grid = static_cast<unsigned>((m * 32 + 255) / 256);
   order_kernel<<<grid, 256, 0, s>>>(o);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;

@@ -348,21 +348,27 @@ GG_API int gg_spmm_csr_f32(const int64_t* row_ptr, const int32_t* col, const flo
  *                 row_offsets[n + 1] (LAST entry = number of edges), qmax; hist becomes the cursors of gg_knn_write
  *   gg_knn_write  second pass (the selected pairs of every row, in column order, into `recs`) + reorder: edges
  *                 grouped by source row, most similar first, ties by ascending column.
+ * Rows are independent: every call works on the row shard [row_begin, row_end) (row_begin a multiple of 128; the
+ * multi-GPU unit) against all n columns, with shard-local per-row arrays (m = row_end - row_begin entries) and
+ * shard-local output slots; "L2" needs the maximum of qmax over the shards between the two phases of gg_knn_plan.
  * pitch: bytes per row of counts: 4, 8, or a multiple of 16 (of 128 above 128) up to 1024.
  * ------------------------------------------------------------------------ */
-GG_API int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
-                 int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks,
-                 int hist_mode /* -1 auto; 0 global atomics, 1 / 2 per-CTA shared memory, 16- / 32-bit bins */,
+GG_API int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
+                 const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max,
+                 int n_ranks, int hist_mode /* -1 auto; 0 global atomics, 1 / 2 per-CTA shared memory, 16- / 32-bit bins */,
                  uint32_t* hist, gg_stream_t st);
-GG_API size_t gg_knn_plan_workspace_bytes(int64_t n);
-GG_API int gg_knn_plan(int64_t n, int n_ranks, int k_nn, int metric, const int32_t* sqnorm, const int32_t* rank_q,
-                uint32_t* hist, int32_t* cut, int32_t* tie_left, int64_t* row_offsets, int32_t* qmax, void* workspace,
-                size_t workspace_bytes, gg_stream_t st);
-GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
-                 int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, int metric, uint32_t* cursors,
-                 const int32_t* cut, const int32_t* tie_left, const int64_t* row_offsets, const int32_t* qmax,
-                 uint64_t* recs /* scratch: `capacity` words */, int64_t* edge_src, int64_t* edge_dst, float* weight,
-                 int64_t capacity /* = row_offsets[n] */, gg_stream_t st);
+GG_API size_t gg_knn_plan_workspace_bytes(int64_t n_rows);
+GG_API int gg_knn_plan(int64_t n, int64_t row_begin, int64_t row_end, int n_ranks, int k_nn, int metric,
+                const int32_t* sqnorm, const int32_t* rank_q, uint32_t* hist, int32_t* cut, int32_t* tie_left,
+                int64_t* row_offsets, int32_t* qmax,
+                int phase /* 0 all; 1 cut ranks + the shard's qmax; 2 finish with the global qmax in place */,
+                void* workspace, size_t workspace_bytes, gg_stream_t st);
+GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
+                 const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max,
+                 int n_ranks, int metric, uint32_t* cursors, const int32_t* cut, const int32_t* tie_left,
+                 const int64_t* row_offsets, const int32_t* qmax, uint64_t* recs /* scratch: `capacity` words */,
+                 int64_t* edge_src, int64_t* edge_dst, float* weight, int64_t capacity /* = row_offsets[m] */,
+                 gg_stream_t st);
 
 #ifdef __cplusplus
 }

@@ -70,12 +70,14 @@ def test_newer_entry_points_validate_their_arguments_without_a_gpu():
     assert lib.gg_rw_pairs(None, None, None, 10, None, 10, 1, 2, 3, 0.0, 1.0, 0, 0, None, None, None, None, 0, None,
                            None) == ERR_ARG                                                     # p must be positive
     one = C.c_void_p(1)   # never dereferenced: validation comes first
-    assert lib.gg_knn_count(one, 24, 100, one, one, 49, one, 5, 49, 30, 0, one, None) == ERR_ARG    # pitch 24
+    assert lib.gg_knn_count(one, 24, 100, 0, 100, one, one, 49, one, 5, 49, 30, 0, one, None) == ERR_ARG    # pitch 24
     assert b"pitch" in lib.gg_last_error()
-    assert lib.gg_knn_count(one, 16, 100, one, one, 49, one, 5, 49, 30, 3, one, None) == ERR_ARG    # hist_mode
-    assert lib.gg_knn_count(one, 16, 100, one, one, 49, one, 5, 49, 2000, 2, one, None) == ERR_ARG  # does not fit
-    assert lib.gg_knn_plan(100, 30, 100, 0, one, None, one, one, one, one, one, one, 1 << 20, None) == ERR_ARG  # k = n
-    assert lib.gg_knn_plan(100, 30, 5, 1, one, None, one, one, one, one, one, one, 1 << 20, None) == ERR_ARG    # L2: rank_q
+    assert lib.gg_knn_count(one, 16, 100, 0, 100, one, one, 49, one, 5, 49, 30, 3, one, None) == ERR_ARG    # hist_mode
+    assert lib.gg_knn_count(one, 16, 100, 0, 100, one, one, 49, one, 5, 49, 2000, 2, one, None) == ERR_ARG  # does not fit
+    assert lib.gg_knn_count(one, 16, 1000, 64, 500, one, one, 49, one, 5, 49, 30, 0, one, None) == ERR_ARG  # shard start
+    assert lib.gg_knn_plan(100, 0, 100, 30, 100, 0, one, None, one, one, one, one, one, 0, one, 1 << 20, None) == ERR_ARG
+    assert lib.gg_knn_plan(100, 0, 100, 30, 5, 1, one, None, one, one, one, one, one, 0, one, 1 << 20, None) == ERR_ARG
+    assert lib.gg_knn_plan(100, 0, 100, 30, 5, 0, one, None, one, one, one, one, one, 3, one, 1 << 20, None) == ERR_ARG
     assert lib.gg_knn_plan_workspace_bytes(65536) >= 2 * 4 * 65537
     assert lib.gg_host_job_wait(None) == ERR_ARG
     assert not lib.gg_host_features_f32_start(None, 10, None, None, 4, 0, None)

@@ -170,3 +170,17 @@ def test_top_n_budget_matches_reference_quirks():
     assert top_n_budget(16384, 0.01, 1_206_888) == 1_206_888
     assert top_n_budget(5, 0.01, 9) == 9
     assert top_n_budget(100, None, 7) == 7
+
+
+def test_knn_row_shards_tile_the_rows():
+    """Row f4b shards rows by 128-row blocks: contiguous, aligned, disjoint, covering, balanced to one block."""
+    from genomic_gnn_b200.core import KNN_ROW_BLOCK, knn_row_shard
+
+    for n in (1, 127, 128, 129, 4096, 65536, 12345):
+        for world in (1, 2, 3, 8):
+            shards = [knn_row_shard(n, world, r) for r in range(world)]
+            assert shards[0][0] == 0 and shards[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+            assert all(lo % KNN_ROW_BLOCK == 0 and lo <= hi for lo, hi in shards)
+            blocks = [-(-(hi - lo) // KNN_ROW_BLOCK) for lo, hi in shards]
+            assert max(blocks) - min(blocks) <= 1

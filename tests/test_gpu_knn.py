@@ -61,6 +61,32 @@ def test_knn_histogram_modes_agree(hist_mode, distance):
     assert torch.equal(got.edge_index, want.edge_index) and torch.equal(got.weight, want.weight)
 
 
+@pytest.mark.parametrize("distance", ["IP", "L2"])
+def test_knn_row_shards_concatenate(distance):
+    """Rows are independent: 128-aligned row shards (the multi-GPU unit), computed separately and agreeing only on the
+    "L2" normaliser, concatenate to the unsharded result."""
+    from genomic_gnn_b200 import core
+
+    built, kc = _built(6, 3, 4000)
+    n = built.db.num_nodes
+    k_nn = 50
+    want = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance)
+    world = 3
+    shards = [core.knn_row_shard(n, world, r) for r in range(world)]
+    assert shards[0][0] == 0 and shards[-1][1] == n and all(a[1] == b[0] for a, b in zip(shards, shards[1:]))
+    qmaxes = []
+    if distance == "L2":   # what the ranks exchange: one integer each
+        for lo, hi in shards:
+            core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, rows=(lo, hi),
+                              qmax_reduce=lambda q: qmaxes.append(q) or max(q, 1))
+    parts = [core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, rows=(lo, hi),
+                               qmax_reduce=(lambda q: max(qmaxes)) if distance == "L2" else None)
+             for lo, hi in shards]
+    ei = torch.cat([p.edge_index for p in parts], dim=1)
+    w = torch.cat([p.weight for p in parts])
+    assert torch.equal(ei, want.edge_index) and torch.equal(w, want.weight)
+
+
 def test_knn_api_and_builder_flag():
     """kf_faiss_to_edge_index_weight on the float matrix the reference passes (np.vstack(labels)), on the labels object,
     and through the mini-batch builder's faiss_ann flag (dataloader.py:108-121: k = int(edges_keep_top_k * N))."""

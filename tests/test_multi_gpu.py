@@ -60,3 +60,40 @@ def test_multi_gpu_equals_single(tmp_path, k, small_k, thr, topk, n_reads):
 
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), k, small_k, thr, topk, n_reads), nprocs=world, join=True)
     assert os.path.exists(tmp_path / "ok")
+
+
+def _knn_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    from genomic_gnn_b200 import core, dist as ggdist
+    from genomic_gnn_b200.synth import synthetic_reads
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        comm = ggdist.TorchComm()
+        built = core.build_graph(synthetic_reads(20_000, 150, seed=5), 7, "2,5", with_kf=False)   # replicated
+        n = built.db.num_nodes
+        for kc in built.kf_counts:
+            for distance in ("IP", "L2"):
+                got = core.kf_knn_edges(kc.counts, kc.sqnorm, int(0.01 * n), distance, comm=comm)
+                if rank == 0:
+                    ref = core.kf_knn_edges(kc.counts, kc.sqnorm, int(0.01 * n), distance)
+                    assert torch.equal(got.edge_index, ref.edge_index) and torch.equal(got.weight, ref.weight)
+        if rank == 0:
+            open(os.path.join(out_dir, "ok"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multi_gpu_knn_equals_single(tmp_path):
+    """Row f4b: per-row kNN KF edges sharded by row range over the ranks (one integer exchanged for "L2", then an
+    all-gather of the edge lists in rank order) == the single-GPU result."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_knn_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert os.path.exists(tmp_path / "ok")
