@@ -7,7 +7,9 @@ gnn_tasks_miniBatch/dataloader.py:108-121 (k = int(edges_keep_top_k * N)).  The 
 default through an approximate IVFFlat index trained with k-means.  What is restated here is the exact search that
 index approximates (faiss.IndexFlatL2 / IndexFlatIP semantics: squared Euclidean distances / inner products of the
 L2-normalised rows, best first) followed by the reference's own post-processing, line by line.  PARITY UNPINNED: no
-FAISS here, no golden vectors in the reference; the anchor is the published definition of the flat indexes.
+FAISS here, no golden vectors in the reference; the anchor is the published definition of the flat indexes, and
+tests/test_oracle.py cross-checks this file against scikit-learn's brute-force NearestNeighbors (an independent
+implementation of the same exact search).
 
 Two deliberate, documented choices where the reference's behaviour is an artefact of FAISS:
   * the reference drops column 0 of the (k + 1)-wide result assuming it is the query itself (gnn_utils.py:207-211);

@@ -222,3 +222,55 @@ def test_knn_tables_rank_like_the_exact_search():
         want_ei, _ = knn.knn_edges(counts, k - s + 1, k_nn, metric)
         assert np.array_equal(np.repeat(codes, k_nn)[keep.ravel()], want_ei[0])
         assert np.array_equal(order.ravel()[keep.ravel()], want_ei[1])
+
+
+def test_knn_oracle_agrees_with_an_independent_exact_search():
+    """oracle/knn.py restates FAISS's flat (exact) search; FAISS is not in the image, scikit-learn's brute-force
+    NearestNeighbors is an independent implementation of the same definition.  Per row: identical distances of the k
+    kept neighbours (float32 round-off apart) and identical neighbour sets above the row's last tie class."""
+    from sklearn.neighbors import NearestNeighbors
+
+    from oracle import knn
+
+    rng = np.random.default_rng(7)
+    k, s, m = 6, 3, 4
+    codes = rng.choice(4**k, size=700, replace=False)
+    d = 4**s
+    counts = np.zeros((codes.size, d), dtype=np.int64)
+    for j in range(k - s + 1):
+        np.add.at(counts, (np.arange(codes.size), (codes >> (2 * (k - s - j))) & (d - 1)), 1)
+    X = counts * (1.0 / m)
+    n, k_nn = X.shape[0], 25
+    # L2: squared Euclidean distances, 1 - d / max d, neighbours at the maximum dropped
+    ei, w = knn.knn_edges(counts, m, k_nn, "L2")
+    nn = NearestNeighbors(n_neighbors=n, algorithm="brute", metric="sqeuclidean").fit(X)
+    dist, idx = nn.kneighbors(X)
+    dmax = 0.0
+    per_row = []
+    for i in range(n):
+        keep = idx[i] != i
+        di, ii = dist[i][keep][:k_nn], idx[i][keep][:k_nn]
+        per_row.append((di, ii, dist[i][keep]))
+        dmax = max(dmax, di.max())
+    starts = np.concatenate([[0], np.cumsum(np.bincount(ei[0], minlength=n))])
+    for i in range(n):
+        di, ii, alld = per_row[i]
+        sim = 1.0 - di / dmax
+        kept = sim > 1e-4
+        seg = slice(starts[i], starts[i + 1])
+        assert seg.stop - seg.start == int(kept.sum())
+        np.testing.assert_allclose(w[seg], sim[kept], rtol=0, atol=2e-6)
+        strict = di[kept] < di[kept].max() - 1e-9        # below the last tie class the choice is forced
+        assert set(ii[kept][strict]) <= set(ei[1][seg])
+    # IP: cosine, zero similarities dropped
+    ei, w = knn.knn_edges(counts, m, k_nn, "IP")
+    Xn = X / np.linalg.norm(X, axis=1, keepdims=True)
+    S = Xn @ Xn.T
+    np.fill_diagonal(S, -1.0)
+    starts = np.concatenate([[0], np.cumsum(np.bincount(ei[0], minlength=n))])
+    for i in range(n):
+        top = np.sort(S[i])[::-1][:k_nn]
+        top = top[top > 1e-4]
+        seg = slice(starts[i], starts[i + 1])
+        np.testing.assert_allclose(w[seg], np.minimum(top, 1.0), rtol=0, atol=2e-6)
+        assert np.all(np.abs(S[i][ei[1][seg]] - w[seg]) < 2e-6)   # every kept edge carries its true cosine
