@@ -274,3 +274,40 @@ def test_knn_oracle_agrees_with_an_independent_exact_search():
         seg = slice(starts[i], starts[i + 1])
         np.testing.assert_allclose(w[seg], np.minimum(top, 1.0), rtol=0, atol=2e-6)
         assert np.all(np.abs(S[i][ei[1][seg]] - w[seg]) < 2e-6)   # every kept edge carries its true cosine
+
+
+def test_knn_rank_tables_order_like_exact_arithmetic():
+    """core.knn_tables for arbitrary sets of squared norms: equal rank <=> equal similarity, lower rank <=> more
+    similar, in exact rational arithmetic ("IP": dot / sqrt(sq_j); "L2": sq_j - 2 dot), and impossible (dot, sq)
+    combinations (Cauchy-Schwarz) / zero dots ("IP") are marked as never-a-neighbour."""
+    from fractions import Fraction
+
+    from hypothesis import given, settings, strategies as st
+
+    from genomic_gnn_b200.core import knn_tables
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.sets(st.integers(min_value=1, max_value=81), min_size=1, max_size=12))
+    def check(sq_set):
+        sq_values = tuple(sorted(sq_set))
+        for metric in ("IP", "L2"):
+            sqid, tab, rank_q, n_ranks = knn_tables(sq_values, metric)
+            sq_max = sq_values[-1]
+            assert tab.shape == (len(sq_values), sq_max + 1)
+            entries = []
+            for sq in sq_values:
+                for dot in range(sq_max + 1):
+                    r = int(tab[sqid[sq], dot])
+                    possible = dot * dot <= sq * sq_max and not (metric == "IP" and dot == 0)
+                    assert (r != 0xFFFF) == possible
+                    if possible:
+                        key = Fraction(dot * dot, sq) if metric == "IP" else -(sq - 2 * dot)
+                        entries.append((r, key))
+                        if metric == "L2":
+                            assert rank_q[r] == sq - 2 * dot
+            assert {r for r, _ in entries} == set(range(n_ranks)) or not entries
+            for (r1, k1) in entries[::7]:
+                for (r2, k2) in entries[::5]:
+                    assert (r1 < r2) == (k1 > k2) and (r1 == r2) == (k1 == k2)
+
+    check()
