@@ -142,6 +142,8 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
     if kmer_frequency_loss_weight != 0:
         for i, lab in enumerate(kmer_freq_labels or []):
             if faiss_ann:
+                if not edges_keep_top_k:   # parsers.py:566-573 asserts the same before training starts
+                    raise ValueError("Faiss ANN only supported with keep_top_k.")
                 k_nn = int(edges_keep_top_k * len(lab))
                 if isinstance(lab, api.KFLabels):
                     res = core.kf_knn_edges(lab.kc.counts, lab.kc.sqnorm, k_nn, faiss_distance)
