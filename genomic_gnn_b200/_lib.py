@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgg_b200.so")
 
 GG_OK = 0
+GG_ABI_VERSION = 2
 GG_SEP = 10
 GG_MAX_K = 13
 GG_KF_BLOCK = 1024
@@ -38,6 +39,7 @@ _P, _I64, _I32, _SZ, _DBL = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_doub
 SIGNATURES = {
     "gg_abi_version": (_I32, []),
     "gg_last_error": (C.c_char_p, []),
+    "gg_build_id": (C.c_char_p, []),
     "gg_stream_padded_bytes": (_SZ, [_I64]),
     "gg_hist_bins": (_SZ, [_I32]),
     "gg_count_reset": (_I32, [_I32, _P, _P, _P, _P]),
@@ -98,19 +100,20 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
 
-        try:
-            _build.build()
-        except Exception as exc:  # loud: no fallback path exists
-            raise GGError(f"libgg_b200.so is missing and could not be built: {exc}") from exc
+    # build() is a no-op when the .so carries the digest of the sources next to it; a library built from older
+    # sources (stale signatures behind an unchanged symbol table) is rebuilt, never loaded
+    try:
+        _build.build()
+    except Exception as exc:  # loud: no fallback path exists
+        raise GGError(f"libgg_b200.so is missing or stale and could not be built: {exc}") from exc
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.gg_abi_version() != 1:
+    if lib.gg_abi_version() != GG_ABI_VERSION:
         raise GGError("libgg_b200.so ABI version mismatch")
     _lib = lib
     return lib

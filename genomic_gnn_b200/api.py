@@ -232,14 +232,20 @@ def _count_result_from_dict(pair_frequency, device=None):
     bridges = torch.tensor(nb_rows if nb_rows else [[0, 0, 0, 0]], dtype=torch.int64).to(torch.int32).to(dev)
     return core.CountResult(k, torch.from_numpy(hist.view(np.int32)).to(dev),
                             torch.from_numpy(first.view(np.int64)).to(dev), bridges, len(nb_rows),
-                            torch.zeros(8, dtype=torch.int64, device=dev), int(overlap.sum()))
+                            torch.zeros(8, dtype=torch.int64, device=dev), int(overlap.sum()),
+                            pos_limit=max(len(keys), 1))  # positions are dict indices: bounds K2's sort keys
 
 
 def build_deBruijn_graph(pair_frequency, normalise: bool = False, remove_N: bool = False,
                          edge_weight_threshold: Optional[float] = None, keep_top_k: Optional[float] = None,
                          create_all_kmers: bool = True, disable_tqdm: bool = True) -> KmerGraph:
-    """src/utils.py:87-165.  Unlike the reference this does not mutate
-    ``pair_frequency``."""
+    """src/utils.py:87-165.  Unlike the reference this does not mutate ``pair_frequency``.
+
+    Only ``remove_N=True`` is built (what every builder passes, kmer_ssgnn.py:181-187): with ``remove_N=False`` the
+    reference keeps an isolated 'N'*k node (utils.py:131,162-163) that shifts every node index, so that case raises
+    instead of silently returning a different graph (same policy as ``inlcudeUNK=True`` above)."""
+    if not remove_N:
+        raise NotImplementedError("remove_N=False keeps an 'N'*k node; the builders always pass remove_N=True")
     if isinstance(pair_frequency, PairFrequency):
         cr = pair_frequency.count_result
     else:

@@ -5,6 +5,8 @@
 The .so is git-ignored but travels to the GPU box with the repo snapshot.
 """
 import concurrent.futures as cf
+import fcntl
+import hashlib
 import os
 import subprocess
 import sys
@@ -21,6 +23,36 @@ FLAGS = [
 ]
 
 
+BUILD_ID_MARK = b"GG_BUILD_ID="
+
+
+def source_hash():
+    """Digest of every file the library is built from: the build id compiled into the .so (gg_build_id())."""
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "gg_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:32]
+
+
+def built_id(lib=LIB):
+    """Build id embedded in an existing .so (None: absent or unreadable)."""
+    try:
+        with open(lib, "rb") as fh:
+            blob = fh.read()
+    except OSError:
+        return None
+    at = blob.find(BUILD_ID_MARK)
+    return None if at < 0 else blob[at + len(BUILD_ID_MARK): at + len(BUILD_ID_MARK) + 32].decode("ascii", "replace")
+
+
+def is_current():
+    return built_id() == source_hash()
+
+
 def _deps_mtime():
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     files.append(os.path.join(os.path.dirname(HERE), "include", "gg_b200.h"))
@@ -29,9 +61,11 @@ def _deps_mtime():
 
 def _compile(src):
     obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-    if os.path.exists(obj) and os.path.getmtime(obj) >= _deps_mtime():
+    stamp = src == "gg_common.cu"   # carries the build id: always recompiled (1 s)
+    if not stamp and os.path.exists(obj) and os.path.getmtime(obj) >= _deps_mtime():
         return obj, ""
-    cmd = [NVCC, *FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
+    extra = ['-DGG_BUILD_ID_STR="%s"' % source_hash()] if stamp else []
+    cmd = [NVCC, *FLAGS, *extra, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -39,12 +73,23 @@ def _compile(src):
 
 
 def build(force=False, verbose=False):
+    """Compile + link unless the .so already carries the build id of the current sources.  Safe to call from several
+    processes at once (one rank per GPU): the work happens under an exclusive file lock and is re-checked inside."""
     os.makedirs(BUILD, exist_ok=True)
+    if not force and is_current():
+        return LIB
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and is_current():
+            return LIB
+        return _build_locked(force, verbose)
+
+
+def _build_locked(force, verbose):
     if force:
         for f in os.listdir(BUILD):
-            os.remove(os.path.join(BUILD, f))
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
-        return LIB
+            if f != ".lock":
+                os.remove(os.path.join(BUILD, f))
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         results = list(ex.map(_compile, SOURCES))
     log = "\n".join(l for _, l in results if l)
@@ -52,10 +97,12 @@ def build(force=False, verbose=False):
         fh.write(log)
     if verbose:
         print(log)
-    cmd = [NVCC, "-shared", "-o", LIB, *[o for o, _ in results], "-Xcompiler", "-fPIC", "-lcudart", "-lpthread"]
+    tmp = LIB + ".tmp%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-o", tmp, *[o for o, _ in results], "-Xcompiler", "-fPIC", "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)   # atomic: a concurrent dlopen sees the old or the new file, never a partial one
     return LIB
 
 

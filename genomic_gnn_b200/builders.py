@@ -12,6 +12,7 @@ so a maintainer can bind them with ``KmerSsgnn.create_graphs = create_graphs``
 ``Data`` / ``HeteroData`` / ``NeighborLoader``; without it (this image) they are
 the minimal stand-ins below with the same field names.
 """
+from collections import Counter
 from typing import List, Optional
 
 import numpy as np
@@ -19,13 +20,16 @@ import torch
 
 from . import api, core
 
-try:  # pragma: no cover - torch_geometric is absent in the build image
-    from torch_geometric.data import Data as _PygData, HeteroData as _PygHetero
-    from torch_geometric.loader import NeighborLoader as _PygNeighborLoader
 
-    HAVE_PYG = True
-except Exception:  # noqa: BLE001
-    HAVE_PYG = False
+def _pyg():
+    """(Data, HeteroData, NeighborLoader) of torch_geometric, or None when it is not importable (this image).
+    Looked up per call so that the tests can run the PyG branch against a recording stand-in in sys.modules."""
+    try:
+        from torch_geometric.data import Data, HeteroData
+        from torch_geometric.loader import NeighborLoader
+    except Exception:  # noqa: BLE001
+        return None
+    return Data, HeteroData, NeighborLoader
 
 
 class GraphData(dict):
@@ -98,15 +102,21 @@ def _as_float_tensor(labels, device):
 
 
 def count_edge_types(layers_config):
-    """gnn_tasks_miniBatch/utils.py count_edge_types: one hop per layer string."""
-    return len(layers_config or [])
+    """gnn_tasks_miniBatch/utils.py:48-64: the number of hops the NeighborLoader samples = how often the most used
+    edge type occurs among the layer strings ("<channels>_<edgeType>"), or 2 when the strings carry no edge type
+    (MLP / RGCN configurations)."""
+    layers = list(layers_config)
+    if len(layers[0].split("_")) > 1:
+        return max(Counter(layer.split("_")[1] for layer in layers).values())
+    return 2
 
 
 # --------------------------------------------------------------------------- a7
 def networkx_to_dataloader_full_batch(graph, labels, labels_to_predict=None, batch_size=1, dummy_dataloader=True,
                                       device="cpu"):
     """gnn_tasks/utils.py:8-51 -> (dataloader, Data)."""
-    data = _PygData() if HAVE_PYG else GraphData()
+    pyg = _pyg()
+    data = pyg[0]() if pyg else GraphData()
     data.edge_index = graph.edge_index.to(device)
     data.weight = graph.weight.to(device)
     data.num_nodes = graph.num_nodes
@@ -130,7 +140,8 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
     approximate FAISS index (index type / nlist / nprobe / m / nbits are accepted and ignored)."""
     if edit_distance_loss_weight != 0:
         raise NotImplementedError("edit-distance (ED) edges are out of scope (SURVEY.md section 2, row 8)")
-    data = _PygHetero() if HAVE_PYG else HeteroGraphData()
+    pyg = _pyg()
+    data = pyg[1]() if pyg else HeteroGraphData()
     data["node"].x = _as_float_tensor(labels, device)
     data["node", "DB", "node"].edge_index = graph.edge_index.to(device)
     data["node", "DB", "node"].edge_attr = graph.weight.to(device)
@@ -168,10 +179,9 @@ def networkx_to_dataloader_mini_batch(graph, labels, labels_to_predict=None, bat
         input_nodes = torch.unique(allidx[:, allidx[0] != allidx[1]])
     else:
         input_nodes = torch.arange(n)
-    if HAVE_PYG:  # pragma: no cover
-        loader = _PygNeighborLoader(data, num_neighbors=[-1] * count_edge_types(layers_config),
-                                    input_nodes=("node", input_nodes), batch_size=batch_size, pin_memory=True,
-                                    shuffle=True, directed=False)
+    if pyg:  # dataloader.py:167-177
+        loader = pyg[2](data, num_neighbors=[-1] * count_edge_types(layers_config), input_nodes=("node", input_nodes),
+                        batch_size=batch_size, pin_memory=True, shuffle=True, directed=False)
     else:
         loader = SeedNodeLoader(data, input_nodes, batch_size, shuffle=True)
     return loader, data

@@ -27,5 +27,13 @@ int sm_count() {
 
 }  // namespace gg
 
+#ifndef GG_BUILD_ID_STR
+#define GG_BUILD_ID_STR "unstamped"
+#endif
+// "GG_BUILD_ID=<digest of csrc/ + gg_b200.h>": genomic_gnn_b200/build.py finds the marker in the file to decide whether
+// the library on disk was built from the sources next to it (a stale .so must never be loaded against a newer header)
+static const char g_build_id[] = "GG_BUILD_ID=" GG_BUILD_ID_STR;
+
 extern "C" int gg_abi_version(void) { return GG_ABI_VERSION; }
+extern "C" const char* gg_build_id(void) { return g_build_id + 12; }
 extern "C" const char* gg_last_error(void) { return gg::g_err; }

@@ -229,6 +229,8 @@ extern "C" int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, cons
                            gg_stream_t st) {
   GG_REQUIRE(k >= 1 && k <= GG_MAX_K, GG_ERR_K, "k outside [1, GG_MAX_K]");
   GG_REQUIRE(pos_bits >= 1 && pos_bits <= 40, GG_ERR_ARG, "pos_bits outside [1, 40]");
+  // the edge sort key is (node rank << pos_bits) | first position, plus one bit for the all-ones "dropped" key
+  GG_REQUIRE(pos_bits + 2 * k + 1 <= 64, GG_ERR_ARG, "pos_bits + 2k + 1 must fit the 64-bit edge sort key");
   GG_REQUIRE(hist && first_pos && node_codes && code_to_node && edge_src && edge_dst && out_ne && workspace,
              GG_ERR_ARG, "null buffer");
   GG_REQUIRE(n_bridges >= 0 && (n_bridges == 0 || bridges), GG_ERR_ARG, "bridge list");

@@ -71,13 +71,30 @@ class NormAdj:
         return ptr_, cols[order].to(torch.int32).contiguous(), vals[order].contiguous()
 
 
+_SPMM_MAX_D = 128   # gg_spmm_csr_f32: channels per call
+
+
 def _spmm(csr, x: torch.Tensor) -> torch.Tensor:
     row_ptr, col, val = csr
-    x = x.contiguous()
-    y = torch.empty_like(x)
-    check(_lib.load().gg_spmm_csr_f32(ptr(row_ptr), ptr(col), ptr(val), int(row_ptr.numel() - 1), ptr(x), int(x.shape[1]),
-                                      ptr(y), _stream()), "gg_spmm_csr_f32")
-    return y
+    if int(row_ptr.numel()) - 1 != int(x.shape[0]):
+        raise ValueError(f"adjacency has {int(row_ptr.numel()) - 1} nodes, features have {int(x.shape[0])} rows")
+    lib = _lib.load()
+    d = int(x.shape[1])
+    if d <= _SPMM_MAX_D:
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.gg_spmm_csr_f32(ptr(row_ptr), ptr(col), ptr(val), int(x.shape[0]), ptr(x), d, ptr(y), _stream()),
+              "gg_spmm_csr_f32")
+        return y
+    # the kernel keeps one row of <= 128 channels per warp: wider layers go through it in column tiles
+    parts = []
+    for c0 in range(0, d, _SPMM_MAX_D):
+        xt = x[:, c0:c0 + _SPMM_MAX_D].contiguous()
+        yt = torch.empty_like(xt)
+        check(lib.gg_spmm_csr_f32(ptr(row_ptr), ptr(col), ptr(val), int(x.shape[0]), ptr(xt), int(xt.shape[1]), ptr(yt),
+                                  _stream()), "gg_spmm_csr_f32")
+        parts.append(yt)
+    return torch.cat(parts, dim=1)
 
 
 class _Aggregate(torch.autograd.Function):
@@ -117,10 +134,21 @@ class GCN(torch.nn.Module):
         self._adj: Dict[str, NormAdj] = {}
 
     def adjacency(self, edges_config, cfg, n):
-        key = cfg["edge_index"]
-        if key not in self._adj:
-            self._adj[key] = NormAdj(edges_config[key], edges_config.get(cfg["edge_weight"]), n)
-        return self._adj[key]
+        """Normalised adjacency of the layer's edge set, cached on the IDENTITY of the tensors it was built from: the
+        reference flow keeps the trained encoder and then runs it on a rebuilt, larger graph (kmer_ssgnn.py:127-146),
+        and mini-batches hand the same encoder a different edges_config per call."""
+        name = cfg["edge_index"]
+        ei, w = edges_config[name], edges_config.get(cfg["edge_weight"])
+        key = (ei.data_ptr(), tuple(ei.shape), ei._version, None if w is None else (w.data_ptr(), w._version), int(n))
+        hit = self._adj.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, NormAdj(ei, w, n))
+            self._adj[name] = hit
+        return hit[1]
+
+    def invalidate(self):
+        """Drop the cached adjacencies (after editing an edge tensor in place)."""
+        self._adj.clear()
 
     def forward(self, x, edges_config):
         for i, (conv, cfg) in enumerate(zip(self.convs, self.layers_config)):

@@ -40,7 +40,7 @@ typedef void* gg_stream_t; /* cudaStream_t */
 #define GG_API
 #endif
 
-#define GG_ABI_VERSION 1
+#define GG_ABI_VERSION 2
 #define GG_OK 0
 #define GG_ERR_ARG (-1)      /* null pointer, negative size, misaligned buffer */
 #define GG_ERR_K (-2)        /* k / small_k outside the supported range */
@@ -54,6 +54,7 @@ typedef void* gg_stream_t; /* cudaStream_t */
 
 GG_API int gg_abi_version(void);
 GG_API const char* gg_last_error(void); /* thread-local, valid until the next failing call */
+GG_API const char* gg_build_id(void);   /* digest of the sources this library was compiled from (build.py) */
 
 /* ------------------------------------------------------------------------
  * K1  counting.  Replaces seq_to_kmers + weighted_directed_edges
