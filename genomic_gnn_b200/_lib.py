@@ -84,6 +84,8 @@ SIGNATURES = {
     "gg_knn_plan": (_I32, [_I64, _I64, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
     "gg_knn_write": (_I32, [_P, _I32, _I64, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P,
                             _P, _P, _P, _I64, _P]),
+    "gg_probe_smem_atomics": (_I32, [_I32, _I32, _P, C.POINTER(C.c_double), _P]),
+    "gg_probe_tensor_i8": (_I32, [_I32, _I32, _P, C.POINTER(C.c_double), _P]),
     "gg_kf_select_workspace_bytes": (_SZ, [_I64]),
     "gg_kf_select": (_I32, [_P, _P, _P, _P, _I64, _P, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P]),
 }

@@ -849,6 +849,73 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
   if (tid == 0 && bars->error) *error_flag = 1;
 }
 
+
+// ======================================================================================
+// Tensor-pipe ceiling probe (bench.py): the CTA-pair kernel's MMA stream with nothing around it -- resident operands
+// (an 8 x 128-byte-K-block A strip and one B stage per CTA, filled once), no TMA refills, no epilogue.  One leader
+// thread per CTA pair issues `iters` tiles of n_kblocks x 4 tcgen05.mma.cta_group::2.kind::i8 (M = 256, N = 256,
+// K = 32) into two alternating TMEM stages.  Timed from the host with CUDA events; the rate is the denominator the
+// kind::i8 roofline fraction of kf_tcgen05_pair_kernel is quoted against, measured at the clocks the bench runs at.
+// ======================================================================================
+__global__ void __launch_bounds__(128, 1) tensor_probe_kernel(int iters, int n_kblocks, uint32_t desc_hi, int* error_flag) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kStageBytes = kTileM * 128;
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_b + kStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool leader = cluster_ctarank() == 0;
+  for (int i = tid; i < (n_kblocks + 1) * kStageBytes / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = (static_cast<uint32_t>(i) * 2654435761u >> 7) & 0x03030303u;  // counts 0..3
+  if (tid == 0) {
+    mbar_init(&bars->a_full, 1);
+    bars->error = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy fills -> visible to the tensor core
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  if (warp == 0 && leader) {
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a)), b_lo = umma_desc_lo(smem_u32(smem_b));
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t tmem_d = tmem_base + (it & 1) * kPairTileN;
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(kb) * (kStageBytes >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int k4 = 0; k4 < 128 / kUmmaK; ++k4) {
+            const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k4 * (kUmmaK >> 4));
+            const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k4 * (kUmmaK >> 4));
+            tc_mma_i8_pair(tmem_d, da, db, kIdescPair, (kb | k4) != 0);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tc_commit_pair(&bars->a_full);  // fires in both CTAs once every MMA above has retired
+    __syncwarp();
+  }
+  mbar_wait(&bars->a_full, 0, &bars->error);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+  if (tid == 0 && bars->error) *error_flag = 1;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -983,6 +1050,32 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kf_tcgen05_pair_kernel, tmap, a, n_bstages, total_units, error_flag, g));
+  return GG_OK;
+}
+
+
+// ops issued by one launch: pairs x iters x n_kblocks x 4 MMAs x 2 x 256 x 256 x 32
+int tensor_probe(int iters, int n_kblocks, int* error_flag, double* h_ops, cudaStream_t s) {
+  GG_REQUIRE(iters >= 1 && n_kblocks >= 1 && n_kblocks <= 8 && error_flag && h_ops, GG_ERR_ARG, "bad probe arguments");
+  const size_t smem_bytes = static_cast<size_t>(n_kblocks + 1) * kTileM * 128 + sizeof(Barriers) + 1024;
+  GG_CUDA_CHECK(cudaFuncSetAttribute(tensor_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem_bytes)));
+  const unsigned pairs = static_cast<unsigned>(gg::sm_count() / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint32_t desc_hi = static_cast<uint32_t>((8 * 128) >> 4) | (1u << 14) | (2u << 29);
+  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tensor_probe_kernel, iters, n_kblocks, desc_hi, error_flag));
+  *h_ops = static_cast<double>(pairs) * iters * n_kblocks * 4.0 * 2.0 * 256.0 * 256.0 * 32.0;
   return GG_OK;
 }
 

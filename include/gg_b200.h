@@ -371,6 +371,21 @@ GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row
                  int64_t* edge_src, int64_t* edge_dst, float* weight, int64_t capacity /* = row_offsets[m] */,
                  gg_stream_t st);
 
+/* ------------------------------------------------------------------------
+ * Hardware-ceiling probes (measurement only; no reference counterpart).  One kernel launch per call on the caller's
+ * stream; *h_updates / *h_ops (HOST out-parameters) = operations that launch performs, to be divided by the launch's
+ * CUDA-event time.
+ *   gg_probe_smem_atomics  K1's secondary ceiling: uniform 32-bit shared-memory atomic adds into a `bins`-entry table
+ *                          per CTA (1024 threads, one CTA per SM) -- the update pattern of the bucket-count kernel.
+ *                          scratch: >= number of SMs uint32.
+ *   gg_probe_tensor_i8     K4's ceiling: the CTA-pair kernel's tcgen05.mma.cta_group::2.kind::i8 stream (M = 256,
+ *                          N = 256, K = 32; uint8 operands resident in shared memory, n_kblocks x 128-byte K blocks
+ *                          per tile) with no TMA and no epilogue.  *h_ops counts 2 ops per multiply-accumulate.
+ *                          error_flag: device int32, set to 1 on a barrier time-out.
+ * ------------------------------------------------------------------------ */
+GG_API int gg_probe_smem_atomics(int bins, int iters, uint32_t* scratch, double* h_updates, gg_stream_t st);
+GG_API int gg_probe_tensor_i8(int iters, int n_kblocks, int32_t* error_flag, double* h_ops, gg_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif
