@@ -259,7 +259,7 @@ def census_launches(step):
                 out["torch"] += 1
             else:
                 out["own"] += 1
-                short = name.split("(")[0].split("<")[0].split("::")[-1]
+                short = name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0].split("<")[0].split("::")[-1]
                 names[short] = names.get(short, 0) + 1
         out["own_kernels"] = names
         out["source"] = "torch.profiler (CUPTI), one untimed step"

@@ -30,6 +30,20 @@ class KfParams(C.Structure):
         ("fast_shift", C.c_int32),
         ("impl", C.c_int32),
         ("d_valid", C.c_int32),
+        ("hist_m", C.c_int32),
+    ]
+
+
+class KfDedupExtra(C.Structure):
+    _fields_ = [
+        ("class_hist", C.c_void_p),
+        ("hist_class_begin", C.c_int64),
+        ("hist_class_end", C.c_int64),
+        ("tie_out", C.c_void_p),
+        ("tie_num", C.c_int64),
+        ("tie_den", C.c_int64),
+        ("row_lo", C.c_int64),
+        ("row_hi", C.c_int64),
     ]
 
 
@@ -55,7 +69,10 @@ SIGNATURES = {
     "gg_kf_counts": (_I32, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
     "gg_kf_features_f32": (_I32, [_P, _I64, _I32, _P, _I32, _P, _P, _P]),
     "gg_kf_rowcnt_elems": (_SZ, [_I64, _I32, _I32]),
-    "gg_kf_emit": (_I32, [C.POINTER(KfParams), _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "gg_kf_emit": (_I32, [C.POINTER(KfParams), _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "gg_kf_class_hist_packed": (_I32, [_P, _I64, _P, _I32, _P, _P]),
+    "gg_kf_select_packed_workspace_bytes": (_SZ, [_I64]),
+    "gg_kf_select_packed": (_I32, [_P, _I64, _P, _I32, _P, C.c_uint64, _P, _P, _P, _P, _P, _I64, _P, _SZ, _P]),
     "gg_kf_place_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "gg_kf_place": (_I32, [C.POINTER(KfParams), _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "gg_kf_expand": (_I32, [_P, _I32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P, _P, _P, _P, _P, _P, _P]),
@@ -64,7 +81,7 @@ SIGNATURES = {
     "gg_kf_dedup_classes_workspace_bytes": (_SZ, [_I64]),
     "gg_kf_dedup_classes": (_I32, [_P, _I32, _I32, _I64, _P, _P, _P, _P, _SZ, _P]),
     "gg_kf_dedup_adj_words": (_SZ, [_I64]),
-    "gg_kf_dedup_score": (_I32, [_P, _I32, _I32, _P, _P, _P, _I64, _P, _I32, _P, _P]),
+    "gg_kf_dedup_score": (_I32, [_P, _I32, _I32, _P, _P, _P, _I64, _P, _I32, _P, C.POINTER(KfDedupExtra), _P]),
     "gg_kf_dedup_count_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "gg_kf_dedup_count": (_I32, [_I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
     "gg_kf_dedup_place": (_I32, [_I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _I32, _I32, _P, _I64, _P, _SZ, _P]),

@@ -6,6 +6,7 @@ Stages: count -> first occurrence -> De Bruijn assembly
 """
 import ctypes as C
 import os
+import threading
 from contextlib import contextmanager
 from dataclasses import dataclass, field
 from fractions import Fraction
@@ -89,7 +90,7 @@ class LocalComm:
         return buf
 
 
-_MAILBOX = {}
+_MAILBOX_TLS = threading.local()   # one mailbox per thread: a pinned buffer is not something two threads can share
 
 
 def read_small(t: torch.Tensor) -> torch.Tensor:
@@ -100,10 +101,11 @@ def read_small(t: torch.Tensor) -> torch.Tensor:
         return t
     n = int(t.numel())
     key = (t.device, t.dtype)
-    box = _MAILBOX.get(key)
+    boxes = _MAILBOX_TLS.__dict__.setdefault("boxes", {})
+    box = boxes.get(key)
     if box is None or box.numel() < n:
         box = torch.empty(max(n, 4096), dtype=t.dtype, pin_memory=True)
-        _MAILBOX[key] = box
+        boxes[key] = box
     box[:n].copy_(t.reshape(-1), non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return box[:n].view(t.shape)
@@ -431,43 +433,75 @@ def kf_features_f32(kc: KFCounts) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- K4-K6
+@dataclass(frozen=True)
+class ScoreTest:
+    """The exact candidate test on integers: a pair with dot product ``dot`` and norm product P = sq_s * sq_t passes
+    iff dot^2 * den > num * P (``inclusive``: >=).  A float64 threshold t is the rational num / den = t^2; the
+    cut-off class (dot_c, P_c) of a binding top-n is num / den = dot_c^2 / P_c."""
+    num: int
+    den: int
+    inclusive: bool = False
+
+    @staticmethod
+    def from_threshold(threshold: float) -> "ScoreTest":
+        if threshold < 0:
+            raise ValueError("negative KF threshold is not supported (the reference would then emit zero-weight "
+                             "lower-triangle pairs)")
+        fr = Fraction(threshold)
+        return ScoreTest(fr.numerator**2, fr.denominator**2, False)
+
+
 @lru_cache(maxsize=64)
-def threshold_tables(threshold: float, sq_max: int):
-    """Exact-rational threshold tables (host, tiny).
-    dmin[P]: smallest integer dot with dot / sqrt(P) > threshold.
-    fast_scale[sq] = floor(threshold^2 * sq * 2^shift): conservative pre-filter."""
-    if threshold < 0:
-        raise ValueError("negative KF threshold is not supported (the reference would then emit zero-weight "
-                         "lower-triangle pairs)")
-    fr = Fraction(threshold)
-    a2, b2 = fr.numerator**2, fr.denominator**2
+def rational_tables(test: ScoreTest, sq_max: int):
+    """Host tables of the scoring kernels (tiny).
+    dmin[P]: smallest integer dot that passes ``test`` against the norm product P (65535: none can).
+    fast_scale[sq]: conservative pre-filter of the wide-row kernels: a candidate always satisfies
+    (dot^2 << shift) > fast_scale[sq_s] * sq_t."""
+    a2, b2 = test.num, test.den
     p_max = sq_max * sq_max
     dmin = np.empty(p_max + 1, dtype=np.uint16)
     for p in range(p_max + 1):
-        dmin[p] = min(isqrt((a2 * p) // b2) + 1, 65535)
+        if test.inclusive:   # dot^2 >= ceil(a2 p / b2)
+            need = -((-a2 * p) // b2)
+            d = 0 if need <= 0 else isqrt(need - 1) + 1
+        else:                # dot^2 > floor(a2 p / b2)
+            d = isqrt((a2 * p) // b2) + 1
+        dmin[p] = min(d, 65535)
     dmin[0] = 65535
     shift = 31 - max(p_max, 1).bit_length()
     shift = max(0, min(shift, 24))
-    scale = np.array([(a2 * sq << shift) // b2 for sq in range(sq_max + 1)], dtype=np.uint64)
+    if test.inclusive:       # strictly below a2 sq 2^shift / b2, so that equality still passes the `>` of the kernels
+        scale = np.array([max(((a2 * sq << shift) - 1) // b2, 0) if sq else 0 for sq in range(sq_max + 1)], dtype=np.uint64)
+    else:
+        scale = np.array([(a2 * sq << shift) // b2 for sq in range(sq_max + 1)], dtype=np.uint64)
     assert int(scale.max()) * sq_max < 2**32 and (p_max << shift) < 2**32
     return dmin, scale.astype(np.uint32), shift, p_max
+
+
+def threshold_tables(threshold: float, sq_max: int):
+    """Exact-rational tables of the strict test cos > threshold (gnn_utils.py:294)."""
+    return rational_tables(ScoreTest.from_threshold(float(threshold)), int(sq_max))
 
 
 _DEVICE_TABLES = {}
 
 
-def _device_threshold_tables(threshold: float, sq_max: int, dev):
-    """Device copies of the threshold tables, cached per (threshold, sq_max, device): the upload is a pageable
-    host-to-device copy that would otherwise synchronise every call."""
-    key = (threshold, sq_max, str(dev))
+def _device_tables(test: ScoreTest, sq_max: int, dev):
+    """Device copies of the tables, cached per (test, sq_max, device): the upload is a pageable host-to-device copy
+    that would otherwise synchronise every call."""
+    key = (test, sq_max, str(dev))
     hit = _DEVICE_TABLES.get(key)
     if hit is None:
-        dmin, scale, shift, p_max = threshold_tables(threshold, sq_max)
+        dmin, scale, shift, p_max = rational_tables(test, sq_max)
         hit = (torch.from_numpy(dmin.view(np.int16)).to(dev), torch.from_numpy(scale.view(np.int32)).to(dev), shift, p_max)
         if len(_DEVICE_TABLES) > 256:
             _DEVICE_TABLES.clear()
         _DEVICE_TABLES[key] = hit
     return hit
+
+
+def _as_test(threshold) -> ScoreTest:
+    return threshold if isinstance(threshold, ScoreTest) else ScoreTest.from_threshold(float(threshold))
 
 
 _DEVICE_LUTS = {}
@@ -490,15 +524,22 @@ def top_n_budget(n_nodes: int, keep_top_k: Optional[float], n_candidates: int) -
 
 @dataclass
 class KFEdges:
-    edge_index: torch.Tensor   # int64 [2, E], s < t, reference emission order
-    weight64: Optional[torch.Tensor]  # float64 [E] (None after a multi-GPU gather)
+    edge_index: torch.Tensor   # int64 [2, E], s < t, reference emission order (this rank's shard when ``sharded``)
+    weight64: Optional[torch.Tensor]  # float64 [E] (None after a multi-GPU build or a streamed top-n)
     weight: torch.Tensor       # float32 [E]
-    n_candidates: int          # pairs above the threshold before the top-n cut
+    n_candidates: int          # pairs above the threshold before the top-n cut (all ranks)
     cutoff: Optional[float] = None   # score of the cut-off class when top-n was binding
     tie_kept: int = 0
     tie_total: int = 0
     impl: str = "auto"
     pending: list = field(default_factory=list)  # in-flight multi-GPU transfers filling edge_index / weight
+    sharded: bool = False      # edge_index / weight hold only this rank's row-block shard (gather=False)
+    per_rank: Optional[list] = None   # edges per rank, in rank (= emission) order
+    resident: bool = True      # False: the edges were produced chunk by chunk into a recycled buffer (sink="discard")
+
+    @property
+    def n_edges(self) -> int:
+        return int(sum(self.per_rank)) if self.per_rank is not None else int(self.edge_index.shape[1])
 
     def wait(self):
         for req in self.pending:
@@ -511,13 +552,20 @@ def _row_blocks(n):
     return (n + _lib.GG_KF_BLOCK - 1) // _lib.GG_KF_BLOCK
 
 
-def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max: int, iblock_begin=0,
-            iblock_end=None, impl="auto", rec_capacity=None, sync=True):
-    """Score all pairs of the row-block shard and stage the candidates.
+def kf_hist_bins(sq_max: int) -> int:
+    """Entries of a score-class table: class (dot, P) lives at dot * (p_max + 1) + P, dot <= sq_max, P <= sq_max^2."""
+    return (sq_max + 1) * (sq_max * sq_max + 1)
+
+
+def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, iblock_begin=0,
+            iblock_end=None, impl="auto", rec_capacity=None, sync=True, class_hist=None, hist_m=0, retry=True):
+    """Score all pairs of the row-block shard and stage the candidates (``threshold``: float or ScoreTest).
     Returns (recs, n_recs, rowcnt, params, counts_scored): the last is the matrix the kernel read (zero-padded to a
     32-byte pitch for the tensor path on narrow rows), which kf_finalize needs to re-multiply narrow rows.
     With ``sync=False`` nothing is read back: n_recs is None and a sixth element, the device status words
-    (gg_kf_emit: [0] candidates found, [2] pipeline error), is returned for the caller to read later."""
+    (gg_kf_emit: [0] candidates found, [2] pipeline error), is returned for the caller to read later.
+    ``class_hist``: device uint64 table (kf_hist_bins entries) the CTA-pair tensor kernel adds the score classes of
+    ALL candidates to; ``retry=False`` returns n_recs > capacity instead of scoring again with more room."""
     lib = _lib.load()
     dev = counts.device
     d_valid = int(counts.shape[1])
@@ -527,8 +575,8 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
     n, d = int(counts.shape[0]), int(counts.shape[1])
     nb = _row_blocks(n)
     iblock_end = nb if iblock_end is None else iblock_end
-    dmin_d, scale_d, shift, p_max = _device_threshold_tables(float(threshold), int(sq_max), dev)
-    params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl], d_valid)
+    dmin_d, scale_d, shift, p_max = _device_tables(_as_test(threshold), int(sq_max), dev)
+    params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl], d_valid, int(hist_m))
     rc_elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
     rowcnt = torch.empty(max(rc_elems, 1), dtype=torch.int64, device=dev)
     status = torch.empty(4, dtype=torch.int64, device=dev)
@@ -538,17 +586,23 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max
         recs = torch.empty((max(rec_capacity, 1), 4), dtype=torch.int32, device=dev)
         with _stage(f"k4_emit_d{d}"):
             check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
-                                 rec_capacity, ptr(rowcnt), ptr(status), _stream()), "gg_kf_emit")
+                                 rec_capacity, ptr(rowcnt), ptr(status), ptr(class_hist), _stream()), "gg_kf_emit")
         if not sync:
             return recs, None, rowcnt, params, counts, status
-        st_host = status.cpu()
+        st_host = read_small(status).tolist()
         if int(st_host[2]) != 0:
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
         found = int(st_host[0])
-        if found <= rec_capacity:
+        if found <= rec_capacity or not retry:
             return recs, found, rowcnt, params, counts
         del recs
         rec_capacity = found
+
+
+def pair_kernel_serves(d: int, impl: str) -> bool:
+    """True when gg_kf_emit runs the CTA-pair tensor kernel for rows of ``d`` bytes -- the kernel that can keep the
+    score-class histogram while it scores."""
+    return d % 128 == 0 and 128 <= d <= 1024 and impl in ("auto", "tcgen05x2")
 
 
 class StagedRecords:
@@ -559,17 +613,23 @@ class StagedRecords:
         self.d = params.d
         self.status4 = status      # device int64[4] while n_recs has not been read: [0] found, [2] pipeline error
         self.redo = redo           # re-scores the shard with room for a given number of records
+        self.found = None
 
     def after_counts(self, mine):
         """``mine`` = this rank's status words as read by kf_resolve."""
         if int(mine[2]) != 0:
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
-        found = int(mine[0])
-        if found > int(self.recs.shape[0]):   # staging buffer too small (rare): score again with the exact size
-            self.recs, self.n_recs, self.rowcnt, self.params, self.scored = self.redo(found)
-        else:
-            self.n_recs = found
+        self.found = int(mine[0])
         self.status4 = None
+
+    def complete(self):
+        """Make sure every candidate has its record (the staging buffer may have been too small: score again)."""
+        if self.n_recs is None:
+            if self.found > int(self.recs.shape[0]):
+                self.recs, self.n_recs, self.rowcnt, self.params, self.scored = self.redo(self.found)
+            else:
+                self.n_recs = self.found
+        return self
 
     def place(self, ordered_ptr, capacity=None):
         """K6a: one packed 8-byte word per edge, in emission order, at ``ordered_ptr`` (room for n_recs words)."""
@@ -587,8 +647,8 @@ class StagedRecords:
 class StagedClasses:
     """Candidates of a row-block shard held as duplicate-row classes + the class-pair bit matrix (gg_kf_dedup_*)."""
 
-    def __init__(self, counts, n, ib0, ib1, members, class_start, n_classes, adj, offsets, n_recs):
-        self.counts, self.n, self.ib0, self.ib1 = counts, n, ib0, ib1
+    def __init__(self, counts, sqnorm, n, ib0, ib1, members, class_start, n_classes, adj, offsets, n_recs):
+        self.counts, self.sqnorm, self.n, self.ib0, self.ib1 = counts, sqnorm, n, ib0, ib1
         self.members, self.class_start, self.n_classes, self.adj, self.offsets = members, class_start, n_classes, adj, offsets
         self.n_recs = n_recs                 # None until kf_resolve has read it
         self.d = int(counts.shape[1])
@@ -599,20 +659,47 @@ class StagedClasses:
         self.n_recs = int(mine[0])
         self.status4 = None
 
+    def complete(self):
+        return self
+
+    def score(self, test: ScoreTest, sq_max: int, extra=None):
+        """(Re)build the class-pair bit matrix for ``test``; ``extra`` = _lib.KfDedupExtra by-products."""
+        lib = _lib.load()
+        dmin_d, _, _, p_max = _device_tables(test, int(sq_max), self.counts.device)
+        with _stage(f"k4_score_d{self.d}"):
+            check(lib.gg_kf_dedup_score(ptr(self.counts), self.d, self.d, ptr(self.sqnorm), ptr(self.members),
+                                        ptr(self.class_start), self.n_classes, ptr(dmin_d), p_max, ptr(self.adj),
+                                        None if extra is None else C.byref(extra), _stream()), "gg_kf_dedup_score")
+
+    def count(self, ib0, ib1):
+        """Exclusive prefix of the candidates per (block pair, row) of [ib0, ib1) under the current bit matrix; the
+        last entry is their number."""
+        lib = _lib.load()
+        dev = self.counts.device
+        elems = int(lib.gg_kf_rowcnt_elems(self.n, ib0, ib1))
+        offsets = torch.empty(elems + 1, dtype=torch.int64, device=dev)
+        cb = int(lib.gg_kf_dedup_count_workspace_bytes(self.n, ib0, ib1))
+        cws = torch.empty(cb, dtype=torch.uint8, device=dev)
+        with _stage(f"k4_count_d{self.d}"):
+            check(lib.gg_kf_dedup_count(self.n, ib0, ib1, ptr(self.adj), ptr(self.members), ptr(self.class_start),
+                                        self.n_classes, ptr(offsets), ptr(cws), cb, _stream()), "gg_kf_dedup_count")
+        return offsets
+
+    def place_range(self, ib0, ib1, offsets, ordered_ptr, capacity):
+        lib = _lib.load()
+        ws = torch.empty(256, dtype=torch.uint8, device=self.counts.device)
+        with _stage(f"k6_place_d{self.d}"):
+            check(lib.gg_kf_dedup_place(self.n, ib0, ib1, ptr(self.adj), ptr(self.members), ptr(self.class_start),
+                                        self.n_classes, ptr(offsets), ptr(self.counts), self.d, self.d, ordered_ptr,
+                                        capacity, ptr(ws), 256, _stream()), "gg_kf_dedup_place")
+
     def place(self, ordered_ptr, capacity=None):
         if not self.n_recs:
             return
-        lib = _lib.load()
-        d = int(self.counts.shape[1])
-        ws = torch.empty(256, dtype=torch.uint8, device=self.counts.device)
-        with _stage(f"k6_place_d{d}"):
-            check(lib.gg_kf_dedup_place(self.n, self.ib0, self.ib1, ptr(self.adj), ptr(self.members),
-                                        ptr(self.class_start), self.n_classes, ptr(self.offsets), ptr(self.counts), d, d,
-                                        ordered_ptr, self.n_recs if capacity is None else capacity, ptr(ws), 256,
-                                        _stream()), "gg_kf_dedup_place")
+        self.place_range(self.ib0, self.ib1, self.offsets, ordered_ptr, self.n_recs if capacity is None else capacity)
 
 
-def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float, sq_max: int, iblock_begin=0,
+def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, iblock_begin=0,
                    iblock_end=None) -> StagedClasses:
     """K4' for narrow rows (<= 16 columns, counts <= 15): group identical rows into classes, score the class pairs,
     count the shard's edges.  One small device read here (the number of classes sizes the bit matrix); the number of
@@ -622,7 +709,6 @@ def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float,
     n, d = int(counts.shape[0]), int(counts.shape[1])
     nb = _row_blocks(n)
     iblock_end = nb if iblock_end is None else iblock_end
-    dmin_d, _, _, p_max = _device_threshold_tables(float(threshold), int(sq_max), dev)
     st = _stream()
     members = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     class_start = torch.empty(n + 1, dtype=torch.int32, device=dev)
@@ -636,18 +722,16 @@ def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float,
     if n_over:
         raise GGError("duplicate-row KF path: a count above 15 does not fit the packed row key")
     adj = torch.empty(max(int(lib.gg_kf_dedup_adj_words(n_classes)), 1), dtype=torch.int32, device=dev)
-    with _stage(f"k4_score_d{d}"):
-        check(lib.gg_kf_dedup_score(ptr(counts), d, d, ptr(sqnorm), ptr(members), ptr(class_start), n_classes, ptr(dmin_d),
-                                    p_max, ptr(adj), st), "gg_kf_dedup_score")
-    elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
-    offsets = torch.empty(elems + 1, dtype=torch.int64, device=dev)
-    cb = int(lib.gg_kf_dedup_count_workspace_bytes(n, iblock_begin, iblock_end))
-    cws = torch.empty(cb, dtype=torch.uint8, device=dev)
-    with _stage(f"k4_count_d{d}"):
-        check(lib.gg_kf_dedup_count(n, iblock_begin, iblock_end, ptr(adj), ptr(members), ptr(class_start), n_classes,
-                                    ptr(offsets), ptr(cws), cb, st), "gg_kf_dedup_count")
+    staged = StagedClasses.__new__(StagedClasses)
+    staged.counts, staged.sqnorm, staged.n, staged.ib0, staged.ib1 = counts, sqnorm, n, iblock_begin, iblock_end
+    staged.members, staged.class_start, staged.n_classes, staged.adj = members, class_start, n_classes, adj
+    staged.d = d
+    staged.score(_as_test(threshold), sq_max)
+    offsets = staged.count(iblock_begin, iblock_end)
     # the shard's edge count stays on the device: the caller reads it together with the other ranks' counts
-    return StagedClasses(counts, n, iblock_begin, iblock_end, members, class_start, n_classes, adj, offsets, None)
+    StagedClasses.__init__(staged, counts, sqnorm, n, iblock_begin, iblock_end, members, class_start, n_classes, adj,
+                           offsets, None)
+    return staged
 
 
 def kf_finalize(staged, sqnorm, want_dot=False, out=None):
@@ -678,6 +762,13 @@ def choose_cutoff(class_hist: np.ndarray, p_max: int, budget: int):
     rationals, keep whole classes while they fit, and mark the class that
     straddles the budget.  Returns (action uint8 table, tie_budget, cutoff score,
     tie_total)."""
+    action, tie_budget, cutoff, tie_total, _ = choose_cutoff_class(class_hist, p_max, budget)
+    return action, tie_budget, cutoff, tie_total
+
+
+def choose_cutoff_class(class_hist: np.ndarray, p_max: int, budget: int):
+    """choose_cutoff + the score of the lowest class that contributes an edge, as the rational dot^2 / P: the cut-off
+    class when one straddles the budget (tie_total > 0), else the last class kept whole."""
     keys = np.nonzero(class_hist)[0]
     dots, ps = keys // (p_max + 1), keys % (p_max + 1)
     cnt = class_hist[keys].astype(np.int64)
@@ -685,7 +776,7 @@ def choose_cutoff(class_hist: np.ndarray, p_max: int, budget: int):
     order = sorted(range(len(keys)), key=lambda i: vals[i], reverse=True)
     action = np.zeros(class_hist.shape[0], dtype=np.uint8)
     taken, i = 0, 0
-    tie_budget, cutoff, tie_total = 0, None, 0
+    tie_budget, cutoff, tie_total, cut = 0, None, 0, None
     while i < len(order) and taken < budget:
         j = i
         while j < len(order) and vals[order[j]] == vals[order[i]]:
@@ -695,13 +786,28 @@ def choose_cutoff(class_hist: np.ndarray, p_max: int, budget: int):
         if taken + size <= budget:
             action[keys[grp]] = 1
             taken += size
+            cut = vals[grp[0]]
         else:
             action[keys[grp]] = 2
             tie_budget, tie_total = budget - taken, size
             cutoff = float(dots[grp[0]]) / float(np.sqrt(float(ps[grp[0]])))
+            cut = vals[grp[0]]
             taken = budget
         i = j
-    return action, tie_budget, cutoff, tie_total
+    return action, tie_budget, cutoff, tie_total, cut
+
+
+def tie_ratio(tie_budget: int, tie_total: int) -> int:
+    """r = ceil(B 2^64 / T) of the spread rule (gg_kf_select_packed): member g of the cut-off class, numbered in global
+    emission order, is kept iff floor((g + 1) r / 2^64) > floor(g r / 2^64).  Exactly B of the T members pass."""
+    if not (0 < tie_budget < tie_total):
+        return 0
+    return -((-tie_budget << 64) // tie_total)
+
+
+def ties_admitted(g: int, ratio: int) -> int:
+    """Members of the cut-off class with global number < g that the spread rule keeps."""
+    return (g * ratio) >> 64
 
 
 @dataclass
@@ -715,10 +821,15 @@ class KFStage:
     impl: str
     staged: object = None          # StagedRecords / StagedClasses; None: no pair can be an edge
     per_rank: Optional[list] = None
+    iblock_begin: int = 0
+    iblock_end: int = 0
+    row_sum: int = 0               # every row of counts sums to this (k - small_k + 1); 0: unknown
+    class_hist: Optional[torch.Tensor] = None   # score classes of this rank's candidates, counted while scoring
 
 
 def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
-             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None) -> KFStage:
+             sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None,
+             row_sum: int = 0) -> KFStage:
     """K4: score this rank's row-block shard; the candidate count stays on the device (kf_resolve reads the counts of
     any number of staged sets, on every rank, with one device read)."""
     _require_cuda()
@@ -727,7 +838,9 @@ def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         raise ValueError("negative KF threshold is not supported")
     if sq_max is None:
         sq_max = int(sqnorm.max().item()) if n else 0
-    st = KFStage(counts, sqnorm, float(threshold), keep_top_k, int(sq_max), impl)
+    iblock_end = _row_blocks(n) if iblock_end is None else iblock_end
+    st = KFStage(counts, sqnorm, float(threshold), keep_top_k, int(sq_max), impl, iblock_begin=iblock_begin,
+                 iblock_end=iblock_end, row_sum=int(row_sum))
     if n < 2 or threshold >= 1.0 or sq_max == 0:
         return st
     d_valid = int(counts.shape[1])
@@ -742,13 +855,16 @@ def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         st.staged = kf_stage_dedup(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end)
     else:
         # staging capacity: the global top-n budget is the natural first guess (a binding threshold stays below it,
-        # a binding top-n overflows once and is re-run with the exact size)
+        # a binding top-n overflows, and is then cut from the score-class table without these records)
         n_pairs = n * (n - 1) // 2
         guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
         # ... capped at 2 GB of records: at k=10 the budget alone would be 1.1e10 records (176 GB)
         rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20), 1 << 27))
+        if keep_top_k is not None and pair_kernel_serves(d_valid, impl):
+            st.class_hist = torch.zeros(kf_hist_bins(int(sq_max)), dtype=torch.int64, device=counts.device)
         recs, _, rowcnt, params, scored, status = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end,
-                                                          impl, rec_capacity=rec_capacity, sync=False)
+                                                          impl, rec_capacity=rec_capacity, sync=False,
+                                                          class_hist=st.class_hist, hist_m=row_sum)
 
         def redo(found):
             return kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl, rec_capacity=found)
@@ -773,35 +889,110 @@ def kf_resolve(stages: List[KFStage], comm=None):
 
 def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
              sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None, comm=None,
-             gather: bool = True) -> KFEdges:
+             gather: bool = True, row_sum: int = 0, chunk_records: Optional[int] = None, sink: str = "device") -> KFEdges:
     """K4-K6.  Reference: gnn_utils.py:240-322.
 
     With ``comm`` (dist.TorchComm) every rank scores its own row-block shard
     [iblock_begin, iblock_end); the only exchanges are an all-gather of the candidate counts,
-    (when the global top-n binds) a sum of the score-class histogram, and the
-    final all-gather of the per-shard edge lists, which concatenate in rank
+    (when the global top-n binds) a sum of the score-class table, and -- unless ``gather=False`` leaves the result
+    sharded -- the final all-gather of the per-shard edge lists, which concatenate in rank
     order to the single-GPU emission order."""
-    st = kf_stage(counts, sqnorm, threshold, keep_top_k, sq_max, impl, iblock_begin, iblock_end)
+    st = kf_stage(counts, sqnorm, threshold, keep_top_k, sq_max, impl, iblock_begin, iblock_end, row_sum)
     kf_resolve([st], comm)
-    return kf_finish(st, comm, gather)
+    return kf_finish(st, comm, gather, chunk_records=chunk_records, sink=sink)
 
 
-def kf_finish(st: KFStage, comm=None, gather: bool = True) -> KFEdges:
-    """K5/K6 (+ the multi-GPU exchange) of a staged and resolved KF set."""
+def _block_pairs_rows(n, b0, b1):
+    """Node pairs s < t whose smaller node lies in row blocks [b0, b1)."""
+    lo, hi = min(b0 * _lib.GG_KF_BLOCK, n), min(b1 * _lib.GG_KF_BLOCK, n)
+    rows = hi - lo
+    return rows * (n - 1) - (lo + hi - 1) * rows // 2
+
+
+class _SelectSink:
+    """Destination of a top-n selection that arrives chunk by chunk in emission order: final edge arrays sized for the
+    edges this rank keeps ("device"), or one recycled chunk-sized buffer when the caller only wants the work done and
+    counted ("discard": the result would not fit the device, e.g. BASELINE config 5 on fewer than 4 GPUs)."""
+
+    def __init__(self, dev, n_out, g_start, want_w64, discard, chunk_cap, out=None):
+        self.discard = discard
+        size = max(min(n_out, chunk_cap) if discard else n_out, 1)
+        if out is not None:
+            self.ei, self.w32 = out
+        else:
+            self.ei = torch.empty((2, size), dtype=torch.int64, device=dev)
+            self.w32 = torch.empty(size, dtype=torch.float32, device=dev)
+        self.w64 = torch.empty(size, dtype=torch.float64, device=dev) if want_w64 and not discard else None
+        self.capacity = int(self.w32.shape[0])
+        self.cursors = torch.tensor([int(g_start), 0], dtype=torch.int64, device=dev)
+        self.kept_before = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def select(self, ordered, n_words, sqnorm, p_max, action_d, ratio):
+        lib = _lib.load()
+        if n_words == 0:
+            return
+        if self.discard:   # recycle the buffer: remember what earlier chunks kept, start again at its front
+            self.kept_before += self.cursors[1:2]
+            self.cursors[1:2].zero_()
+        wb = int(lib.gg_kf_select_packed_workspace_bytes(n_words))
+        ws = torch.empty(wb, dtype=torch.uint8, device=ordered.device)
+        with _stage("k5_select"):
+            check(lib.gg_kf_select_packed(ptr(ordered), n_words, ptr(sqnorm), p_max, ptr(action_d), C.c_uint64(ratio),
+                                          ptr(self.cursors), ptr(self.ei[0]), ptr(self.ei[1]), ptr(self.w64),
+                                          ptr(self.w32), self.capacity, ptr(ws), wb, _stream()), "gg_kf_select_packed")
+
+    def totals(self):
+        """(members of the cut-off class seen up to here in global numbering, edges kept by this rank)."""
+        g, kept = read_small(self.cursors).tolist()
+        return int(g), int(kept) + (int(read_small(self.kept_before)[0]) if self.discard else 0)
+
+
+def _plan_chunks(n, b0, b1, expect_words, cap):
+    """Split row blocks [b0, b1) into consecutive ranges whose expected number of packed words stays below ``cap``
+    (uniform density over the shard's node pairs; a range that still overflows is halved by the caller)."""
+    pairs = max(_block_pairs_rows(n, b0, b1), 1)
+    density = expect_words / pairs
+    out, lo = [], b0
+    while lo < b1:
+        hi = lo + 1
+        while hi < b1 and _block_pairs_rows(n, lo, hi + 1) * density * 1.1 <= cap:
+            hi += 1
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def kf_finish(st: KFStage, comm=None, gather: bool = True, chunk_records: Optional[int] = None,
+              sink: str = "device") -> KFEdges:
+    """K5/K6 (+ the multi-GPU exchange) of a staged and resolved KF set.
+
+    Threshold-bound sets (candidates <= int(N^2 p), or no top-n at all) are placed and expanded as they were scored.
+    When the global top-n binds (gnn_utils.py:311-317) the cut-off comes from the table of exact score classes
+    (dot, sq_s sq_t): counted inside the scoring kernels when they can (CTA-pair tensor kernel, duplicate-row classes)
+    -- then the candidates are never materialised: the shard is re-scored in row-block chunks against the cut-off,
+    >= for the cut-off class, and gg_kf_select_packed keeps what survives -- or from the placed candidates otherwise.
+    Members of the cut-off class are kept by the spread rule (tie_ratio): the same members for every world size and
+    chunking, an equal share on every rank."""
     lib = _lib.load()
     comm = comm or LocalComm()
     counts, sqnorm, threshold, keep_top_k, sq_max, impl = st.counts, st.sqnorm, st.threshold, st.keep_top_k, st.sq_max, st.impl
     dev = counts.device
     n = int(counts.shape[0])
+    if sink not in ("device", "discard"):
+        raise ValueError("sink must be 'device' or 'discard'")
     if st.staged is None:
         return KFEdges(torch.zeros((2, 0), dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.float64, device=dev),
-                       torch.zeros(0, dtype=torch.float32, device=dev), 0, impl=impl)
+                       torch.zeros(0, dtype=torch.float32, device=dev), 0, impl=impl, per_rank=[0] * comm.world,
+                       sharded=comm.world > 1 and not gather)
     staged, per_rank = st.staged, st.per_rank
-    n_recs = staged.n_recs
     n_total = sum(per_rank)
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total
     exchange = gather and comm.world > 1
+    if need_cut:
+        return _kf_finish_top_n(st, comm, gather, budget, n_total, chunk_records, sink)
+    staged.complete()
+    n_recs = staged.n_recs
 
     def shared_buffers(sizes):
         """Output tensors sized for every rank; this rank's slice starts at `lo`."""
@@ -809,8 +1000,7 @@ def kf_finish(st: KFStage, comm=None, gather: bool = True) -> KFEdges:
         return (torch.empty((2, max(total, 1)), dtype=torch.int64, device=dev),
                 torch.empty(max(total, 1), dtype=torch.float32, device=dev), total, lo)
 
-    full_ei = full_w = None
-    if exchange and not need_cut:
+    if exchange:
         # C2 on the packed form: K6a places this rank's edges as 8-byte words into its segment of an all-ranks
         # buffer, ONE in-place all-gather moves 8 instead of 20 bytes per edge, and K6b expands the gathered words
         # into edge_index / weight on every rank.  (float64 weights are not produced here: only the function-level
@@ -826,62 +1016,161 @@ def kf_finish(st: KFStage, comm=None, gather: bool = True) -> KFEdges:
         with _stage(f"k6_expand_d{staged.d}"):
             check(lib.gg_kf_expand(ptr(ordered), comm.world, seg_first, seg_size, ptr(sqnorm), ptr(full_ei[0]),
                                    ptr(full_ei[1]), None, ptr(full_w), None, _stream()), "gg_kf_expand")
-        return KFEdges(full_ei[:, :e_total], None, full_w[:e_total], n_total, None, 0, 0, impl)
-    ei, w64, w32, dot = kf_finalize(staged, sqnorm, want_dot=need_cut)
-    p_max_tables = _device_threshold_tables(float(threshold), int(sq_max), dev)[3]
-    del staged
-    cutoff, tie_budget, tie_total = None, 0, 0
-    if need_cut:
-        p_max = p_max_tables
-        hist = torch.zeros((sq_max + 1) * (p_max + 1), dtype=torch.int64, device=dev)
-        src, dst = ei[0].contiguous(), ei[1].contiguous()
+        return KFEdges(full_ei[:, :e_total], None, full_w[:e_total], n_total, None, 0, 0, impl, per_rank=list(per_rank))
+    ei, w64, w32, _ = kf_finalize(staged, sqnorm)
+    return KFEdges(ei.contiguous(), w64, w32, n_total, None, 0, 0, impl, per_rank=list(per_rank),
+                   sharded=comm.world > 1)
+
+
+def _kf_finish_top_n(st: KFStage, comm, gather, budget, n_total, chunk_records, sink) -> KFEdges:
+    """The binding global top-n (see kf_finish)."""
+    lib = _lib.load()
+    counts, sqnorm, sq_max, impl, staged = st.counts, st.sqnorm, st.sq_max, st.impl, st.staged
+    dev = counts.device
+    n = int(counts.shape[0])
+    b0, b1 = st.iblock_begin, st.iblock_end
+    test = ScoreTest.from_threshold(st.threshold)
+    p_max = sq_max * sq_max
+    bins = kf_hist_bins(sq_max)
+    dedup = isinstance(staged, StagedClasses)
+    streamed = dedup or st.class_hist is not None
+    chunk_cap = int(chunk_records) if chunk_records else 1 << 27
+    ordered_all = None
+    # ---- 1. the global table of score classes
+    if dedup:
+        # class pairs weighted by their member counts; every rank scores its slice of the class-pair triangle
+        hist = torch.zeros(bins, dtype=torch.int64, device=dev)
+        u = staged.n_classes
+        cut = [int(round(u * (1.0 - (1.0 - r / comm.world) ** 0.5))) for r in range(comm.world)] + [u]
+        extra = _lib.KfDedupExtra(hist.data_ptr(), cut[comm.rank], cut[comm.rank + 1], None, 0, 0, 0, 0)
+        staged.score(test, sq_max, extra)
+        local_hist = None
+    elif st.class_hist is not None:
+        hist = st.class_hist
+        local_hist = read_small(hist).numpy().copy() if comm.world > 1 else None
+    else:
+        # candidates materialised (any other scoring kernel): place them and count the classes of the placed words
+        staged.complete()
+        ordered_all = torch.empty(max(staged.n_recs, 1), dtype=torch.int64, device=dev)
+        staged.place(ptr(ordered_all))
+        hist = torch.zeros(bins, dtype=torch.int64, device=dev)
         with _stage("k5_class_hist"):
-            check(lib.gg_kf_class_hist(ptr(src), ptr(dst), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(hist), _stream()),
-                  "gg_kf_class_hist")
-        local_hist = hist.cpu().numpy()
-        global_hist = comm.sum_tensor_(hist).cpu().numpy() if comm.world > 1 else local_hist
-        action, tie_budget, cutoff, tie_total = choose_cutoff(global_hist, p_max, budget)
-        # the cut-off class is cut in emission order: lower ranks (earlier row blocks) are served first
-        local_ties = int(local_hist[action == 2].sum())
-        before = sum(comm.gather_ints(local_ties)[: comm.rank])
-        local_tie_budget = min(max(tie_budget - before, 0), local_ties)
-        expect = int(local_hist[action == 1].sum()) + local_tie_budget
-        per_rank = comm.gather_ints(expect) if comm.world > 1 else [expect]
-        action_d = torch.from_numpy(action).to(dev)
-        if exchange:
-            full_ei, full_w, e_total, lo = shared_buffers(per_rank)
-            out, o32 = full_ei[:, lo:], full_w[lo:]
-        else:
-            out = torch.empty((2, max(expect, 1)), dtype=torch.int64, device=dev)
-            o32 = torch.empty(max(expect, 1), dtype=torch.float32, device=dev)
-        o64 = torch.empty(max(expect, 1), dtype=torch.float64, device=dev)
-        cnt = torch.empty(1, dtype=torch.int64, device=dev)
-        ws_bytes = int(lib.gg_kf_select_workspace_bytes(n_recs))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with _stage("k5_select"):
-            check(lib.gg_kf_select(ptr(src), ptr(dst), ptr(w64), ptr(dot), n_recs, ptr(sqnorm), p_max, ptr(action_d),
-                                   local_tie_budget, ptr(out[0]), ptr(out[1]), ptr(o64), ptr(o32), ptr(cnt), ptr(ws),
-                                   ws_bytes, _stream()), "gg_kf_select")
-        kept = int(cnt.item())
-        if kept != expect:
-            raise GGError(f"top-n select kept {kept} edges, expected {expect}")
-        ei, w64, w32 = out[:, :expect], o64[:expect], o32[:expect]
-    pending = []
+            check(lib.gg_kf_class_hist_packed(ptr(ordered_all), staged.n_recs, ptr(sqnorm), p_max, ptr(hist), _stream()),
+                  "gg_kf_class_hist_packed")
+        local_hist = read_small(hist).numpy().copy() if comm.world > 1 else None
+    if comm.world > 1:
+        with _stage("c5_reduce_class_hist"):
+            comm.sum_tensor_(hist)
+    global_hist = read_small(hist).numpy().copy()
+    if int(global_hist.sum()) != n_total:
+        raise GGError(f"score-class table holds {int(global_hist.sum())} candidates, the scoring pass counted {n_total}")
+    action, tie_budget, cutoff, tie_total, cut_class = choose_cutoff_class(global_hist, p_max, budget)
+    ratio = tie_ratio(tie_budget, tie_total)
+    action_d = torch.from_numpy(action).to(dev)
+    # ---- 2. what this rank will keep: everything above the cut-off class + its share of the class
+    cut_test = ScoreTest(cut_class.numerator, cut_class.denominator, True)   # >= the lowest class that contributes
+    have_tie = tie_total > 0
+    if dedup:
+        # second scoring pass against the cut-off (>=): the bit matrix the chunks are emitted from, and this rank's
+        # members of the cut-off class / pairs above it from the class sizes at its row boundaries
+        sums = torch.zeros(2, dtype=torch.int64, device=dev)
+        row_lo, row_hi = min(b0 * _lib.GG_KF_BLOCK, n), min(b1 * _lib.GG_KF_BLOCK, n)
+        extra = _lib.KfDedupExtra(None, 0, 0, sums.data_ptr(), cut_class.numerator, cut_class.denominator, row_lo, row_hi)
+        staged.score(cut_test, sq_max, extra)
+        local_offsets = staged.count(b0, b1)
+        t_lo, t_hi = read_small(sums).tolist()
+        local_ties = int(t_lo) - int(t_hi) if have_tie else 0
+        local_ge = int(read_small(local_offsets[-1:])[0])
+        local_above = local_ge - local_ties
+    else:
+        lh = local_hist if local_hist is not None else global_hist
+        local_ties, local_above = int(lh[action == 2].sum()), int(lh[action == 1].sum())
+        local_ge = local_ties + local_above
+    ties_per_rank = comm.gather_ints(local_ties) if comm.world > 1 else [local_ties]
+    above_per_rank = comm.gather_ints(local_above) if comm.world > 1 else [local_above]
+    g_start = sum(ties_per_rank[: comm.rank])
+    kept_per_rank = []
+    g = 0
+    for r in range(comm.world):
+        kept_per_rank.append(above_per_rank[r] + ties_admitted(g + ties_per_rank[r], ratio) - ties_admitted(g, ratio))
+        g += ties_per_rank[r]
+    if g != tie_total or sum(kept_per_rank) != budget:
+        raise GGError(f"top-n accounting: {g} members of the cut-off class (table: {tie_total}), "
+                      f"{sum(kept_per_rank)} edges kept (budget {budget})")
+    mine = kept_per_rank[comm.rank]
+    exchange = gather and comm.world > 1
+    discard = sink == "discard"
+    full_ei = full_w = None
+    out = None
     if exchange:
-        # C2: zero-copy all-gather(v) -- every rank's edges already sit in its slice; one batch of point-to-point
-        # transfers fills in the other slices.  The float64 weights stay sharded (only the function-level API wants
-        # them).  The transfers are waited for here: NCCL's send/receive kernels take SMs, and the persistent Gram
-        # kernels (one CTA or CTA pair per SM) lose a whole wave when they cannot all be resident -- measured 2x
-        # on the next set's scoring when the exchange was left in flight underneath it.
+        total, lo = sum(kept_per_rank), sum(kept_per_rank[: comm.rank])
+        full_ei = torch.empty((2, max(total, 1)), dtype=torch.int64, device=dev)
+        full_w = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+        out = (full_ei[:, lo: lo + max(mine, 1)], full_w[lo: lo + max(mine, 1)])
+    dest = _SelectSink(dev, mine, g_start, want_w64=comm.world == 1, discard=discard, chunk_cap=chunk_cap, out=out)
+    # ---- 3. emission
+    if not streamed:
+        step = 1 << 30   # gg_kf_select_packed takes at most 2^31 - 1 words per call
+        for lo in range(0, staged.n_recs, step):
+            dest.select(ordered_all[lo: lo + step], min(step, staged.n_recs - lo), sqnorm, p_max, action_d, ratio)
+    else:
+        if dedup:
+            # the shard's offsets are exact: cut it into runs of row blocks of at most chunk_cap words (one read)
+            stride = _row_blocks(n) * _lib.GG_KF_BLOCK
+            marks = read_small(local_offsets[:: stride][: b1 - b0 + 1].contiguous()).tolist()
+            chunks, lo = [], b0
+            while lo < b1:
+                hi = lo + 1
+                while hi < b1 and marks[hi + 1 - b0] - marks[lo - b0] <= chunk_cap:
+                    hi += 1
+                chunks.append((lo, hi))
+                lo = hi
+            todo = list(reversed(chunks))
+        else:
+            staged.recs = staged.rowcnt = None       # the first pass's records are not used: free them
+            todo = list(reversed(_plan_chunks(n, b0, b1, local_ge, chunk_cap)))
+        while todo:
+            c0, c1 = todo.pop()
+            if dedup:
+                base, end = int(marks[c0 - b0]), int(marks[c1 - b0])
+                found = end - base
+            else:
+                recs, found, rowcnt, params, scored = kf_emit(counts, sqnorm, cut_test, sq_max, c0, c1, impl,
+                                                              rec_capacity=chunk_cap, hist_m=st.row_sum, retry=False)
+                if found > chunk_cap and c1 - c0 > 1:    # denser than planned: halve the range
+                    del recs, rowcnt
+                    mid = (c0 + c1) // 2
+                    todo.extend([(mid, c1), (c0, mid)])
+                    continue
+            if found == 0:
+                continue
+            ordered = torch.empty(found, dtype=torch.int64, device=dev)
+            if dedup:
+                # positions in local_offsets count from the shard's first edge: shift the output pointer instead
+                staged.place_range(c0, c1, C.c_void_p(local_offsets.data_ptr() + 8 * (c0 - b0) * stride),
+                                   C.c_void_p(ordered.data_ptr() - 8 * base), end)
+            else:
+                if found > chunk_cap:               # a single row block beyond the chunk size: score it with room
+                    recs, found, rowcnt, params, scored = kf_emit(counts, sqnorm, cut_test, sq_max, c0, c1, impl,
+                                                                  rec_capacity=found, hist_m=st.row_sum)
+                StagedRecords(recs, found, rowcnt, params, scored).place(ptr(ordered))
+                del recs, rowcnt
+            dest.select(ordered, found, sqnorm, p_max, action_d, ratio)
+            del ordered
+    g_end, kept = dest.totals()
+    if kept != mine or g_end != g_start + local_ties:
+        raise GGError(f"top-n select kept {kept} edges (expected {mine}) and saw {g_end - g_start} members of the "
+                      f"cut-off class (expected {local_ties})")
+    if exchange:
         with _stage("c2_exchange_edges"):
-            pending = comm.exchange_slices([full_ei[0], full_ei[1], full_w], per_rank)
-            for req in pending:
+            for req in comm.exchange_slices([full_ei[0], full_ei[1], full_w], kept_per_rank):
                 req.wait()
-            pending = []
-        ei, w32, w64 = full_ei[:, :e_total], full_w[:e_total], None
-    res = KFEdges(ei if exchange else ei.contiguous(), w64, w32, n_total, cutoff, tie_budget, tie_total, impl)
-    res.pending = pending
-    return res
+        total = sum(kept_per_rank)
+        return KFEdges(full_ei[:, :total], None, full_w[:total], n_total, cutoff, tie_budget, tie_total, impl,
+                       per_rank=kept_per_rank)
+    shown = min(mine, dest.capacity) if discard else mine
+    return KFEdges(dest.ei[:, :shown], None if dest.w64 is None else dest.w64[:shown], dest.w32[:shown], n_total, cutoff,
+                   tie_budget, tie_total, impl, per_rank=kept_per_rank, sharded=comm.world > 1, resident=not discard)
 
 
 # --------------------------------------------------------------------------- whole path on one GPU
@@ -1042,7 +1331,8 @@ class BuiltGraph:
 
 
 def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_threshold=0.0, edges_keep_top_k=None,
-                kf_impl="auto", with_kf=True, comm=None) -> BuiltGraph:
+                kf_impl="auto", with_kf=True, comm=None, kf_gather: bool = True, kf_sink: str = "device",
+                kf_chunk_records: Optional[int] = None, keep_features: bool = True) -> BuiltGraph:
     """kmer_ssgnn.py:162-213 + sampling_task.py:128-161.
 
     Single GPU by default.  With ``comm`` (dist.TorchComm) ``sequences`` is this
@@ -1074,7 +1364,7 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     small = [int(s) for s in str(small_k).split(",")]
     kcs = kf_counts_many(db.node_codes, k, small)
-    xs = [kf_features_f32(kc) for kc in kcs]
+    xs = [kf_features_f32(kc) for kc in kcs] if keep_features else []
     out = BuiltGraph(k, db, kcs, xs)
     if with_kf:
         b0, b1 = 0, None
@@ -1084,9 +1374,9 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
             b0, b1 = dist.kf_block_range(_row_blocks(db.num_nodes), comm.world, comm.rank)
         # every set is scored first; ONE exchange / device read then brings the candidate counts of all of them
         stages = [kf_stage(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl,
-                           iblock_begin=b0, iblock_end=b1) for kc in kcs]
+                           iblock_begin=b0, iblock_end=b1, row_sum=kc.m) for kc in kcs]
         kf_resolve(stages, comm)
-        out.kf = [kf_finish(st, comm) for st in stages]
+        out.kf = [kf_finish(st, comm, gather=kf_gather, chunk_records=kf_chunk_records, sink=kf_sink) for st in stages]
         for kf in out.kf:  # multi-GPU: the edge exchanges of earlier sets ran underneath the scoring of later ones
             kf.wait()
     return out

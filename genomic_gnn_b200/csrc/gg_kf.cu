@@ -341,6 +341,95 @@ __global__ void __launch_bounds__(256) select_scatter_kernel(const uint8_t* keep
   }
 }
 
+// ---- the same on PACKED words (s | dot << 24, t): the form the placement kernels write and the exchanges move
+__device__ __forceinline__ uint32_t packed_class_key(uint2 e, const int32_t* sqnorm, int32_t p_max) {
+  const uint32_t s = e.x & 0xFFFFFFu, dot = e.x >> 24;
+  const uint32_t p = static_cast<uint32_t>(__ldg(sqnorm + s)) * static_cast<uint32_t>(__ldg(sqnorm + e.y));
+  return dot * static_cast<uint32_t>(p_max + 1) + p;
+}
+
+__global__ void __launch_bounds__(256) class_hist_packed_kernel(const uint2* ordered, long long n, const int32_t* sqnorm,
+                                                                int32_t p_max, unsigned long long* hist) {
+  for (long long base = blockIdx.x * static_cast<long long>(blockDim.x); base < n;
+       base += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const bool ok = i < n;
+    const uint32_t key = ok ? packed_class_key(__ldg(ordered + i), sqnorm, p_max) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (ok && (__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(hist + key, static_cast<unsigned long long>(__popc(peers)));
+  }
+}
+
+__global__ void __launch_bounds__(256) packed_action_kernel(const uint2* ordered, long long n, const int32_t* sqnorm,
+                                                            int32_t p_max, const uint8_t* action, uint8_t* act_out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    act_out[i] = action[packed_class_key(__ldg(ordered + i), sqnorm, p_max)];
+}
+
+struct IsTie32 {
+  __host__ __device__ uint32_t operator()(uint8_t a) const { return a == 2 ? 1u : 0u; }
+};
+
+// Spread rule for the cut-off class: of its T members, numbered g = 0 .. T-1 in GLOBAL emission order, exactly B are
+// kept -- those where floor((g + 1) r / 2^64) > floor(g r / 2^64) with r = ceil(B 2^64 / T).  The rule needs nothing
+// but g, so any sharding of the emission order (ranks, row-block chunks) selects the same members, and every shard
+// keeps its fair share of them.
+__host__ __device__ __forceinline__ bool tie_admitted(unsigned long long g, unsigned long long r) {
+#ifdef __CUDA_ARCH__
+  return __umul64hi(g + 1ull, r) > __umul64hi(g, r);
+#else
+  return static_cast<unsigned long long>((static_cast<unsigned __int128>(g + 1ull) * r) >> 64) >
+         static_cast<unsigned long long>((static_cast<unsigned __int128>(g) * r) >> 64);
+#endif
+}
+
+struct KeepOf {
+  const uint8_t* act;
+  const uint32_t* tie_rank;
+  const long long* cursors;  // [0] members of the cut-off class emitted before this call (global numbering)
+  unsigned long long r;
+  __host__ __device__ uint32_t operator()(long long i) const {
+    const uint8_t a = act[i];
+    if (a == 1) return 1u;
+    if (a != 2) return 0u;
+    return tie_admitted(static_cast<unsigned long long>(cursors[0]) + tie_rank[i], r) ? 1u : 0u;
+  }
+};
+
+__global__ void __launch_bounds__(256) packed_scatter_kernel(const uint2* ordered, long long n, KeepOf keep,
+                                                             const uint32_t* pos, const int32_t* sqnorm,
+                                                             long long out_capacity, int64_t* o_src, int64_t* o_dst,
+                                                             double* o_w64, float* o_w32, long long* totals) {
+  const long long out0 = keep.cursors[1];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint32_t kept = keep(i);
+    if (kept) {
+      const long long o = out0 + pos[i];
+      if (o < out_capacity) {
+        const uint2 e = __ldg(ordered + i);
+        const uint32_t s = e.x & 0xFFFFFFu, dot = e.x >> 24, t = e.y;
+        o_src[o] = s;
+        o_dst[o] = t;
+        const double p = static_cast<double>(static_cast<long long>(__ldg(sqnorm + s)) * static_cast<long long>(__ldg(sqnorm + t)));
+        const double w = static_cast<double>(dot) / sqrt(p);
+        if (o_w64) o_w64[o] = w;
+        if (o_w32) o_w32[o] = static_cast<float>(w);
+      }
+    }
+    if (i == n - 1) {  // totals of this call, applied to the cursors by the kernel behind this one
+      totals[0] = static_cast<long long>(keep.tie_rank[i]) + (keep.act[i] == 2 ? 1 : 0);
+      totals[1] = static_cast<long long>(pos[i]) + kept;
+    }
+  }
+}
+
+__global__ void advance_cursors_kernel(long long* cursors, const long long* totals) {
+  cursors[0] += totals[0];
+  cursors[1] += totals[1];
+}
+
 inline int grid_for(long long n) {
   long long g = (n + 255) / 256;
   const long long cap = static_cast<long long>(gg::sm_count()) * 8;
@@ -377,7 +466,7 @@ extern "C" size_t gg_kf_rowcnt_elems(int64_t n, int iblock_begin, int iblock_end
 
 extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const int32_t* sqnorm, const uint16_t* dmin,
                           const uint32_t* fast_scale, gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt,
-                          int64_t* kf_status, gg_stream_t st) {
+                          int64_t* kf_status, uint64_t* class_hist, gg_stream_t st) {
   if (int rc = check_params(p)) return rc;
   GG_REQUIRE(kf_status, GG_ERR_ARG, "null status");
   cudaStream_t s = gg::as_stream(st);
@@ -405,6 +494,9 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   a.out.recs = recs;
   a.out.capacity = rec_capacity;
   a.out.status = reinterpret_cast<unsigned long long*>(kf_status);
+  a.class_hist = reinterpret_cast<unsigned long long*>(class_hist);
+  a.hist_m = p->hist_m;
+  a.p_max = p->p_max;
 
   int impl = p->impl;
   const bool mma_ok = p->d == 32 || p->d == 64 || (p->d % 128 == 0 && p->d <= 1024);
@@ -416,6 +508,9 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
            : (mma_ok ? GG_KF_IMPL_TCGEN05 : (dp4a_ok ? GG_KF_IMPL_DP4A : GG_KF_IMPL_NAIVE));
   const long long units = static_cast<long long>(a.ib1 - a.ib0) * a.n_jblocks * kStripsPerBlock;
   GG_REQUIRE(units < (1ll << 31), GG_ERR_ARG, "too many work units for one launch; shard the row blocks");
+  GG_REQUIRE(class_hist == nullptr || impl == GG_KF_IMPL_TCGEN05_PAIR, GG_ERR_ARG,
+             "the in-kernel score-class histogram exists for the CTA-pair tensor path only");
+  GG_REQUIRE(p->hist_m >= 0, GG_ERR_ARG, "negative hist_m");
   switch (impl) {
     case GG_KF_IMPL_DP4A: {
       int sq_max = 0;  // p_max = sq_max^2 by construction (core.threshold_tables)
@@ -534,6 +629,88 @@ extern "C" int gg_kf_class_hist(const int64_t* edge_src, const int64_t* edge_dst
   GG_REQUIRE(edge_src && edge_dst && dot && sqnorm && class_hist, GG_ERR_ARG, "null buffer");
   class_hist_kernel<<<grid_for(n_edges), 256, 0, gg::as_stream(st)>>>(edge_src, edge_dst, dot, n_edges, sqnorm, p_max,
                                                                      class_hist);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+extern "C" int gg_kf_class_hist_packed(const uint64_t* ordered, int64_t n_edges, const int32_t* sqnorm, int32_t p_max,
+                                       uint64_t* class_hist, gg_stream_t st) {
+  GG_REQUIRE(n_edges >= 0 && p_max >= 0, GG_ERR_ARG, "bad size");
+  if (n_edges == 0) return GG_OK;
+  GG_REQUIRE(ordered && sqnorm && class_hist, GG_ERR_ARG, "null buffer");
+  class_hist_packed_kernel<<<grid_for(n_edges), 256, 0, gg::as_stream(st)>>>(
+      reinterpret_cast<const uint2*>(ordered), n_edges, sqnorm, p_max, reinterpret_cast<unsigned long long*>(class_hist));
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+namespace {
+template <typename Op, typename In>
+size_t scan32_temp_bytes(long long n) {
+  size_t bytes = 0;
+  cub::TransformInputIterator<uint32_t, Op, const In*> it(nullptr, Op());
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, static_cast<uint32_t*>(nullptr), n);
+  return bytes;
+}
+size_t keep_scan_temp_bytes(long long n) {
+  size_t bytes = 0;
+  cub::TransformInputIterator<uint32_t, KeepOf, cub::CountingInputIterator<long long>> it(
+      cub::CountingInputIterator<long long>(0), KeepOf{nullptr, nullptr, nullptr, 0ull});
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, static_cast<uint32_t*>(nullptr), n);
+  return bytes;
+}
+}  // namespace
+
+extern "C" size_t gg_kf_select_packed_workspace_bytes(int64_t n_edges) {
+  const long long n = n_edges > 0 ? n_edges : 1;
+  gg::Carver c(nullptr);
+  c.take<uint8_t>(n);
+  c.take<uint32_t>(n);
+  c.take<uint32_t>(n);
+  c.take<long long>(2);
+  const size_t a = scan32_temp_bytes<IsTie32, uint8_t>(n), b = keep_scan_temp_bytes(n);
+  c.take<char>(a > b ? a : b);
+  return c.used();
+}
+
+extern "C" int gg_kf_select_packed(const uint64_t* ordered, int64_t n_edges, const int32_t* sqnorm, int32_t p_max,
+                                   const uint8_t* class_action, uint64_t tie_ratio, int64_t* cursors,
+                                   int64_t* out_src, int64_t* out_dst, double* out_w64, float* out_w32,
+                                   int64_t out_capacity, void* workspace, size_t workspace_bytes, gg_stream_t st) {
+  GG_REQUIRE(n_edges >= 0 && n_edges < (1ll << 31) && p_max >= 0 && out_capacity >= 0, GG_ERR_ARG,
+             "bad size (at most 2^31 - 1 packed words per call)");
+  if (n_edges == 0) return GG_OK;
+  GG_REQUIRE(ordered && sqnorm && class_action && cursors && out_src && out_dst && workspace, GG_ERR_ARG, "null buffer");
+  GG_REQUIRE(workspace_bytes >= gg_kf_select_packed_workspace_bytes(n_edges), GG_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t s = gg::as_stream(st);
+  gg::Carver c(workspace);
+  uint8_t* act = c.take<uint8_t>(n_edges);
+  uint32_t* tie_rank = c.take<uint32_t>(n_edges);
+  uint32_t* pos = c.take<uint32_t>(n_edges);
+  long long* totals = c.take<long long>(2);
+  const size_t ta = scan32_temp_bytes<IsTie32, uint8_t>(n_edges), tb = keep_scan_temp_bytes(n_edges);
+  const size_t temp_bytes = ta > tb ? ta : tb;
+  void* temp = c.take<char>(temp_bytes);
+  const int g = grid_for(n_edges);
+  const uint2* words = reinterpret_cast<const uint2*>(ordered);
+  packed_action_kernel<<<g, 256, 0, s>>>(words, n_edges, sqnorm, p_max, class_action, act);
+  GG_CUDA_CHECK(cudaGetLastError());
+  {
+    cub::TransformInputIterator<uint32_t, IsTie32, const uint8_t*> it(act, IsTie32());
+    size_t b = temp_bytes;
+    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, b, it, tie_rank, n_edges, s));
+  }
+  const KeepOf keep{act, tie_rank, reinterpret_cast<const long long*>(cursors), static_cast<unsigned long long>(tie_ratio)};
+  {
+    cub::TransformInputIterator<uint32_t, KeepOf, cub::CountingInputIterator<long long>> it(
+        cub::CountingInputIterator<long long>(0), keep);
+    size_t b = temp_bytes;
+    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, b, it, pos, n_edges, s));
+  }
+  packed_scatter_kernel<<<g, 256, 0, s>>>(words, n_edges, keep, pos, sqnorm, out_capacity, out_src, out_dst, out_w64,
+                                          out_w32, totals);
+  GG_CUDA_CHECK(cudaGetLastError());
+  advance_cursors_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(cursors), totals);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

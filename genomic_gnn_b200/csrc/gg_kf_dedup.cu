@@ -89,7 +89,28 @@ struct ScoreArgs {
   int sq_max;
   uint32_t* adj;
   int adj_words;
+  // HIST: class_hist[dot * (p_max + 1) + sq_a * sq_b] += number of NODE pairs s < t the passing class pair stands for
+  // (|A| |B|, or |A| (|A| - 1) / 2 inside one class), accumulated for row classes [hist_begin, hist_end) only so that
+  // ranks can split the class-pair triangle and sum their tables
+  unsigned long long* class_hist;
+  int p_max, hist_begin, hist_end;
+  // TIES: node pairs of the cut-off class (dot^2 * tie_den == tie_num * P) whose smaller node lies at or beyond
+  // row_lo / row_hi: tie_out[0], tie_out[1] (their difference = the members of the class this row shard emits)
+  long long tie_num, tie_den;
+  int row_lo, row_hi;
+  unsigned long long* tie_out;
 };
+
+// members of class c with node id >= row (members ascend inside a class)
+__device__ __forceinline__ int members_at_or_after(const int32_t* members, int m0, int m1, int row) {
+  int lo = m0, hi = m1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(members + mid) < row) lo = mid + 1;
+    else hi = mid;
+  }
+  return m1 - lo;
+}
 
 // words == 16 marks 16-byte rows at a 16-byte pitch in a 16-byte aligned matrix: one vector load
 __device__ __forceinline__ uint4 load_row(const uint8_t* counts, int pitch, int words, int node) {
@@ -112,24 +133,38 @@ __device__ __forceinline__ uint32_t dot16(const uint4& a, const uint4& b) {
 // tile in shared memory (one broadcast 16-byte load per column class serves 4 x 128 pairs); the per-row threshold
 // column thr[sq_b][row] makes the exact test one conflict-free shared-memory byte load, because all threads look at
 // the same b and hence the same sq_b.
+// EXTRA: 0 plain, 1 HIST, 2 TIES (see ScoreArgs)
+template <int EXTRA>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint4* brow = reinterpret_cast<uint4*>(smem);
   uint32_t* boff = reinterpret_cast<uint32_t*>(smem + kScoreB * sizeof(uint4));  // sq_b * kScoreA
   uint8_t* thr = smem + kScoreB * (sizeof(uint4) + sizeof(uint32_t));            // [sq_max + 1][kScoreA]
+  // EXTRA: per column class of the tile, its size (HIST) or its members at/after row_lo and row_hi (TIES)
+  uint32_t* bw0 = reinterpret_cast<uint32_t*>(thr + static_cast<size_t>(a.sq_max + 1) * kScoreA);
+  uint32_t* bw1 = bw0 + kScoreB;
   const int a0 = blockIdx.y * kScoreA, b0 = blockIdx.x * kScoreB;
   if (b0 + kScoreB <= a0) return;  // every column class of this tile lies before every row class
   uint4 ra[kScoreRows];
   int sqa[kScoreRows];
+  uint32_t aw0[kScoreRows], aw1[kScoreRows];
+  unsigned long long tie0 = 0, tie1 = 0;
 #pragma unroll
   for (int r = 0; r < kScoreRows; ++r) {
     const int ca = a0 + r * kScoreThreads + threadIdx.x;
     ra[r] = make_uint4(0u, 0u, 0u, 0u);
     sqa[r] = 0;
+    aw0[r] = aw1[r] = 0;
     if (ca < a.n_classes) {
-      const int rep = __ldg(a.members + __ldg(a.class_start + ca));
+      const int m0 = __ldg(a.class_start + ca), m1 = __ldg(a.class_start + ca + 1);
+      const int rep = __ldg(a.members + m0);
       ra[r] = load_row(a.counts, a.pitch, a.words, rep);
       sqa[r] = __ldg(a.sqnorm + rep);
+      if (EXTRA == 1) aw0[r] = static_cast<uint32_t>(m1 - m0);
+      if (EXTRA == 2) {
+        aw0[r] = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_lo));
+        aw1[r] = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_hi));
+      }
     }
   }
   for (int sq = 0; sq <= a.sq_max; ++sq) {
@@ -143,13 +178,24 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
     const int cb = b0 + t;
     uint4 rb = make_uint4(0u, 0u, 0u, 0u);
     int sqb = 0;
+    uint32_t w0 = 0, w1 = 0;
     if (cb < a.n_classes) {
-      const int rep = __ldg(a.members + __ldg(a.class_start + cb));
+      const int m0 = __ldg(a.class_start + cb), m1 = __ldg(a.class_start + cb + 1);
+      const int rep = __ldg(a.members + m0);
       rb = load_row(a.counts, a.pitch, a.words, rep);
       sqb = __ldg(a.sqnorm + rep);
+      if (EXTRA == 1) w0 = static_cast<uint32_t>(m1 - m0);
+      if (EXTRA == 2) {
+        w0 = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_lo));
+        w1 = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_hi));
+      }
     }
     brow[t] = rb;
     boff[t] = static_cast<uint32_t>(sqb * kScoreA);
+    if (EXTRA) {
+      bw0[t] = w0;
+      bw1[t] = w1;
+    }
   }
   __syncthreads();
   const uint8_t* my_thr = thr + threadIdx.x;
@@ -179,11 +225,36 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
         else if (cb0 < ca) m &= ~((1u << (ca - cb0)) - 1u);
         if (!m) continue;
         atomicOr(a.adj + static_cast<size_t>(ca) * a.adj_words + (cb0 >> 5), m);
+        const bool count_row = EXTRA == 2 || (EXTRA == 1 && ca >= a.hist_begin && ca < a.hist_end);
         for (; m; m &= m - 1) {
-          const int cb = cb0 + __ffs(m) - 1;
+          const int tb = t0 + __ffs(m) - 1, cb = b0 + tb;
           if (cb != ca) atomicOr(a.adj + static_cast<size_t>(cb) * a.adj_words + (ca >> 5), 1u << (ca & 31));
+          if (EXTRA && count_row) {
+            const unsigned long long dot = dot16(ra[r], brow[tb]);
+            const unsigned long long p = static_cast<unsigned long long>(sqa[r]) * (boff[tb] / kScoreA);
+            if (EXTRA == 1) {
+              const unsigned long long wa = aw0[r];
+              const unsigned long long w = cb == ca ? wa * (wa - 1ull) / 2ull : wa * bw0[tb];
+              if (w) atomicAdd(a.class_hist + dot * static_cast<unsigned long long>(a.p_max + 1) + p, w);
+            } else if (static_cast<long long>(dot * dot) * a.tie_den == a.tie_num * static_cast<long long>(p)) {
+              const unsigned long long x0 = aw0[r], x1 = aw1[r];
+              tie0 += cb == ca ? x0 * (x0 - 1ull) / 2ull : x0 * bw0[tb];
+              tie1 += cb == ca ? x1 * (x1 - 1ull) / 2ull : x1 * bw1[tb];
+            }
+          }
         }
       }
+    }
+  }
+  if (EXTRA == 2) {  // one pair of atomics per warp
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      tie0 += __shfl_xor_sync(0xFFFFFFFFu, tie0, o);
+      tie1 += __shfl_xor_sync(0xFFFFFFFFu, tie1, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (tie0 | tie1)) {
+      atomicAdd(a.tie_out, tie0);
+      atomicAdd(a.tie_out + 1, tie1);
     }
   }
 }
@@ -272,10 +343,14 @@ __global__ void __launch_bounds__(RowsCfg<PLACE, BIG>::kRowThreads) class_rows_k
     const int c = s_class;
     if (c >= a.n_classes) break;
     const int m0 = __ldg(a.class_start + c), m1 = __ldg(a.class_start + c + 1);
-    // members ascend: skip classes without a row in this shard (uniform across the CTA)
-    if (__ldg(a.members + m1 - 1) < row_lo || __ldg(a.members + m0) >= row_hi) {
-      __syncthreads();  // s_class is rewritten at the top of the loop
-      continue;
+    // members ascend: skip classes without a row in this shard (uniform across the CTA).  The first member at or
+    // after row_lo decides: shards of a few row blocks (top-n chunks) hold a member of only a few percent of the classes
+    {
+      const int first_in = m1 - members_at_or_after(a.members, m0, m1, row_lo);
+      if (first_in >= m1 || __ldg(a.members + first_in) >= row_hi) {
+        __syncthreads();  // s_class is rewritten at the top of the loop
+        continue;
+      }
     }
     for (int w = threadIdx.x; w < bm_padded / 4; w += kRowThreads) reinterpret_cast<uint4*>(bm)[w] = make_uint4(0u, 0u, 0u, 0u);
     // neighbour classes of this class: compact the set bits of its adjacency row into the work list ...
@@ -576,7 +651,8 @@ extern "C" size_t gg_kf_dedup_adj_words(int64_t n_classes) {
 
 extern "C" int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, const int32_t* sqnorm,
                                  const int32_t* members, const int32_t* class_start, int64_t n_classes,
-                                 const uint16_t* dmin, int32_t p_max, uint32_t* adj, gg_stream_t st) {
+                                 const uint16_t* dmin, int32_t p_max, uint32_t* adj, const gg_kf_dedup_extra_t* extra,
+                                 gg_stream_t st) {
   GG_REQUIRE(n_classes >= 0 && n_classes <= kMaxBitmapNodes, GG_ERR_ARG, "bad class count");
   GG_REQUIRE(d_valid >= 4 && d_valid <= 16 && d_valid % 4 == 0 && pitch >= d_valid && pitch % 4 == 0, GG_ERR_ARG,
              "duplicate-row path needs 4..16 columns");
@@ -588,13 +664,46 @@ extern "C" int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, 
   cudaStream_t s = gg::as_stream(st);
   const int adj_words = static_cast<int>((n_classes + 31) / 32);
   GG_CUDA_CHECK(cudaMemsetAsync(adj, 0, gg_kf_dedup_adj_words(n_classes) * sizeof(uint32_t), s));
-  ScoreArgs a{counts, pitch, row_words(counts, pitch, d_valid), sqnorm, members, class_start,
-              static_cast<int>(n_classes), dmin, sq_max, adj, adj_words};
-  const size_t smem = kScoreB * (sizeof(uint4) + sizeof(uint32_t)) + static_cast<size_t>(sq_max + 1) * kScoreA;
-  GG_CUDA_CHECK(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  ScoreArgs a{};
+  a.counts = counts;
+  a.pitch = pitch;
+  a.words = row_words(counts, pitch, d_valid);
+  a.sqnorm = sqnorm;
+  a.members = members;
+  a.class_start = class_start;
+  a.n_classes = static_cast<int>(n_classes);
+  a.dmin = dmin;
+  a.sq_max = sq_max;
+  a.adj = adj;
+  a.adj_words = adj_words;
+  a.p_max = p_max;
+  int mode = 0;
+  if (extra != nullptr && extra->class_hist != nullptr) {
+    GG_REQUIRE(extra->tie_out == nullptr, GG_ERR_ARG, "class_hist and tie_out are separate passes");
+    GG_REQUIRE(extra->hist_class_begin >= 0 && extra->hist_class_begin <= extra->hist_class_end, GG_ERR_ARG,
+               "bad class range for the histogram");
+    mode = 1;
+    a.class_hist = reinterpret_cast<unsigned long long*>(extra->class_hist);
+    a.hist_begin = static_cast<int>(extra->hist_class_begin);
+    a.hist_end = static_cast<int>(extra->hist_class_end < n_classes ? extra->hist_class_end : n_classes);
+  } else if (extra != nullptr && extra->tie_out != nullptr) {
+    GG_REQUIRE(extra->tie_num > 0 && extra->tie_den > 0 && extra->tie_num <= (1 << 16) && extra->tie_den <= (1ll << 32),
+               GG_ERR_ARG, "cut-off class must be dot^2 / P with dot <= 255");
+    GG_REQUIRE(extra->row_lo >= 0 && extra->row_lo <= extra->row_hi, GG_ERR_ARG, "bad row shard");
+    mode = 2;
+    a.tie_num = extra->tie_num;
+    a.tie_den = extra->tie_den;
+    a.row_lo = static_cast<int>(extra->row_lo);
+    a.row_hi = static_cast<int>(extra->row_hi);
+    a.tie_out = reinterpret_cast<unsigned long long*>(extra->tie_out);
+  }
+  const size_t smem = kScoreB * (sizeof(uint4) + sizeof(uint32_t)) + static_cast<size_t>(sq_max + 1) * kScoreA +
+                      2 * kScoreB * sizeof(uint32_t);
+  auto kernel = mode == 0 ? score_kernel<0> : (mode == 1 ? score_kernel<1> : score_kernel<2>);
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>((n_classes + kScoreB - 1) / kScoreB),
             static_cast<unsigned>((n_classes + kScoreA - 1) / kScoreA));
-  score_kernel<<<grid, kScoreThreads, smem, s>>>(a);
+  kernel<<<grid, kScoreThreads, smem, s>>>(a);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

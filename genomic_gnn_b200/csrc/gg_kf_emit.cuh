@@ -35,6 +35,13 @@ struct KfArgs {
   int fast_shift;
   uint8_t* rowcnt;  // one 64-bit word per (block pair, row): byte t = candidates of that row in column tile t
   EmitOut out;
+  // Optional exact score-class histogram of the candidates (global top-n BEFORE emission, gnn_utils.py:311-317):
+  // class_hist[dot * (p_max + 1) + sq_s * sq_t] += 1 per candidate.  hist_m > 0 promises that every row sums to
+  // hist_m (rows made by gg_kf_counts: m = k - small_k + 1), which lets the tensor kernel keep a compact
+  // shared-memory histogram keyed by ((sq - m) / 2, dot); 0 = no such promise.
+  unsigned long long* class_hist;
+  int hist_m;
+  int p_max;
 };
 
 // CAP trades shared memory for global-cursor traffic: every flush is one returning atomic on a single address,

@@ -583,6 +583,16 @@ __device__ __forceinline__ int pair_last_tile(const KfArgs& a, const PairWalk& w
   return static_cast<int>(t < kPairTilesPerBlock ? t : kPairTilesPerBlock);
 }
 
+// Score-class histogram inside the epilogue (HIST): a candidate's class is (dot, sq_s * sq_t).  When every row sums to
+// m (KfArgs::hist_m) a squared norm is m + 2 * id with id < kHistSq for m <= 6, so classes with dot < kHistDots fit a
+// compact per-CTA table [id_s][id_t][dot] of 32-bit counters in shared memory (8 KB); the by far most frequent class
+// of a thread -- dot 1 against an all-distinct column (sq_t = m) -- is counted in a register and folded in once per
+// unit, because 20 lanes of a warp hitting one shared-memory word serialise.  Everything else (larger dots, rows that
+// break the promise) goes to the global table directly.  The table is added to the global one when the CTA ends.
+constexpr int kHistSq = 16, kHistDots = 8, kHistBins = kHistSq * kHistSq * kHistDots;
+using PairStage = WarpStageT<32>;  // 12 x 1.5 KB: leaves room for the histogram next to four B stages at D = 1024
+
+template <bool HIST>
 __global__ void __launch_bounds__(kThreads, 1)
 kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n_bstages, long long total_units,
                        int* error_flag, Geom g) {
@@ -594,12 +604,18 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
   uint16_t* sqn = reinterpret_cast<uint16_t*>(smem_b + static_cast<size_t>(n_bstages) * kStageBytes);
-  WarpStage* stages = reinterpret_cast<WarpStage*>(sqn + kEpiGroups * kPairPanel);
+  PairStage* stages = reinterpret_cast<PairStage*>(sqn + kEpiGroups * kPairPanel);
   Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
+  uint32_t* sh_hist = reinterpret_cast<uint32_t*>(bars + 1);  // HIST only: [kHistBins]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  const uint32_t hist_m = HIST ? static_cast<uint32_t>(a.hist_m) : 0u;
+  const bool hist_compact = HIST && hist_m >= 1 && hist_m * hist_m - hist_m <= 2u * (kHistSq - 1);
+  if (HIST) {
+    for (int i = tid; i < kHistBins; i += kThreads) sh_hist[i] = 0u;
+  }
 
   if (tid == 0) {
     mbar_init(&bars->a_full, 1);
@@ -729,7 +745,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
     }
   } else {
     // ===================== epilogue groups: 128-column half tiles round-robin =====================
-    WarpStage& ws = stages[warp];
+    PairStage& ws = stages[warp];
     if (lane == 0) ws.fill = 0;
     __syncwarp();
     const int group = warp / 4;
@@ -738,6 +754,8 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
     if (n_units > 0) {
       PairWalk w = pair_walk_begin(a, u0, n_units);
       uint32_t tile_seq = 0;
+      // HIST: this thread's compact row slot (kHistBins: the row breaks the promise) and its register-counted class
+      uint32_t h_row = kHistBins, h_mode = 0xFFFFFFFFu, h_priv = 0;
       for (; w.left > 0; pair_walk_next(a, w)) {
         const long long col0 = static_cast<long long>(w.j_block) * kBlock;
         const int cols_in_block = static_cast<int>(min(static_cast<long long>(kBlock), a.n - col0));
@@ -787,6 +805,12 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
                   sq_i = static_cast<uint32_t>(__ldg(a.sqnorm + s));
                   scale_i = __ldg(a.fast_scale + sq_i);
                 }
+                if (HIST) {
+                  const uint32_t id = (sq_i - hist_m) >> 1;
+                  const bool fits = hist_compact && row_ok && sq_i >= hist_m && !((sq_i - hist_m) & 1u) && id < kHistSq;
+                  h_row = fits ? id * kHistSq * kHistDots : static_cast<uint32_t>(kHistBins);
+                  h_mode = fits ? h_row + 1u : 0xFFFFFFFFu;  // (id_t = 0, dot = 1)
+                }
                 panel_loaded = true;
               }
               const uint32_t taddr =
@@ -820,7 +844,20 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
                   uint32_t exact = 0;
                   for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {
                     const int b = __ffs(m2) - 1;
-                    if (stage_get_dot(ws, b, lane) >= __ldg(a.dmin + sq_i * my_sqn[c0 + b])) exact |= 1u << b;
+                    const uint32_t dot = stage_get_dot(ws, b, lane), sq_j = my_sqn[c0 + b];
+                    if (dot >= __ldg(a.dmin + sq_i * sq_j)) {
+                      exact |= 1u << b;
+                      if (HIST) {
+                        const uint32_t idj = (sq_j - hist_m) >> 1;
+                        if (h_row < kHistBins && dot < kHistDots && sq_j >= hist_m && !((sq_j - hist_m) & 1u) && idj < kHistSq) {
+                          const uint32_t key = h_row + idj * kHistDots + dot;
+                          if (key == h_mode) ++h_priv;
+                          else atomicAdd(sh_hist + key, 1u);
+                        } else {
+                          atomicAdd(a.class_hist + static_cast<size_t>(dot) * (a.p_max + 1) + sq_i * sq_j, 1ull);
+                        }
+                      }
+                    }
                   }
                   stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0),
                                tile_cnt);
@@ -834,6 +871,10 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
             if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->acc_empty[acc]), 0));
           }
         }
+        if (HIST && h_priv) {  // the row (and with it h_mode) may change with the next unit
+          atomicAdd(sh_hist + h_mode, h_priv);
+          h_priv = 0;
+        }
       }
       stage_flush(ws, a.out, lane);
     }
@@ -841,6 +882,15 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
 
   tc_fence_before();
   __syncthreads();
+  if (HIST) {  // fold this CTA's compact table into the global (dot, P) table
+    for (int i = tid; i < kHistBins; i += kThreads) {
+      const uint32_t c = sh_hist[i];
+      if (!c) continue;
+      const uint32_t dot = i % kHistDots, idj = (i / kHistDots) % kHistSq, idi = i / (kHistDots * kHistSq);
+      const uint32_t p = (hist_m + 2u * idi) * (hist_m + 2u * idj);
+      atomicAdd(a.class_hist + static_cast<size_t>(dot) * (a.p_max + 1) + p, static_cast<unsigned long long>(c));
+    }
+  }
   cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading the pair's operands
   if (warp == kMmaWarp) {
     tc_fence_after();
@@ -1020,8 +1070,10 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
     gg::set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     return GG_ERR_CUDA;
   }
+  const bool hist = a.class_hist != nullptr;
   const size_t fixed = static_cast<size_t>(g.n_kblocks) * g.stage_bytes + kEpiGroups * kPairPanel * sizeof(uint16_t) +
-                       (kEpiThreads / 32) * sizeof(WarpStage) + sizeof(Barriers) + 1024;
+                       (kEpiThreads / 32) * sizeof(PairStage) + sizeof(Barriers) +
+                       (hist ? kHistBins * sizeof(uint32_t) : 0) + 1024;
   int dev = 0, max_smem = 0;
   GG_CUDA_CHECK(cudaGetDevice(&dev));
   GG_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -1029,8 +1081,8 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
   if (n_bstages > kMaxBStages) n_bstages = kMaxBStages;
   GG_REQUIRE(n_bstages >= 2, GG_ERR_ARG, "not enough shared memory for the B ring");
   const size_t smem_bytes = fixed + static_cast<size_t>(n_bstages) * g.stage_bytes;
-  GG_CUDA_CHECK(cudaFuncSetAttribute(kf_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem_bytes)));
+  auto kernel = hist ? kf_tcgen05_pair_kernel<true> : kf_tcgen05_pair_kernel<false>;
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   long long total_units = 0;  // (strip pair, column block) units of this shard
   for (int ib = a.ib0; ib < a.ib1; ++ib) total_units += static_cast<long long>(kPairsPerBlock) * (a.n_jblocks - ib);
   if (total_units == 0) return GG_OK;
@@ -1049,7 +1101,7 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kf_tcgen05_pair_kernel, tmap, a, n_bstages, total_units, error_flag, g));
+  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, a, n_bstages, total_units, error_flag, g));
   return GG_OK;
 }
 

@@ -98,6 +98,11 @@ class TorchComm:
         return cat.movedim(0, dim).contiguous()
 
 
+    def all_gather_into(self, out: torch.Tensor, mine: torch.Tensor):
+        """out[rank * len(mine) : (rank + 1) * len(mine)] = every rank's ``mine`` (equal sizes)."""
+        dist_.all_gather_into_tensor(out, mine, group=self.group)
+        return out
+
     def all_gather_padded_(self, buf: torch.Tensor, stride: int):
         """In-place all-gather: ``buf`` holds world * stride elements and this rank has filled its own segment
         [rank * stride, (rank + 1) * stride)."""
@@ -170,7 +175,7 @@ def _reduce_counts_gathered(cr, comm: TorchComm, piece: torch.Tensor):
     world, length = comm.world, int(piece.numel())
     bins = int(cr.hist.numel())
     everyone = torch.empty(world * length, dtype=torch.int64, device=piece.device)
-    dist_.all_gather_into_tensor(everyone, piece, group=comm.group)
+    comm.all_gather_into(everyone, piece)
     hist = torch.empty(bins, dtype=torch.int32, device=piece.device)
     first = torch.empty(bins, dtype=torch.int64, device=piece.device)
     check(lib.gg_count_merge(ptr(everyone), world, length, cr.k, ptr(hist), ptr(first), _stream()), "gg_count_merge")

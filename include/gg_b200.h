@@ -194,14 +194,22 @@ typedef struct {
   int32_t impl;         /* GG_KF_IMPL_* */
   int32_t d_valid;      /* bytes of a row that can be non-zero (<= d; rows may be zero-padded to the 32-byte pitch
                            the tensor path needs); 0 means d */
+  int32_t hist_m;       /* > 0: promise that every row of counts sums to hist_m (rows made by gg_kf_counts:
+                           k - small_k + 1), which lets gg_kf_emit keep its score-class histogram in shared memory;
+                           0: no promise (the histogram is still exact, only slower) */
 } gg_kf_params_t;
 
 /* kf_status (device int64[4]): [0] candidates found (may exceed rec_capacity: re-run larger),
- * [1] records written, [2..3] reserved. */
+ * [1] records written, [2..3] reserved.
+ * class_hist (nullable; GG_KF_IMPL_TCGEN05_PAIR only): uint64[(sqnorm_max + 1) * (p_max + 1)], NOT zeroed by the call;
+ * class_hist[dot * (p_max + 1) + sqnorm_s * sqnorm_t] += 1 for every candidate, whether or not its record fitted
+ * rec_capacity -- the exact score classes of the global top-n (gnn_utils.py:311-317) BEFORE anything is emitted, so
+ * that a binding top-n never needs the candidates materialised (k = 10, threshold 0: 5.5e11 of them). */
 GG_API size_t gg_kf_rowcnt_elems(int64_t n, int iblock_begin, int iblock_end);
 GG_API int gg_kf_emit(const gg_kf_params_t* h_params, const uint8_t* counts, const int32_t* sqnorm,
                const uint16_t* dmin, const uint32_t* fast_scale /* [max sqnorm + 1] */,
-               gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt, int64_t* kf_status, gg_stream_t st);
+               gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt, int64_t* kf_status, uint64_t* class_hist,
+               gg_stream_t st);
 
 /* gg_kf_finalize = gg_kf_place (records -> one packed 64-bit word per edge, in emission order: s | dot << 24 in the low
  * half, t in the high half) followed by gg_kf_expand (packed words -> edge_index / weights, coalesced).  Multi-GPU
@@ -238,9 +246,24 @@ GG_API int gg_kf_dedup_classes(const uint8_t* counts, int pitch, int d_valid, in
                         int32_t* class_start, int64_t* dd_status, void* workspace, size_t workspace_bytes,
                         gg_stream_t st);
 GG_API size_t gg_kf_dedup_adj_words(int64_t n_classes);
+/* Optional by-products of a scoring pass (host struct, nullable; at most one of class_hist / tie_out set):
+ *   class_hist  uint64[(sqnorm_max + 1) * (p_max + 1)], not zeroed: for every passing class pair (A, B) with A in
+ *               [hist_class_begin, hist_class_end), class_hist[dot * (p_max + 1) + sq_A * sq_B] += the node pairs
+ *               s < t it stands for (|A| |B|; |A| (|A| - 1) / 2 for A = B) -- the score classes of the global top-n
+ *               before anything is emitted; ranks split the class range and sum their tables.
+ *   tie_out     uint64[2], not zeroed: node pairs of the class dot^2 / P == tie_num / tie_den (the cut-off class)
+ *               whose smaller node is >= row_lo ([0]) and >= row_hi ([1]); [0] - [1] = the members of that class the
+ *               row shard [row_lo, row_hi) emits. */
+typedef struct {
+  uint64_t* class_hist;
+  int64_t hist_class_begin, hist_class_end;
+  uint64_t* tie_out;
+  int64_t tie_num, tie_den;
+  int64_t row_lo, row_hi;
+} gg_kf_dedup_extra_t;
 GG_API int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, const int32_t* sqnorm, const int32_t* members,
                       const int32_t* class_start, int64_t n_classes, const uint16_t* dmin, int32_t p_max,
-                      uint32_t* adj, gg_stream_t st);
+                      uint32_t* adj, const gg_kf_dedup_extra_t* h_extra, gg_stream_t st);
 GG_API size_t gg_kf_dedup_count_workspace_bytes(int64_t n, int iblock_begin, int iblock_end);
 GG_API int gg_kf_dedup_count(int64_t n, int iblock_begin, int iblock_end, const uint32_t* adj, const int32_t* members,
                       const int32_t* class_start, int64_t n_classes, uint64_t* offsets, void* workspace,
@@ -263,6 +286,25 @@ GG_API int gg_kf_finalize(const gg_kf_params_t* h_params, const gg_kf_rec_t* rec
  * `tie_budget` in emission order), 0 drop.  out_count[0] = edges kept. */
 GG_API int gg_kf_class_hist(const int64_t* edge_src, const int64_t* edge_dst, const uint32_t* dot, int64_t n_edges,
                      const int32_t* sqnorm, int32_t p_max, unsigned long long* class_hist, gg_stream_t st);
+/* The same two steps on PACKED words (the output of gg_kf_place / gg_kf_dedup_place), for top-n selection without
+ * ever expanding what is dropped, one chunk of the emission order at a time:
+ *   gg_kf_class_hist_packed  class_hist[dot * (p_max + 1) + P] += 1 per word (not zeroed by the call)
+ *   gg_kf_select_packed      keeps words of class_action 1 and, of the cut-off class (action 2), member number g
+ *                            (GLOBAL emission order, g = cursors[0] + rank inside this call) iff
+ *                            floor((g + 1) r / 2^64) > floor(g r / 2^64), r = tie_ratio = ceil(B 2^64 / T) for B of T
+ *                            members to keep: the choice depends on g alone, so ranks and chunks need no
+ *                            coordination beyond their starting g.  Kept words are expanded to out_src / out_dst /
+ *                            out_w64 (nullable) / out_w32 (nullable) from index cursors[1] on (nothing is written at
+ *                            or beyond out_capacity); the call then advances cursors[0] by the members of the cut-off
+ *                            class it saw and cursors[1] by the edges it kept (device int64[2], caller-initialised).
+ *                            At most 2^31 - 1 words per call. */
+GG_API int gg_kf_class_hist_packed(const uint64_t* ordered, int64_t n_edges, const int32_t* sqnorm, int32_t p_max,
+                            uint64_t* class_hist, gg_stream_t st);
+GG_API size_t gg_kf_select_packed_workspace_bytes(int64_t n_edges);
+GG_API int gg_kf_select_packed(const uint64_t* ordered, int64_t n_edges, const int32_t* sqnorm, int32_t p_max,
+                        const uint8_t* class_action, uint64_t tie_ratio, int64_t* cursors, int64_t* out_src,
+                        int64_t* out_dst, double* out_w64, float* out_w32, int64_t out_capacity, void* workspace,
+                        size_t workspace_bytes, gg_stream_t st);
 GG_API size_t gg_kf_select_workspace_bytes(int64_t n_edges);
 GG_API int gg_kf_select(const int64_t* edge_src, const int64_t* edge_dst, const double* weight64, const uint32_t* dot,
                  int64_t n_edges, const int32_t* sqnorm, int32_t p_max, const uint8_t* class_action,

@@ -208,10 +208,29 @@ def top_n_budget(n_nodes, keep_top_k, n_candidates):
     return n_candidates if top_n == 0 else top_n
 
 
+def tie_ratio(tie_budget, tie_total):
+    """r = ceil(B 2^64 / T): the fixed-point slope of the spread rule below (0: nothing to cut)."""
+    if not (0 < tie_budget < tie_total):
+        return 0
+    return -((-tie_budget << 64) // tie_total)
+
+
+def spread_keep(tie_total, tie_budget):
+    """Which of the T members of the cut-off class, numbered g = 0..T-1 in emission order, the CUDA path keeps when B
+    of them fit the budget: member g iff floor((g+1) r / 2^64) > floor(g r / 2^64), r = ceil(B 2^64 / T).  Exactly B
+    pass, evenly spread over the emission order -- so that every row-block shard of a multi-GPU build keeps its share
+    and the choice does not depend on how the order is cut into shards or chunks.  (The reference keeps whichever
+    members np.argpartition's introselect happens to leave in the top-n slots, gnn_utils.py:311-317: any B of the T
+    are an equally faithful answer, see tie_aware_compare.)  Returns a bool mask of length T."""
+    r = tie_ratio(tie_budget, tie_total)
+    steps = (np.arange(tie_total + 1, dtype=object) * r) >> 64
+    return np.asarray(steps[1:] > steps[:-1], dtype=bool)
+
+
 def kf_edges_exact(counts, threshold=0.0, keep_top_k=None, chunk_size=1024):
     """The CUDA path's KF contract: candidates by the exact test, then, when the
     global top-n budget binds, every pair strictly above the cut-off score class
-    plus the first members of the cut-off class in emission order.  Output keeps
+    plus the members of the cut-off class picked by ``spread_keep``.  Output keeps
     emission order.  Returns (edge_index int64[2,E], weight float64[E])."""
     s, t, dot, prod = kf_candidates(counts, threshold, chunk_size)
     n = counts.shape[0]
@@ -245,7 +264,7 @@ def kf_edges_exact(counts, threshold=0.0, keep_top_k=None, chunk_size=1024):
         keep = kept_cls[inv]
         if cut_val is not None and room > 0:
             tie = np.nonzero(np.isin(inv, cut_val))[0]
-            keep[tie[:room]] = True
+            keep[tie[spread_keep(tie.shape[0], room)]] = True
         s, t, dot, prod = s[keep], t[keep], dot[keep], prod[keep]
     return np.stack([s, t], axis=0).astype(np.int64), kf_weight(dot, prod)
 

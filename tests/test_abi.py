@@ -42,7 +42,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     lib = _lib.load()
     assert lib.gg_count_reset(99, None, None, None, None) == -2        # GG_ERR_K
     assert b"k outside" in lib.gg_last_error()
-    assert lib.gg_kf_emit(None, None, None, None, None, None, 0, None, None, None) == -1  # GG_ERR_ARG
+    assert lib.gg_kf_emit(None, None, None, None, None, None, 0, None, None, None, None) == -1  # GG_ERR_ARG
 
 
 def test_newer_entry_points_validate_their_arguments_without_a_gpu():
@@ -60,7 +60,14 @@ def test_newer_entry_points_validate_their_arguments_without_a_gpu():
     assert lib.gg_kf_dedup_classes(None, 16, 64, 100, None, None, None, None, 0, None) == ERR_ARG    # > 16 columns
     assert lib.gg_kf_dedup_classes(None, 16, 16, (1 << 20) + 1, None, None, None, None, 0, None) == ERR_ARG
     assert lib.gg_kf_dedup_adj_words(17444) == 17444 * 546
-    assert lib.gg_kf_dedup_score(None, 16, 16, None, None, None, 10, None, 50, None, None) == ERR_ARG  # p_max not a square
+    assert lib.gg_kf_dedup_score(None, 16, 16, None, None, None, 10, None, 50, None, None, None) == ERR_ARG  # p_max not a square
+    assert lib.gg_kf_select_packed(None, 1 << 31, None, 16, None, 0, None, None, None, None, None, 0, None, 0, None) == ERR_ARG
+    assert lib.gg_kf_select_packed(None, 10, None, 16, None, 0, None, None, None, None, None, 0, None, 0, None) == ERR_ARG
+    assert lib.gg_kf_select_packed_workspace_bytes(1 << 20) >= 9 * (1 << 20)
+    assert lib.gg_kf_class_hist_packed(None, 10, None, 16, None, None) == ERR_ARG
+    assert lib.gg_kf_class_hist_packed(None, 0, None, 16, None, None) == 0
+    assert lib.gg_probe_smem_atomics(1000, 1, None, None, None) == ERR_ARG                     # not a power of two
+    assert lib.gg_probe_tensor_i8(0, 8, None, None, None) == ERR_ARG
     assert lib.gg_kf_dedup_count(100, 0, 5, None, None, None, 10, None, None, 0, None) == ERR_ARG    # shard past the end
     assert lib.gg_db_build(None, None, None, 0, 8, 1, 0, -1.0, None, None, None, None, None, None, 0, None, None, 0, 41,
                            None) == ERR_ARG

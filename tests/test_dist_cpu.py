@@ -157,7 +157,7 @@ def test_choose_cutoff_matches_oracle_policy():
         act = action[dot * (p_max + 1) + prod]
         keep = act == 1
         ties = np.nonzero(act == 2)[0]
-        keep[ties[:tie_budget]] = True
+        keep[ties[fast.spread_keep(len(ties), tie_budget)]] = True
         assert int(keep.sum()) == budget
         ei, w = fast.kf_edges_exact(counts, 0.0, frac)
         assert np.array_equal(ei, np.stack([s[keep], t[keep]]))
@@ -184,3 +184,80 @@ def test_knn_row_shards_tile_the_rows():
             assert all(lo % KNN_ROW_BLOCK == 0 and lo <= hi for lo, hi in shards)
             blocks = [-(-(hi - lo) // KNN_ROW_BLOCK) for lo, hi in shards]
             assert max(blocks) - min(blocks) <= 1
+
+
+def test_spread_rule_keeps_exactly_the_budget_and_ignores_sharding():
+    """The cut-off class rule of gg_kf_select_packed (core.tie_ratio / ties_admitted) against the oracle's statement:
+    exactly B of T members, and a rank / chunk that starts at global member g0 needs nothing but g0."""
+    from genomic_gnn_b200.core import tie_ratio, ties_admitted
+
+    rng = np.random.default_rng(5)
+    cases = [(10, 3), (19416, 16476), (7, 6), (2, 1), (1000, 1), (12345, 6172), (2**20 + 3, 2**19)]
+    cases += [(int(t), int(rng.integers(1, t))) for t in rng.integers(2, 50_000, size=20)]
+    for total, budget in cases:
+        mask = fast.spread_keep(total, budget)
+        assert mask.shape == (total,) and int(mask.sum()) == budget
+        r = tie_ratio(budget, total)
+        assert r == fast.tie_ratio(budget, total) and 0 < r < 2**64
+        prefix = np.concatenate([[0], np.cumsum(mask)])
+        cuts = sorted({0, total, *map(int, rng.integers(0, total + 1, size=6))})
+        for g in cuts:
+            assert ties_admitted(g, r) == int(prefix[g])
+        # evenly spread: any window holds its proportional share +- 1
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            assert abs((prefix[b] - prefix[a]) - (b - a) * budget / total) <= 1.0
+    # sizes of BASELINE config 5 (5.5e11 pairs): still exact in 64.64 fixed point
+    total, budget = 17_203_456_789, 9_876_543_210
+    r = tie_ratio(budget, total)
+    assert ties_admitted(total, r) == budget and ties_admitted(0, r) == 0
+    assert all(0 <= ties_admitted(g + 1, r) - ties_admitted(g, r) <= 1 for g in (0, 1, 12345, total - 2, total - 1))
+    assert tie_ratio(0, 5) == 0 and tie_ratio(5, 5) == 0
+
+
+def test_rational_tables_are_exact_for_strict_and_inclusive_tests():
+    """dmin / fast_scale of the scoring kernels against brute force over every (dot, sq_s, sq_t): strict `>` for a
+    threshold, `>=` for a cut-off class; the pre-filter never rejects a passing pair."""
+    from fractions import Fraction
+
+    from genomic_gnn_b200.core import ScoreTest, rational_tables, threshold_tables
+
+    sq_max = 16
+    tests = [ScoreTest.from_threshold(0.8), ScoreTest.from_threshold(0.0), ScoreTest.from_threshold(0.5),
+             ScoreTest(1, 36, True), ScoreTest(4, 9, True), ScoreTest(9, 16, True), ScoreTest(1, 1, True),
+             ScoreTest(4, 9, False)]
+    for test in tests:
+        dmin, scale, shift, p_max = rational_tables(test, sq_max)
+        assert p_max == sq_max * sq_max and dmin.shape == (p_max + 1,)
+        cut = Fraction(test.num, test.den)
+        for si in range(1, sq_max + 1):
+            for sj in range(1, sq_max + 1):
+                p = si * sj
+                for dot in range(0, sq_max + 1):
+                    val = Fraction(dot * dot, p)
+                    passes = val >= cut if test.inclusive else val > cut
+                    if test.inclusive and test.num == 0:
+                        continue
+                    assert (dot >= int(dmin[p])) == passes, (test, dot, si, sj)
+                    if passes:
+                        assert ((dot * dot) << shift) > int(scale[si]) * sj, (test, dot, si, sj)
+    d1, s1, sh1, _ = threshold_tables(0.8, sq_max)
+    d2, s2, sh2, _ = rational_tables(ScoreTest.from_threshold(0.8), sq_max)
+    assert np.array_equal(d1, d2) and np.array_equal(s1, s2) and sh1 == sh2
+
+
+def test_choose_cutoff_class_reports_the_lowest_contributing_class():
+    from fractions import Fraction
+
+    from genomic_gnn_b200.core import choose_cutoff_class
+
+    p_max = 16
+    hist = np.zeros(5 * (p_max + 1), dtype=np.int64)
+    hist[4 * (p_max + 1) + 16] = 10     # cos 1
+    hist[2 * (p_max + 1) + 8] = 20      # cos^2 = 1/2
+    hist[1 * (p_max + 1) + 4] = 30      # cos^2 = 1/4
+    hist[2 * (p_max + 1) + 16] = 5      # cos^2 = 1/4 as well (same class, another (dot, P))
+    action, tb, cutoff, tt, cut = choose_cutoff_class(hist, p_max, 40)
+    assert (tb, tt, cut) == (10, 35, Fraction(1, 4)) and abs(cutoff - 0.5) < 1e-15
+    assert action[1 * (p_max + 1) + 4] == 2 and action[2 * (p_max + 1) + 16] == 2 and action[2 * (p_max + 1) + 8] == 1
+    action, tb, cutoff, tt, cut = choose_cutoff_class(hist, p_max, 30)   # lands exactly on a class boundary
+    assert (tb, tt, cut) == (0, 0, Fraction(1, 2)) and cutoff is None and int((action == 2).sum()) == 0
