@@ -61,6 +61,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end loop")
     ap.add_argument("--no-probes", action="store_true", help="skip the hardware-ceiling probes and the launch census")
+    ap.add_argument("--kf-output", default="auto", choices=["auto", "gathered", "sharded", "discard"],
+                    help="gathered: every rank ends with every KF edge (configs 1-4); sharded: every rank keeps the edges "
+                         "of its own row blocks (config 5: 1.1e10 edges per set fit no single device); discard: sharded, "
+                         "and a binding top-n recycles one chunk buffer (the result exceeds this many GPUs' memory); "
+                         "auto: gathered up to k=8, else sharded when the shards fit, else discard")
+    ap.add_argument("--chunk-records", type=int, default=0, help="packed words per top-n emission chunk (0: 2^27)")
     ap.add_argument("--debug-no-flush", action="store_true")
     ap.add_argument("--debug-no-clocks", action="store_true")
     ap.add_argument("--debug-timer-in-headline", action="store_true")
@@ -68,7 +74,7 @@ def parse_args():
 
 
 def workload_name(a):
-    name = {8: "config4", 7: "config3", 6: "config2", 3: "config1"}.get(a.k, "custom")  # BASELINE.json configs by k
+    name = {10: "config5", 8: "config4", 7: "config3", 6: "config2", 3: "config1"}.get(a.k, "custom")  # BASELINE.json configs by k
     return (f"{name}: k={a.k}, small_k={a.small_k}, KF threshold={a.threshold}, top_k={a.top_k}, "
             f"{a.reads} synthetic {a.read_len}-bp reads (uniform ACGT, seed 0)")
 
@@ -92,7 +98,7 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_sample(a, reads_arr, count_reads=20_000, kf_row_blocks=1, feat_nodes=8192):
+def cpu_reference_sample(a, reads_arr, count_reads=20_000, kf_row_blocks=1, feat_nodes=8192, kf_nodes_cap=65_536):
     """Bounded sample of the reference's CPU path, scaled to the full workload.
     Returns (estimated seconds for the full workload, description, detail dict)."""
     from oracle import fast, faithful
@@ -111,14 +117,18 @@ def cpu_reference_sample(a, reads_arr, count_reads=20_000, kf_row_blocks=1, feat
     codes = None
     detail = {"count_s_scaled": t_count, "db_s": t_db, "n_nodes": n_nodes}
     t_feat = t_kf = 0.0
-    nb = (n_nodes + 1023) // 1024
+    # the KF sample scores `rb` row blocks against the first `n_kf` nodes (all of them up to 65,536: beyond that the
+    # float64 feature matrix alone is gigabytes) and is scaled by block pairs to the full node count
+    n_full = max(n_nodes, min(4**k, (n_total * max(a.read_len - k, 1))))   # every k-mer occurs at BASELINE read counts
+    n_kf = min(n_nodes, kf_nodes_cap)
+    nb_full, nb = (n_full + 1023) // 1024, (n_kf + 1023) // 1024
     rb = min(kf_row_blocks, nb)
-    pair_scale = (nb * (nb + 1) / 2) / sum(nb - i for i in range(rb))
+    pair_scale = (nb_full * (nb_full + 1) / 2) / sum(nb - i for i in range(rb))
     for s in (int(x) for x in a.small_k.split(",")):
         sub = nodes[: min(feat_nodes, n_nodes)]
         t0 = time.perf_counter()
         faithful.node_embedding_initial(sub, "kmer_frequency", k, s)
-        tf = (time.perf_counter() - t0) * (n_nodes / len(sub))
+        tf = (time.perf_counter() - t0) * (n_full / len(sub))
         if codes is None:
             lut = np.zeros(256, np.int64)
             lut[np.frombuffer(b"ACGT", np.uint8)] = np.arange(4)
@@ -126,7 +136,7 @@ def cpu_reference_sample(a, reads_arr, count_reads=20_000, kf_row_blocks=1, feat
             codes = np.zeros(n_nodes, np.int64)
             for j in range(k):
                 codes = codes * 4 + lut[arr[:, j]]
-        x, _ = fast.features_from_counts(fast.subkmer_counts(codes, k, s), k, s)  # untimed: input of the timed KF sample
+        x, _ = fast.features_from_counts(fast.subkmer_counts(codes[:n_kf], k, s), k, s)  # untimed: input of the timed KF sample
         t0 = time.perf_counter()
         faithful.cosine_similarity_to_edge_index_weight(x, threshold=a.threshold, keep_top_k=None, row_blocks=rb)
         tk = (time.perf_counter() - t0) * pair_scale
@@ -135,9 +145,10 @@ def cpu_reference_sample(a, reads_arr, count_reads=20_000, kf_row_blocks=1, feat
         t_feat += tf
         t_kf += tk
     total = t_count + t_db + t_feat + t_kf
-    desc = (f"counting: first {count_reads} reads x{n_total / count_reads:.0f}; DB assembly in full; features: first "
-            f"{min(feat_nodes, n_nodes)} nodes x{n_nodes / min(feat_nodes, n_nodes):.0f}; KF: first {rb} of {nb} row blocks "
-            f"x{pair_scale:.1f} by block pairs; counting/features are single-thread Python, KF is numpy/BLAS")
+    desc = (f"counting: first {count_reads} reads x{n_total / count_reads:.0f}; DB assembly of the sample; features: first "
+            f"{min(feat_nodes, n_nodes)} nodes x{n_full / min(feat_nodes, n_nodes):.0f}; KF: {rb} row block(s) against "
+            f"{n_kf} nodes x{pair_scale:.1f} by block pairs to {n_full} nodes; counting/features are single-thread Python, "
+            f"KF is numpy/BLAS")
     return total, desc, detail
 
 
@@ -320,10 +331,21 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- our arm
+def kf_output_mode(a, world):
+    """Where the KF edge sets end up (see --kf-output)."""
+    if a.kf_output != "auto":
+        return a.kf_output
+    if a.k <= 8 or a.top_k is None:
+        return "gathered"
+    n = 4**a.k
+    per_rank = len(a.small_k.split(",")) * int(n * n * a.top_k) * 20 / world + 24e9   # kept edges + chunk staging
+    return "sharded" if per_rank < 0.8 * 180e9 else "discard"
+
+
 def run_ours(a):
     import torch
 
-    from genomic_gnn_b200 import core, dist as ggdist
+    from genomic_gnn_b200 import core, dist as ggdist, hostshare
     from genomic_gnn_b200.synth import synthetic_reads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -343,12 +365,17 @@ def run_ours(a):
     reads_all = synthetic_reads(a.reads, a.read_len, seed=0)
     lo, hi = ggdist.shard_bounds(a.reads, world, rank)
     reads_host = torch.from_numpy(reads_all[lo:hi].copy()).pin_memory()
+    del reads_all
     pos_base = lo * a.read_len
     resident = core.upload_reads(reads_host, pos_base=pos_base)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    n_small = len(a.small_k.split(","))
+    small_ks = [int(x) for x in a.small_k.split(",")]
+    n_small = len(small_ks)
+    mode = kf_output_mode(a, world)
+    big = a.k >= 9                       # config 5: no float32 feature matrices (4 GB per wide set), sharded KF output
     kw = dict(k=a.k, small_k=a.small_k, edges_threshold=a.threshold, edges_keep_top_k=a.top_k, kf_impl=a.kf_impl,
-              comm=comm)
+              comm=comm, kf_gather=mode == "gathered", kf_sink="discard" if mode == "discard" else "device",
+              kf_chunk_records=a.chunk_records or None, keep_features=not big)
 
     def barrier():
         torch.cuda.synchronize()
@@ -361,25 +388,45 @@ def run_ours(a):
     def step_resident():
         return core.build_graph(resident, **kw)
 
+    # end to end: pinned host reads -> H2D -> build -> graph tensors in host memory.  One GPU: the public host-to-host
+    # call (copies overlapped with the kernels).  Several GPUs: every rank uploads its reads, builds with the KF sets
+    # left sharded and copies ITS shard into a host arena shared by all ranks -- no edge all-gather, all PCIe links busy.
+    # Config 5: the KF edge sets stay sharded on the devices (BASELINE: "output left sharded"; 220 GB per set do not
+    # belong in host memory); what comes down is the De Bruijn graph.
+    arena = None
+    if not a.no_e2e and world > 1 and not big:
+        n_nodes_max = min(4**a.k, a.reads * a.read_len)
+        budgets = [int(n_nodes_max**2 * a.top_k) if a.top_k else n_nodes_max * 64 for _ in small_ks]
+        arena = hostshare.SharedHostArena(comm, hostshare.arena_bytes_for(n_nodes_max, a.k, small_ks, budgets))
+    kw_e2e = dict(kw, kf_gather=False) if world > 1 else kw
+
     def step_e2e():
-        if world == 1:   # public host-to-host call: chunked H2D under the counting, D2H under the KF kernels
+        if world == 1 and not big:
             g = core.build_graph_to_host(reads_host, a.k, a.small_k, edges_threshold=a.threshold,
                                          edges_keep_top_k=a.top_k, kf_impl=a.kf_impl)
             return g, g.d2h_bytes
         stream = core.upload_reads(reads_host, pos_base=pos_base)     # H2D of this rank's reads (pinned source)
-        built = core.build_graph(stream, **kw)
-        nbytes = core.graph_to_host(built).d2h_bytes if rank == 0 else 0   # rank 0 delivers the graph to the host
-        torch.cuda.current_stream().synchronize()
-        return built, nbytes
+        built = core.build_graph(stream, **kw_e2e)
+        if big:
+            nbytes = 0
+            if rank == 0:
+                nbytes = core.graph_to_host(core.BuiltGraph(built.k, built.db, [], [], [])).d2h_bytes
+            summary = [kf.per_rank for kf in built.kf]                # the step's result for the KF sets: edges per rank
+            torch.cuda.current_stream().synchronize()
+            return (built, summary), nbytes
+        host = hostshare.deliver_graph(built, arena, comm)
+        return host, host.d2h_bytes
 
     def timed_loop(fn, steps, warmup, timer=None):
         last = None
         for _ in range(warmup):
-            last = fn()          # keep the previous result alive exactly as the timed loop does (pinned-buffer reuse)
+            last = None          # release the previous result first: config 5 keeps tens of GB per step
+            last = fn()
         barrier()
         core.set_timer(timer)
         total_ms = 0.0
         for _ in range(steps):
+            last = None
             if not a.debug_no_flush:
                 flush.fill_(1)                                        # evict L2 between timed iterations
             torch.cuda.synchronize()
@@ -409,22 +456,45 @@ def run_ours(a):
     # headline: K clean steps; the per-stage CUDA events (roofline numbers) come from a separate short pass so that
     # their host-side cost cannot leak into the headline
     total_ms, built = timed_loop(step_resident, a.steps, a.warmup, timer if a.debug_timer_in_headline else None)
+    stage_steps = a.steps
     if not a.debug_timer_in_headline:
-        timed_loop(step_resident, min(a.steps, 5), 1, timer)
-    stage_ms = {k_: statistics.mean(v) for k_, v in timer.summary().items()}
+        kf_meta = [(kf.n_edges, kf.per_rank, kf.n_candidates, kf.cutoff, kf.tie_kept, kf.tie_total, kf.resident) for kf in built.kf]
+        if big:
+            built.kf = []        # free the kept shards before the next build allocates its own
+        stage_steps = min(a.steps, 2 if big else 5)
+        _, built2 = timed_loop(step_resident, stage_steps, 0 if big else 1, timer)
+        if not big:
+            built = built2
+        del built2
+    else:
+        kf_meta = [(kf.n_edges, kf.per_rank, kf.n_candidates, kf.cutoff, kf.tie_kept, kf.tie_total, kf.resident) for kf in built.kf]
+    # a stage may launch several times per step (top-n: scoring pass + one emission per chunk): sum, then per step
+    stage_ms = {k_: sum(v) / stage_steps for k_, v in timer.summary().items()}
+    stage_launches = {k_: len(v) / stage_steps for k_, v in timer.summary().items()}
+    n_nodes, db_edges = built.db.num_nodes, built.db.num_edges
+    launches = census_launches(step_resident) if rank == 0 and not a.no_probes and not big else None
+    if big:
+        built = None
     if a.no_e2e:
         e2e_ms, d2h_bytes = float("nan"), 0
     else:
-        e2e_ms, (_, d2h_bytes) = timed_loop(step_e2e, a.steps, max(a.warmup, 3))
+        e2e_ms, (_, d2h_bytes) = timed_loop(step_e2e, a.steps if not big else min(a.steps, 2), max(a.warmup, 3) if not big else 1)
+        e2e_ms = e2e_ms / (a.steps if not big else min(a.steps, 2))
+    if world > 1:                        # bytes delivered by ALL ranks
+        import torch.distributed as dist
+
+        t = torch.tensor([float(d2h_bytes)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        d2h_bytes = int(t.item())
     clock_info = clocks.stop() if clocks else None
+    if arena is not None:
+        arena.close()
 
     ms_per_step = total_ms / a.steps
     value = a.reads / (ms_per_step * 1e-3)
-    kf_ms = sum(v for k_, v in stage_ms.items() if k_.startswith(("k4_", "k5_", "k6_", "c2_")))
-    kf_edges = sum(int(kf.edge_index.shape[1]) for kf in built.kf)
-    n_nodes = built.db.num_nodes
+    kf_ms = sum(v for k_, v in stage_ms.items() if k_.startswith(("k4_", "k5_", "k6_", "c2_", "c5_")))
+    kf_edges = sum(m[0] for m in kf_meta)
 
-    launches = census_launches(step_resident) if rank == 0 and not a.no_probes else None
     peaks = measured_peaks()
     local_bytes = (hi - lo) * a.read_len + 4 ** (a.k + 1) * 4
     rooflines = {}
@@ -433,26 +503,35 @@ def run_ours(a):
         rooflines["k1_count"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms": stage_ms["k1_count"],
                                  "algorithmic_bytes": local_bytes, "peak_source": peaks["source"]}
-        if "smem_atomics" in probes:
+        windows = (hi - lo) * max(a.read_len - a.k, 0)
+        rate = windows / (stage_ms["k1_count"] * 1e-3)
+        if "smem_atomics" in probes and a.k <= 8:
             # secondary ceiling: one histogram update per (k+1)-mer window, against the measured shared-memory atomic
             # rate -- the bound of a 4^(k+1)-bin histogram over near-uniform keys on this GPU
-            windows = (hi - lo) * max(a.read_len - a.k, 0)
-            rate = windows / (stage_ms["k1_count"] * 1e-3)
             rooflines["k1_count"]["atomic_ceiling"] = {
                 "updates": windows, "achieved_updates_per_s": rate, "peak_updates_per_s": probes["smem_atomics"]["updates_per_s"],
                 "frac": rate / probes["smem_atomics"]["updates_per_s"],
                 "how": "gg_probe_smem_atomics: uniform 32-bit ATOMS into a 32,768-bin table per CTA, 1024 threads x all SMs"}
-    for s in (int(x) for x in a.small_k.split(",")):
+        elif a.k >= 9:
+            rooflines["k1_count"]["atomic_ceiling"] = {
+                "updates": windows, "achieved_updates_per_s": rate,
+                "note": "4^(k+1) >= 2^20 bins: one RED per window into the L2-resident table (the partition path stops at k=8)"}
+    for i, s in enumerate(small_ks):
         d = 4**s
         pairs = n_nodes * (n_nodes - 1) / 2 / world  # strict upper triangle, this rank's share (balanced shards)
         flops = 2 * d * pairs
         key = next((c for c in (f"k4_emit_d{d}", f"k4_emit_d{max(d, 32)}") if c in stage_ms), None)  # narrow rows are padded
         if key is not None:
-            ach = flops / (stage_ms[key] * 1e-3) / 1e12
+            # a binding top-n scores the shard twice on the tensor path: once for the class table, once chunk by chunk
+            # against the cut-off -- both passes are algorithmic work of this method, both are credited
+            n_emit = stage_launches[key]
+            passes = 2 if (n_emit > 1 and kf_meta[i][3] is not None) else 1
+            ach = passes * flops / (stage_ms[key] * 1e-3) / 1e12
             rooflines[key] = {"bound": "tensor" if d >= 128 else "alu", "achieved": ach, "peak": peaks["tflops"],
                               "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "ms": stage_ms[key],
-                              "algorithmic_flops": flops, "peak_source": peaks["source"] + " bf16 burst",
-                              "pairs_per_s": pairs / (stage_ms[key] * 1e-3)}
+                              "algorithmic_flops": passes * flops, "gram_passes": passes, "launches_per_step": n_emit,
+                              "peak_source": peaks["source"] + " bf16 burst",
+                              "pairs_per_s": passes * pairs / (stage_ms[key] * 1e-3)}
             if d >= 128 and "tensor_i8" in probes:
                 # the kernel computes in kind::i8 (2x the bf16 rate): quote it against the int8 MMA rate measured here,
                 # in this process, and keep the bf16 figure of MEASURED_PEAKS.json as a note
@@ -462,15 +541,12 @@ def run_ours(a):
                                                           "source": peaks["source"] + " bf16 burst (MEASURED_PEAKS.json)"}})
         elif f"k4_score_d{d}" in stage_ms:
             # duplicate-row path: classes + class-pair scoring + per-class count and placement stand in for the emit
-            # and place kernels; credited with the same algorithmic pair count although it scores far fewer pairs
+            # and place kernels.  ALU / issue-bound: a tensor fraction means nothing here.  Quote the edges it writes
+            # against the HBM write floor instead: 8 bytes per packed edge (place) + 20 per expanded edge.
             parts = [f"k4_classes_d{d}", f"k4_score_d{d}", f"k4_count_d{d}", f"k6_place_d{d}"]
             ms = sum(stage_ms.get(p_, 0.0) for p_ in parts)
-            ach = flops / (ms * 1e-3) / 1e12
-            # ALU / issue-bound path: a tensor fraction means nothing here.  Quote the edges it writes against the HBM
-            # write floor instead: 8 bytes per packed edge (place) + 20 bytes per expanded edge (edge_index + weight).
-            kf_i = [int(x) for x in a.small_k.split(",")].index(s)
-            e_local = int(built.kf[kf_i].edge_index.shape[1]) / world
-            ms_all = ms + stage_ms.get(f"k6_expand_d{d}", 0.0)
+            e_local = (kf_meta[i][1][rank] if (kf_meta[i][1] and mode != "gathered") else kf_meta[i][0] / world)
+            ms_all = ms + stage_ms.get(f"k6_expand_d{d}", 0.0) + (stage_ms.get("k5_select", 0.0) if kf_meta[i][3] is not None else 0.0)
             out_bytes = e_local * 28.0
             ach_gbs = out_bytes / (ms_all * 1e-3) / 1e9
             rooflines[f"k4_dedup_d{d}"] = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -481,37 +557,42 @@ def run_ours(a):
                                            "note": "issue-bound sparse class sweeps; floor = edge bytes written once"}
     dominant = max(rooflines, key=lambda k_: rooflines[k_]["ms"]) if rooflines else None
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if rooflines and os.path.exists(traffic_file):  # per-launch DRAM bytes from the committed ncu --set full capture
+    if rooflines and os.path.exists(traffic_file) and not big:  # per-launch DRAM bytes from the committed ncu --set full capture
         with open(traffic_file) as fh:
             measured = json.load(fh)
         for key_, r_ in rooflines.items():
             r_["traffic"] = measured.get(key_)
 
+    static_launches = our_launches_per_step(small_ks, a.k, n_nodes)
     line = {
         "metric": metric_name(a), "value": value, "unit": "reads/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8 counts, int32/fp32 accumulate, f64 weights",
         "data": "synthetic",
         "config": bench_config(a),
-        "run": {"parallelism": f"reads and KF row blocks sharded over {world} GPU(s)",
+        "run": {"parallelism": f"reads and KF row blocks sharded over {world} GPU(s)", "kf_output": mode,
                 "l2": "256 MiB buffer written between timed iterations", "kf_impl": a.kf_impl},
         "kf_edges_per_s": kf_edges / (kf_ms * 1e-3) if kf_ms else None,
         "kf_pairs_per_s": n_small * n_nodes * (n_nodes - 1) / 2 / (kf_ms * 1e-3) if kf_ms else None,
-        "kf_edges": kf_edges, "nodes": n_nodes, "db_edges": built.db.num_edges,
-        "stage_ms": stage_ms,
-        "e2e": {"value": a.reads / (e2e_ms / a.steps * 1e-3), "unit": "reads/s", "ms_per_step": e2e_ms / a.steps,
-                "h2d_bytes_per_step": (hi - lo) * a.read_len, "d2h_bytes_per_step": d2h_bytes},
-        "gpu_launches": (launches["own"] if launches else
-                         our_launches_per_step([int(x) for x in a.small_k.split(",")], a.k, n_nodes)) * a.steps,
-        "gpu_launches_per_step": launches or {"own": our_launches_per_step([int(x) for x in a.small_k.split(",")], a.k, n_nodes),
-                                              "source": "static count (profiler unavailable)"},
+        "kf_edges": kf_edges, "nodes": n_nodes, "db_edges": db_edges,
+        "kf_sets": [{"small_k": s_, "edges": m[0], "edges_per_rank": m[1], "candidates": m[2], "cutoff": m[3],
+                     "cutoff_class_kept": m[4], "cutoff_class_size": m[5], "resident": m[6]}
+                    for s_, m in zip(small_ks, kf_meta)],
+        "stage_ms": stage_ms, "stage_launches_per_step": stage_launches,
+        "e2e": {"value": a.reads / (e2e_ms * 1e-3), "unit": "reads/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": a.reads * a.read_len, "d2h_bytes_per_step": d2h_bytes,
+                "delivery": ("KF edge sets stay sharded on the devices (config 5); De Bruijn graph to pinned host memory" if big
+                             else ("every rank copies its shard into one page-locked shared-memory arena" if world > 1
+                                   else "build_graph_to_host: copies overlapped with the kernels"))},
+        "gpu_launches": (launches["own"] if launches else static_launches) * a.steps,
+        "gpu_launches_per_step": launches or {"own": static_launches, "source": "static count (no profiler pass)"},
         "probes": probes,
         "roofline": {"kernel": dominant, **rooflines[dominant]} if dominant else None,
         "rooflines": rooflines,
         "clocks": clock_info,
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        sec, desc, detail = cpu_reference_sample(a, reads_all[:50_000])
+        sec, desc, detail = cpu_reference_sample(a, synthetic_reads(min(a.reads, 50_000), a.read_len, seed=0))
         line["cpu_baseline"] = {"value": a.reads / sec, "unit": "reads/s", "cores": blas_threads(), "kind": "port",
                                 "sample": desc, "host_cpus": os.cpu_count(), "est_seconds_full_workload": sec,
                                 "detail": detail}

@@ -83,7 +83,7 @@ SIGNATURES = {
     "gg_kf_dedup_adj_words": (_SZ, [_I64]),
     "gg_kf_dedup_score": (_I32, [_P, _I32, _I32, _P, _P, _P, _I64, _P, _I32, _P, C.POINTER(KfDedupExtra), _P]),
     "gg_kf_dedup_count_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
-    "gg_kf_dedup_count": (_I32, [_I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "gg_kf_dedup_count": (_I32, [_I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "gg_kf_dedup_place": (_I32, [_I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _I32, _I32, _P, _I64, _P, _SZ, _P]),
     "gg_kf_class_hist": (_I32, [_P, _P, _P, _I64, _P, _I32, _P, _P]),
     "gg_count_pairs_stride": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I64, _P, _I64, _P, _P]),
@@ -145,5 +145,7 @@ def check(rc, what):
 
 
 def ptr(t):
-    """Device (or host) pointer of a torch tensor / None."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device (or host) pointer of a torch tensor / None (a ready-made c_void_p passes through)."""
+    if t is None or isinstance(t, C.c_void_p):
+        return t
+    return C.c_void_p(t.data_ptr())

@@ -654,9 +654,13 @@ class StagedClasses:
         self.d = int(counts.shape[1])
         self.status4 = torch.zeros(4, dtype=torch.int64, device=counts.device)
         self.status4[0:1].copy_(offsets[-1:], non_blocking=True)   # the shard's edge count, still on the device
+        self.total_override = None
 
     def after_counts(self, mine):
         self.n_recs = int(mine[0])
+        # [1] != 0: the scoring pass found more candidates in the whole matrix ([3]) than the top-n budget, and the
+        # per-row counting pass was skipped on the device (its result would not be used)
+        self.total_override = int(mine[3]) if int(mine[1]) != 0 else None
         self.status4 = None
 
     def complete(self):
@@ -671,9 +675,9 @@ class StagedClasses:
                                         ptr(self.class_start), self.n_classes, ptr(dmin_d), p_max, ptr(self.adj),
                                         None if extra is None else C.byref(extra), _stream()), "gg_kf_dedup_score")
 
-    def count(self, ib0, ib1):
+    def count(self, ib0, ib1, skip_flag=None):
         """Exclusive prefix of the candidates per (block pair, row) of [ib0, ib1) under the current bit matrix; the
-        last entry is their number."""
+        last entry is their number.  ``skip_flag``: device int64, non-zero = leave everything zero."""
         lib = _lib.load()
         dev = self.counts.device
         elems = int(lib.gg_kf_rowcnt_elems(self.n, ib0, ib1))
@@ -682,7 +686,8 @@ class StagedClasses:
         cws = torch.empty(cb, dtype=torch.uint8, device=dev)
         with _stage(f"k4_count_d{self.d}"):
             check(lib.gg_kf_dedup_count(self.n, ib0, ib1, ptr(self.adj), ptr(self.members), ptr(self.class_start),
-                                        self.n_classes, ptr(offsets), ptr(cws), cb, _stream()), "gg_kf_dedup_count")
+                                        self.n_classes, ptr(offsets), ptr(skip_flag), ptr(cws), cb, _stream()),
+                  "gg_kf_dedup_count")
         return offsets
 
     def place_range(self, ib0, ib1, offsets, ordered_ptr, capacity):
@@ -700,10 +705,13 @@ class StagedClasses:
 
 
 def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, iblock_begin=0,
-                   iblock_end=None) -> StagedClasses:
+                   iblock_end=None, top_n_cap: Optional[int] = None) -> StagedClasses:
     """K4' for narrow rows (<= 16 columns, counts <= 15): group identical rows into classes, score the class pairs,
     count the shard's edges.  One small device read here (the number of classes sizes the bit matrix); the number of
-    edges stays on the device for kf_resolve."""
+    edges stays on the device for kf_resolve.  ``top_n_cap`` = int(N^2 p) of a global top-n: the scoring pass then
+    also totals the candidates of the whole matrix (class pairs x member counts, no atomics per pair), and when they
+    exceed the cap -- the top-n will cut, from the class table -- the per-row counting pass turns itself off on the
+    device: at threshold 0 it would expand nearly every class against nearly every node for nothing."""
     lib = _lib.load()
     dev = counts.device
     n, d = int(counts.shape[0]), int(counts.shape[1])
@@ -726,11 +734,20 @@ def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max
     staged.counts, staged.sqnorm, staged.n, staged.ib0, staged.ib1 = counts, sqnorm, n, iblock_begin, iblock_end
     staged.members, staged.class_start, staged.n_classes, staged.adj = members, class_start, n_classes, adj
     staged.d = d
-    staged.score(_as_test(threshold), sq_max)
-    offsets = staged.count(iblock_begin, iblock_end)
+    if top_n_cap:
+        total = torch.zeros(2, dtype=torch.int64, device=dev)
+        staged.score(_as_test(threshold), sq_max, _lib.KfDedupExtra(None, 0, 0, total.data_ptr(), 0, 0, 0, 0))
+        binding = (total[0:1] > int(top_n_cap)).to(torch.int64)
+        offsets = staged.count(iblock_begin, iblock_end, skip_flag=binding)
+    else:
+        staged.score(_as_test(threshold), sq_max)
+        offsets = staged.count(iblock_begin, iblock_end)
     # the shard's edge count stays on the device: the caller reads it together with the other ranks' counts
     StagedClasses.__init__(staged, counts, sqnorm, n, iblock_begin, iblock_end, members, class_start, n_classes, adj,
                            offsets, None)
+    if top_n_cap:
+        staged.status4[1:2].copy_(binding, non_blocking=True)
+        staged.status4[3:4].copy_(total[0:1], non_blocking=True)
     return staged
 
 
@@ -852,7 +869,8 @@ def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
             raise ValueError("the duplicate-row KF path needs <= 16 columns, counts <= 15 and <= 2^20 nodes")
         use_dedup = False
     if use_dedup:
-        st.staged = kf_stage_dedup(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end)
+        cap = int(n**2 * keep_top_k) if keep_top_k is not None else None
+        st.staged = kf_stage_dedup(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, top_n_cap=cap)
     else:
         # staging capacity: the global top-n budget is the natural first guess (a binding threshold stays below it,
         # a binding top-n overflows, and is then cut from the score-class table without these records)
@@ -942,8 +960,10 @@ class _SelectSink:
                                           ptr(self.w32), self.capacity, ptr(ws), wb, _stream()), "gg_kf_select_packed")
 
     def totals(self):
-        """(members of the cut-off class seen up to here in global numbering, edges kept by this rank)."""
+        """(members of the cut-off class seen up to here in global numbering, edges kept by this rank); ``last`` =
+        edges sitting in the buffer now (all of them, or the last chunk's when the buffer is recycled)."""
         g, kept = read_small(self.cursors).tolist()
+        self.last = min(int(kept), self.capacity)
         return int(g), int(kept) + (int(read_small(self.kept_before)[0]) if self.discard else 0)
 
 
@@ -986,6 +1006,8 @@ def kf_finish(st: KFStage, comm=None, gather: bool = True, chunk_records: Option
                        sharded=comm.world > 1 and not gather)
     staged, per_rank = st.staged, st.per_rank
     n_total = sum(per_rank)
+    if getattr(staged, "total_override", None) is not None:   # duplicate-row path: counted per class pair, no shard counts
+        n_total = staged.total_override
     budget = top_n_budget(n, keep_top_k, n_total)
     need_cut = budget < n_total
     exchange = gather and comm.world > 1
@@ -1168,7 +1190,7 @@ def _kf_finish_top_n(st: KFStage, comm, gather, budget, n_total, chunk_records, 
         total = sum(kept_per_rank)
         return KFEdges(full_ei[:, :total], None, full_w[:total], n_total, cutoff, tie_budget, tie_total, impl,
                        per_rank=kept_per_rank)
-    shown = min(mine, dest.capacity) if discard else mine
+    shown = dest.last if discard else mine
     return KFEdges(dest.ei[:, :shown], None if dest.w64 is None else dest.w64[:shown], dest.w32[:shown], n_total, cutoff,
                    tie_budget, tie_total, impl, per_rank=kept_per_rank, sharded=comm.world > 1, resident=not discard)
 

@@ -133,7 +133,7 @@ __device__ __forceinline__ uint32_t dot16(const uint4& a, const uint4& b) {
 // tile in shared memory (one broadcast 16-byte load per column class serves 4 x 128 pairs); the per-row threshold
 // column thr[sq_b][row] makes the exact test one conflict-free shared-memory byte load, because all threads look at
 // the same b and hence the same sq_b.
-// EXTRA: 0 plain, 1 HIST, 2 TIES (see ScoreArgs)
+// EXTRA: 0 plain, 1 HIST, 2 TIES, 3 COUNT (see ScoreArgs; COUNT: tie_out[0] += node pairs of ALL passing class pairs)
 template <int EXTRA>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
       const int rep = __ldg(a.members + m0);
       ra[r] = load_row(a.counts, a.pitch, a.words, rep);
       sqa[r] = __ldg(a.sqnorm + rep);
-      if (EXTRA == 1) aw0[r] = static_cast<uint32_t>(m1 - m0);
+      if (EXTRA == 1 || EXTRA == 3) aw0[r] = static_cast<uint32_t>(m1 - m0);
       if (EXTRA == 2) {
         aw0[r] = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_lo));
         aw1[r] = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_hi));
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
       const int rep = __ldg(a.members + m0);
       rb = load_row(a.counts, a.pitch, a.words, rep);
       sqb = __ldg(a.sqnorm + rep);
-      if (EXTRA == 1) w0 = static_cast<uint32_t>(m1 - m0);
+      if (EXTRA == 1 || EXTRA == 3) w0 = static_cast<uint32_t>(m1 - m0);
       if (EXTRA == 2) {
         w0 = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_lo));
         w1 = static_cast<uint32_t>(members_at_or_after(a.members, m0, m1, a.row_hi));
@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
         for (; m; m &= m - 1) {
           const int tb = t0 + __ffs(m) - 1, cb = b0 + tb;
           if (cb != ca) atomicOr(a.adj + static_cast<size_t>(cb) * a.adj_words + (ca >> 5), 1u << (ca & 31));
-          if (EXTRA && count_row) {
+          if (EXTRA == 3) {
+            const unsigned long long wa = aw0[r];
+            tie0 += cb == ca ? wa * (wa - 1ull) / 2ull : wa * bw0[tb];
+          } else if (EXTRA && count_row) {
             const unsigned long long dot = dot16(ra[r], brow[tb]);
             const unsigned long long p = static_cast<unsigned long long>(sqa[r]) * (boff[tb] / kScoreA);
             if (EXTRA == 1) {
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
       }
     }
   }
-  if (EXTRA == 2) {  // one pair of atomics per warp
+  if (EXTRA == 2 || EXTRA == 3) {  // one pair of atomics per warp
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       tie0 += __shfl_xor_sync(0xFFFFFFFFu, tie0, o);
@@ -274,6 +277,7 @@ struct RowsArgs {
   int pitch, words;
   uint2* ordered;
   long long capacity;
+  const long long* skip_flag;  // pass 1, nullable: non-zero = the caller will not use the counts, do nothing
 };
 
 __host__ __device__ __forceinline__ long long rowcnt_word(int i_local, int n_jblocks, int j, int r) {
@@ -334,6 +338,7 @@ __global__ void __launch_bounds__(RowsCfg<PLACE, BIG>::kRowThreads) class_rows_k
   constexpr unsigned int kNbCap = 2 * kListCap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row_lo = a.ib0 * kBlock, row_hi = a.ib1 * kBlock;
+  if (!PLACE && a.skip_flag != nullptr && *a.skip_flag != 0) return;  // uniform: nothing has been written yet
   while (true) {
     if (threadIdx.x == 0) {
       s_class = static_cast<int>(atomicAdd(cursor, 1u));
@@ -686,6 +691,9 @@ extern "C" int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, 
     a.class_hist = reinterpret_cast<unsigned long long*>(extra->class_hist);
     a.hist_begin = static_cast<int>(extra->hist_class_begin);
     a.hist_end = static_cast<int>(extra->hist_class_end < n_classes ? extra->hist_class_end : n_classes);
+  } else if (extra != nullptr && extra->tie_out != nullptr && extra->tie_num == 0 && extra->tie_den == 0) {
+    mode = 3;  // COUNT
+    a.tie_out = reinterpret_cast<unsigned long long*>(extra->tie_out);
   } else if (extra != nullptr && extra->tie_out != nullptr) {
     GG_REQUIRE(extra->tie_num > 0 && extra->tie_den > 0 && extra->tie_num <= (1 << 16) && extra->tie_den <= (1ll << 32),
                GG_ERR_ARG, "cut-off class must be dot^2 / P with dot <= 255");
@@ -699,7 +707,7 @@ extern "C" int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, 
   }
   const size_t smem = kScoreB * (sizeof(uint4) + sizeof(uint32_t)) + static_cast<size_t>(sq_max + 1) * kScoreA +
                       2 * kScoreB * sizeof(uint32_t);
-  auto kernel = mode == 0 ? score_kernel<0> : (mode == 1 ? score_kernel<1> : score_kernel<2>);
+  auto kernel = mode == 0 ? score_kernel<0> : (mode == 1 ? score_kernel<1> : (mode == 2 ? score_kernel<2> : score_kernel<3>));
   GG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>((n_classes + kScoreB - 1) / kScoreB),
             static_cast<unsigned>((n_classes + kScoreA - 1) / kScoreA));
@@ -742,8 +750,10 @@ static int fill_rows_args(RowsArgs& a, int64_t n, int ib0, int ib1, const uint32
 /* offsets: [gg_kf_rowcnt_elems(n, ib0, ib1) + 1]; the last entry is the number of edges of the shard */
 extern "C" int gg_kf_dedup_count(int64_t n, int iblock_begin, int iblock_end, const uint32_t* adj,
                                  const int32_t* members, const int32_t* class_start, int64_t n_classes,
-                                 uint64_t* offsets, void* workspace, size_t workspace_bytes, gg_stream_t st) {
+                                 uint64_t* offsets, const int64_t* skip_flag, void* workspace, size_t workspace_bytes,
+                                 gg_stream_t st) {
   RowsArgs a{};
+  a.skip_flag = reinterpret_cast<const long long*>(skip_flag);
   if (int rc = fill_rows_args(a, n, iblock_begin, iblock_end, adj, members, class_start, n_classes)) return rc;
   GG_REQUIRE(offsets && workspace, GG_ERR_ARG, "null buffer");
   GG_REQUIRE(workspace_bytes >= gg_kf_dedup_count_workspace_bytes(n, iblock_begin, iblock_end), GG_ERR_WORKSPACE,

@@ -253,7 +253,8 @@ GG_API size_t gg_kf_dedup_adj_words(int64_t n_classes);
  *               before anything is emitted; ranks split the class range and sum their tables.
  *   tie_out     uint64[2], not zeroed: node pairs of the class dot^2 / P == tie_num / tie_den (the cut-off class)
  *               whose smaller node is >= row_lo ([0]) and >= row_hi ([1]); [0] - [1] = the members of that class the
- *               row shard [row_lo, row_hi) emits. */
+ *               row shard [row_lo, row_hi) emits.  With tie_num == tie_den == 0: tie_out[0] += the node pairs of ALL
+ *               passing class pairs, i.e. the number of candidates of the whole matrix. */
 typedef struct {
   uint64_t* class_hist;
   int64_t hist_class_begin, hist_class_end;
@@ -266,8 +267,10 @@ GG_API int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, cons
                       uint32_t* adj, const gg_kf_dedup_extra_t* h_extra, gg_stream_t st);
 GG_API size_t gg_kf_dedup_count_workspace_bytes(int64_t n, int iblock_begin, int iblock_end);
 GG_API int gg_kf_dedup_count(int64_t n, int iblock_begin, int iblock_end, const uint32_t* adj, const int32_t* members,
-                      const int32_t* class_start, int64_t n_classes, uint64_t* offsets, void* workspace,
-                      size_t workspace_bytes, gg_stream_t st);
+                      const int32_t* class_start, int64_t n_classes, uint64_t* offsets,
+                      const int64_t* skip_flag /* nullable device word: non-zero = leave every count at zero (the caller
+                                                  already knows it will cut by top-n and not use them) */,
+                      void* workspace, size_t workspace_bytes, gg_stream_t st);
 GG_API int gg_kf_dedup_place(int64_t n, int iblock_begin, int iblock_end, const uint32_t* adj, const int32_t* members,
                       const int32_t* class_start, int64_t n_classes, const uint64_t* offsets, const uint8_t* counts,
                       int pitch, int d_valid, uint64_t* ordered, int64_t capacity, void* workspace /* >= 256 bytes */,

@@ -68,7 +68,7 @@ def test_newer_entry_points_validate_their_arguments_without_a_gpu():
     assert lib.gg_kf_class_hist_packed(None, 0, None, 16, None, None) == 0
     assert lib.gg_probe_smem_atomics(1000, 1, None, None, None) == ERR_ARG                     # not a power of two
     assert lib.gg_probe_tensor_i8(0, 8, None, None, None) == ERR_ARG
-    assert lib.gg_kf_dedup_count(100, 0, 5, None, None, None, 10, None, None, 0, None) == ERR_ARG    # shard past the end
+    assert lib.gg_kf_dedup_count(100, 0, 5, None, None, None, 10, None, None, None, 0, None) == ERR_ARG    # shard past the end
     assert lib.gg_db_build(None, None, None, 0, 8, 1, 0, -1.0, None, None, None, None, None, None, 0, None, None, 0, 41,
                            None) == ERR_ARG
     assert lib.gg_rw_pairs(None, None, None, 10, None, 10, 1, 64, 3, 1.0, 1.0, 0, 0, None, None, None, None, 0, None,
