@@ -331,6 +331,40 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- our arm
+def builder_e2e(a, reads_host, steps):
+    """The call the reference makes: KmerSsgnnMb.create_graphs(self, k) (kmer_ssgnn_miniBatch.py:160-285) with
+    ``self.ssgnn_dataset`` a Python list of read strings (kmer_ssgnn.py:56-57), timed host to host -- list[str] in,
+    HeteroData-shaped CPU tensors + loader out -- with the share spent marshalling the strings."""
+    import types
+
+    import torch
+
+    import genomic_gnn_b200 as gg
+
+    arr = reads_host.numpy()
+    seqs = [bytes(r).decode("ascii") for r in arr]
+    me = types.SimpleNamespace(ssgnn_dataset=seqs, strides=[1], small_k=a.small_k, create_all_kmers=False,
+                               disable_tqdm=True, representation_ss_initial_labels="kmer_frequency", batch_size=256,
+                               kmer_frequency_loss_weight=1.0, edit_distance_loss_weight=0.0,
+                               edges_threshold=a.threshold, edges_keep_top_k=a.top_k, layers_config=["32_KF0"],
+                               representation_ss_last_layer_edge_type="KF0", ss_task="CL", faiss_ann=False)
+    times, marshal = [], []
+    for i in range(3 + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gg.create_graphs_mini_batch(me, a.k)
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append((time.perf_counter() - t0) * 1e3)
+            marshal.append(me.build_info["marshal_ms"])
+    ms = statistics.mean(times)
+    return {"value": a.reads / (ms * 1e-3), "unit": "reads/s", "ms_per_step": ms, "marshal_ms": statistics.mean(marshal),
+            "marshal_share": statistics.mean(marshal) / ms, "input": "list[str]", "timer": "host wall clock, CUDA synchronised",
+            "call": "genomic_gnn_b200.create_graphs_mini_batch(self, k)", "steps": steps,
+            "kf_edges": [int(me.torch_graph["node", f"KF{i}", "node"].edge_index.shape[1])
+                         for i in range(len(a.small_k.split(",")))]}
+
+
 def kf_output_mode(a, world):
     """Where the KF edge sets end up (see --kf-output)."""
     if a.kf_output != "auto":
@@ -591,6 +625,8 @@ def run_ours(a):
         "rooflines": rooflines,
         "clocks": clock_info,
     }
+    if rank == 0 and world == 1 and not big and not a.no_e2e:
+        line["e2e_builder"] = builder_e2e(a, reads_host, min(a.steps, 5))
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         sec, desc, detail = cpu_reference_sample(a, synthetic_reads(min(a.reads, 50_000), a.read_len, seed=0))
         line["cpu_baseline"] = {"value": a.reads / sec, "unit": "reads/s", "cores": blas_threads(), "kind": "port",

@@ -138,6 +138,29 @@ def load():
     return lib
 
 
+_pyhost = None
+
+
+def load_pyhost():
+    """libgg_pyhost.so (csrc/gg_pyhost.c): list[str] -> byte stream.  PyDLL: its calls take Python objects and keep
+    the GIL until they release it themselves."""
+    global _pyhost
+    if _pyhost is None:
+        from . import build as _build
+
+        lib = C.PyDLL(_build.build_pyhost())
+        lib.gg_py_reads_scan.restype = C.c_void_p
+        lib.gg_py_reads_scan.argtypes = [C.py_object, C.c_int, C.POINTER(C.c_int64)]
+        lib.gg_py_reads_copy.restype = C.c_int
+        lib.gg_py_reads_copy.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        lib.gg_py_reads_offset.restype = C.c_int64
+        lib.gg_py_reads_offset.argtypes = [C.c_void_p, C.c_int64]
+        lib.gg_py_reads_free.restype = None
+        lib.gg_py_reads_free.argtypes = [C.c_void_p]
+        _pyhost = lib
+    return _pyhost
+
+
 def check(rc, what):
     if rc != GG_OK:
         msg = load().gg_last_error().decode("utf-8", "replace")

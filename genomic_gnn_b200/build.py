@@ -16,6 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgg_b200.so")
 SOURCES = ["gg_common.cu", "gg_count.cu", "gg_db.cu", "gg_feat.cu", "gg_kf.cu", "gg_kf_mma.cu", "gg_kf_dedup.cu", "gg_index.cu", "gg_rw.cu", "gg_host.cu", "gg_spmm.cu", "gg_knn.cu", "gg_probe.cu"]
+PYHOST_SRC = os.path.join(CSRC, "gg_pyhost.c")
+PYHOST_LIB = os.path.join(HERE, "libgg_pyhost.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,7 +31,7 @@ BUILD_ID_MARK = b"GG_BUILD_ID="
 def source_hash():
     """Digest of every file the library is built from: the build id compiled into the .so (gg_build_id())."""
     h = hashlib.sha256()
-    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "gg_pyhost.c")
     files.append(os.path.join(os.path.dirname(HERE), "include", "gg_b200.h"))
     for f in files:
         h.update(os.path.basename(f).encode() + b"\0")
@@ -53,8 +55,29 @@ def is_current():
     return built_id() == source_hash()
 
 
+def build_pyhost(force=False):
+    """libgg_pyhost.so: the CPython-facing marshalling helper (plain C, gcc).  Rebuilt when its source is newer."""
+    import sysconfig
+
+    if not force and os.path.exists(PYHOST_LIB) and os.path.getmtime(PYHOST_LIB) >= os.path.getmtime(PYHOST_SRC):
+        return PYHOST_LIB
+    os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock_pyhost"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(PYHOST_LIB) and os.path.getmtime(PYHOST_LIB) >= os.path.getmtime(PYHOST_SRC):
+            return PYHOST_LIB
+        tmp = PYHOST_LIB + ".tmp%d" % os.getpid()
+        cmd = ["gcc", "-O2", "-shared", "-fPIC", "-fvisibility=hidden", "-I" + sysconfig.get_paths()["include"],
+               PYHOST_SRC, "-o", tmp, "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("gcc failed for gg_pyhost.c:\n%s\n%s" % (r.stdout, r.stderr))
+        os.replace(tmp, PYHOST_LIB)
+    return PYHOST_LIB
+
+
 def _deps_mtime():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "gg_pyhost.c"]
     files.append(os.path.join(os.path.dirname(HERE), "include", "gg_b200.h"))
     return max(os.path.getmtime(f) for f in files)
 
@@ -76,6 +99,7 @@ def build(force=False, verbose=False):
     """Compile + link unless the .so already carries the build id of the current sources.  Safe to call from several
     processes at once (one rank per GPU): the work happens under an exclusive file lock and is re-checked inside."""
     os.makedirs(BUILD, exist_ok=True)
+    build_pyhost(force)
     if not force and is_current():
         return LIB
     with open(os.path.join(BUILD, ".lock"), "w") as lock:

@@ -212,8 +212,37 @@ def _common_graph(self, k):
                       for s in str(self.small_k).split(",")]
 
 
+def _fused_host_build(self, k, with_kf):
+    """The builders' usual case in ONE pipelined pass (core.build_graph_to_host): list[str] reads marshalled natively
+    under their own upload, kernels back to back without intermediate Python objects, every tensor copied to pinned
+    host memory under the kernels that follow it.  Usual case = single stride, k-mer-frequency labels, exact KF edges,
+    CPU-side loaders (what kmer_ssgnn.py:162-213 / kmer_ssgnn_miniBatch.py:160-199 run with the default flags).
+    Returns None when the configuration needs the step-by-step path."""
+    if (len(list(getattr(self, "strides", [1]))) != 1 or int(list(getattr(self, "strides", [1]))[0]) != 1
+            or getattr(self, "representation_ss_initial_labels", "kmer_frequency") != "kmer_frequency"
+            or getattr(self, "faiss_ann", False) or str(getattr(self, "graph_device", "cpu")) != "cpu"
+            or not isinstance(self.ssgnn_dataset, (list, tuple)) or len(self.ssgnn_dataset) == 0):
+        return None
+    host = core.build_graph_to_host(self.ssgnn_dataset, k, str(self.small_k), create_all_kmers=self.create_all_kmers,
+                                    edges_threshold=float(getattr(self, "edges_threshold", 0.0) or 0.0),
+                                    edges_keep_top_k=getattr(self, "edges_keep_top_k", None), with_kf=with_kf)
+    self.graph = api.KmerGraph(host.db)
+    self.kf_labels = [api.KFLabels(kc) for kc in host.kf_counts]
+    return host
+
+
 def create_graphs(self, k: int):
     """Full-batch builder: KmerSsgnn.create_graphs (kmer_ssgnn.py:162-230)."""
+    host = _fused_host_build(self, k, with_kf=False)
+    if host is not None:
+        pyg = _pyg()
+        data = pyg[0]() if pyg else GraphData()
+        data.edge_index, data.weight, data.num_nodes = host.edge_index, host.weight, host.num_nodes
+        data.x, data.y = host.x[0], list(host.x)
+        self.dataloader = torch.utils.data.DataLoader([0], batch_size=1, num_workers=0)
+        self.torch_graph = data
+        self.num_features = 4 ** int(str(self.small_k)[0])  # sic: first character (kmer_ssgnn.py:213)
+        return
     _common_graph(self, k)
     device = getattr(self, "graph_device", "cpu")
     if getattr(self, "representation_ss_initial_labels", "kmer_frequency") == "one_hot":
@@ -232,6 +261,35 @@ def create_graphs(self, k: int):
 
 def create_graphs_mini_batch(self, k: int):
     """Mini-batch builder: KmerSsgnnMb.create_graphs (kmer_ssgnn_miniBatch.py:160-285)."""
+    if getattr(self, "edit_distance_loss_weight", 0) != 0:
+        raise NotImplementedError("edit-distance (ED) edges are out of scope (SURVEY.md section 2, row 8)")
+    with_kf = getattr(self, "kmer_frequency_loss_weight", 0) != 0
+    host = _fused_host_build(self, k, with_kf=with_kf)
+    if host is not None:
+        pyg = _pyg()
+        data = pyg[1]() if pyg else HeteroGraphData()
+        data["node"].x = host.x[0]
+        data["node", "DB", "node"].edge_index = host.edge_index
+        data["node", "DB", "node"].edge_attr = host.weight
+        for i, x in enumerate(host.x):
+            data["node"][f"y_{i}"] = x
+        for i, (ei, w) in enumerate(zip(host.kf_edge_index, host.kf_weight)):
+            data["node", f"KF{i}", "node"].edge_index = ei
+            data["node", f"KF{i}", "node"].edge_attr = w
+        input_nodes = torch.arange(host.num_nodes)   # dataloader.py:154-165: ss_task is "CL" here, never "Sampling"
+        layers = [*self.layers_config, "1_" + self.representation_ss_last_layer_edge_type]
+        if getattr(self, "ss_task", None) == "Sampling":
+            allidx = torch.cat([data[rel].edge_index for rel in data.edge_types], dim=1)
+            input_nodes = torch.unique(allidx[:, allidx[0] != allidx[1]])
+        if pyg:
+            loader = pyg[2](data, num_neighbors=[-1] * count_edge_types(layers), input_nodes=("node", input_nodes),
+                            batch_size=self.batch_size, pin_memory=True, shuffle=True, directed=False)
+        else:
+            loader = SeedNodeLoader(data, input_nodes, self.batch_size, shuffle=True)
+        self.dataloader, self.torch_graph = loader, data
+        self.num_features = 4 ** int(str(self.small_k)[0])
+        self.build_info = {"marshal_ms": host.marshal_ms, "h2d_bytes": host.h2d_bytes, "d2h_bytes": host.d2h_bytes}
+        return
     _common_graph(self, k)
     device = getattr(self, "graph_device", "cpu")
     one_hot = getattr(self, "representation_ss_initial_labels", "kmer_frequency") == "one_hot"

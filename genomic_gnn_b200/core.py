@@ -1418,6 +1418,9 @@ class HostGraph:
     kf_weight: List[torch.Tensor]
     h2d_bytes: int = 0
     d2h_bytes: int = 0
+    db: Optional["DBGraph"] = None                 # the device-resident originals (builders keep them for transform())
+    kf_counts: Optional[List["KFCounts"]] = None
+    marshal_ms: float = 0.0                        # host time spent turning list[str] input into the byte stream
 
 
 def graph_to_host(built: "BuiltGraph", host_expand: bool = True) -> "HostGraph":
@@ -1478,22 +1481,64 @@ def _copy_stream():
 _HOST_THREADS = max(1, min(8, (os.cpu_count() or 2) // 2))
 
 
-def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kmers=False, edges_threshold=0.0,
-                        edges_keep_top_k=None, kf_impl="auto", chunks: int = 8, host_expand: bool = True) -> HostGraph:
+class _PackedReads:
+    """list[str] -> ASCII stream in pinned memory through libgg_pyhost.so (csrc/gg_pyhost.c): one pass over the list
+    for (pointer, length) of every read, then native threads copy read ranges while the GIL is released."""
+
+    def __init__(self, reads, threads):
+        self.lib = _lib.load_pyhost()
+        info = (C.c_int64 * 4)()
+        self.handle = self.lib.gg_py_reads_scan(reads, threads, info)
+        if not self.handle:
+            if info[3] >= 0:
+                raise ValueError(f"read {int(info[3])} is not an ASCII str")
+            raise ValueError("reads must be a list or tuple of str")
+        self.n_reads, self.n_bytes, self.fixed_len = int(info[0]), int(info[1]), int(info[2])
+        self.threads = threads
+        self.flat = torch.empty(max(self.n_bytes, 1), dtype=torch.uint8, pin_memory=True)
+
+    def copy(self, lo, hi):
+        if self.lib.gg_py_reads_copy(self.handle, lo, hi, C.c_void_p(self.flat.data_ptr()), self.threads) != 0:
+            raise GGError("gg_py_reads_copy rejected its arguments")
+
+    def close(self):
+        if self.handle:
+            self.lib.gg_py_reads_free(self.handle)
+            self.handle = None
+
+
+def build_graph_to_host(reads, k: int, small_k="2", create_all_kmers=False, edges_threshold=0.0,
+                        edges_keep_top_k=None, kf_impl="auto", chunks: int = 8, host_expand: bool = True,
+                        with_kf: bool = True) -> HostGraph:
     """The whole path from host reads to host graph tensors (what ``create_graphs`` hands to the CPU-side PyG
     loaders), with the PCIe copies overlapped with the kernels: the reads go up in ``chunks`` pieces that are
     counted as they land, the DB graph and the features go down while the KF sets are scored, and each KF set
     goes down while the next one is scored.
 
-    ``reads``: uint8 [n_reads, read_len] ASCII on the host (pinned memory avoids a staging copy)."""
+    ``reads``: uint8 [n_reads, read_len] ASCII on the host (pinned memory avoids a staging copy), or the reference's
+    own input type, a list of read strings (kmer_ssgnn.py:56-57) -- marshalled natively, piece by piece, under the
+    uploads (ragged reads go up in one piece)."""
     _require_cuda()
     lib = _lib.load()
-    if not (isinstance(reads, torch.Tensor) and reads.dtype == torch.uint8 and reads.dim() == 2 and not reads.is_cuda):
-        raise ValueError("reads must be a host uint8 [n_reads, read_len] tensor")
     if not (1 <= k <= _lib.GG_MAX_K):
         raise ValueError(f"k must be in [1, {_lib.GG_MAX_K}]")
-    n_reads, length = int(reads.shape[0]), int(reads.shape[1])
-    n_bytes = n_reads * length
+    packed, marshal_ms = None, 0.0
+    if isinstance(reads, (list, tuple)):
+        import time as _time
+
+        t0 = _time.perf_counter()
+        packed = _PackedReads(reads, _HOST_THREADS)
+        marshal_ms = (_time.perf_counter() - t0) * 1e3
+        n_reads, length, n_bytes, flat = packed.n_reads, packed.fixed_len, packed.n_bytes, packed.flat
+        if n_reads == 0:
+            packed.close()
+            raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
+    elif isinstance(reads, torch.Tensor) and reads.dtype == torch.uint8 and reads.dim() == 2 and not reads.is_cuda:
+        n_reads, length = int(reads.shape[0]), int(reads.shape[1])
+        n_bytes = n_reads * length
+        flat = reads.reshape(-1)
+    else:
+        raise ValueError("reads must be a host uint8 [n_reads, read_len] tensor or a list of str")
     dev = torch.device("cuda", torch.cuda.current_device())
     main, side = torch.cuda.current_stream(), _copy_stream()
     buf = torch.empty(_padded(n_bytes), dtype=torch.uint8, device=dev)
@@ -1507,26 +1552,40 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
     check(lib.gg_count_reset(k, ptr(hist), ptr(first), ptr(status), st), "gg_count_reset")
     side.wait_stream(main)
     buf.record_stream(side)
-    flat = reads.reshape(-1)
-    per = max(16, -(-n_reads // max(chunks, 1) // 16) * 16)  # reads per piece, multiple of 16: 16-byte aligned offsets
-    ws_bytes = int(lib.gg_count_part_workspace_bytes(per * length, k))  # one workspace serves every piece in turn
+    if length > 0:   # fixed-length rows: pieces of whole reads, a multiple of 16 of them so that every piece is aligned
+        per = max(16, -(-n_reads // max(chunks, 1) // 16) * 16)
+        pieces = [(lo, min(n_reads, lo + per), lo * length, min(n_reads, lo + per) * length) for lo in range(0, n_reads, per)]
+    else:            # '\n'-separated stream: one piece
+        per = n_reads
+        pieces = [(0, n_reads, 0, n_bytes)]
+    piece_bytes = max(b1 - b0 for _, _, b0, b1 in pieces)
+    ws_bytes = int(lib.gg_count_part_workspace_bytes(piece_bytes, k))  # one workspace serves every piece in turn
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-    for lo in range(0, n_reads, per):
-        hi = min(n_reads, lo + per)
-        with torch.cuda.stream(side):
-            buf[lo * length : hi * length].copy_(flat[lo * length : hi * length], non_blocking=True)
-            landed = torch.cuda.Event()
-            landed.record(side)
-        main.wait_event(landed)
-        piece = C.c_void_p(buf.data_ptr() + lo * length)
-        with _stage("k1_count"):
-            if ws is not None:
-                check(lib.gg_count_kp1mers_part(piece, (hi - lo) * length, length, k, lo * length, ptr(hist),
-                                                ptr(bridges), cap, ptr(status), ptr(ws), ws_bytes, st),
-                      "gg_count_kp1mers_part")
-            else:
-                check(lib.gg_count_kp1mers(piece, (hi - lo) * length, length, k, lo * length, ptr(hist), ptr(bridges),
-                                           cap, ptr(status), st), "gg_count_kp1mers")
+    try:
+        for lo, hi, b0, b1 in pieces:
+            if packed is not None:
+                import time as _time
+
+                t0 = _time.perf_counter()
+                packed.copy(lo, hi)       # native threads, GIL released; earlier pieces are uploading / being counted
+                marshal_ms += (_time.perf_counter() - t0) * 1e3
+            with torch.cuda.stream(side):
+                buf[b0:b1].copy_(flat[b0:b1], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(side)
+            main.wait_event(landed)
+            piece = C.c_void_p(buf.data_ptr() + b0)
+            with _stage("k1_count"):
+                if ws is not None:
+                    check(lib.gg_count_kp1mers_part(piece, b1 - b0, length, k, b0, ptr(hist), ptr(bridges), cap,
+                                                    ptr(status), ptr(ws), ws_bytes, st), "gg_count_kp1mers_part")
+                else:
+                    check(lib.gg_count_kp1mers(piece, b1 - b0, length, k, b0, ptr(hist), ptr(bridges), cap, ptr(status),
+                                               st), "gg_count_kp1mers")
+    finally:
+        if packed is not None:
+            side.synchronize()            # the uploads read the staging buffer
+            packed.close()
     with _stage("k1_first"):
         check(lib.gg_first_occurrence(ptr(buf), n_bytes, length, k, 0, ptr(hist), ptr(first), ptr(status), st),
               "gg_first_occurrence")
@@ -1592,8 +1651,9 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
     try:
         # one set at a time here (not stage-all-first as in build_graph): the first set's edges, the largest transfer
         # of the step, start going down while the second set is still being scored -- measured 17.2 vs 18.5 ms
-        for kc in kcs:
-            kf = kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl)
+        for kc in (kcs if with_kf else []):
+            kf = kf_edges(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl,
+                          row_sum=kc.m)
             e, w = down([kf.edge_index, kf.weight])
             kf_ei.append(e)
             kf_w.append(w)
@@ -1602,4 +1662,5 @@ def build_graph_to_host(reads: torch.Tensor, k: int, small_k="2", create_all_kme
         rcs = [lib.gg_host_job_wait(C.c_void_p(job[0])) for job in workers]
     for rc in rcs:
         check(rc, "gg_host_job_wait")
-    return HostGraph(k, db.num_nodes, h_codes, h_ei, h_w, h_x, kf_ei, kf_w, n_bytes, d2h)
+    return HostGraph(k, db.num_nodes, h_codes, h_ei, h_w, h_x, kf_ei, kf_w, n_bytes, d2h, db=db, kf_counts=kcs,
+                     marshal_ms=marshal_ms)

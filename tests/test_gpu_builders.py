@@ -106,3 +106,72 @@ def test_unsupported_options_fail_loudly():
     reads = fast.reads_to_strings(fast.synthetic_reads(50, 60, seed=1))
     with pytest.raises(NotImplementedError):
         gg.create_graphs_mini_batch(_self(reads, edit_distance_loss_weight=1.0), 3)
+
+
+# --------------------------------------------------------------------------- BASELINE-size builder runs against reference digests
+def _sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("digest,batch", [("digest_cfg3_k7_100k.npz", 1024), ("digest_cfg4_k8_100k.npz", 256)])
+def test_mini_batch_builder_at_baseline_sizes_matches_reference_digest(digest, batch):
+    """create_graphs(self, k) of KmerSsgnnMb as the reference calls it -- ``ssgnn_dataset`` a list of 100,000 read
+    strings, config 3 / config 4 flags (k=7 / 8, small_k=2,5, threshold 0.8, top_k 0.01, batch 1024 / 256) -- against
+    digests of the REAL reference's tensors (oracle/make_golden.py): node order, DB edges and weights, float32
+    features, every KF edge set and its float32 weights."""
+    import os
+
+    import genomic_gnn_b200 as gg
+    from ._util import GOLDEN, sort_edges
+
+    z = np.load(os.path.join(GOLDEN, digest))
+    k, n_reads = int(z["k"]), int(z["n_reads"])
+    reads = fast.reads_to_strings(fast.synthetic_reads(n_reads, 150, seed=int(z["seed"])))
+    me = _self(reads, small_k="2,5", batch_size=batch, edges_threshold=float(z["threshold"]),
+               edges_keep_top_k=float(z["keep_top_k"]), layers_config=["32_KF0"])
+    gg.create_graphs_mini_batch(me, k)
+    data = me.torch_graph
+    assert me.graph.number_of_nodes() == int(z["num_nodes"]) and me.num_features == 16
+    assert _sha(gg.api.encode_kmers(me.graph.nodes(), k)) == str(z["node_codes_sha"])
+    db = data["node", "DB", "node"]
+    assert not db.edge_index.is_cuda and db.edge_index.dtype == torch.int64 and db.edge_attr.dtype == torch.float32
+    assert _sha(db.edge_index.numpy()) == str(z["db_edge_index_sha"]) and _sha(db.edge_attr.numpy()) == str(z["db_weight_sha"])
+    assert _sha(data["node"].x.numpy()) == str(z["x_s2_sha_f32"])
+    for i, s in enumerate((2, 5)):
+        assert _sha(data["node"][f"y_{i}"].numpy()) == str(z[f"x_s{s}_sha_f32"])
+        kf = data["node", f"KF{i}", "node"]
+        assert kf.edge_index.shape[1] == int(z[f"kf_s{s}_E"])            # threshold-bound at these configs
+        keys, ws = sort_edges(kf.edge_index.numpy(), kf.edge_attr.numpy())
+        assert _sha(keys) == str(z[f"kf_s{s}_set_sha"]) and _sha(ws) == str(z[f"kf_s{s}_w32_sha"])
+    assert len(me.dataloader) == -(-int(z["num_nodes"]) // batch)
+    assert me.build_info["h2d_bytes"] == n_reads * 150 and me.build_info["marshal_ms"] > 0
+    # kf_labels stay usable as the reference's float64 matrices (np.vstack at sampling_task.py:146-150)
+    assert np.vstack(me.kf_labels[0]).shape == (int(z["num_nodes"]), 16)
+
+
+def test_fused_builder_equals_stepwise_builder_on_ragged_reads():
+    """The one-pass host build (list[str] -> native packing -> pipelined build) and the step-by-step API calls give the
+    same builder attributes, on reads of unequal length with N runs (the '\\n'-separated stream layout)."""
+    import genomic_gnn_b200 as gg
+    from genomic_gnn_b200 import builders
+
+    rng = np.random.default_rng(4)
+    reads = []
+    for r in fast.reads_to_strings(fast.synthetic_reads(600, 120, seed=6)):
+        r = r[: int(rng.integers(0, 121))]
+        reads.append("".join("N" if rng.random() < 0.02 else ch for ch in r))
+    fused, step = _self(reads, small_k="2,3", edges_keep_top_k=None), _self(tuple(reads), small_k="2,3", edges_keep_top_k=None)
+    gg.create_graphs_mini_batch(fused, 4)
+    assert hasattr(fused, "build_info")
+    step.graph_device = torch.device("cpu")                    # anything but the string "cpu" takes the step-by-step path
+    assert builders._fused_host_build(step, 4, True) is None
+    gg.create_graphs_mini_batch(step, 4)
+    assert fused.graph.nodes() == step.graph.nodes()
+    a, b = fused.torch_graph, step.torch_graph
+    for rel in (("node", "DB", "node"), ("node", "KF0", "node"), ("node", "KF1", "node")):
+        assert torch.equal(a[rel].edge_index, b[rel].edge_index) and torch.equal(a[rel].edge_attr, b[rel].edge_attr)
+    assert torch.equal(a["node"].x, b["node"].x) and torch.equal(a["node"]["y_1"], b["node"]["y_1"])
+    with pytest.raises(ValueError):
+        gg.create_graphs_mini_batch(_self(["ACGT", 7]), 3)
