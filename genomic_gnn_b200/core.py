@@ -47,11 +47,27 @@ def set_timer(timer: Optional[StageTimer]):
     _TIMER = timer
 
 
+_STAGE_PREFIX = threading.local()
+
+
+@contextmanager
+def _stage_prefix(prefix):
+    """Stages timed inside are recorded under ``prefix + name`` (the chunked re-emission of a binding top-n is kept
+    apart from the first scoring pass)."""
+    old = getattr(_STAGE_PREFIX, "value", "")
+    _STAGE_PREFIX.value = prefix
+    try:
+        yield
+    finally:
+        _STAGE_PREFIX.value = old
+
+
 @contextmanager
 def _stage(name):
     if _TIMER is None:
         yield
         return
+    name = getattr(_STAGE_PREFIX, "value", "") + name
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     try:
@@ -592,11 +608,19 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, 
         st_host = read_small(status).tolist()
         if int(st_host[2]) != 0:
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
-        found = int(st_host[0])
-        if found <= rec_capacity or not retry:
-            return recs, found, rowcnt, params, counts
+        found, slots = int(st_host[0]), max(int(st_host[0]), int(st_host[1]))
+        if slots <= rec_capacity or not retry:
+            out = _Emit((recs[:min(slots, rec_capacity)], found, rowcnt, params, counts))
+            out.slots = slots
+            return out
         del recs
-        rec_capacity = found
+        rec_capacity = slots + slots // 16 + (1 << 16)   # block reservations vary a little from run to run
+
+
+class _Emit(tuple):
+    """kf_emit's (recs, n_recs, rowcnt, params, counts_scored) + ``slots``: record slots the kernel used
+    (>= n_recs: the CTA-pair kernel pads its slot blocks); more than the capacity means records were dropped."""
+    slots = 0
 
 
 def pair_kernel_serves(d: int, impl: str) -> bool:
@@ -613,22 +637,24 @@ class StagedRecords:
         self.d = params.d
         self.status4 = status      # device int64[4] while n_recs has not been read: [0] found, [2] pipeline error
         self.redo = redo           # re-scores the shard with room for a given number of records
-        self.found = None
+        self.found = self.slots = None
 
     def after_counts(self, mine):
         """``mine`` = this rank's status words as read by kf_resolve."""
         if int(mine[2]) != 0:
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
         self.found = int(mine[0])
+        self.slots = max(self.found, int(mine[1]))
         self.status4 = None
 
     def complete(self):
         """Make sure every candidate has its record (the staging buffer may have been too small: score again)."""
         if self.n_recs is None:
-            if self.found > int(self.recs.shape[0]):
-                self.recs, self.n_recs, self.rowcnt, self.params, self.scored = self.redo(self.found)
+            if self.slots > int(self.recs.shape[0]):
+                self.recs, self.n_recs, self.rowcnt, self.params, self.scored = self.redo(self.slots + self.slots // 16 + (1 << 16))
             else:
                 self.n_recs = self.found
+                self.recs = self.recs[: self.slots]
         return self
 
     def place(self, ordered_ptr, capacity=None):
@@ -639,8 +665,8 @@ class StagedRecords:
         p = self.params
         pw = int(lib.gg_kf_place_workspace_bytes(p.n, p.iblock_begin, p.iblock_end))
         pws = torch.empty(pw, dtype=torch.uint8, device=self.recs.device)
-        with _stage(f"k6_place_d{p.d}"):
-            check(lib.gg_kf_place(C.byref(p), ptr(self.recs), self.n_recs, ptr(self.rowcnt), ptr(self.scored),
+        with _stage(f"k6_place_d{p.d}"):   # every record slot is scanned (padding records are skipped on the device)
+            check(lib.gg_kf_place(C.byref(p), ptr(self.recs), int(self.recs.shape[0]), ptr(self.rowcnt), ptr(self.scored),
                                   ordered_ptr, ptr(pws), pw, _stream()), "gg_kf_place")
 
 
@@ -884,8 +910,8 @@ def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
                                                           impl, rec_capacity=rec_capacity, sync=False,
                                                           class_hist=st.class_hist, hist_m=row_sum)
 
-        def redo(found):
-            return kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl, rec_capacity=found)
+        def redo(room):
+            return kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl, rec_capacity=room)
 
         st.staged = StagedRecords(recs, None, rowcnt, params, scored, status, redo)
     return st
@@ -975,7 +1001,7 @@ def _plan_chunks(n, b0, b1, expect_words, cap):
     out, lo = [], b0
     while lo < b1:
         hi = lo + 1
-        while hi < b1 and _block_pairs_rows(n, lo, hi + 1) * density * 1.1 <= cap:
+        while hi < b1 and _block_pairs_rows(n, lo, hi + 1) * density * 1.25 <= cap:   # slot blocks are padded: ~12 % slack
             hi += 1
         out.append((lo, hi))
         lo = hi
@@ -1157,10 +1183,12 @@ def _kf_finish_top_n(st: KFStage, comm, gather, budget, n_total, chunk_records, 
                 base, end = int(marks[c0 - b0]), int(marks[c1 - b0])
                 found = end - base
             else:
-                recs, found, rowcnt, params, scored = kf_emit(counts, sqnorm, cut_test, sq_max, c0, c1, impl,
-                                                              rec_capacity=chunk_cap, hist_m=st.row_sum, retry=False)
-                if found > chunk_cap and c1 - c0 > 1:    # denser than planned: halve the range
-                    del recs, rowcnt
+                with _stage_prefix("re_"):
+                    res = kf_emit(counts, sqnorm, cut_test, sq_max, c0, c1, impl, rec_capacity=chunk_cap,
+                                  hist_m=st.row_sum, retry=False)
+                recs, found, rowcnt, params, scored = res
+                if res.slots > chunk_cap and c1 - c0 > 1:    # denser than planned: halve the range
+                    del recs, rowcnt, res
                     mid = (c0 + c1) // 2
                     todo.extend([(mid, c1), (c0, mid)])
                     continue
@@ -1172,9 +1200,11 @@ def _kf_finish_top_n(st: KFStage, comm, gather, budget, n_total, chunk_records, 
                 staged.place_range(c0, c1, C.c_void_p(local_offsets.data_ptr() + 8 * (c0 - b0) * stride),
                                    C.c_void_p(ordered.data_ptr() - 8 * base), end)
             else:
-                if found > chunk_cap:               # a single row block beyond the chunk size: score it with room
-                    recs, found, rowcnt, params, scored = kf_emit(counts, sqnorm, cut_test, sq_max, c0, c1, impl,
-                                                                  rec_capacity=found, hist_m=st.row_sum)
+                if res.slots > chunk_cap:           # a single row block beyond the chunk size: score it with room
+                    with _stage_prefix("re_"):
+                        recs, found, rowcnt, params, scored = kf_emit(counts, sqnorm, cut_test, sq_max, c0, c1, impl,
+                                                                      rec_capacity=res.slots + res.slots // 16 + (1 << 16),
+                                                                      hist_m=st.row_sum)
                 StagedRecords(recs, found, rowcnt, params, scored).place(ptr(ordered))
                 del recs, rowcnt
             dest.select(ordered, found, sqnorm, p_max, action_d, ratio)

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(256) place_kernel(const gg_kf_rec_t* recs, lon
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_recs;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 rc = __ldg(reinterpret_cast<const uint4*>(recs) + i);
+    if (rc.x == kNoRec) continue;  // padding of a reserved slot block (block_commit)
     const uint32_t s = rc.x, t = rc.y;
     const long long word = rowcnt_word(static_cast<int>(s / kBlock) - ib0, n_jblocks, static_cast<int>(t / kBlock),
                                        static_cast<int>(s % kBlock));

@@ -20,8 +20,10 @@ constexpr int kStageCap = 64;        // default: records staged per warp before 
 struct EmitOut {
   gg_kf_rec_t* recs;
   long long capacity;
-  unsigned long long* status;  // [0] candidates (also the global write cursor)
+  unsigned long long* status;  // [0] candidates (also the global write cursor, except for block_commit: [1])
 };
+
+constexpr uint32_t kNoRec = 0xFFFFFFFFu;  // gg_kf_rec_t::s of a padding record (block_commit); placement skips it
 
 struct KfArgs {
   const uint8_t* counts;
@@ -166,6 +168,78 @@ __device__ __forceinline__ void stage_commit_tile(WS& ws, const EmitOut& out, in
     __syncwarp();
   }
   tile_cnt += n_l;
+}
+
+// ---- block commit (CTA-pair tensor kernel): records go straight to global memory, into slot blocks a warp reserves
+// from the cursor status[1] -- 32 slots at first, doubling to 1024 -- so a dense shard (top-n re-emission at threshold
+// 0: ~35 candidates per warp and 32-column chunk) costs one returning atomic per ~1000 records instead of one per
+// chunk on a single address.  Unused slots of a block are padded with kNoRec records; the exact candidate count is
+// kept per thread and added to status[0] once per warp.  After a reservation lands beyond the capacity nothing more
+// is reserved or written (the caller scores again with the exact size, or -- global top-n -- never needed the records).
+struct BlockCursor {
+  unsigned long long base;
+  int used, size;
+  bool dead;
+  unsigned long long found;  // per thread
+};
+
+__device__ __forceinline__ void block_pad(const BlockCursor& bc, const EmitOut& out, int lane) {
+  uint4* dst = reinterpret_cast<uint4*>(out.recs);
+  for (int i = bc.used + lane; i < bc.size; i += 32)
+    if (static_cast<long long>(bc.base + i) < out.capacity) dst[bc.base + i] = make_uint4(kNoRec, 0u, 0u, 0u);
+}
+
+template <class WS>
+__device__ __forceinline__ void block_commit(BlockCursor& bc, const WS& ws, const EmitOut& out, int lane, uint32_t exact,
+                                             uint32_t s, uint32_t t0, uint32_t& tile_cnt) {
+  const int n_l = __popc(exact);
+  bc.found += n_l;
+  if (bc.dead) {
+    tile_cnt += n_l;
+    return;
+  }
+  int incl = n_l;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  if (total == 0) return;
+  if (bc.used + total > bc.size) {
+    block_pad(bc, out, lane);
+    int next = bc.size * 2 < 32 ? 32 : (bc.size * 2 > 1024 ? 1024 : bc.size * 2);
+    if (next < total) next = (total + 31) & ~31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(out.status + 1, static_cast<unsigned long long>(next));
+    bc.base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    bc.used = 0;
+    bc.size = next;
+    if (static_cast<long long>(bc.base) >= out.capacity) {  // uniform: the record buffer is full, count only from now on
+      bc.dead = true;
+      bc.size = 0;
+      tile_cnt += n_l;
+      return;
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out.recs);
+  const unsigned long long pos = bc.base + bc.used + (incl - n_l);
+  int i = 0;
+  for (uint32_t m = exact; m; m &= m - 1, ++i) {
+    const int b = __ffs(m) - 1;
+    if (static_cast<long long>(pos + i) < out.capacity)
+      dst[pos + i] = make_uint4(s, t0 + b, tile_cnt + i, stage_get_dot(ws, b, lane));
+  }
+  bc.used += total;
+  tile_cnt += n_l;
+}
+
+__device__ __forceinline__ void block_finish(BlockCursor& bc, const EmitOut& out, int lane) {
+  if (!bc.dead) block_pad(bc, out, lane);
+  unsigned long long f = bc.found;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xFFFFFFFFu, f, o);
+  if (lane == 0 && f) atomicAdd(out.status, f);
 }
 
 // valid-column bits of the 32-column chunk starting at block-local column c0

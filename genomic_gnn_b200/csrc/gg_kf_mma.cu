@@ -590,7 +590,9 @@ __device__ __forceinline__ int pair_last_tile(const KfArgs& a, const PairWalk& w
 // unit, because 20 lanes of a warp hitting one shared-memory word serialise.  Everything else (larger dots, rows that
 // break the promise) goes to the global table directly.  The table is added to the global one when the CTA ends.
 constexpr int kHistSq = 16, kHistDots = 8, kHistBins = kHistSq * kHistSq * kHistDots;
-using PairStage = WarpStageT<32>;  // 12 x 1.5 KB: leaves room for the histogram next to four B stages at D = 1024
+struct PairStage {       // per epilogue warp: the dots of the current 32-column chunk (stage_get_dot); records go
+  uint32_t dotw[8][32];  // straight to global memory through block_commit
+};
 
 template <bool HIST>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -746,8 +748,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
   } else {
     // ===================== epilogue groups: 128-column half tiles round-robin =====================
     PairStage& ws = stages[warp];
-    if (lane == 0) ws.fill = 0;
-    __syncwarp();
+    BlockCursor bc{0ull, 0, 0, false, 0ull};
     const int group = warp / 4;
     const int gt = tid % kGroupThreads;
     uint16_t* my_sqn = sqn + group * kPairPanel;  // [kBlock] column norms + [8] smallest norm per 128-column tile
@@ -859,7 +860,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
                       }
                     }
                   }
-                  stage_commit(ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0),
+                  block_commit(bc, ws, a.out, lane, exact, static_cast<uint32_t>(s), static_cast<uint32_t>(col0 + c0),
                                tile_cnt);
                 }
               }
@@ -876,7 +877,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
           h_priv = 0;
         }
       }
-      stage_flush(ws, a.out, lane);
+      block_finish(bc, a.out, lane);
     }
   }
 

@@ -199,8 +199,10 @@ typedef struct {
                            0: no promise (the histogram is still exact, only slower) */
 } gg_kf_params_t;
 
-/* kf_status (device int64[4]): [0] candidates found (may exceed rec_capacity: re-run larger),
- * [1] records written, [2..3] reserved.
+/* kf_status (device int64[4]): [0] candidates found, exact (may exceed rec_capacity: re-run larger), [1] record slots
+ * used when that is more than [0] (GG_KF_IMPL_TCGEN05_PAIR reserves slots in blocks and pads unused ones with records
+ * whose s is 0xFFFFFFFF: pass max([0], [1]) as n_recs to gg_kf_place, which skips them, and size `ordered` by [0]; once
+ * a reservation lands beyond rec_capacity nothing more is reserved or written), [2] pipeline error, [3] reserved.
  * class_hist (nullable; GG_KF_IMPL_TCGEN05_PAIR only): uint64[(sqnorm_max + 1) * (p_max + 1)], NOT zeroed by the call;
  * class_hist[dot * (p_max + 1) + sqnorm_s * sqnorm_t] += 1 for every candidate, whether or not its record fitted
  * rec_capacity -- the exact score classes of the global top-n (gnn_utils.py:311-317) BEFORE anything is emitted, so

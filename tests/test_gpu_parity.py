@@ -322,7 +322,7 @@ def test_packed_shards_expand_like_a_multi_gpu_exchange(gg):
         stages = [core.kf_stage(kc.counts, kc.sqnorm, 0.8, None, sq_max=kc.m**2, impl=impl, iblock_begin=a, iblock_end=b)
                   for a, b in shards]
         core.kf_resolve(stages)
-        sizes = [st.staged.n_recs for st in stages]
+        sizes = [st.staged.complete().n_recs for st in stages]
         stride = max(sizes)
         ordered = torch.zeros(len(shards) * stride, dtype=torch.int64, device="cuda")
         for r, st in enumerate(stages):
