@@ -67,6 +67,7 @@ def parse_args():
                          "and a binding top-n recycles one chunk buffer (the result exceeds this many GPUs' memory); "
                          "auto: gathered up to k=8, else sharded when the shards fit, else discard")
     ap.add_argument("--chunk-records", type=int, default=0, help="packed words per top-n emission chunk (0: 2^27)")
+    ap.add_argument("--nccl-only", action="store_true", help="keep every exchange on NCCL (no NVLink peer-memory pushes)")
     ap.add_argument("--debug-no-flush", action="store_true")
     ap.add_argument("--debug-no-clocks", action="store_true")
     ap.add_argument("--debug-timer-in-headline", action="store_true")
@@ -394,6 +395,8 @@ def run_ours(a):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = ggdist.TorchComm()
+        if not a.nccl_only:   # count pieces, candidate counts and packed KF edges over NVLink peer memory
+            comm.enable_peer_exchange((1 << 30) if a.k <= 8 else (256 << 20))
     assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}"
 
     reads_all = synthetic_reads(a.reads, a.read_len, seed=0)
@@ -608,6 +611,9 @@ def run_ours(a):
         "data": "synthetic",
         "config": bench_config(a),
         "run": {"parallelism": f"reads and KF row blocks sharded over {world} GPU(s)", "kf_output": mode,
+                "exchange": ("none" if world == 1 else
+                             ("gg_peer_push over NVLink peer memory (symmetric memory), NCCL for the rest"
+                              if comm.peers is not None else "NCCL (" + getattr(comm, "peer_error", "--nccl-only") + ")")),
                 "l2": "256 MiB buffer written between timed iterations", "kf_impl": a.kf_impl},
         "kf_edges_per_s": kf_edges / (kf_ms * 1e-3) if kf_ms else None,
         "kf_pairs_per_s": n_small * n_nodes * (n_nodes - 1) / 2 / (kf_ms * 1e-3) if kf_ms else None,

@@ -47,6 +47,13 @@ class KfDedupExtra(C.Structure):
     ]
 
 
+GG_MAX_PEERS = 16
+
+
+class Peers(C.Structure):
+    _fields_ = [("n", C.c_int), ("ptr", C.c_void_p * GG_MAX_PEERS)]
+
+
 _P, _I64, _I32, _SZ, _DBL = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes); mirrors include/gg_b200.h one to one
@@ -101,6 +108,9 @@ SIGNATURES = {
     "gg_knn_plan": (_I32, [_I64, _I64, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
     "gg_knn_write": (_I32, [_P, _I32, _I64, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P,
                             _P, _P, _P, _I64, _P]),
+    "gg_peer_push": (_I32, [_P, _I64, C.POINTER(Peers), _P]),
+    "gg_peer_signal": (_I32, [C.POINTER(Peers), _I32, C.c_uint32, _P]),
+    "gg_peer_wait": (_I32, [_P, _I32, _I32, _I32, C.c_uint32, _P, _P]),
     "gg_probe_smem_atomics": (_I32, [_I32, _I32, _P, C.POINTER(C.c_double), _P]),
     "gg_probe_tensor_i8": (_I32, [_I32, _I32, _P, C.POINTER(C.c_double), _P]),
     "gg_kf_select_workspace_bytes": (_SZ, [_I64]),

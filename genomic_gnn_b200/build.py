@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgg_b200.so")
-SOURCES = ["gg_common.cu", "gg_count.cu", "gg_db.cu", "gg_feat.cu", "gg_kf.cu", "gg_kf_mma.cu", "gg_kf_dedup.cu", "gg_index.cu", "gg_rw.cu", "gg_host.cu", "gg_spmm.cu", "gg_knn.cu", "gg_probe.cu"]
+SOURCES = ["gg_common.cu", "gg_count.cu", "gg_db.cu", "gg_feat.cu", "gg_kf.cu", "gg_kf_mma.cu", "gg_kf_dedup.cu", "gg_index.cu", "gg_rw.cu", "gg_host.cu", "gg_spmm.cu", "gg_knn.cu", "gg_probe.cu", "gg_peer.cu"]
 PYHOST_SRC = os.path.join(CSRC, "gg_pyhost.c")
 PYHOST_LIB = os.path.join(HERE, "libgg_pyhost.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -221,6 +221,7 @@ def _fused_host_build(self, k, with_kf):
     if (len(list(getattr(self, "strides", [1]))) != 1 or int(list(getattr(self, "strides", [1]))[0]) != 1
             or getattr(self, "representation_ss_initial_labels", "kmer_frequency") != "kmer_frequency"
             or getattr(self, "faiss_ann", False) or str(getattr(self, "graph_device", "cpu")) != "cpu"
+            or getattr(self, "gg_stepwise", False)   # opt-out: run the four API calls one by one
             or not isinstance(self.ssgnn_dataset, (list, tuple)) or len(self.ssgnn_dataset) == 0):
         return None
     host = core.build_graph_to_host(self.ssgnn_dataset, k, str(self.small_k), create_all_kmers=self.create_all_kmers,

@@ -201,11 +201,18 @@ class CountResult:
     pos_limit: int = 1 << 40  # every first-occurrence / bridge position is below this (bounds K2's radix sorts)
 
 
-def count_piece(k: int, dev) -> torch.Tensor:
+def count_piece(k: int, dev, comm=None) -> torch.Tensor:
     """One contiguous int64 buffer holding a rank's K1 outputs -- [hist: bins int32][first_pos: bins int64]
-    [status: 8 int64][pos_limit] -- so that a multi-GPU build exchanges them with ONE all-gather (dist.reduce_counts)."""
+    [status: 8 int64][pos_limit] -- so that a multi-GPU build exchanges them with ONE all-gather (dist.reduce_counts).
+    With a ``comm`` that hands out gather buffers the piece is this rank's segment of one (peer memory when enabled)."""
     bins = int(_lib.load().gg_hist_bins(k))
-    return torch.empty(bins // 2 + bins + _lib.ST_WORDS + 1, dtype=torch.int64, device=dev)
+    length = (bins // 2 + bins + _lib.ST_WORDS + 1 + 1) // 2 * 2     # 16-byte segments
+    if comm is not None and hasattr(comm, "gather_buffer"):
+        everyone = comm.gather_buffer(length, torch.int64)
+        piece = everyone[comm.rank * length: (comm.rank + 1) * length]
+        piece._gg_everyone = everyone
+        return piece
+    return torch.empty(length, dtype=torch.int64, device=dev)
 
 
 def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, first_occurrence: bool = True,
@@ -232,7 +239,7 @@ def count_kp1mers(stream: ReadStream, k: int, bridge_capacity: int = 1 << 16, fi
         hist = piece[: bins // 2].view(torch.int32)
         first = piece[bins // 2: bins // 2 + bins]
         status = piece[bins // 2 + bins: bins // 2 + bins + _lib.ST_WORDS]
-        piece[-1:].fill_(stream.pos_base + stream.n_bytes)
+        piece[bins // 2 + bins + _lib.ST_WORDS: bins // 2 + bins + _lib.ST_WORDS + 1].fill_(stream.pos_base + stream.n_bytes)
     if impl == "auto":
         impl = "part" if int(lib.gg_count_part_workspace_bytes(stream.n_bytes, k)) else "l2"
     ws_bytes = 0
@@ -1053,8 +1060,9 @@ def kf_finish(st: KFStage, comm=None, gather: bool = True, chunk_records: Option
         # buffer, ONE in-place all-gather moves 8 instead of 20 bytes per edge, and K6b expands the gathered words
         # into edge_index / weight on every rank.  (float64 weights are not produced here: only the function-level
         # API wants them.)
-        stride = max(max(per_rank), 1)
-        ordered = torch.empty(comm.world * stride, dtype=torch.int64, device=dev)
+        stride = (max(max(per_rank), 1) + 1) // 2 * 2        # 16-byte segments
+        ordered = (comm.gather_buffer(stride, torch.int64) if hasattr(comm, "gather_buffer")
+                   else torch.empty(comm.world * stride, dtype=torch.int64, device=dev))
         staged.place(C.c_void_p(ordered.data_ptr() + 8 * comm.rank * stride))
         with _stage("c2_gather_packed_edges"):
             comm.all_gather_padded_(ordered, stride)
@@ -1393,6 +1401,8 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
     ranks, the De Bruijn assembly and features run replicated, KF is sharded by
     row block."""
     comm = comm or LocalComm()
+    if hasattr(comm, "begin_build"):
+        comm.begin_build()
     stream = upload_reads(sequences)
     if comm.world > 1:
         from . import dist
@@ -1400,7 +1410,7 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
         capacity = 1 << 16
         while True:  # K1 without a host round trip; reduce_counts reads every rank's status in its one device read
             try:
-                piece = count_piece(k, stream.data.device)
+                piece = count_piece(k, stream.data.device, comm)
                 local = count_kp1mers(stream, k, bridge_capacity=capacity, sync=False, piece=piece)
                 with _stage("c1_reduce_counts"):
                     cr = dist.reduce_counts(local, comm, piece=piece)

@@ -10,6 +10,7 @@
   Nothing here touches a kernel: it is host logic over
 tensors, which is why the CPU tests can cover it with gloo.
 """
+import ctypes as C
 from typing import List, Tuple
 
 import torch
@@ -44,6 +45,89 @@ def kf_block_range(n_blocks: int, world: int, rank: int) -> Tuple[int, int]:
     return kf_block_ranges(n_blocks, world)[rank]
 
 
+class PeerSpace:
+    """NVLink peer memory for the latency-bound exchanges of a multi-GPU build (gg_peer_push / _signal / _wait).
+
+    One symmetric allocation (torch.distributed._symmetric_memory: every rank's buffer is mapped into every rank's
+    address space, plus a pad of 32-bit flags per rank), used as two halves that alternate from build to build;
+    inside a build, regions are handed out by a bump allocator in the same order on every rank, so a region has the
+    same offset everywhere.  ``all_gather(offset, seg_bytes)``: this rank has written segment ``rank`` of the region;
+    on return (stream order) every segment is there.
+
+    Why alternating halves are enough: a rank can only be pushing for exchange e of build s + 1 once every peer has
+    signalled exchange e - 1 of build s + 1, i.e. once every peer has left build s behind on its own stream -- so
+    nobody still reads a region of build s - 1, whose memory build s + 1 reuses."""
+
+    CHANNELS = 16
+
+    def __init__(self, comm, nbytes: int):
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self.comm = comm
+        self.half = max(int(nbytes) // 2, 1 << 20) // 4096 * 4096
+        group = comm.group if comm.group is not None else dist_.group.WORLD
+        self.buf = symm.empty(2 * self.half, dtype=torch.uint8, device=comm.device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.pads = [int(p) for p in self.hdl.signal_pad_ptrs]
+        if int(self.hdl.signal_pad_size) < 4 * self.CHANNELS * comm.world:
+            raise RuntimeError("signal pad too small")
+        self.flag_peers = _lib.Peers(comm.world, (C.c_void_p * _lib.GG_MAX_PEERS)(
+            *[None if r == comm.rank else self.pads[r] for r in range(comm.world)]))
+        self.seq = [0] * self.CHANNELS
+        self.parity, self.top, self.channel = 0, 0, 0
+        self.status = torch.zeros(1, dtype=torch.int64, device=comm.device)
+        self.used = 0
+
+    def begin_build(self):
+        self.parity ^= 1
+        self.top, self.channel = 0, 0
+
+    def alloc(self, nbytes: int):
+        """Offset of a fresh region of this build, or None when the half is exhausted (callers fall back to NCCL;
+        every rank takes the same decision because every rank asks for the same sizes)."""
+        off = (self.top + 255) // 256 * 256
+        if off + nbytes > self.half or self.channel >= self.CHANNELS:
+            return None
+        self.top = off + nbytes
+        return self.parity * self.half + off
+
+    def view(self, offset: int, nbytes: int, dtype) -> torch.Tensor:
+        return self.buf[offset: offset + nbytes].view(dtype)
+
+    def holds(self, t: torch.Tensor) -> bool:
+        lo = self.buf.data_ptr()
+        return lo <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= lo + 2 * self.half
+
+    def all_gather(self, offset: int, seg_bytes: int):
+        from . import _lib
+        from .core import _stream, check
+
+        lib = _lib.load()
+        comm = self.comm
+        if seg_bytes % 16:
+            raise ValueError("segments must be multiples of 16 bytes")
+        mine = offset + comm.rank * seg_bytes
+        dst = _lib.Peers(comm.world, (C.c_void_p * _lib.GG_MAX_PEERS)(
+            *[None if r == comm.rank else self.base[r] + mine for r in range(comm.world)]))
+        ch = self.channel
+        self.channel += 1
+        self.seq[ch] += 1
+        st = _stream()
+        check(lib.gg_peer_push(C.c_void_p(self.base[comm.rank] + mine), seg_bytes, C.byref(dst), st), "gg_peer_push")
+        check(lib.gg_peer_signal(C.byref(self.flag_peers), ch * comm.world + comm.rank, self.seq[ch], st), "gg_peer_signal")
+        check(lib.gg_peer_wait(C.c_void_p(self.pads[comm.rank]), ch * comm.world, comm.world, comm.rank, self.seq[ch],
+                               C.c_void_p(self.status.data_ptr()), st), "gg_peer_wait")
+        self.used += 1
+
+    def check(self):
+        """Raise if a wait ever gave up on a peer (call at a point where the host synchronises anyway)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer exchange: a rank never signalled (gg_peer_wait timed out)")
+
+
 class TorchComm:
     """The four exchange primitives the pipeline needs, over a torch.distributed group."""
 
@@ -53,6 +137,38 @@ class TorchComm:
         self.rank = dist_.get_rank(group)
         backend = dist_.get_backend(group)
         self.device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        self.peers = None
+
+    def enable_peer_exchange(self, nbytes: int = 1 << 30) -> bool:
+        """Route the small / latency-bound exchanges (count pieces, candidate counts, packed KF edges) through NVLink
+        peer memory instead of NCCL.  Returns False -- and leaves NCCL in charge -- when symmetric memory cannot be
+        set up on this box; the decision is taken together (all ranks or none)."""
+        ok, err = 1, None
+        try:
+            self.peers = PeerSpace(self, nbytes)
+        except Exception as exc:  # noqa: BLE001
+            ok, err, self.peers = 0, exc, None
+        flag = torch.tensor([ok], dtype=torch.int64, device=self.device)
+        dist_.all_reduce(flag, op=dist_.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.peers = None
+            self.peer_error = repr(err) if err is not None else "another rank failed"
+            return False
+        return True
+
+    def begin_build(self):
+        if self.peers is not None:
+            self.peers.begin_build()
+
+    def gather_buffer(self, n_elems_per_rank: int, dtype) -> torch.Tensor:
+        """world * n_elems_per_rank elements for an in-place all-gather (all_gather_padded_): peer memory when it fits."""
+        size = torch.empty(0, dtype=dtype).element_size()
+        seg = n_elems_per_rank * size
+        if self.peers is not None and seg % 16 == 0:
+            off = self.peers.alloc(self.world * seg)
+            if off is not None:
+                return self.peers.view(off, self.world * seg, dtype)
+        return torch.empty(self.world * n_elems_per_rank, dtype=dtype, device=self.device)
 
     def sum_int(self, x: int) -> int:
         t = torch.tensor([int(x)], dtype=torch.int64, device=self.device)
@@ -76,12 +192,21 @@ class TorchComm:
     def gather_device_ints(self, t: torch.Tensor) -> List[List[int]]:
         """all-gather of a small int64 vector that already lives on the device: no upload, one read for all ranks.
         Returns one list per rank."""
-        t = t.contiguous()
-        out = torch.empty(self.world * t.numel(), dtype=torch.int64, device=t.device)
-        dist_.all_gather_into_tensor(out, t, group=self.group)
         from .core import read_small
 
-        return read_small(out).view(self.world, t.numel()).tolist()
+        t = t.contiguous()
+        n = int(t.numel())
+        pad = (n + 1) // 2 * 2          # 16-byte segments
+        out = self.gather_buffer(pad, torch.int64)
+        if self.peers is not None and self.peers.holds(out):
+            out[self.rank * pad: self.rank * pad + n].copy_(t)
+            self.peers.all_gather(out.data_ptr() - self.peers.buf.data_ptr(), pad * 8)
+        else:
+            out = torch.empty(self.world * pad, dtype=torch.int64, device=t.device)
+            mine = torch.zeros(pad, dtype=torch.int64, device=t.device)
+            mine[:n] = t
+            dist_.all_gather_into_tensor(out, mine, group=self.group)
+        return read_small(out).view(self.world, pad)[:, :n].tolist()
 
     def gather_cat(self, t: torch.Tensor, dim: int = 0) -> torch.Tensor:
         """all-gather(v) along ``dim`` and concatenate in rank order."""
@@ -99,7 +224,13 @@ class TorchComm:
 
 
     def all_gather_into(self, out: torch.Tensor, mine: torch.Tensor):
-        """out[rank * len(mine) : (rank + 1) * len(mine)] = every rank's ``mine`` (equal sizes)."""
+        """out[rank * len(mine) : (rank + 1) * len(mine)] = every rank's ``mine`` (equal sizes).  When ``out`` is peer
+        memory (gather_buffer) and ``mine`` already is its own segment of it, the exchange is a push over NVLink."""
+        seg = mine.numel() * mine.element_size()
+        if (self.peers is not None and self.peers.holds(out) and seg % 16 == 0
+                and mine.data_ptr() == out.data_ptr() + self.rank * seg):
+            self.peers.all_gather(out.data_ptr() - self.peers.buf.data_ptr(), seg)
+            return out
         dist_.all_gather_into_tensor(out, mine, group=self.group)
         return out
 
@@ -107,8 +238,7 @@ class TorchComm:
         """In-place all-gather: ``buf`` holds world * stride elements and this rank has filled its own segment
         [rank * stride, (rank + 1) * stride)."""
         mine = buf[self.rank * stride : (self.rank + 1) * stride]
-        dist_.all_gather_into_tensor(buf, mine, group=self.group)
-        return buf
+        return self.all_gather_into(buf, mine)
 
     def exchange_slices(self, tensors, sizes):
         """Zero-copy all-gather(v): every tensor in ``tensors`` is 1-D, already sized for ALL ranks, and holds this
@@ -174,13 +304,16 @@ def _reduce_counts_gathered(cr, comm: TorchComm, piece: torch.Tensor):
     lib = _lib.load()
     world, length = comm.world, int(piece.numel())
     bins = int(cr.hist.numel())
-    everyone = torch.empty(world * length, dtype=torch.int64, device=piece.device)
+    everyone = getattr(piece, "_gg_everyone", None)   # core.count_piece: the piece is a segment of a gather buffer
+    if everyone is None:
+        everyone = torch.empty(world * length, dtype=torch.int64, device=piece.device)
     comm.all_gather_into(everyone, piece)
     hist = torch.empty(bins, dtype=torch.int32, device=piece.device)
     first = torch.empty(bins, dtype=torch.int64, device=piece.device)
     check(lib.gg_count_merge(ptr(everyone), world, length, cr.k, ptr(hist), ptr(first), _stream()), "gg_count_merge")
-    n_tail = _lib.ST_WORDS + 1
-    tails = read_small(everyone.view(world, length)[:, length - n_tail:].contiguous()).tolist()
+    n_tail = _lib.ST_WORDS + 1                    # status words + end of the rank's stream piece, right behind first_pos
+    tail_at = bins // 2 + bins
+    tails = read_small(everyone.view(world, length)[:, tail_at: tail_at + n_tail].contiguous()).tolist()
     bad = sum(int(t[_lib.ST_BAD_BYTES]) for t in tails)
     if bad > 0:
         raise ValueError(f"{bad} input bytes outside the alphabet ACGTN")

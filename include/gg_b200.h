@@ -419,6 +419,29 @@ GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row
                  gg_stream_t st);
 
 /* ------------------------------------------------------------------------
+ * Multi-GPU exchanges over NVLink peer memory (no reference counterpart: the reference is single-device).
+ * Every rank owns one buffer of a symmetric allocation that all ranks of the box have mapped, plus a pad of 32-bit
+ * flags; the HOST arrays below hold, per rank, the address of that rank's buffer (+ the common offset) / flag pad in
+ * the caller's address space (null = skip that rank, e.g. the caller itself).
+ *   gg_peer_push    copy n_bytes (multiple of 16) from src to h_dst->ptr[r] for every r -- my segment into the same
+ *                   place of every peer's buffer;
+ *   gg_peer_signal  after everything earlier on the stream: flag pad of every peer, word `index`, = value
+ *                   (system-scope release);
+ *   gg_peer_wait    return (on the stream) once flags[first + r] has reached `value` for every r in [0, count) but
+ *                   `skip` (serial numbers: compared as signed differences); a peer that never arrives after ~2^31
+ *                   polls increments status[0] instead of hanging the device.
+ * ------------------------------------------------------------------------ */
+#define GG_MAX_PEERS 16
+typedef struct {
+  int n;
+  void* ptr[GG_MAX_PEERS];
+} gg_peers_t;
+GG_API int gg_peer_push(const void* src, int64_t n_bytes, const gg_peers_t* h_dst, gg_stream_t st);
+GG_API int gg_peer_signal(const gg_peers_t* h_flags, int index, uint32_t value, gg_stream_t st);
+GG_API int gg_peer_wait(const uint32_t* flags, int first, int count, int skip, uint32_t value, int64_t* status,
+                 gg_stream_t st);
+
+/* ------------------------------------------------------------------------
  * Hardware-ceiling probes (measurement only; no reference counterpart).  One kernel launch per call on the caller's
  * stream; *h_updates / *h_ops (HOST out-parameters) = operations that launch performs, to be divided by the launch's
  * CUDA-event time.

@@ -165,7 +165,7 @@ def test_fused_builder_equals_stepwise_builder_on_ragged_reads():
     fused, step = _self(reads, small_k="2,3", edges_keep_top_k=None), _self(tuple(reads), small_k="2,3", edges_keep_top_k=None)
     gg.create_graphs_mini_batch(fused, 4)
     assert hasattr(fused, "build_info")
-    step.graph_device = torch.device("cpu")                    # anything but the string "cpu" takes the step-by-step path
+    step.gg_stepwise = True                                    # the four reference-signature calls, one by one
     assert builders._fused_host_build(step, 4, True) is None
     gg.create_graphs_mini_batch(step, 4)
     assert fused.graph.nodes() == step.graph.nodes()
