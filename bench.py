@@ -393,7 +393,10 @@ def run_ours(a):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        # a rank that dies must take the others down in minutes, not in NCCL's default half hour
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
         comm = ggdist.TorchComm()
         if not a.nccl_only:   # count pieces, candidate counts and packed KF edges over NVLink peer memory
             comm.enable_peer_exchange((1 << 30) if a.k <= 8 else (256 << 20))

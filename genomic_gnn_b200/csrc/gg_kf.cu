@@ -498,6 +498,7 @@ extern "C" int gg_kf_emit(const gg_kf_params_t* p, const uint8_t* counts, const 
   a.class_hist = reinterpret_cast<unsigned long long*>(class_hist);
   a.hist_m = p->hist_m;
   a.p_max = p->p_max;
+  a.interleave = 0;
 
   int impl = p->impl;
   const bool mma_ok = p->d == 32 || p->d == 64 || (p->d % 128 == 0 && p->d <= 1024);

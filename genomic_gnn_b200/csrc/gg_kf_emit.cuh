@@ -44,6 +44,7 @@ struct KfArgs {
   unsigned long long* class_hist;
   int hist_m;
   int p_max;
+  int interleave;  // CTA-pair kernel: strip-pair rows dealt round-robin (serpentine) to the CTA pairs, see pair_walk_begin
 };
 
 // CAP trades shared memory for global-cursor traffic: every flush is one returning atomic on a single address,

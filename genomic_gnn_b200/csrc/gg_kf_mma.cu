@@ -545,34 +545,85 @@ __device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t desc_a,
       : "memory");
 }
 
+// Two ways to hand the (strip pair, column block) units of a shard to the CTA pairs:
+//   contiguous  every CTA pair takes a contiguous range of the strip-pair-major unit sequence (few A reloads, perfect
+//               balance; the way to split a shard of FEWER strip pairs than CTA pairs, e.g. one chunk of a top-n
+//               re-emission, and the rows of the last partial wave below);
+//   interleaved whole strip-pair rows dealt round-robin, serpentine from wave to wave so that the row lengths even out.
+//               All CTA pairs then sit in the same wave of <= 74 neighbouring strip pairs and walk their column blocks
+//               J = I, I + 1, ... side by side, a window of a few dozen column blocks apart: the B tiles they stream
+//               are shared through L2 instead of being fetched from HBM once per strip pair.  That is what decides
+//               the speed once the matrix outgrows L2 (k >= 9: 268 MB and up; at k = 10 the contiguous order moved
+//               2.1 TB of B tiles per pass and ran at the HBM rate, not the tensor rate).
 struct PairWalk {
   int pair, i_block, j_block;  // global strip-pair index (strips 2*pair, 2*pair+1), its row block, column block
-  long long left;
+  long long left;              // units still to do (both phases)
+  // phase 0: whole rows of the full waves, dealt serpentine; phase 1: a contiguous range of the remaining rows' units
+  int wave, n_waves, slot, n_slots;
+  long long tail_first, tail_units;
 };
-__device__ __forceinline__ long long pair_units_before_block(int i_local, int ib0, int n_j) {
-  const long long a = i_local;
-  return kPairsPerBlock * (a * (n_j - ib0) - a * (a - 1) / 2);
+// units of the shard's strip pairs [ib0 * kPairsPerBlock, sp), strip-pair-major
+__device__ __forceinline__ long long pair_units_before(const KfArgs& a, int sp) {
+  const long long il = sp / kPairsPerBlock - a.ib0;
+  return kPairsPerBlock * (il * (a.n_jblocks - a.ib0) - il * (il - 1) / 2) +
+         static_cast<long long>(sp % kPairsPerBlock) * (a.n_jblocks - sp / kPairsPerBlock);
 }
-__device__ PairWalk pair_walk_begin(const KfArgs& a, long long first_unit, long long n_units) {
+__device__ __forceinline__ int serpentine_pair(const KfArgs& a, int wave, int slot, int n_slots) {
+  return a.ib0 * kPairsPerBlock + wave * n_slots + ((wave & 1) ? n_slots - 1 - slot : slot);
+}
+// position the walk on unit `u` (strip-pair-major index inside the shard)
+__device__ void pair_walk_seek(const KfArgs& a, PairWalk& w, long long u) {
+  int lo = a.ib0 * kPairsPerBlock, hi = a.ib1 * kPairsPerBlock;  // last strip pair whose first unit is <= u
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pair_units_before(a, mid) <= u) lo = mid;
+    else hi = mid;
+  }
+  w.pair = lo;
+  w.i_block = lo / kPairsPerBlock;
+  w.j_block = w.i_block + static_cast<int>(u - pair_units_before(a, lo));
+}
+__device__ PairWalk pair_walk_begin(const KfArgs& a, int slot, int n_slots) {
   PairWalk w;
-  int il = 0;
-  const int n_il = a.ib1 - a.ib0;
-  while (il + 1 < n_il && pair_units_before_block(il + 1, a.ib0, a.n_jblocks) <= first_unit) ++il;
-  const long long rem = first_unit - pair_units_before_block(il, a.ib0, a.n_jblocks);
-  w.i_block = a.ib0 + il;
-  const int per_pair = a.n_jblocks - w.i_block;
-  w.pair = w.i_block * kPairsPerBlock + static_cast<int>(rem / per_pair);
-  w.j_block = w.i_block + static_cast<int>(rem % per_pair);
-  w.left = n_units;
+  w.slot = slot;
+  w.n_slots = n_slots;
+  w.wave = 0;
+  const int sp0 = a.ib0 * kPairsPerBlock, sp1 = a.ib1 * kPairsPerBlock;
+  w.n_waves = a.interleave ? (sp1 - sp0) / n_slots : 0;
+  w.left = 0;
+  for (int wave = 0; wave < w.n_waves; ++wave)
+    w.left += a.n_jblocks - serpentine_pair(a, wave, slot, n_slots) / kPairsPerBlock;
+  // what the full waves leave over, split evenly unit by unit
+  const long long tail0 = pair_units_before(a, sp0 + w.n_waves * n_slots), tail_all = pair_units_before(a, sp1) - tail0;
+  const long long base = tail_all / n_slots, extra = tail_all % n_slots;
+  w.tail_first = tail0 + base * slot + (slot < extra ? slot : extra);
+  w.tail_units = base + (slot < extra ? 1 : 0);
+  w.left += w.tail_units;
+  if (w.n_waves > 0) {
+    w.pair = serpentine_pair(a, 0, slot, n_slots);
+    w.i_block = w.pair / kPairsPerBlock;
+    w.j_block = w.i_block;
+  } else if (w.tail_units > 0) {
+    pair_walk_seek(a, w, w.tail_first);
+  }
   return w;
 }
 __device__ __forceinline__ void pair_walk_next(const KfArgs& a, PairWalk& w) {
   --w.left;
-  if (++w.j_block == a.n_jblocks) {
-    ++w.pair;
-    w.i_block = w.pair / kPairsPerBlock;
-    w.j_block = w.i_block;
+  if (++w.j_block < a.n_jblocks) return;
+  if (w.wave < w.n_waves) {          // phase 0: next row of the serpentine, or over to the tail
+    if (++w.wave < w.n_waves) {
+      w.pair = serpentine_pair(a, w.wave, w.slot, w.n_slots);
+      w.i_block = w.pair / kPairsPerBlock;
+      w.j_block = w.i_block;
+    } else if (w.left > 0) {
+      pair_walk_seek(a, w, w.tail_first);
+    }
+    return;
   }
+  ++w.pair;                            // phase 1: contiguous
+  w.i_block = w.pair / kPairsPerBlock;
+  w.j_block = w.i_block;
 }
 __device__ __forceinline__ int pair_first_tile(const PairWalk& w) {
   return w.i_block == w.j_block ? (w.pair % kPairsPerBlock) : 0;  // 256-column tile holding the pair's diagonal
@@ -650,16 +701,14 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
   constexpr uint32_t tmem_base = 0;
 
   const uint32_t n_pairs_grid = gridDim.x / 2, pair_id = blockIdx.x / 2;
-  const long long base_units = total_units / n_pairs_grid, extra = total_units % n_pairs_grid;
-  const long long u0 = base_units * pair_id + (pair_id < extra ? pair_id : extra);
-  const long long n_units = base_units + (pair_id < extra ? 1 : 0);
+  const long long n_units = total_units;  // > 0 (checked by the launcher); every role derives its own share in pair_walk_begin
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (both CTAs; transactions complete on the leader's barriers) ==========
     if (n_units > 0) {
       if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
       const uint32_t a_full_leader = map_to_cta(smem_u32(&bars->a_full), 0);
-      PairWalk w = pair_walk_begin(a, u0, n_units);
+      PairWalk w = pair_walk_begin(a, static_cast<int>(pair_id), static_cast<int>(n_pairs_grid));
       int cur_pair = -1;
       uint32_t a_round = 0, stage = 0, round = 0;
       for (; w.left > 0; pair_walk_next(a, w)) {
@@ -697,7 +746,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && n_units > 0) {
-      PairWalk w = pair_walk_begin(a, u0, n_units);
+      PairWalk w = pair_walk_begin(a, static_cast<int>(pair_id), static_cast<int>(n_pairs_grid));
       int cur_pair = -1;
       uint32_t a_round = 0, stage = 0, round = 0, acc = 0, acc_round = 0;
       const uint32_t desc_hi = g.desc_hi;
@@ -753,7 +802,7 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
     const int gt = tid % kGroupThreads;
     uint16_t* my_sqn = sqn + group * kPairPanel;  // [kBlock] column norms + [8] smallest norm per 128-column tile
     if (n_units > 0) {
-      PairWalk w = pair_walk_begin(a, u0, n_units);
+      PairWalk w = pair_walk_begin(a, static_cast<int>(pair_id), static_cast<int>(n_pairs_grid));
       uint32_t tile_seq = 0;
       // HIST: this thread's compact row slot (kHistBins: the row breaks the promise) and its register-counted class
       uint32_t h_row = kHistBins, h_mode = 0xFFFFFFFFu, h_priv = 0;
@@ -1089,6 +1138,11 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
   if (total_units == 0) return GG_OK;
   const long long pairs = gg::sm_count() / 2;
   const unsigned grid = 2u * static_cast<unsigned>(total_units < pairs ? total_units : pairs);
+  // A matrix that does not fit L2 and enough strip-pair rows for every CTA pair to take whole ones: deal the rows
+  // wave by wave (shared B window in L2); the rows of the last, partial wave are split unit by unit as before.
+  KfArgs args = a;
+  args.interleave = (static_cast<double>(a.n) * a.d > 96e6 &&
+                     static_cast<long long>(a.ib1 - a.ib0) * kPairsPerBlock >= 2 * pairs) ? 1 : 0;
   int* error_flag = reinterpret_cast<int*>(a.out.status + 2);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -1102,7 +1156,7 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, a, n_bstages, total_units, error_flag, g));
+  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, args, n_bstages, total_units, error_flag, g));
   return GG_OK;
 }
 

@@ -43,7 +43,7 @@ __global__ void wait_kernel(const uint32_t* flags, int first, int count, int ski
   if (r < count && r != skip) {
     const uint32_t* f = flags + first + r;
     bool ok = false;
-    for (long long spin = 0; spin < (1ll << 31); ++spin) {
+    for (long long spin = 0; spin < (1ll << 26); ++spin) {   // ~10 s: a build is milliseconds
       uint32_t v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if (static_cast<int32_t>(v - value) >= 0) {

@@ -70,7 +70,11 @@ class PeerSpace:
         group = comm.group if comm.group is not None else dist_.group.WORLD
         self.buf = symm.empty(2 * self.half, dtype=torch.uint8, device=comm.device)
         self.hdl = symm.rendezvous(self.buf, group)
-        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        # buffer_ptrs are the bases of the symmetric allocations; this tensor starts hdl.offset bytes into them
+        skew = int(getattr(self.hdl, "offset", 0) or 0)
+        self.base = [int(p) + skew for p in self.hdl.buffer_ptrs]
+        if self.base[comm.rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric memory: own buffer pointer does not match the tensor")
         self.pads = [int(p) for p in self.hdl.signal_pad_ptrs]
         if int(self.hdl.signal_pad_size) < 4 * self.CHANNELS * comm.world:
             raise RuntimeError("signal pad too small")

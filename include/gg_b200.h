@@ -428,8 +428,8 @@ GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row
  *   gg_peer_signal  after everything earlier on the stream: flag pad of every peer, word `index`, = value
  *                   (system-scope release);
  *   gg_peer_wait    return (on the stream) once flags[first + r] has reached `value` for every r in [0, count) but
- *                   `skip` (serial numbers: compared as signed differences); a peer that never arrives after ~2^31
- *                   polls increments status[0] instead of hanging the device.
+ *                   `skip` (serial numbers: compared as signed differences); a peer that never arrives after 2^26
+ *                   polls (~10 s) increments status[0] instead of hanging the device.
  * ------------------------------------------------------------------------ */
 #define GG_MAX_PEERS 16
 typedef struct {
