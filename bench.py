@@ -242,18 +242,29 @@ def run_reference_arm(a, rank):
     print(json.dumps(line), flush=True)
 
 
-def census_launches(step):
+def census_launches(step, profile=True):
     """Kernel launches of ONE untimed step, counted by torch.profiler (CUPTI): kernels of libgg_b200.so ("own"),
-    CUB sort / scan kernels instantiated inside it, torch's own elementwise / copy kernels, NCCL."""
+    CUB sort / scan kernels instantiated inside it, torch's own elementwise / copy kernels, NCCL.  The step runs exactly
+    once whatever happens to the profiler: other ranks are running it too."""
     import torch
 
-    try:
-        from torch.profiler import ProfilerActivity, profile
+    ran = [False]
 
-        torch.cuda.synchronize()
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    def once():
+        if not ran[0]:
+            ran[0] = True
             step()
             torch.cuda.synchronize()
+
+    if not profile:      # a rank that only has to take part in the step's exchanges
+        once()
+        return None
+    try:
+        from torch.profiler import ProfilerActivity, profile as torch_profile
+
+        torch.cuda.synchronize()
+        with torch_profile(activities=[ProfilerActivity.CUDA]) as prof:
+            once()
         out = {"own": 0, "cub": 0, "torch": 0, "nccl": 0, "memcpy_memset": 0}
         names = {}
         for ev in prof.events():
@@ -278,6 +289,7 @@ def census_launches(step):
         return out
     except Exception as exc:  # noqa: BLE001
         sys.stderr.write(f"launch census unavailable: {exc}\n")
+        once()
         return None
 
 
@@ -512,7 +524,8 @@ def run_ours(a):
     stage_ms = {k_: sum(v) / stage_steps for k_, v in timer.summary().items()}
     stage_launches = {k_: len(v) / stage_steps for k_, v in timer.summary().items()}
     n_nodes, db_edges = built.db.num_nodes, built.db.num_edges
-    launches = census_launches(step_resident) if rank == 0 and not a.no_probes and not big else None
+    # every rank runs the step (it holds collectives); rank 0 profiles it
+    launches = census_launches(step_resident, rank == 0) if not a.no_probes and not big else None
     if big:
         built = None
     if a.no_e2e:

@@ -175,3 +175,25 @@ def test_fused_builder_equals_stepwise_builder_on_ragged_reads():
     assert torch.equal(a["node"].x, b["node"].x) and torch.equal(a["node"]["y_1"], b["node"]["y_1"])
     with pytest.raises(ValueError):
         gg.create_graphs_mini_batch(_self(["ACGT", 7]), 3)
+
+
+def test_shared_host_arena_delivery_single_rank():
+    """hostshare.deliver_graph with one rank: every tensor of a device build lands in the page-locked shared-memory
+    arena (the multi-rank flavour, where every rank writes its own shard, runs in tests/test_multi_gpu.py)."""
+    from genomic_gnn_b200 import core, hostshare
+
+    reads = fast.synthetic_reads(5000, 150, seed=3)
+    built = core.build_graph(reads, 6, "2,4", edges_threshold=0.8, edges_keep_top_k=0.01)
+    arena = hostshare.SharedHostArena(None, hostshare.arena_bytes_for(built.db.num_nodes, 6, [2, 4],
+                                                                       [kf.n_edges for kf in built.kf]))
+    try:
+        host = hostshare.deliver_graph(built, arena, None)
+        assert torch.equal(host.node_codes, built.db.node_codes.cpu()) and torch.equal(host.edge_index, built.db.edge_index.cpu())
+        assert torch.equal(host.weight, built.db.weight.cpu())
+        for i, kf in enumerate(built.kf):
+            assert torch.equal(host.x[i], built.x[i].cpu())
+            assert torch.equal(host.kf_edge_index[i], kf.edge_index.cpu()) and torch.equal(host.kf_weight[i], kf.weight.cpu())
+        assert host.d2h_bytes > 0 and not host.edge_index.is_cuda
+        del host
+    finally:
+        arena.close()
