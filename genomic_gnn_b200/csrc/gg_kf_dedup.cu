@@ -40,16 +40,19 @@ __global__ void __launch_bounds__(kThreads) row_key_kernel(const uint8_t* counts
   if (i >= n) return;
   const uint32_t* row = reinterpret_cast<const uint32_t*>(counts + i * pitch);
   unsigned long long key = 0;
-  uint32_t over = 0;
+  uint32_t over = 0, sq = 0;
   for (int w = 0; w < words; ++w) {
     const uint32_t v = __ldg(row + w);
     over |= v & 0xF0F0F0F0u;
     const uint32_t nib = (v & 0xFu) | ((v >> 4) & 0xF0u) | ((v >> 8) & 0xF00u) | ((v >> 12) & 0xF000u);
     key |= static_cast<unsigned long long>(nib) << (16 * w);
+    sq = __dp4a(v & 0x0F0F0F0Fu, v & 0x0F0F0F0Fu, sq);
   }
   if (over) atomicAdd(status + 1, 1ull);  // a count above 15 does not fit the packed key: caller must not use this path
   keys[i] = key;
-  hkeys[i] = mix32(key);
+  // sort key: squared norm (<= 225 for rows this path accepts) above 24 bits of the mix -- classes of equal norm end up
+  // next to each other, which lets the class-pair histogram count long runs of columns with one norm product
+  hkeys[i] = ((sq > 255u ? 255u : sq) << 24) | (mix32(key) >> 8);
   idx[i] = static_cast<int32_t>(i);
 }
 
@@ -101,6 +104,18 @@ struct ScoreArgs {
   unsigned long long* tie_out;
 };
 
+__device__ __forceinline__ void hist_flush_row(const ScoreArgs& a, uint32_t* acc, int r, unsigned long long p,
+                                               unsigned long long wa) {
+  for (int dot = 0; dot < 16; ++dot) {
+    uint32_t* slot = acc + (dot * 4 + r) * 128 + threadIdx.x;   // [kHistDots][kScoreRows][kScoreThreads]
+    const uint32_t v = *slot;
+    if (v) {
+      atomicAdd(a.class_hist + static_cast<unsigned long long>(dot) * (a.p_max + 1) + p, wa * v);
+      *slot = 0u;
+    }
+  }
+}
+
 // members of class c with node id >= row (members ascend inside a class)
 __device__ __forceinline__ int members_at_or_after(const int32_t* members, int m0, int m1, int row) {
   int lo = m0, hi = m1;
@@ -133,6 +148,12 @@ __device__ __forceinline__ uint32_t dot16(const uint4& a, const uint4& b) {
 // tile in shared memory (one broadcast 16-byte load per column class serves 4 x 128 pairs); the per-row threshold
 // column thr[sq_b][row] makes the exact test one conflict-free shared-memory byte load, because all threads look at
 // the same b and hence the same sq_b.
+constexpr int kHistDots = 16;  // dots counted in the private table (larger ones are rare at small_k <= 2: direct atomics)
+
+struct ScoreArgs;
+__device__ __forceinline__ void hist_flush_row(const ScoreArgs& a, uint32_t* acc, int r, unsigned long long p,
+                                               unsigned long long wa);
+
 // EXTRA: 0 plain, 1 HIST, 2 TIES, 3 COUNT (see ScoreArgs; COUNT: tie_out[0] += node pairs of ALL passing class pairs)
 template <int EXTRA>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
@@ -143,6 +164,13 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
   // EXTRA: per column class of the tile, its size (HIST) or its members at/after row_lo and row_hi (TIES)
   uint32_t* bw0 = reinterpret_cast<uint32_t*>(thr + static_cast<size_t>(a.sq_max + 1) * kScoreA);
   uint32_t* bw1 = bw0 + kScoreB;
+  // HIST: private counters acc[dot][row][thread] of column-class sizes for the current run of columns with one squared
+  // norm (classes are sorted by it): a run costs one atomic per (row, dot) instead of one per class pair
+  uint32_t* acc = bw1 + kScoreB;
+  uint32_t run_sq[kScoreRows] = {0u, 0u, 0u, 0u};
+  if (EXTRA == 1) {
+    for (int i = threadIdx.x; i < kHistDots * kScoreA; i += kScoreThreads) acc[i] = 0u;
+  }
   const int a0 = blockIdx.y * kScoreA, b0 = blockIdx.x * kScoreB;
   if (b0 + kScoreB <= a0) return;  // every column class of this tile lies before every row class
   uint4 ra[kScoreRows];
@@ -237,8 +265,17 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
             const unsigned long long p = static_cast<unsigned long long>(sqa[r]) * (boff[tb] / kScoreA);
             if (EXTRA == 1) {
               const unsigned long long wa = aw0[r];
-              const unsigned long long w = cb == ca ? wa * (wa - 1ull) / 2ull : wa * bw0[tb];
-              if (w) atomicAdd(a.class_hist + dot * static_cast<unsigned long long>(a.p_max + 1) + p, w);
+              const uint32_t sqb = boff[tb] / kScoreA;
+              if (cb == ca || dot >= kHistDots) {
+                const unsigned long long w = cb == ca ? wa * (wa - 1ull) / 2ull : wa * bw0[tb];
+                if (w) atomicAdd(a.class_hist + dot * static_cast<unsigned long long>(a.p_max + 1) + p, w);
+              } else {
+                if (sqb != run_sq[r]) {
+                  hist_flush_row(a, acc, r, static_cast<unsigned long long>(sqa[r]) * run_sq[r], wa);
+                  run_sq[r] = sqb;
+                }
+                acc[(static_cast<int>(dot) * kScoreRows + r) * kScoreThreads + threadIdx.x] += bw0[tb];
+              }
             } else if (static_cast<long long>(dot * dot) * a.tie_den == a.tie_num * static_cast<long long>(p)) {
               const unsigned long long x0 = aw0[r], x1 = aw1[r];
               tie0 += cb == ca ? x0 * (x0 - 1ull) / 2ull : x0 * bw0[tb];
@@ -248,6 +285,11 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
         }
       }
     }
+  }
+  if (EXTRA == 1) {
+#pragma unroll
+    for (int r = 0; r < kScoreRows; ++r)
+      hist_flush_row(a, acc, r, static_cast<unsigned long long>(sqa[r]) * run_sq[r], aw0[r]);
   }
   if (EXTRA == 2 || EXTRA == 3) {  // one pair of atomics per warp
 #pragma unroll
@@ -706,7 +748,7 @@ extern "C" int gg_kf_dedup_score(const uint8_t* counts, int pitch, int d_valid, 
     a.tie_out = reinterpret_cast<unsigned long long*>(extra->tie_out);
   }
   const size_t smem = kScoreB * (sizeof(uint4) + sizeof(uint32_t)) + static_cast<size_t>(sq_max + 1) * kScoreA +
-                      2 * kScoreB * sizeof(uint32_t);
+                      2 * kScoreB * sizeof(uint32_t) + (mode == 1 ? kHistDots * kScoreA * sizeof(uint32_t) : 0);
   auto kernel = mode == 0 ? score_kernel<0> : (mode == 1 ? score_kernel<1> : (mode == 2 ? score_kernel<2> : score_kernel<3>));
   GG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>((n_classes + kScoreB - 1) / kScoreB),

@@ -447,7 +447,8 @@ def test_count_pieces_merge_like_a_multi_gpu_build(gg):
                               C.c_void_p(first.data_ptr()), None) == 0
     torch.cuda.synchronize()
     assert torch.equal(hist, whole.hist) and torch.equal(first, whole.first_pos)
-    tails = everyone.view(2, -1)[:, -(_lib.ST_WORDS + 1):].cpu()
+    at = bins // 2 + bins                  # status words + stream end sit right behind first_pos (core.count_piece)
+    tails = everyone.view(2, -1)[:, at: at + _lib.ST_WORDS + 1].cpu()
     assert int(tails[:, _lib.ST_BRIDGES].sum()) == whole.n_bridges and tails[:, -1].tolist() == [half * 150, 6000 * 150]
 
 
