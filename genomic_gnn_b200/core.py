@@ -337,13 +337,25 @@ class DBGraph:
     weight64: torch.Tensor      # float64 [E]
 
 
+class _NeedBridges(Exception):
+    """build_db ran on a count whose status had not been read and found bridge records (args[0] of them)."""
+
+
 def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weight_threshold=None,
              keep_top_k=None) -> DBGraph:
-    """K2.  Reference: src/utils.py:87-165 + from_networkx.  keep_top_k = the quantile pruning of utils.py:151-160."""
+    """K2.  Reference: src/utils.py:87-165 + from_networkx.  keep_top_k = the quantile pruning of utils.py:151-160.
+
+    A count whose status words are still on the device (``cr.n_bridges < 0``: count_kp1mers(sync=False)) is assembled
+    on the assumption that it holds no bridge records -- reads without an internal N run have none -- and K1's status
+    comes back in the SAME device read as K2's node / edge counts: one host round trip for both stages.  Illegal bytes
+    raise here; bridge records make the call fix ``cr.n_bridges`` and assemble again (capacity permitting)."""
     lib = _lib.load()
     dev = cr.hist.device
     k = cr.k
     bins = cr.hist.numel()
+    speculative = cr.n_bridges < 0
+    if speculative:
+        cr.n_bridges = 0
     cap = bins + cr.n_bridges
     ws_bytes = int(lib.gg_db_workspace_bytes(k, cr.n_bridges))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -361,7 +373,22 @@ def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weigh
                               int(bool(create_all_kmers)), thr, ptr(node_codes), ptr(code_to_node), ptr(edges[0]),
                               ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes,
                               max(1, min(40, int(cr.pos_limit - 1).bit_length())), _stream()), "gg_db_build")
-    n, e = (int(x) for x in read_small(ne).tolist())
+    if speculative:
+        both = read_small(torch.cat([ne, cr.status])).tolist()
+        n, e, st_host = int(both[0]), int(both[1]), both[2:]
+        if int(st_host[_lib.ST_BAD_BYTES]) > 0:
+            raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN "
+                             "(the reference fails on these at gnn_utils.py:471)")
+        cr.n_nonzero = int(st_host[_lib.ST_NONZERO])
+        nb = int(st_host[_lib.ST_BRIDGES])
+        if nb > 0:
+            if nb > int(cr.bridges.shape[0]):
+                cr.n_bridges = -1
+                raise _NeedBridges(nb)            # the caller counts again with room for every bridge record
+            cr.n_bridges = nb
+            return build_db(cr, normalise, create_all_kmers, edge_weight_threshold, keep_top_k)
+    else:
+        n, e = (int(x) for x in read_small(ne).tolist())
     ei, w32, w64 = edges[:, :e].contiguous(), w32[:e], w64[:e]
     if keep_top_k is not None and e > 0:
         pw = int(lib.gg_db_prune_workspace_bytes(e))
@@ -1417,11 +1444,16 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
                 break
             except OverflowError as exc:  # same decision on every rank: the counts were all-reduced
                 capacity = int(exc.args[0])
+        db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
     else:
-        cr = count_kp1mers(stream, k)
-    if cr.n_nonzero == 0 and cr.n_bridges == 0:
-        raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
-    db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
+        # K1 and K2 back to back, one device read for both (build_db); the rare stream with more internal-N bridge
+        # records than the default room is counted again with room for all of them
+        cr = count_kp1mers(stream, k, sync=False)
+        try:
+            db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
+        except _NeedBridges as need:
+            cr = count_kp1mers(stream, k, bridge_capacity=int(need.args[0]))
+            db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
     if db.num_edges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     small = [int(s) for s in str(small_k).split(",")]

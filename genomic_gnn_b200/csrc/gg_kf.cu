@@ -361,67 +361,69 @@ __global__ void __launch_bounds__(256) class_hist_packed_kernel(const uint2* ord
   }
 }
 
-__global__ void __launch_bounds__(256) packed_action_kernel(const uint2* ordered, long long n, const int32_t* sqnorm,
-                                                            int32_t p_max, const uint8_t* action, uint8_t* act_out) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    act_out[i] = action[packed_class_key(__ldg(ordered + i), sqnorm, p_max)];
-}
-
-struct IsTie32 {
-  __host__ __device__ uint32_t operator()(uint8_t a) const { return a == 2 ? 1u : 0u; }
-};
-
 // Spread rule for the cut-off class: of its T members, numbered g = 0 .. T-1 in GLOBAL emission order, exactly B are
 // kept -- those where floor((g + 1) r / 2^64) > floor(g r / 2^64) with r = ceil(B 2^64 / T).  The rule needs nothing
 // but g, so any sharding of the emission order (ranks, row-block chunks) selects the same members, and every shard
-// keeps its fair share of them.
-__host__ __device__ __forceinline__ bool tie_admitted(unsigned long long g, unsigned long long r) {
+// keeps its fair share of them.  Members kept among the first g: floor(g r / 2^64).
+__host__ __device__ __forceinline__ unsigned long long ties_kept_before(unsigned long long g, unsigned long long r) {
 #ifdef __CUDA_ARCH__
-  return __umul64hi(g + 1ull, r) > __umul64hi(g, r);
+  return __umul64hi(g, r);
 #else
-  return static_cast<unsigned long long>((static_cast<unsigned __int128>(g + 1ull) * r) >> 64) >
-         static_cast<unsigned long long>((static_cast<unsigned __int128>(g) * r) >> 64);
+  return static_cast<unsigned long long>((static_cast<unsigned __int128>(g) * r) >> 64);
 #endif
 }
 
-struct KeepOf {
-  const uint8_t* act;
-  const uint32_t* tie_rank;
-  const long long* cursors;  // [0] members of the cut-off class emitted before this call (global numbering)
-  unsigned long long r;
-  __host__ __device__ uint32_t operator()(long long i) const {
-    const uint8_t a = act[i];
-    if (a == 1) return 1u;
-    if (a != 2) return 0u;
-    return tie_admitted(static_cast<unsigned long long>(cursors[0]) + tie_rank[i], r) ? 1u : 0u;
+// One scan serves the whole selection: its element is (1 << 32) for an edge above the cut-off class, 1 for a member of
+// the class, 0 for anything to drop; the exclusive prefix of word i is then (edges above before i) << 32 | (members
+// before i), and because the rule above depends on the member NUMBER only, the output slot of word i follows from
+// the prefix alone: above + ties_kept_before(g0 + members) - ties_kept_before(g0).
+struct ClassOf {
+  const uint2* ordered;
+  const int32_t* sqnorm;
+  const uint8_t* action;
+  int32_t p_max;
+  __host__ __device__ unsigned long long operator()(long long i) const {
+#ifdef __CUDA_ARCH__
+    const uint8_t a = action[packed_class_key(__ldg(ordered + i), sqnorm, p_max)];
+    return a == 1 ? (1ull << 32) : (a == 2 ? 1ull : 0ull);
+#else
+    return 0ull;
+#endif
   }
 };
 
-__global__ void __launch_bounds__(256) packed_scatter_kernel(const uint2* ordered, long long n, KeepOf keep,
-                                                             const uint32_t* pos, const int32_t* sqnorm,
-                                                             long long out_capacity, int64_t* o_src, int64_t* o_dst,
-                                                             double* o_w64, float* o_w32, long long* totals) {
-  const long long out0 = keep.cursors[1];
+__global__ void __launch_bounds__(256) packed_scatter_kernel(const uint2* ordered, long long n, const int32_t* sqnorm,
+                                                             int32_t p_max, const uint8_t* action,
+                                                             const unsigned long long* prefix, unsigned long long r,
+                                                             const long long* cursors, long long out_capacity,
+                                                             int64_t* o_src, int64_t* o_dst, double* o_w64, float* o_w32,
+                                                             long long* totals) {
+  const unsigned long long g0 = static_cast<unsigned long long>(cursors[0]);
+  const long long out0 = cursors[1];
+  const unsigned long long kept0 = ties_kept_before(g0, r);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint32_t kept = keep(i);
+    const uint2 e = __ldg(ordered + i);
+    const uint32_t s = e.x & 0xFFFFFFu, dot = e.x >> 24, t = e.y;
+    const long long p = static_cast<long long>(__ldg(sqnorm + s)) * static_cast<long long>(__ldg(sqnorm + t));
+    const uint8_t act = action[dot * static_cast<uint32_t>(p_max + 1) + static_cast<uint32_t>(p)];
+    const unsigned long long pre = prefix[i];
+    const unsigned long long above = pre >> 32, g = g0 + (pre & 0xFFFFFFFFull);
+    const bool kept = act == 1 || (act == 2 && ties_kept_before(g + 1ull, r) > ties_kept_before(g, r));
     if (kept) {
-      const long long o = out0 + pos[i];
+      const long long o = out0 + static_cast<long long>(above + (ties_kept_before(g, r) - kept0));
       if (o < out_capacity) {
-        const uint2 e = __ldg(ordered + i);
-        const uint32_t s = e.x & 0xFFFFFFu, dot = e.x >> 24, t = e.y;
         o_src[o] = s;
         o_dst[o] = t;
-        const double p = static_cast<double>(static_cast<long long>(__ldg(sqnorm + s)) * static_cast<long long>(__ldg(sqnorm + t)));
-        const double w = static_cast<double>(dot) / sqrt(p);
+        const double w = static_cast<double>(dot) / sqrt(static_cast<double>(p));
         if (o_w64) o_w64[o] = w;
         if (o_w32) o_w32[o] = static_cast<float>(w);
       }
     }
     if (i == n - 1) {  // totals of this call, applied to the cursors by the kernel behind this one
-      totals[0] = static_cast<long long>(keep.tie_rank[i]) + (keep.act[i] == 2 ? 1 : 0);
-      totals[1] = static_cast<long long>(pos[i]) + kept;
+      const unsigned long long members = (pre & 0xFFFFFFFFull) + (act == 2 ? 1ull : 0ull);
+      totals[0] = static_cast<long long>(members);
+      totals[1] = static_cast<long long>(above + (act == 1 ? 1ull : 0ull) + (ties_kept_before(g0 + members, r) - kept0));
     }
   }
 }
@@ -647,18 +649,11 @@ extern "C" int gg_kf_class_hist_packed(const uint64_t* ordered, int64_t n_edges,
 }
 
 namespace {
-template <typename Op, typename In>
-size_t scan32_temp_bytes(long long n) {
+size_t class_scan_temp_bytes(long long n) {
   size_t bytes = 0;
-  cub::TransformInputIterator<uint32_t, Op, const In*> it(nullptr, Op());
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, static_cast<uint32_t*>(nullptr), n);
-  return bytes;
-}
-size_t keep_scan_temp_bytes(long long n) {
-  size_t bytes = 0;
-  cub::TransformInputIterator<uint32_t, KeepOf, cub::CountingInputIterator<long long>> it(
-      cub::CountingInputIterator<long long>(0), KeepOf{nullptr, nullptr, nullptr, 0ull});
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, static_cast<uint32_t*>(nullptr), n);
+  cub::TransformInputIterator<unsigned long long, ClassOf, cub::CountingInputIterator<long long>> it(
+      cub::CountingInputIterator<long long>(0), ClassOf{nullptr, nullptr, nullptr, 0});
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, static_cast<unsigned long long*>(nullptr), n);
   return bytes;
 }
 }  // namespace
@@ -666,12 +661,9 @@ size_t keep_scan_temp_bytes(long long n) {
 extern "C" size_t gg_kf_select_packed_workspace_bytes(int64_t n_edges) {
   const long long n = n_edges > 0 ? n_edges : 1;
   gg::Carver c(nullptr);
-  c.take<uint8_t>(n);
-  c.take<uint32_t>(n);
-  c.take<uint32_t>(n);
+  c.take<unsigned long long>(n);
   c.take<long long>(2);
-  const size_t a = scan32_temp_bytes<IsTie32, uint8_t>(n), b = keep_scan_temp_bytes(n);
-  c.take<char>(a > b ? a : b);
+  c.take<char>(class_scan_temp_bytes(n));
   return c.used();
 }
 
@@ -686,31 +678,20 @@ extern "C" int gg_kf_select_packed(const uint64_t* ordered, int64_t n_edges, con
   GG_REQUIRE(workspace_bytes >= gg_kf_select_packed_workspace_bytes(n_edges), GG_ERR_WORKSPACE, "workspace too small");
   cudaStream_t s = gg::as_stream(st);
   gg::Carver c(workspace);
-  uint8_t* act = c.take<uint8_t>(n_edges);
-  uint32_t* tie_rank = c.take<uint32_t>(n_edges);
-  uint32_t* pos = c.take<uint32_t>(n_edges);
+  unsigned long long* prefix = c.take<unsigned long long>(n_edges);
   long long* totals = c.take<long long>(2);
-  const size_t ta = scan32_temp_bytes<IsTie32, uint8_t>(n_edges), tb = keep_scan_temp_bytes(n_edges);
-  const size_t temp_bytes = ta > tb ? ta : tb;
+  size_t temp_bytes = class_scan_temp_bytes(n_edges);
   void* temp = c.take<char>(temp_bytes);
-  const int g = grid_for(n_edges);
   const uint2* words = reinterpret_cast<const uint2*>(ordered);
-  packed_action_kernel<<<g, 256, 0, s>>>(words, n_edges, sqnorm, p_max, class_action, act);
-  GG_CUDA_CHECK(cudaGetLastError());
   {
-    cub::TransformInputIterator<uint32_t, IsTie32, const uint8_t*> it(act, IsTie32());
-    size_t b = temp_bytes;
-    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, b, it, tie_rank, n_edges, s));
+    cub::TransformInputIterator<unsigned long long, ClassOf, cub::CountingInputIterator<long long>> it(
+        cub::CountingInputIterator<long long>(0), ClassOf{words, sqnorm, class_action, p_max});
+    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, prefix, n_edges, s));
   }
-  const KeepOf keep{act, tie_rank, reinterpret_cast<const long long*>(cursors), static_cast<unsigned long long>(tie_ratio)};
-  {
-    cub::TransformInputIterator<uint32_t, KeepOf, cub::CountingInputIterator<long long>> it(
-        cub::CountingInputIterator<long long>(0), keep);
-    size_t b = temp_bytes;
-    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, b, it, pos, n_edges, s));
-  }
-  packed_scatter_kernel<<<g, 256, 0, s>>>(words, n_edges, keep, pos, sqnorm, out_capacity, out_src, out_dst, out_w64,
-                                          out_w32, totals);
+  packed_scatter_kernel<<<grid_for(n_edges), 256, 0, s>>>(words, n_edges, sqnorm, p_max, class_action, prefix,
+                                                          static_cast<unsigned long long>(tie_ratio),
+                                                          reinterpret_cast<const long long*>(cursors), out_capacity,
+                                                          out_src, out_dst, out_w64, out_w32, totals);
   GG_CUDA_CHECK(cudaGetLastError());
   advance_cursors_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(cursors), totals);
   GG_CUDA_CHECK(cudaGetLastError());

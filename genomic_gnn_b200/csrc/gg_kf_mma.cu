@@ -880,10 +880,13 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
 #pragma unroll
                 for (int b = 0; b < 32; ++b) hot |= v[b] >= tmin;
                 if (!__any_sync(0xFFFFFFFFu, hot)) continue;
+                // Second level: the same bound per column (3 instructions a score; the tighter pre-filter through
+                // fast_scale cost 8 and, once candidates are dense -- a top-n re-emission at threshold 0 passes the
+                // first level in every chunk --, made the epilogue the kernel: 574 warp-instructions per 32 x 32
+                // scores, tensor pipe 34 % active).  The exact test below sorts out what the bound lets through.
                 uint32_t mask = 0;
 #pragma unroll
-                for (int b = 0; b < 32; ++b)
-                  mask |= static_cast<uint32_t>(((v[b] * v[b]) << a.fast_shift) > scale_i * my_sqn[c0 + b]) << b;
+                for (int b = 0; b < 32; ++b) mask |= static_cast<uint32_t>(v[b] >= tmin) << b;
                 mask &= chunk_col_mask(cols_in_block, c0);
                 if (diag) mask &= chunk_diag_mask(r, c0);
                 if (!row_ok) mask = 0;
@@ -895,7 +898,8 @@ kf_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap, KfArgs a, int n
                   for (uint32_t m2 = mask; m2; m2 &= m2 - 1) {
                     const int b = __ffs(m2) - 1;
                     const uint32_t dot = stage_get_dot(ws, b, lane), sq_j = my_sqn[c0 + b];
-                    if (dot >= __ldg(a.dmin + sq_i * sq_j)) {
+                    // a column with the tile's smallest norm (most of them: all-distinct rows) has dmin == tmin
+                    if (sq_j == tile_min_sq || dot >= __ldg(a.dmin + sq_i * sq_j)) {
                       exact |= 1u << b;
                       if (HIST) {
                         const uint32_t idj = (sq_j - hist_m) >> 1;
