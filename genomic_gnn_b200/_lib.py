@@ -74,6 +74,7 @@ SIGNATURES = {
     "gg_db_workspace_bytes": (_SZ, [_I32, _I64]),
     "gg_db_build": (_I32, [_P, _P, _P, _I64, _I32, _I32, _I32, _DBL, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _SZ, _I32, _P]),
     "gg_kf_counts": (_I32, [_P, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "gg_kf_counts_upto": (_I32, [_P, _I64, _P, _I32, _I32, _P, _P, _P, _P]),
     "gg_kf_features_f32": (_I32, [_P, _I64, _I32, _P, _I32, _P, _P, _P]),
     "gg_kf_rowcnt_elems": (_SZ, [_I64, _I32, _I32]),
     "gg_kf_emit": (_I32, [C.POINTER(KfParams), _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P]),

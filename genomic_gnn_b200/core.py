@@ -127,6 +127,35 @@ def read_small(t: torch.Tensor) -> torch.Tensor:
     return box[:n].view(t.shape)
 
 
+class PendingRead:
+    """A small device tensor on its way to the host: the copy is queued on the current stream now, ``get()`` waits for
+    THAT copy only (an event), not for whatever the caller queued behind it.  A build hands the GPU its next kernels
+    first and collects the sizes they do not depend on afterwards, so the device never idles across the read.
+    Slots come from a per-thread ring of pinned buffers (a slot is reused after kSlots further reads)."""
+    kSlots, kSlotBytes = 16, 8192
+
+    def __init__(self, t: torch.Tensor):
+        ring = _MAILBOX_TLS.__dict__.setdefault("ring", None)
+        if ring is None:
+            ring = _MAILBOX_TLS.ring = [torch.empty(self.kSlots * self.kSlotBytes, dtype=torch.uint8, pin_memory=True), 0]
+        nbytes = int(t.numel()) * t.element_size()
+        if nbytes > self.kSlotBytes:
+            raise ValueError("PendingRead is for small tensors")
+        slot = ring[1] % self.kSlots
+        ring[1] += 1
+        self.box = ring[0][slot * self.kSlotBytes: slot * self.kSlotBytes + nbytes].view(t.dtype).view(t.shape)
+        self.box.copy_(t, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def get(self) -> torch.Tensor:
+        """Host view of the data (valid until kSlots further reads have been issued by this thread)."""
+        if self.event is not None:
+            self.event.synchronize()
+            self.event = None
+        return self.box
+
+
 def _require_cuda():
     if not torch.cuda.is_available():
         raise GGError("genomic_gnn_b200 needs a CUDA device: the graph-construction path has no CPU fallback")
@@ -341,21 +370,13 @@ class _NeedBridges(Exception):
     """build_db ran on a count whose status had not been read and found bridge records (args[0] of them)."""
 
 
-def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weight_threshold=None,
-             keep_top_k=None) -> DBGraph:
-    """K2.  Reference: src/utils.py:87-165 + from_networkx.  keep_top_k = the quantile pruning of utils.py:151-160.
-
-    A count whose status words are still on the device (``cr.n_bridges < 0``: count_kp1mers(sync=False)) is assembled
-    on the assumption that it holds no bridge records -- reads without an internal N run have none -- and K1's status
-    comes back in the SAME device read as K2's node / edge counts: one host round trip for both stages.  Illegal bytes
-    raise here; bridge records make the call fix ``cr.n_bridges`` and assemble again (capacity permitting)."""
+def _db_launch(cr: "CountResult", normalise, create_all_kmers, edge_weight_threshold):
+    """Queue gg_db_build; every output is sized by its upper bound (4^k nodes, 4^(k+1) + bridges edges) and the actual
+    (N, E) stay on the device in ``ne``."""
     lib = _lib.load()
     dev = cr.hist.device
     k = cr.k
     bins = cr.hist.numel()
-    speculative = cr.n_bridges < 0
-    if speculative:
-        cr.n_bridges = 0
     cap = bins + cr.n_bridges
     ws_bytes = int(lib.gg_db_workspace_bytes(k, cr.n_bridges))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -373,19 +394,45 @@ def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weigh
                               int(bool(create_all_kmers)), thr, ptr(node_codes), ptr(code_to_node), ptr(edges[0]),
                               ptr(edges[1]), ptr(w64), ptr(w32), cap, ptr(ne), ptr(ws), ws_bytes,
                               max(1, min(40, int(cr.pos_limit - 1).bit_length())), _stream()), "gg_db_build")
+    return node_codes, code_to_node, edges, w64, w32, ne
+
+
+def _db_check_speculation(cr: "CountResult", st_host) -> bool:
+    """K1's status words, read after a De Bruijn assembly that assumed a stream without bridge records.  Raises on
+    illegal bytes; True = bridge records exist and ``cr.n_bridges`` now says how many (assemble again)."""
+    if int(st_host[_lib.ST_BAD_BYTES]) > 0:
+        raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN "
+                         "(the reference fails on these at gnn_utils.py:471)")
+    cr.n_nonzero = int(st_host[_lib.ST_NONZERO])
+    nb = int(st_host[_lib.ST_BRIDGES])
+    if nb > 0:
+        if nb > int(cr.bridges.shape[0]):
+            cr.n_bridges = -1
+            raise _NeedBridges(nb)            # the caller counts again with room for every bridge record
+        cr.n_bridges = nb
+        return True
+    return False
+
+
+def build_db(cr: CountResult, normalise=True, create_all_kmers=False, edge_weight_threshold=None,
+             keep_top_k=None) -> DBGraph:
+    """K2.  Reference: src/utils.py:87-165 + from_networkx.  keep_top_k = the quantile pruning of utils.py:151-160.
+
+    A count whose status words are still on the device (``cr.n_bridges < 0``: count_kp1mers(sync=False)) is assembled
+    on the assumption that it holds no bridge records -- reads without an internal N run have none -- and K1's status
+    comes back in the SAME device read as K2's node / edge counts: one host round trip for both stages.  Illegal bytes
+    raise here; bridge records make the call fix ``cr.n_bridges`` and assemble again (capacity permitting)."""
+    lib = _lib.load()
+    dev = cr.hist.device
+    k = cr.k
+    speculative = cr.n_bridges < 0
+    if speculative:
+        cr.n_bridges = 0
+    node_codes, code_to_node, edges, w64, w32, ne = _db_launch(cr, normalise, create_all_kmers, edge_weight_threshold)
     if speculative:
         both = read_small(torch.cat([ne, cr.status])).tolist()
-        n, e, st_host = int(both[0]), int(both[1]), both[2:]
-        if int(st_host[_lib.ST_BAD_BYTES]) > 0:
-            raise ValueError(f"{int(st_host[_lib.ST_BAD_BYTES])} input bytes outside the alphabet ACGTN "
-                             "(the reference fails on these at gnn_utils.py:471)")
-        cr.n_nonzero = int(st_host[_lib.ST_NONZERO])
-        nb = int(st_host[_lib.ST_BRIDGES])
-        if nb > 0:
-            if nb > int(cr.bridges.shape[0]):
-                cr.n_bridges = -1
-                raise _NeedBridges(nb)            # the caller counts again with room for every bridge record
-            cr.n_bridges = nb
+        n, e = int(both[0]), int(both[1])
+        if _db_check_speculation(cr, both[2:]):
             return build_db(cr, normalise, create_all_kmers, edge_weight_threshold, keep_top_k)
     else:
         n, e = (int(x) for x in read_small(ne).tolist())
@@ -454,6 +501,53 @@ def kf_counts_many(node_codes: torch.Tensor, k: int, small_ks) -> List[KFCounts]
         kc.col_keep = _col_keep_from_host(host[lo:lo + d], dev)
         lo += d
     return out
+
+
+# counts matrices of the one-read flow are sized for 4^k rows before N is known: keep that for tables up to this size
+_FUSED_COUNTS_BYTES = 2 << 30
+
+
+def count_db_counts(stream: "ReadStream", k: int, small_ks, create_all_kmers=False):
+    """K1 + K1b + K2 + K3 counts of a single-GPU build with ONE device read: the De Bruijn assembly assumes a stream
+    without bridge records (build_db), the sub-k-mer counts are made for 4^k candidate rows with N read on the device
+    (gg_kf_counts_upto), and N, E, K1's status words and every column-presence flag come back together.
+    Returns (DBGraph, [KFCounts], CountResult).  Streams with bridge records, and tables too large to over-allocate,
+    take the step-by-step path: the first two are None and the count comes back for build_db (its ``n_bridges`` says how
+    many bridge records it holds; -1: more than it had room for, count again)."""
+    lib = _lib.load()
+    ds = [4**int(s) for s in small_ks]
+    cr = count_kp1mers(stream, k, sync=False)
+    if 4**k * sum(ds) > _FUSED_COUNTS_BYTES:
+        return None, None, cr
+    cr.n_bridges = 0
+    node_codes, code_to_node, edges, w64, w32, ne = _db_launch(cr, True, create_all_kmers, None)
+    dev = node_codes.device
+    n_max = 4**k
+    present = torch.empty(sum(ds), dtype=torch.int32, device=dev)
+    raw, lo = [], 0
+    for s_, d in zip(small_ks, ds):
+        counts = torch.empty((n_max, d), dtype=torch.uint8, device=dev)
+        sqnorm = torch.empty(n_max, dtype=torch.int32, device=dev)
+        with _stage(f"k3_counts_d{d}"):
+            check(lib.gg_kf_counts_upto(ptr(node_codes), n_max, ptr(ne), k, int(s_), ptr(counts), ptr(sqnorm),
+                                        C.c_void_p(present.data_ptr() + 4 * lo), _stream()), "gg_kf_counts_upto")
+        raw.append((int(s_), counts, sqnorm))
+        lo += d
+    both = read_small(torch.cat([ne, cr.status, present.view(torch.int64)]))
+    head = both[: 2 + _lib.ST_WORDS].tolist()
+    n, e = int(head[0]), int(head[1])
+    try:
+        if _db_check_speculation(cr, head[2:]):
+            return None, None, cr          # bridge records: assemble with them, step by step
+    except _NeedBridges:
+        return None, None, cr
+    host = both[2 + _lib.ST_WORDS:].numpy().view(np.int32).copy()
+    db = DBGraph(k, n, e, node_codes[:n], code_to_node, edges[:, :e].contiguous(), w32[:e], w64[:e])
+    kcs, lo = [], 0
+    for (s_, counts, sqnorm), d in zip(raw, ds):
+        kcs.append(KFCounts(k, s_, counts[:n], sqnorm[:n], _col_keep_from_host(host[lo:lo + d], dev)))
+        lo += d
+    return db, kcs, cr
 
 
 def kf_counts(node_codes: torch.Tensor, k: int, s: int) -> KFCounts:
@@ -772,6 +866,14 @@ def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max
     also totals the candidates of the whole matrix (class pairs x member counts, no atomics per pair), and when they
     exceed the cap -- the top-n will cut, from the class table -- the per-row counting pass turns itself off on the
     device: at threshold 0 it would expand nearly every class against nearly every node for nothing."""
+    return kf_stage_dedup_begin(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, top_n_cap)()
+
+
+def kf_stage_dedup_begin(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, iblock_begin=0,
+                         iblock_end=None, top_n_cap: Optional[int] = None):
+    """First half of kf_stage_dedup: the class kernels are queued and the class count is on its way to the host.
+    Returns the second half (scoring + counting) as a callable; work queued between the two calls runs while the host
+    waits for the class count."""
     lib = _lib.load()
     dev = counts.device
     n, d = int(counts.shape[0]), int(counts.shape[1])
@@ -786,29 +888,34 @@ def kf_stage_dedup(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max
     with _stage(f"k4_classes_d{d}"):
         check(lib.gg_kf_dedup_classes(ptr(counts), d, d, n, ptr(members), ptr(class_start), ptr(status), ptr(ws), wb, st),
               "gg_kf_dedup_classes")
-    n_classes, n_over = (int(x) for x in read_small(status).tolist())
-    if n_over:
-        raise GGError("duplicate-row KF path: a count above 15 does not fit the packed row key")
-    adj = torch.empty(max(int(lib.gg_kf_dedup_adj_words(n_classes)), 1), dtype=torch.int32, device=dev)
-    staged = StagedClasses.__new__(StagedClasses)
-    staged.counts, staged.sqnorm, staged.n, staged.ib0, staged.ib1 = counts, sqnorm, n, iblock_begin, iblock_end
-    staged.members, staged.class_start, staged.n_classes, staged.adj = members, class_start, n_classes, adj
-    staged.d = d
-    if top_n_cap:
-        total = torch.zeros(2, dtype=torch.int64, device=dev)
-        staged.score(_as_test(threshold), sq_max, _lib.KfDedupExtra(None, 0, 0, total.data_ptr(), 0, 0, 0, 0))
-        binding = (total[0:1] > int(top_n_cap)).to(torch.int64)
-        offsets = staged.count(iblock_begin, iblock_end, skip_flag=binding)
-    else:
-        staged.score(_as_test(threshold), sq_max)
-        offsets = staged.count(iblock_begin, iblock_end)
-    # the shard's edge count stays on the device: the caller reads it together with the other ranks' counts
-    StagedClasses.__init__(staged, counts, sqnorm, n, iblock_begin, iblock_end, members, class_start, n_classes, adj,
-                           offsets, None)
-    if top_n_cap:
-        staged.status4[1:2].copy_(binding, non_blocking=True)
-        staged.status4[3:4].copy_(total[0:1], non_blocking=True)
-    return staged
+    pending = PendingRead(status)
+
+    def finish() -> StagedClasses:
+        n_classes, n_over = (int(x) for x in pending.get().tolist())
+        if n_over:
+            raise GGError("duplicate-row KF path: a count above 15 does not fit the packed row key")
+        adj = torch.empty(max(int(lib.gg_kf_dedup_adj_words(n_classes)), 1), dtype=torch.int32, device=dev)
+        staged = StagedClasses.__new__(StagedClasses)
+        staged.counts, staged.sqnorm, staged.n, staged.ib0, staged.ib1 = counts, sqnorm, n, iblock_begin, iblock_end
+        staged.members, staged.class_start, staged.n_classes, staged.adj = members, class_start, n_classes, adj
+        staged.d = d
+        if top_n_cap:
+            total = torch.zeros(2, dtype=torch.int64, device=dev)
+            staged.score(_as_test(threshold), sq_max, _lib.KfDedupExtra(None, 0, 0, total.data_ptr(), 0, 0, 0, 0))
+            binding = (total[0:1] > int(top_n_cap)).to(torch.int64)
+            offsets = staged.count(iblock_begin, iblock_end, skip_flag=binding)
+        else:
+            staged.score(_as_test(threshold), sq_max)
+            offsets = staged.count(iblock_begin, iblock_end)
+        # the shard's edge count stays on the device: the caller reads it together with the other ranks' counts
+        StagedClasses.__init__(staged, counts, sqnorm, n, iblock_begin, iblock_end, members, class_start, n_classes, adj,
+                               offsets, None)
+        if top_n_cap:
+            staged.status4[1:2].copy_(binding, non_blocking=True)
+            staged.status4[3:4].copy_(total[0:1], non_blocking=True)
+        return staged
+
+    return finish
 
 
 def kf_finalize(staged, sqnorm, want_dot=False, out=None):
@@ -902,13 +1009,16 @@ class KFStage:
     iblock_end: int = 0
     row_sum: int = 0               # every row of counts sums to this (k - small_k + 1); 0: unknown
     class_hist: Optional[torch.Tensor] = None   # score classes of this rank's candidates, counted while scoring
+    finish_stage: object = None    # kf_stage(defer=True): second half of a duplicate-row staging, not yet run
 
 
 def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
              sq_max: Optional[int] = None, impl: str = "auto", iblock_begin=0, iblock_end=None,
-             row_sum: int = 0) -> KFStage:
+             row_sum: int = 0, defer: bool = False) -> KFStage:
     """K4: score this rank's row-block shard; the candidate count stays on the device (kf_resolve reads the counts of
-    any number of staged sets, on every rank, with one device read)."""
+    any number of staged sets, on every rank, with one device read).  ``defer``: a set that goes through duplicate-row
+    classes only queues its class kernels; ``st.finish_stage()`` (set when deferred) waits for the class count and queues
+    the rest -- whatever the caller queues in between runs while the host waits."""
     _require_cuda()
     n = int(counts.shape[0])
     if threshold < 0:
@@ -930,7 +1040,15 @@ def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         use_dedup = False
     if use_dedup:
         cap = int(n**2 * keep_top_k) if keep_top_k is not None else None
-        st.staged = kf_stage_dedup(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, top_n_cap=cap)
+        second_half = kf_stage_dedup_begin(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, top_n_cap=cap)
+        if defer:
+            def finish_stage():
+                st.staged = second_half()
+                st.finish_stage = None
+
+            st.finish_stage = finish_stage
+        else:
+            st.staged = second_half()
     else:
         # staging capacity: the global top-n budget is the natural first guess (a binding threshold stays below it,
         # a binding top-n overflows, and is then cut from the score-class table without these records)
@@ -963,6 +1081,51 @@ def kf_resolve(stages: List[KFStage], comm=None):
     for i, st in enumerate(live):
         st.staged.after_counts(table[comm.rank][4 * i: 4 * i + 4])
         st.per_rank = [int(table[r][4 * i]) for r in range(comm.world)]
+
+
+def kf_sets_overlapped(kcs, threshold: float, keep_top_k: Optional[float], impl: str = "auto", between=None) -> List["KFEdges"]:
+    """Every KF set of a single-GPU build with no idle device across the three size reads it needs (class count of the
+    duplicate-row sets, candidate counts of the record sets, edge counts of the duplicate-row sets): each read is a
+    PendingRead queued BEHIND work that does not depend on it, so the host collects it while the device is busy.
+    Order on the stream: scoring of the wide sets | class kernels of the narrow sets | placement of the wide sets |
+    class-pair scoring + counting of the narrow sets | ``between()`` (the caller's independent kernels: float features)
+    | placement of the narrow sets.  Same results as kf_stage + kf_resolve + kf_finish set by set."""
+    stages = [None] * len(kcs)
+
+    def stage(indices):
+        """Queue the scoring of these sets; returns (sets staged as records, their pending candidate counts)."""
+        for i in indices:
+            kc = kcs[i]
+            stages[i] = kf_stage(kc.counts, kc.sqnorm, threshold, keep_top_k, sq_max=kc.m * kc.m, impl=impl,
+                                 row_sum=kc.m, defer=True)
+        recs = [stages[i] for i in indices if stages[i].staged is not None]
+        return recs, (PendingRead(torch.cat([st.staged.status4 for st in recs])) if recs else None)
+
+    done = {}
+
+    def finish(group, pending):
+        if pending is None:
+            return
+        table = pending.get().tolist()
+        for j, st in enumerate(group):
+            st.staged.after_counts(table[4 * j: 4 * j + 4])
+            st.per_rank = [int(table[4 * j])]
+        for st in group:
+            done[id(st)] = kf_finish(st)
+
+    # wide sets first: their scoring kernels are the long ones, everything else queues up behind them
+    wide, p_wide = stage([i for i in range(len(kcs)) if int(kcs[i].counts.shape[1]) > 16])
+    small, p_small = stage([i for i in range(len(kcs)) if int(kcs[i].counts.shape[1]) <= 16])
+    narrow = [st for st in stages if st.finish_stage is not None]
+    finish(wide, p_wide)                   # placement + expansion of the wide sets queued
+    for st in narrow:                      # class counts are in: class-pair scoring + counting queued
+        st.finish_stage()
+    p_narrow = PendingRead(torch.cat([st.staged.status4 for st in narrow])) if narrow else None
+    finish(small, p_small)                 # narrow sets that went through the record path (few nodes)
+    if between is not None:
+        between()                          # the caller's kernels cover the read of the narrow sets' edge counts
+    finish(narrow, p_narrow)
+    return [done[id(st)] if id(st) in done else kf_finish(st) for st in stages]
 
 
 def kf_edges(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0, keep_top_k: Optional[float] = None,
@@ -1431,6 +1594,7 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
     if hasattr(comm, "begin_build"):
         comm.begin_build()
     stream = upload_reads(sequences)
+    fused_kcs = None
     if comm.world > 1:
         from . import dist
 
@@ -1446,18 +1610,32 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
                 capacity = int(exc.args[0])
         db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
     else:
-        # K1 and K2 back to back, one device read for both (build_db); the rare stream with more internal-N bridge
-        # records than the default room is counted again with room for all of them
-        cr = count_kp1mers(stream, k, sync=False)
-        try:
-            db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
-        except _NeedBridges as need:
-            cr = count_kp1mers(stream, k, bridge_capacity=int(need.args[0]))
-            db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
+        # K1, K2 and K3's counts back to back with one device read for all three (count_db_counts); streams with
+        # bridge records (internal N runs) take K1 and K2 with one read (build_db), and the rare stream with more of them
+        # than the default room is counted again with room for all
+        db, fused_kcs, cr = count_db_counts(stream, k, [int(s) for s in str(small_k).split(",")], create_all_kmers)
+        if db is None:
+            try:
+                if cr.n_bridges == -1 and int(read_small(cr.status)[_lib.ST_BRIDGES]) > int(cr.bridges.shape[0]):
+                    raise _NeedBridges(int(read_small(cr.status)[_lib.ST_BRIDGES]))
+                db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
+            except _NeedBridges as need:
+                cr = count_kp1mers(stream, k, bridge_capacity=int(need.args[0]))
+                db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
     if db.num_edges == 0:
         raise ValueError("no k-mer pairs in the input (the reference raises IndexError at utils.py:122)")
     small = [int(s) for s in str(small_k).split(",")]
-    kcs = kf_counts_many(db.node_codes, k, small)
+    kcs = fused_kcs if fused_kcs is not None else kf_counts_many(db.node_codes, k, small)
+    if with_kf and comm.world == 1 and kf_gather and kf_sink == "device" and kf_chunk_records is None:
+        # one GPU: the float features are queued between the placements, where they cover a size read
+        out = BuiltGraph(k, db, kcs, [])
+
+        def features():
+            if keep_features:
+                out.x = [kf_features_f32(kc) for kc in kcs]
+
+        out.kf = kf_sets_overlapped(kcs, edges_threshold, edges_keep_top_k, kf_impl, between=features)
+        return out
     xs = [kf_features_f32(kc) for kc in kcs] if keep_features else []
     out = BuiltGraph(k, db, kcs, xs)
     if with_kf:

@@ -112,8 +112,10 @@ __global__ void node_sort_input_kernel(const unsigned long long* node_key, int64
   }
 }
 
+// `deg` (nullable): kept out-edges of node i among the four (k+1)-mer bins of its code -- the input of the sort-free
+// edge ordering (edge_write_grouped_kernel)
 __global__ void node_rank_kernel(const uint64_t* key, const uint32_t* val, int64_t n_codes, int64_t* node_codes,
-                                 int32_t* code_to_node, int64_t* out_n) {
+                                 int32_t* code_to_node, int64_t* out_n, const uint8_t* kept, int32_t* deg) {
   GRID_STRIDE(i, n_codes) {
     const bool valid = key[i] != kInf;
     code_to_node[val[i]] = valid ? static_cast<int32_t>(i) : -1;
@@ -121,6 +123,7 @@ __global__ void node_rank_kernel(const uint64_t* key, const uint32_t* val, int64
       node_codes[i] = val[i];
       if (i + 1 == n_codes || key[i + 1] == kInf) *out_n = i + 1;
     }
+    if (deg) deg[i] = valid ? __popc(reinterpret_cast<const uint32_t*>(kept)[val[i]]) : 0;  // kept[] holds 0 / 1 bytes
   }
 }
 
@@ -157,6 +160,57 @@ __global__ void edge_write_kernel(Universe un, const uint64_t* key, const uint32
   }
 }
 
+// Edge order without a sort (streams without bridge records): an edge is a kept (k+1)-mer bin 4u + b, so a source has
+// at most four of them.  PyG order = sources in node order, a source's edges by first occurrence of the pair: node i
+// writes its <= 4 edges, ordered by position with a 4-element network, at the exclusive prefix sum of the degrees.
+__global__ void edge_write_grouped_kernel(Universe un, const uint8_t* kept, const int64_t* node_codes,
+                                          const int64_t* out_n, const int32_t* offset,
+                                          const unsigned long long* out_count, const int32_t* code_to_node,
+                                          int normalise, int64_t n_codes, int64_t* src, int64_t* dst, double* w64,
+                                          float* w32, int64_t* out_e) {
+  const int64_t n_nodes = *out_n;
+  GRID_STRIDE(i, n_codes) {
+    if (i >= n_nodes) continue;
+    const uint32_t u = static_cast<uint32_t>(node_codes[i]);
+    uint64_t pos[4];
+    int b[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int x = 0; x < 4; ++x) pos[x] = kept[4ll * u + x] ? un.first_pos[4ll * u + x] : kInf;
+#define GG_CSWAP(x, y)                        \
+  if (pos[y] < pos[x]) {                      \
+    const uint64_t tp = pos[x];               \
+    pos[x] = pos[y];                          \
+    pos[y] = tp;                              \
+    const int tb = b[x];                      \
+    b[x] = b[y];                              \
+    b[y] = tb;                                \
+  }
+    GG_CSWAP(0, 1) GG_CSWAP(2, 3) GG_CSWAP(0, 2) GG_CSWAP(1, 3) GG_CSWAP(1, 2)
+#undef GG_CSWAP
+    const int64_t at = offset[i];
+    const unsigned long long tot = out_count[u];
+    int n_out = 0;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      if (pos[x] == kInf) continue;
+      const int64_t e = 4ll * u + b[x];
+      const double w = edge_weight(un.hist[e], tot, normalise);
+      src[at + n_out] = i;
+      dst[at + n_out] = code_to_node[e & ((1ll << (2 * un.k)) - 1)];
+      if (w64) w64[at + n_out] = w;
+      if (w32) w32[at + n_out] = static_cast<float>(w);
+      ++n_out;
+    }
+    if (i + 1 == n_nodes) *out_e = at + n_out;
+  }
+}
+
+size_t degree_scan_temp_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr), n);
+  return bytes;
+}
+
 inline int grid_for(int64_t n) {
   int64_t g = (n + 255) / 256;
   const int64_t cap = static_cast<int64_t>(gg::sm_count()) * 8;
@@ -184,6 +238,7 @@ struct Layout {
   uint32_t *val_in, *val_out;
   uint64_t *b_key_in, *b_key, *b_pos_in, *b_pos_sorted, *b_pos;
   uint32_t* b_cnt;
+  int32_t *deg, *deg_offset;
   void* cub_temp;
   size_t cub_bytes;
   size_t total;
@@ -208,7 +263,12 @@ Layout carve(void* ws, int k, int64_t n_bridges) {
   l.b_pos_sorted = c.take<uint64_t>(nb);
   l.b_pos = c.take<uint64_t>(nb);
   l.b_cnt = c.take<uint32_t>(nb);
-  l.cub_bytes = sort_temp_bytes(uni);
+  l.deg = c.take<int32_t>(n_codes);
+  l.deg_offset = c.take<int32_t>(n_codes);
+  {
+    const size_t a = sort_temp_bytes(uni), b = degree_scan_temp_bytes(n_codes);
+    l.cub_bytes = a > b ? a : b;
+  }
   l.cub_temp = c.take<char>(l.cub_bytes);
   l.total = c.used();
   return l;
@@ -267,7 +327,18 @@ extern "C" int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, cons
     GG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(l.cub_temp, tb, l.key_in, l.key_out, l.val_in, l.val_out, n_codes,
                                                   0, node_bits, s));
   }
-  node_rank_kernel<<<grid_for(n_codes), 256, 0, s>>>(l.key_out, l.val_out, n_codes, node_codes, code_to_node, out_ne);
+  const bool grouped = n_bridges == 0;  // every edge is a (k+1)-mer bin: order them per source, no sort
+  node_rank_kernel<<<grid_for(n_codes), 256, 0, s>>>(l.key_out, l.val_out, n_codes, node_codes, code_to_node, out_ne,
+                                                     l.kept, grouped ? l.deg : nullptr);
+  if (grouped) {
+    size_t tb = l.cub_bytes;
+    GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(l.cub_temp, tb, l.deg, l.deg_offset, static_cast<int>(n_codes), s));
+    edge_write_grouped_kernel<<<grid_for(n_codes), 256, 0, s>>>(un, l.kept, node_codes, out_ne, l.deg_offset, l.out_count,
+                                                                code_to_node, normalise, n_codes, edge_src, edge_dst,
+                                                                weight64, weight32, out_ne + 1);
+    GG_CUDA_CHECK(cudaGetLastError());
+    return GG_OK;
+  }
 
   edge_sort_input_kernel<<<grid_for(uni), 256, 0, s>>>(un, l.kept, code_to_node, pos_bits, l.key_in, l.val_in);
   {

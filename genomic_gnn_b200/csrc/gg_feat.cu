@@ -8,10 +8,15 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) counts_kernel(const int64_t* node_codes, int64_t n, int k, int s,
-                                                     uint8_t* counts, int32_t* sqnorm, uint32_t* col_present) {
+// n_dev (nullable): the number of rows, still on the device (at most n; rows beyond it keep their zeros)
+__global__ void __launch_bounds__(256) counts_kernel(const int64_t* node_codes, int64_t n, const int64_t* n_dev, int k,
+                                                     int s, uint8_t* counts, int32_t* sqnorm, uint32_t* col_present) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
+  if (n_dev != nullptr && i >= *n_dev) {
+    sqnorm[i] = 0;
+    return;
+  }
   const uint64_t code = static_cast<uint64_t>(node_codes[i]);
   const int64_t d = 1ll << (2 * s);
   const uint64_t smask = static_cast<uint64_t>(d - 1);
@@ -65,8 +70,8 @@ __global__ void __launch_bounds__(256) features_all_kernel(const uint32_t* count
 
 }  // namespace
 
-extern "C" int gg_kf_counts(const int64_t* node_codes, int64_t n, int k, int s, uint8_t* counts, int32_t* sqnorm,
-                            uint32_t* col_present, gg_stream_t st) {
+static int kf_counts_impl(const int64_t* node_codes, int64_t n, const int64_t* n_dev, int k, int s, uint8_t* counts,
+                          int32_t* sqnorm, uint32_t* col_present, gg_stream_t st) {
   GG_REQUIRE(k >= 1 && k <= 31, GG_ERR_K, "k outside [1, 31]");
   GG_REQUIRE(s >= 1 && s <= k && s <= 8, GG_ERR_K, "small_k outside [1, min(k, 8)]");
   GG_REQUIRE(k - s + 1 <= 15, GG_ERR_K, "k - small_k + 1 must be <= 15 (uint8 counts, uint16 dmin)");
@@ -76,10 +81,21 @@ extern "C" int gg_kf_counts(const int64_t* node_codes, int64_t n, int k, int s, 
   GG_CUDA_CHECK(cudaMemsetAsync(col_present, 0, d * sizeof(uint32_t), stream));
   if (n == 0) return GG_OK;
   GG_CUDA_CHECK(cudaMemsetAsync(counts, 0, static_cast<size_t>(n) * d, stream));
-  counts_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(node_codes, n, k, s, counts, sqnorm,
+  counts_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(node_codes, n, n_dev, k, s, counts, sqnorm,
                                                                             col_present);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
+}
+
+extern "C" int gg_kf_counts(const int64_t* node_codes, int64_t n, int k, int s, uint8_t* counts, int32_t* sqnorm,
+                            uint32_t* col_present, gg_stream_t st) {
+  return kf_counts_impl(node_codes, n, nullptr, k, s, counts, sqnorm, col_present, st);
+}
+
+extern "C" int gg_kf_counts_upto(const int64_t* node_codes, int64_t n_max, const int64_t* n_dev, int k, int s,
+                                 uint8_t* counts, int32_t* sqnorm, uint32_t* col_present, gg_stream_t st) {
+  GG_REQUIRE(n_dev != nullptr, GG_ERR_ARG, "null row count");
+  return kf_counts_impl(node_codes, n_max, n_dev, k, s, counts, sqnorm, col_present, st);
 }
 
 extern "C" int gg_kf_features_f32(const uint8_t* counts, int64_t n, int d, const int32_t* col_keep, int d_keep,

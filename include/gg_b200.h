@@ -157,6 +157,11 @@ GG_API int gg_db_build(const uint32_t* hist, const uint64_t* first_pos, const gg
  * ------------------------------------------------------------------------ */
 GG_API int gg_kf_counts(const int64_t* node_codes, int64_t n, int k, int s, uint8_t* counts, int32_t* sqnorm,
                  uint32_t* col_present, gg_stream_t st);
+/* The same with the number of nodes still on the device (*n_dev <= n_max, e.g. out_ne[0] of gg_db_build queued just
+ * before): buffers are sized for n_max rows, rows [*n_dev, n_max) of counts / sqnorm are zero.  Lets a build read N, E,
+ * K1's status words and the column-presence flags in ONE device read. */
+GG_API int gg_kf_counts_upto(const int64_t* node_codes, int64_t n_max, const int64_t* n_dev, int k, int s, uint8_t* counts,
+                      int32_t* sqnorm, uint32_t* col_present, gg_stream_t st);
 GG_API int gg_kf_features_f32(const uint8_t* counts, int64_t n, int d, const int32_t* col_keep, int d_keep,
                        const float* value_lut, float* x, gg_stream_t st);
 

@@ -31,3 +31,9 @@ for e in evs[1:]:
 print("gaps > 8 us:", len(gaps), "total", sum(g[0] for g in gaps) / 1e3, "ms")
 for g in sorted(gaps, reverse=True)[:25]:
     print(f"{g[0]:7.1f} us at {g[1]:.3f} ms  after {g[2]}  -> before {g[3]}")
+if len(sys.argv) > 1:   # full timeline: start (ms), duration (us), gap before (us), name
+    with open(sys.argv[1], "w") as fh:
+        prev = evs[0].time_range.start
+        for e in evs:
+            fh.write(f"{(e.time_range.start - t0) / 1e3:8.3f} {e.time_range.end - e.time_range.start:8.1f} {e.time_range.start - prev:7.1f}  {e.name[:90]}\n")
+            prev = max(prev, e.time_range.end)
