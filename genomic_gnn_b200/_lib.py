@@ -104,6 +104,7 @@ SIGNATURES = {
     "gg_spmm_csr_f32": (_I32, [_P, _P, _P, _I64, _P, _I32, _P, _P]),
     "gg_rw_pairs": (_I32, [_P, _P, _P, _I64, _P, _I64, _I32, _I32, _I32, _DBL, _DBL, C.c_uint64, _I32, _P, _P, _P, _P, _I64,
                            _P, _P]),
+    "gg_knn_set_impl": (_I32, [_I32]),
     "gg_knn_count": (_I32, [_P, _I32, _I64, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "gg_knn_plan_workspace_bytes": (_SZ, [_I64]),
     "gg_knn_plan": (_I32, [_I64, _I64, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),

@@ -1479,8 +1479,11 @@ def knn_row_shard(n: int, world: int, rank: int):
     return min(lo, n), hi
 
 
+KNN_IMPL = {"auto": 0, "mma": 1, "tcgen05": 2}
+
+
 def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance: str = "L2", hist_mode: int = -1,
-                 rows=None, qmax_reduce=None, comm=None, gather: bool = True) -> KnnEdges:
+                 rows=None, qmax_reduce=None, comm=None, gather: bool = True, impl: str = "auto") -> KnnEdges:
     """Exact per-row k-nearest-neighbour KF edges: what kf_faiss_to_edge_index_weight (gnn_utils.py:122-237)
     approximates through FAISS.  Two passes over the Gram matrix (gg_knn_count / gg_knn_write), no sort by value.
 
@@ -1488,11 +1491,16 @@ def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance
     knn_row_shard() of the rows against all columns, the ranks agree on the "L2" normaliser (max over ranks of one
     integer) and, unless ``gather=False``, all-gather their edge lists in rank order = the single-GPU result.
     ``rows=(lo, hi)`` computes one shard explicitly (``qmax_reduce``: callable mapping the shard's integer
-    maximum distance to the global one).  ``hist_mode`` forces where pass 1 accumulates (tests): 0 global atomics,
-    1 / 2 shared memory 16- / 32-bit."""
+    maximum distance to the global one).  ``impl``: "auto" = both Gram passes on the tcgen05 CTA-pair kernel for rows
+    of 128..1024 bytes (small_k >= 4), the mma.sync kernel otherwise; "mma" / "tcgen05" force one (tests).
+    ``hist_mode`` forces where pass 1 of the mma.sync kernel accumulates (tests): 0 global atomics, 1 / 2 shared memory
+    16- / 32-bit."""
     if distance not in KNN_METRICS:
         raise ValueError("distance must be 'IP' or 'L2'")
+    if impl not in KNN_IMPL:
+        raise ValueError("impl must be 'auto', 'mma' or 'tcgen05'")
     lib = _lib.load()
+    check(lib.gg_knn_set_impl(KNN_IMPL[impl]), "gg_knn_set_impl")
     dev = counts.device
     n, pitch = int(counts.shape[0]), int(counts.shape[1])
     empty = KnnEdges(torch.zeros((2, 0), dtype=torch.int64, device=dev), torch.zeros(0, dtype=torch.float32, device=dev),

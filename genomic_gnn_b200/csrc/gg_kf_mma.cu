@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include "gg_kf_emit.cuh"
+#include "gg_knn_tc.cuh"
 
 namespace ggkf {
 namespace {
@@ -1020,6 +1021,374 @@ __global__ void __launch_bounds__(128, 1) tensor_probe_kernel(int iters, int n_k
   if (tid == 0 && bars->error) *error_flag = 1;
 }
 
+
+// ======================================================================================
+// Per-row kNN KF edges (the faiss_ann mode, reference gnn_utils.py:122-237) on the same CTA-pair Gram: the FULL matrix
+// this time -- every row against every column -- because a row's neighbours lie on both sides of the diagonal.
+// A CTA pair owns strip pairs of 256 rows (A resident) and streams all columns past them; a thread of an epilogue
+// group is one row, as above.  Ranks come from the host table rank_tab[class of sq_j][dot] (gg_knn.cu).
+//   pass 1  per-row rank histograms in shared memory.  Only non-zero dots cost per-pair work (1.5 % of the pairs of
+//           1024-column rows): the zero-dot members of a column class are its size minus the row's non-zero count
+//           for that class, added when the strip is finished.  All three epilogue groups, any order.
+//   pass 2  the selected pairs of every row in COLUMN order (ties of the cut rank are taken in that order while the
+//           row's budget lasts): ONE epilogue group takes every half tile in sequence, so a row's running position is
+//           a register of its thread -- the group needs ~1,000 cycles per half tile, the tensor pipe 2,100 (D = 1024).
+//           Zero-dot columns are selected through per-chunk class masks built once per half tile.
+// ======================================================================================
+constexpr uint32_t kKnnNoRank = 0xFFFFu;
+
+__device__ __forceinline__ void bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kThreads, 1)
+knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_bstages, int* error_flag, Geom g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kKBlock = 128;
+  constexpr int kStageBytes = kTileM * kKBlock;
+  const int n_kblocks = g.n_kblocks;
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
+  uint8_t* panel = smem_b + static_cast<size_t>(n_bstages) * kStageBytes;         // [kEpiGroups][kBlock] column classes
+  PairStage* stages = reinterpret_cast<PairStage*>(panel + kEpiGroups * kBlock);
+  Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
+  const int tstride = a.dot_max + 1;
+  const int tab_elems = (a.n_sq + 1) * tstride;                                    // + an all-"never" class
+  uint16_t* rank_tab = reinterpret_cast<uint16_t*>(bars + 1);
+  uint32_t* colcount = reinterpret_cast<uint32_t*>(rank_tab + ((tab_elems + 1) & ~1));  // [kKnnTcMaxSq]
+  uint32_t* clsmask = colcount + kKnnTcMaxSq;                                      // pass 2: [2][4][kKnnTcMaxSq]
+  uint32_t* nz = clsmask + 2 * 4 * kKnnTcMaxSq;                                    // pass 1: [128][n_sq]
+  uint32_t* shist = nz + kTileM * a.n_sq;                                          // pass 1: [128][hwords]
+  const int hwords = a.hist16 ? (a.n_ranks + 1) >> 1 : a.n_ranks;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  for (int i = tid; i < tab_elems; i += kThreads)
+    rank_tab[i] = i < a.n_sq * tstride ? a.rank_tab[i] : static_cast<uint16_t>(kKnnNoRank);
+  if (tid < kKnnTcMaxSq) colcount[tid] = 0u;
+  if (PASS == 1) {
+    for (int i = tid; i < kTileM * (a.n_sq + hwords); i += kThreads) nz[i] = 0u;
+  }
+  if (tid == 0) {
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    for (int i = 0; i < n_bstages; ++i) {
+      mbar_init(&bars->b_full[i], 1);
+      mbar_init(&bars->b_empty[i], 1);
+    }
+    for (int i = 0; i < kPairAccStages; ++i) {
+      mbar_init(&bars->acc_full[i], 1);
+      mbar_init(&bars->acc_empty[i], 2 * 2 * (kGroupThreads / 32));  // 2 CTAs x 2 half tiles x 4 warps
+    }
+    bars->error = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PASS == 1) {  // columns per class (real columns only): a warp counts 32 columns per step with one ballot per class
+    uint32_t mine = 0;
+    for (long long j0 = static_cast<long long>(warp) * 32; j0 < a.n; j0 += (kThreads / 32) * 32) {
+      const long long j = j0 + lane;
+      uint32_t cls = 0xFFu;
+      if (j < a.n) {
+        const int sq = __ldg(a.sqnorm + j);
+        if (sq >= 0 && sq <= a.sq_max) cls = __ldg(a.sqid + sq);
+      }
+      for (int c = 0; c < a.n_sq; ++c) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cls == static_cast<uint32_t>(c));
+        if (lane == c) mine += __popc(m);
+      }
+    }
+    if (lane < a.n_sq && mine) atomicAdd(colcount + lane, mine);
+    __syncthreads();
+  }
+  cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  if (bars->tmem_base != 0) {
+    if (tid == 0) *error_flag = 2;
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0;
+
+  const int n_pairs_grid = static_cast<int>(gridDim.x / 2), pair_id = static_cast<int>(blockIdx.x / 2);
+  const int n_sp = static_cast<int>((a.row_end - a.row_begin + 2 * kTileM - 1) / (2 * kTileM));  // strip pairs of the shard
+  const int n_ct = static_cast<int>((a.n + kPairTileN - 1) / kPairTileN);                        // 256-column tiles
+
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer (both CTAs; transactions complete on the leader's barriers) ==========
+    if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    const uint32_t a_full_leader = map_to_cta(smem_u32(&bars->a_full), 0);
+    uint32_t a_round = 0, stage = 0, round = 0;
+    for (int sp = pair_id; sp < n_sp; sp += n_pairs_grid) {
+      if (a_round > 0) mbar_wait_warp(&bars->a_empty, (a_round - 1) & 1, &bars->error);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(&bars->a_full, 2u * static_cast<uint32_t>(n_kblocks) * kStageBytes);
+        const int row = static_cast<int>(a.row_begin) + (2 * sp + static_cast<int>(rank)) * kTileM;
+        for (int kb = 0; kb < n_kblocks; ++kb)
+          tma_load_2d_pair(smem_a + static_cast<size_t>(kb) * kStageBytes, &tmap, a_full_leader, kb * kKBlock, row);
+      }
+      __syncwarp();
+      ++a_round;
+      for (int ct = 0; ct < n_ct; ++ct) {
+        const int col = ct * kPairTileN + static_cast<int>(rank) * kTileM;  // this CTA's half of B
+        for (int kb = 0; kb < n_kblocks; ++kb) {
+          if (round > 0) mbar_wait_warp(&bars->b_empty[stage], (round - 1) & 1, &bars->error);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(&bars->b_full[stage], 2u * kStageBytes);
+            tma_load_2d_pair(smem_b + static_cast<size_t>(stage) * kStageBytes, &tmap,
+                             map_to_cta(smem_u32(&bars->b_full[stage]), 0), kb * kKBlock, col);
+          }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(n_bstages)) {
+            stage = 0;
+            ++round;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      uint32_t a_round = 0, stage = 0, round = 0, acc = 0, acc_round = 0;
+      const uint32_t desc_hi = g.desc_hi;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(smem_a));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b));
+      for (int sp = pair_id; sp < n_sp; sp += n_pairs_grid) {
+        if (a_round > 0 && elect_one()) tc_commit_pair(&bars->a_empty);
+        __syncwarp();
+        mbar_wait_warp(&bars->a_full, a_round & 1, &bars->error);
+        tc_fence_after();
+        ++a_round;
+        for (int ct = 0; ct < n_ct; ++ct) {
+          if (acc_round > 0) mbar_wait_warp(&bars->acc_empty[acc], (acc_round - 1) & 1, &bars->error);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * kPairTileN;
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            mbar_wait_warp(&bars->b_full[stage], round & 1, &bars->error);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(kb) * (kStageBytes >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k4 = 0; k4 < kKBlock / kUmmaK; ++k4) {
+                const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k4 * (kUmmaK >> 4));
+                const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k4 * (kUmmaK >> 4));
+                tc_mma_i8_pair(tmem_d, da, db, kIdescPair, (kb | k4) != 0);
+              }
+              tc_commit_pair(&bars->b_empty[stage]);
+              if (kb == n_kblocks - 1) tc_commit_pair(&bars->acc_full[acc]);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(n_bstages)) {
+              stage = 0;
+              ++round;
+            }
+          }
+          if (++acc == kPairAccStages) {
+            acc = 0;
+            ++acc_round;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    PairStage& ws = stages[warp];
+    const int group = warp / 4;
+    const int gt = tid % kGroupThreads;  // row of the strip = TMEM lane
+    uint8_t* my_panel = panel + group * kBlock;
+    const bool active = PASS == 1 || group == 0;  // pass 2: one group, every half tile in column order
+    uint32_t tile_seq = 0;
+    for (int sp = pair_id; sp < n_sp && active; sp += n_pairs_grid) {
+      const long long row = a.row_begin + static_cast<long long>(2 * sp + static_cast<int>(rank)) * kTileM + gt;
+      const bool row_ok = row < a.row_end;
+      const long long loc = row - a.row_begin;
+      // pass 2: the row's plan and running state
+      int cut = -1, budget = 0, seen = 0;
+      long long out_at = 0;
+      uint32_t zsel = 0, ztie = 0;  // classes whose zero-dot columns rank above / at the cut
+      if (PASS == 2 && row_ok) {
+        cut = __ldg(a.cut + loc);
+        budget = __ldg(a.tie_left + loc);
+        out_at = __ldg(a.row_off + loc);
+        for (int c = 0; c < a.n_sq; ++c) {
+          const int r0 = rank_tab[c * tstride];
+          zsel |= static_cast<uint32_t>(r0 < cut) << c;   // 0xFFFF is above every cut
+          ztie |= static_cast<uint32_t>(r0 == cut) << c;
+        }
+      }
+      int panel_block = -1;
+      for (int ct = 0; ct < n_ct; ++ct, ++tile_seq) {
+        const uint32_t acc = tile_seq % kPairAccStages;
+        const uint32_t acc_parity = (tile_seq / kPairAccStages) & 1;
+        for (int half = 0; half < 2; ++half) {
+          if (PASS == 1 && (2 * tile_seq + half) % kEpiGroups != static_cast<uint32_t>(group)) continue;
+          const long long c0 = static_cast<long long>(ct) * kPairTileN + half * kTile;  // first column of the half tile
+          const int jb = static_cast<int>(c0 / kBlock);
+          if (jb != panel_block && c0 < a.n) {  // column classes of the next 1024 columns (uniform per group)
+            bar_sync(2 + group, kGroupThreads);
+            for (int c = gt; c < kBlock; c += kGroupThreads) {
+              const long long j = static_cast<long long>(jb) * kBlock + c;
+              uint32_t cls = 0xFFu;
+              if (j < a.n) {
+                const int sq = __ldg(a.sqnorm + j);
+                if (sq >= 0 && sq <= a.sq_max) cls = __ldg(a.sqid + sq);
+              }
+              my_panel[c] = static_cast<uint8_t>(cls == 0xFFu ? a.n_sq : cls);
+            }
+            bar_sync(2 + group, kGroupThreads);
+            panel_block = jb;
+          }
+          const int pc0 = static_cast<int>(c0 - static_cast<long long>(jb) * kBlock);  // panel index of the half tile
+          uint32_t* my_masks = clsmask + ((2 * tile_seq + half) & 1) * 4 * kKnnTcMaxSq;
+          if (PASS == 2 && c0 < a.n) {
+            // class masks of the four 32-column chunks: warp q of the group makes chunk q
+            const int q = warp & 3;
+            const uint32_t cls = my_panel[pc0 + q * 32 + lane];
+            uint32_t mine = 0;
+            for (int c = 0; c < a.n_sq; ++c) {
+              const uint32_t m = __ballot_sync(0xFFFFFFFFu, cls == static_cast<uint32_t>(c));
+              if (lane == c) mine = m;
+            }
+            my_masks[q * kKnnTcMaxSq + lane] = mine;
+            bar_sync(2 + group, kGroupThreads);
+          }
+          mbar_wait(&bars->acc_full[acc], acc_parity, &bars->error);
+          tc_fence_after();
+          if (c0 < a.n) {
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * kPairTileN + half * kTile;
+#pragma unroll 1
+            for (int cc = 0; cc < kTile; cc += 32) {
+              uint32_t v[32];
+              tc_ld32(taddr + cc, v);
+              uint32_t nzmask = 0;
+#pragma unroll
+              for (int b = 0; b < 32; ++b) nzmask |= static_cast<uint32_t>(v[b] != 0u) << b;
+              if (!row_ok) nzmask = 0;
+              const bool any_nz = __any_sync(0xFFFFFFFFu, nzmask != 0u);
+              if (any_nz) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  ws.dotw[j][lane] = v[4 * j] | (v[4 * j + 1] << 8) | (v[4 * j + 2] << 16) | (v[4 * j + 3] << 24);
+              }
+              const long long cbase = c0 + cc;            // global column of bit 0
+              const long long self = row - cbase;          // bit of the row's own column, if inside the chunk
+              if (PASS == 1) {
+                for (uint32_t m2 = nzmask; m2; m2 &= m2 - 1) {
+                  const int b = __ffs(m2) - 1;
+                  const uint32_t cls = my_panel[pc0 + cc + b];
+                  if (cls >= static_cast<uint32_t>(a.n_sq)) continue;
+                  atomicAdd(nz + gt * a.n_sq + cls, 1u);   // the self pair too: it is not a zero-dot column
+                  if (b == self) continue;
+                  const uint32_t dot = stage_get_dot(ws, b, lane);
+                  const uint32_t r = rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
+                  if (r == kKnnNoRank) continue;
+                  if (a.hist16) atomicAdd(shist + gt * hwords + (r >> 1), 1u << ((r & 1u) * 16));
+                  else atomicAdd(shist + gt * hwords + r, 1u);
+                }
+              } else {
+                uint32_t sel = 0, tie = 0;
+                for (uint32_t zm = zsel; zm; zm &= zm - 1) sel |= my_masks[(cc >> 5) * kKnnTcMaxSq + __ffs(zm) - 1];
+                for (uint32_t zm = ztie; zm; zm &= zm - 1) tie |= my_masks[(cc >> 5) * kKnnTcMaxSq + __ffs(zm) - 1];
+                sel &= ~nzmask;
+                tie &= ~nzmask;
+                for (uint32_t m2 = nzmask; m2; m2 &= m2 - 1) {
+                  const int b = __ffs(m2) - 1;
+                  const uint32_t cls = my_panel[pc0 + cc + b];
+                  const uint32_t dot = stage_get_dot(ws, b, lane);
+                  const int r = rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
+                  sel |= static_cast<uint32_t>(r < cut) << b;
+                  tie |= static_cast<uint32_t>(r == cut) << b;
+                }
+                if (self >= 0 && self < 32) {
+                  sel &= ~(1u << self);
+                  tie &= ~(1u << self);
+                }
+                if (tie) {  // members of the cut rank are taken in column order while the row's budget lasts
+                  const int t = __popc(tie), room = budget - seen;
+                  seen += t;
+                  if (room <= 0) {
+                    tie = 0;
+                  } else {
+                    for (int x = t - room; x > 0; --x) tie &= ~(0x80000000u >> __clz(tie));
+                  }
+                }
+                const uint32_t fin = sel | tie;
+                for (uint32_t m2 = fin; m2; m2 &= m2 - 1) {
+                  const int b = __ffs(m2) - 1;
+                  const uint32_t cls = my_panel[pc0 + cc + b];
+                  const uint32_t dot = ((nzmask >> b) & 1u) ? stage_get_dot(ws, b, lane) : 0u;
+                  const uint32_t r = rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
+                  a.recs[out_at++] = static_cast<uint64_t>(cbase + b) | static_cast<uint64_t>(dot) << 32 |
+                                     static_cast<uint64_t>(r) << 48;
+                }
+              }
+              __syncwarp();  // the staged dots are rewritten by the next chunk
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->acc_empty[acc]), 0));
+        }
+      }
+      if (PASS == 1) {
+        // the strip is finished: zero-dot members of every class, then the rows go out and the tables are cleared
+        bar_sync(1, kEpiThreads);
+        if (tid < kTileM && row_ok) {   // group 0: thread <-> row
+          // an all-zero row meets itself with dot 0: that column is not a neighbour
+          const int sq_row = __ldg(a.sqnorm + row);
+          const uint32_t own = sq_row == 0 ? __ldg(a.sqid) : 0xFFu;
+          for (int c = 0; c < a.n_sq; ++c) {
+            const uint32_t r0 = rank_tab[c * tstride];
+            if (r0 == kKnnNoRank) continue;
+            const uint32_t z = colcount[c] - nz[tid * a.n_sq + c] - (static_cast<uint32_t>(c) == own ? 1u : 0u);
+            if (a.hist16) shist[tid * hwords + (r0 >> 1)] += z << ((r0 & 1u) * 16);
+            else shist[tid * hwords + r0] += z;
+          }
+        }
+        bar_sync(1, kEpiThreads);
+        {
+          const long long first = a.row_begin + static_cast<long long>(2 * sp + static_cast<int>(rank)) * kTileM;
+          const long long left = a.row_end - first;
+          const int rows_here = left >= kTileM ? kTileM : (left > 0 ? static_cast<int>(left) : 0);
+          uint32_t* out = a.hist + (first - a.row_begin) * a.n_ranks;
+          for (int i = tid; i < rows_here * a.n_ranks; i += kEpiThreads) {
+            const int r = i / a.n_ranks, j = i - r * a.n_ranks;
+            out[i] = a.hist16 ? (shist[r * hwords + (j >> 1)] >> ((j & 1) * 16)) & 0xFFFFu : shist[r * hwords + j];
+          }
+        }
+        bar_sync(1, kEpiThreads);
+        for (int i = tid; i < kTileM * (a.n_sq + hwords); i += kEpiThreads) nz[i] = 0u;
+        bar_sync(1, kEpiThreads);
+      }
+    }
+    if (!active) {
+      // pass 2, groups 1 and 2: nothing to score; their share of the acc_empty arrivals is made by group 0 (it takes both
+      // halves of every tile)
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading the pair's operands
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+  if (tid == 0 && bars->error) *error_flag = 1;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1161,6 +1530,96 @@ int emit_tcgen05_pair(const KfArgs& a, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, args, n_bstages, total_units, error_flag, g));
+  return GG_OK;
+}
+
+
+// ---- per-row kNN on the CTA-pair Gram ------------------------------------------------------------------
+__device__ int g_knn_tc_error;  // set before a trap (mbarrier time-out, TMEM base): the launch then fails as a whole
+
+static size_t knn_tc_fixed_smem(const KnnTcArgs& a, int pass) {
+  const int n_kblocks = a.d / kMaxKBlock;
+  const int tab_elems = (a.n_sq + 1) * (a.dot_max + 1);
+  const int hwords = a.hist16 ? (a.n_ranks + 1) / 2 : a.n_ranks;
+  size_t bytes = static_cast<size_t>(n_kblocks) * kTileM * kMaxKBlock + kEpiGroups * kBlock +
+                 (kEpiThreads / 32) * sizeof(PairStage) + sizeof(Barriers) + 2 * static_cast<size_t>((tab_elems + 1) & ~1) +
+                 (kKnnTcMaxSq + 2 * 4 * kKnnTcMaxSq) * sizeof(uint32_t) + 1024;
+  if (pass == 1) bytes += static_cast<size_t>(kTileM) * (a.n_sq + hwords) * sizeof(uint32_t);
+  return bytes;
+}
+
+bool knn_tc_eligible(int pitch, long long n, int n_sq, int dot_max, int n_ranks, int pass) {
+  if (pitch % kMaxKBlock != 0 || pitch < kMaxKBlock || pitch > kMaxD) return false;
+  if (n_sq < 1 || n_sq > kKnnTcMaxSq || dot_max > 255 || n >= (1ll << 31)) return false;
+  if (encode_tiled() == nullptr) return false;
+  KnnTcArgs a{};
+  a.d = pitch;
+  a.n = n;
+  a.n_sq = n_sq;
+  a.dot_max = dot_max;
+  a.n_ranks = n_ranks;
+  a.hist16 = n <= 65536 ? 1 : 0;
+  int dev = 0, max_smem = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+    return false;
+  // at least three B stages: with fewer the tensor pipe waits for every TMA round trip
+  return knn_tc_fixed_smem(a, pass) + 3 * static_cast<size_t>(kTileM) * kMaxKBlock <= static_cast<size_t>(max_smem);
+}
+
+int knn_tc_launch(const KnnTcArgs& a, int pass, int* error_flag, cudaStream_t s) {
+  if (error_flag == nullptr) GG_CUDA_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&error_flag), g_knn_tc_error));
+  GG_REQUIRE(pass == 1 || pass == 2, GG_ERR_ARG, "pass must be 1 or 2");
+  GG_REQUIRE(a.d % kMaxKBlock == 0 && a.d >= kMaxKBlock && a.d <= kMaxD, GG_ERR_ARG,
+             "tcgen05 kNN kernel needs a row pitch that is a multiple of 128 up to 1024 bytes");
+  GG_REQUIRE(a.row_begin % kTileM == 0 && a.row_begin < a.row_end && a.row_end <= a.n, GG_ERR_ARG, "bad row shard");
+  EncodeTiledFn encode = encode_tiled();
+  GG_REQUIRE(encode != nullptr, GG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  Geom g;
+  g.kb_bytes = kMaxKBlock;
+  g.n_kblocks = a.d / g.kb_bytes;
+  g.stage_bytes = kTileM * g.kb_bytes;
+  g.mma_per_kb = g.kb_bytes / kUmmaK;
+  g.desc_hi = static_cast<uint32_t>((8 * g.kb_bytes) >> 4) | (1u << 14) | (2u << 29);
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(a.d), static_cast<cuuint64_t>(a.n)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(a.d)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(g.kb_bytes), kTileM};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(a.counts), dims, strides, box,
+                            elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    gg::set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return GG_ERR_CUDA;
+  }
+  const size_t fixed = knn_tc_fixed_smem(a, pass);
+  int dev = 0, max_smem = 0;
+  GG_CUDA_CHECK(cudaGetDevice(&dev));
+  GG_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  GG_REQUIRE(fixed + 2 * static_cast<size_t>(g.stage_bytes) <= static_cast<size_t>(max_smem), GG_ERR_ARG,
+             "not enough shared memory for the B ring");
+  int n_bstages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / g.stage_bytes);
+  if (n_bstages > kMaxBStages) n_bstages = kMaxBStages;
+  const size_t smem_bytes = fixed + static_cast<size_t>(n_bstages) * g.stage_bytes;
+  auto kernel = pass == 1 ? knn_tc_pair_kernel<1> : knn_tc_pair_kernel<2>;
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+  const long long n_sp = (a.row_end - a.row_begin + 2 * kTileM - 1) / (2 * kTileM);
+  const long long pairs = gg::sm_count() / 2;
+  const unsigned grid = 2u * static_cast<unsigned>(n_sp < pairs ? n_sp : pairs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, a, n_bstages, error_flag, g));
   return GG_OK;
 }
 

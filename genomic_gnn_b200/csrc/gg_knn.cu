@@ -22,8 +22,13 @@
 #include <cub/cub.cuh>
 
 #include "gg_common.cuh"
+#include "gg_knn_tc.cuh"
+
+#include <atomic>
 
 namespace {
+
+std::atomic<int> g_knn_impl{0};  // gg_knn_set_impl: 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel (error when it cannot serve)
 
 constexpr int kRows = 128;     // rows per CTA: 8 warps x 16
 constexpr int kCols = 128;     // columns per tile
@@ -498,7 +503,39 @@ int launch_knn(const KnnArgs& a, size_t smem, cudaStream_t s) {
   return GG_OK;
 }
 
+// the tcgen05 CTA-pair Gram serves rows of 128..1024 bytes (small_k >= 4) with at most 32 norm classes
+int use_tc(const KnnArgs& a, int pass, bool& yes) {
+  const int impl = g_knn_impl.load();
+  yes = impl != 1 && ggkf::knn_tc_eligible(a.pitch, a.n, a.n_sq, a.dot_max, a.n_ranks, pass);
+  GG_REQUIRE(impl != 2 || yes, GG_ERR_ARG, "the tcgen05 kNN kernel cannot serve this shape (row pitch, classes, shared memory)");
+  return GG_OK;
+}
+
+ggkf::KnnTcArgs tc_args(const KnnArgs& a) {
+  ggkf::KnnTcArgs t{};
+  t.counts = a.counts;
+  t.d = a.pitch;
+  t.n = a.n;
+  t.row_begin = a.row_begin;
+  t.row_end = a.row_end;
+  t.sqnorm = a.sqnorm;
+  t.sqid = a.sqid;
+  t.sq_max = a.sq_max;
+  t.rank_tab = a.rank_tab;
+  t.n_sq = a.n_sq;
+  t.dot_max = a.dot_max;
+  t.n_ranks = a.n_ranks;
+  t.hist16 = a.n <= 65536 ? 1 : 0;
+  return t;
+}
+
 }  // namespace
+
+extern "C" int gg_knn_set_impl(int impl) {
+  GG_REQUIRE(impl >= 0 && impl <= 2, GG_ERR_ARG, "impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+  g_knn_impl.store(impl);
+  return GG_OK;
+}
 
 /* pass 1: hist[row_end - row_begin][n_ranks] of the row shard.  hist_mode: -1 auto, 0 global atomics, 1 shared memory
  * 16-bit (n <= 65536), 2 shared memory 32-bit; a forced shared-memory mode that does not fit is an error. */
@@ -511,6 +548,15 @@ extern "C" int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, int64_t
   if (rc != GG_OK) return rc;
   GG_REQUIRE(hist, GG_ERR_ARG, "null histogram");
   GG_REQUIRE(hist_mode >= -1 && hist_mode <= 2, GG_ERR_ARG, "hist_mode must be -1, 0, 1 or 2");
+  if (hist_mode < 0) {  // a forced histogram mode names the mma.sync kernel
+    bool tc = false;
+    if (int rc2 = use_tc(a, 1, tc)) return rc2;
+    if (tc) {
+      ggkf::KnnTcArgs t = tc_args(a);
+      t.hist = hist;
+      return ggkf::knn_tc_launch(t, 1, nullptr, gg::as_stream(st));
+    }
+  }
   const size_t base = knn_base_smem(a.kpad, a.chunk, n_sq, dot_max);
   const bool fits32 = base + hist_smem(kHistSmem32, n_ranks) <= kSmemLimit;
   const bool fits16 = n <= 65536 && base + hist_smem(kHistSmem16, n_ranks) <= kSmemLimit;
@@ -601,7 +647,19 @@ extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t
   a.row_off = row_offsets;
   a.recs = recs;
   cudaStream_t s = gg::as_stream(st);
-  const int rc2 = launch_knn<2, kHistGlobal>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s);
+  bool tc = false;
+  if (int rc3 = use_tc(a, 2, tc)) return rc3;
+  int rc2;
+  if (tc) {
+    ggkf::KnnTcArgs t = tc_args(a);
+    t.cut = cut;
+    t.tie_left = tie_left;
+    t.row_off = row_offsets;
+    t.recs = recs;
+    rc2 = ggkf::knn_tc_launch(t, 2, nullptr, s);
+  } else {
+    rc2 = launch_knn<2, kHistGlobal>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s);
+  }
   if (rc2 != GG_OK) return rc2;
   const int64_t m = row_end - row_begin;
   OrderArgs o{recs, row_offsets, m, row_begin, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};

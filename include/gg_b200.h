@@ -406,6 +406,9 @@ GG_API int gg_spmm_csr_f32(const int64_t* row_ptr, const int32_t* col, const flo
  * shard-local output slots; "L2" needs the maximum of qmax over the shards between the two phases of gg_knn_plan.
  * pitch: bytes per row of counts: 4, 8, or a multiple of 16 (of 128 above 128) up to 1024.
  * ------------------------------------------------------------------------ */
+/* Which Gram kernel serves both passes: 0 = auto (the tcgen05 CTA-pair kernel for rows of 128..1024 bytes with at most
+ * 32 norm classes, else the mma.sync kernel), 1 = mma.sync only, 2 = tcgen05 or an error.  Process-wide. */
+GG_API int gg_knn_set_impl(int impl);
 GG_API int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
                  const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max,
                  int n_ranks, int hist_mode /* -1 auto; 0 global atomics, 1 / 2 per-CTA shared memory, 16- / 32-bit bins */,

@@ -47,6 +47,35 @@ def test_knn_matches_exact_search(k, s, n_reads, frac, distance):
     assert np.bincount(ei[0], minlength=n).max() <= k_nn
 
 
+@pytest.mark.parametrize("k,s,n_reads,frac", [
+    (6, 5, 4000, 0.01),      # D = 1024, N = 4096: 16 strip pairs, 16 column tiles
+    (7, 5, 30, 0.004),       # ragged N: partial strip pair, partial column tile
+    (6, 4, 4000, 0.3),       # D = 256, large k: cuts deep in the ranking, IP rows run out of positive neighbours
+    (8, 5, 60000, 0.01),     # BASELINE config 4 size: N = 65,536, D = 1024, k = 655
+    (9, 4, 400000, 0.0005),  # N ~ 262k > 65,536: 32-bit shared-memory histograms
+])
+@pytest.mark.parametrize("distance", ["IP", "L2"])
+def test_knn_tcgen05_matches_mma(k, s, n_reads, frac, distance):
+    """Both Gram passes on the tcgen05 CTA-pair kernel (rank histograms with the zero-dot classes by subtraction, pass 2
+    by one epilogue group in column order) against the mma.sync kernel: identical edges, order and weights -- whole and
+    as a 128-aligned row shard."""
+    from genomic_gnn_b200 import core
+
+    built, kc = _built(k, s, n_reads, seed=0 if k >= 8 else 3)
+    n = built.db.num_nodes
+    k_nn = max(1, int(frac * n))
+    a = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, impl="mma")
+    b = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, impl="tcgen05")
+    assert a.edge_index.shape[1] > 0
+    assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight, b.weight)
+    if n >= 1024 and k <= 8:
+        lo, hi = 384, min(n, 384 + 640)   # a shard that starts inside a strip pair
+        fix = (lambda q: q) if distance == "L2" else None
+        a1 = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, rows=(lo, hi), qmax_reduce=fix, impl="mma")
+        b1 = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, rows=(lo, hi), qmax_reduce=fix, impl="tcgen05")
+        assert torch.equal(a1.edge_index, b1.edge_index) and torch.equal(a1.weight, b1.weight)
+
+
 @pytest.mark.parametrize("hist_mode", [0, 1, 2])
 @pytest.mark.parametrize("distance", ["IP", "L2"])
 def test_knn_histogram_modes_agree(hist_mode, distance):
