@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgg_b200.so")
 
 GG_OK = 0
-GG_ABI_VERSION = 2
+GG_ABI_VERSION = 3
 GG_SEP = 10
 GG_MAX_K = 13
 GG_KF_BLOCK = 1024
@@ -108,8 +108,9 @@ SIGNATURES = {
     "gg_knn_count": (_I32, [_P, _I32, _I64, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "gg_knn_plan_workspace_bytes": (_SZ, [_I64]),
     "gg_knn_plan": (_I32, [_I64, _I64, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
+    "gg_knn_write_scratch_words": (_SZ, [_I32, _I64, _I32, _I32, _I32, _I64, _I64]),
     "gg_knn_write": (_I32, [_P, _I32, _I64, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P,
-                            _P, _P, _P, _I64, _P]),
+                            _I64, _P, _P, _P, _I64, _P]),
     "gg_peer_push": (_I32, [_P, _I64, C.POINTER(Peers), _P]),
     "gg_peer_signal": (_I32, [C.POINTER(Peers), _I32, C.c_uint32, _P]),
     "gg_peer_wait": (_I32, [_P, _I32, _I32, _I32, C.c_uint32, _P, _P]),

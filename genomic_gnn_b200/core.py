@@ -1565,11 +1565,12 @@ def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance
     edge_index = torch.empty((2, n_edges), dtype=torch.int64, device=dev)
     weight = torch.empty(n_edges, dtype=torch.float32, device=dev)
     if n_edges:
-        recs = torch.empty(n_edges, dtype=torch.int64, device=dev)
+        words = int(lib.gg_knn_write_scratch_words(pitch, n, n_sq, dot_max, n_ranks, m, n_edges))
+        recs = torch.empty(words, dtype=torch.int64, device=dev)
         with _stage(f"knn_write_d{pitch}"):
             check(lib.gg_knn_write(ptr(counts), pitch, n, lo, hi, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq,
                                    dot_max, n_ranks, metric, ptr(hist), ptr(cut), ptr(tie_left), ptr(row_off), ptr(qmax),
-                                   ptr(recs), C.c_void_p(edge_index.data_ptr()),
+                                   ptr(recs), words, C.c_void_p(edge_index.data_ptr()),
                                    C.c_void_p(edge_index.data_ptr() + 8 * n_edges), ptr(weight), n_edges, st),
                   "gg_knn_write")
     if sharded and gather:

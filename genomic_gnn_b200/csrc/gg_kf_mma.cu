@@ -1028,18 +1028,50 @@ __global__ void __launch_bounds__(128, 1) tensor_probe_kernel(int iters, int n_k
 // A CTA pair owns strip pairs of 256 rows (A resident) and streams all columns past them; a thread of an epilogue
 // group is one row, as above.  Ranks come from the host table rank_tab[class of sq_j][dot] (gg_knn.cu).
 //   pass 1  per-row rank histograms in shared memory.  Only non-zero dots cost per-pair work (1.5 % of the pairs of
-//           1024-column rows): the zero-dot members of a column class are its size minus the row's non-zero count
-//           for that class, added when the strip is finished.  All three epilogue groups, any order.
+//           1024-column rows): the 32 dots of a chunk are packed four to a word with byte permutes, a lane looks only at
+//           its non-zero words, and the zero-dot members of a column class are its size minus the row's non-zero count
+//           for that class, added when the strip is finished.  All three epilogue groups, half tiles round-robin.
 //   pass 2  the selected pairs of every row in COLUMN order (ties of the cut rank are taken in that order while the
-//           row's budget lasts): ONE epilogue group takes every half tile in sequence, so a row's running position is
-//           a register of its thread -- the group needs ~1,000 cycles per half tile, the tensor pipe 2,100 (D = 1024).
-//           Zero-dot columns are selected through per-chunk class masks built once per half tile.
+//           row's budget lasts).  The columns are cut into three contiguous thirds, the tiles of the thirds interleaved
+//           on the tensor pipe, and epilogue group g walks third g in order: a row's running position and tie count
+//           are registers of its thread in that group.  Every third keeps the ties its own budget allows; the reorder
+//           kernel (gg_knn.cu) reads the thirds in order and applies the budget across them.  Zero-dot columns are
+//           selected through per-chunk class masks built once per half tile.
 // ======================================================================================
 constexpr uint32_t kKnnNoRank = 0xFFFFu;
 
 __device__ __forceinline__ void bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+
+// low bytes of four accumulators -> one word (dots are <= 255)
+__device__ __forceinline__ uint32_t pack4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+  return __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+}
+// bit 7 of every non-zero byte
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) {
+  return (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;
+}
+// the j-th of eight registers (j is not a compile-time constant: a select tree instead of local memory)
+__device__ __forceinline__ uint32_t pick8(const uint32_t (&w)[8], int j) {
+  const uint32_t x0 = (j & 1) ? w[1] : w[0], x1 = (j & 1) ? w[3] : w[2], x2 = (j & 1) ? w[5] : w[4], x3 = (j & 1) ? w[7] : w[6];
+  const uint32_t y0 = (j & 2) ? x1 : x0, y1 = (j & 2) ? x3 : x2;
+  return (j & 4) ? y1 : y0;
+}
+
+// Pass 2 deals 128-column blocks, not tiles: half h of the issue sequence (tile h / 2, CTA h % 2 of the pair loads it)
+// is the next block of column third h % 3, so that with two accumulator tiles in flight all three epilogue groups --
+// group g owns the halves with h % 3 == g -- have work.  The two halves of a B tile need not be neighbours: each CTA
+// of the pair loads its own.
+struct KnnBlocks {
+  int n_blk, third;  // 128-column blocks of the matrix, blocks per third
+  __device__ __forceinline__ int tiles() const { return (3 * third + 1) / 2; }
+  // first column of half h; beyond the last column (TMA zero fill, nothing to score) when the third has no such block
+  __device__ __forceinline__ long long col(int h, long long n) const {
+    const int i = h / 3, blk = (h % 3) * third + i;
+    return (i < third && blk < n_blk) ? static_cast<long long>(blk) * kTile : (n + kTile - 1) / kTile * kTile;
+  }
+};
 
 template <int PASS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -1052,15 +1084,17 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem_a + static_cast<size_t>(n_kblocks) * kStageBytes;
   uint8_t* panel = smem_b + static_cast<size_t>(n_bstages) * kStageBytes;         // [kEpiGroups][kBlock] column classes
-  PairStage* stages = reinterpret_cast<PairStage*>(panel + kEpiGroups * kBlock);
-  Barriers* bars = reinterpret_cast<Barriers*>(stages + kEpiThreads / 32);
+  Barriers* bars = reinterpret_cast<Barriers*>(panel + kEpiGroups * kBlock);
   const int tstride = a.dot_max + 1;
   const int tab_elems = (a.n_sq + 1) * tstride;                                    // + an all-"never" class
   uint16_t* rank_tab = reinterpret_cast<uint16_t*>(bars + 1);
   uint32_t* colcount = reinterpret_cast<uint32_t*>(rank_tab + ((tab_elems + 1) & ~1));  // [kKnnTcMaxSq]
-  uint32_t* clsmask = colcount + kKnnTcMaxSq;                                      // pass 2: [2][4][kKnnTcMaxSq]
-  uint32_t* nz = clsmask + 2 * 4 * kKnnTcMaxSq;                                    // pass 1: [128][n_sq]
-  uint32_t* shist = nz + kTileM * a.n_sq;                                          // pass 1: [128][hwords]
+  // pass 1: nz [128][n_sq], shist [128][hwords].  pass 2: class masks [kEpiGroups][2][4][kKnnTcMaxSq], then the packed
+  // dots of the current chunk per epilogue warp (PairStage)
+  uint32_t* nz = colcount + kKnnTcMaxSq;
+  uint32_t* shist = nz + kTileM * a.n_sq;
+  uint32_t* clsmask = colcount + kKnnTcMaxSq;
+  PairStage* stages = reinterpret_cast<PairStage*>(clsmask + kEpiGroups * 2 * 4 * kKnnTcMaxSq);
   const int hwords = a.hist16 ? (a.n_ranks + 1) >> 1 : a.n_ranks;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1122,7 +1156,11 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
 
   const int n_pairs_grid = static_cast<int>(gridDim.x / 2), pair_id = static_cast<int>(blockIdx.x / 2);
   const int n_sp = static_cast<int>((a.row_end - a.row_begin + 2 * kTileM - 1) / (2 * kTileM));  // strip pairs of the shard
-  const int n_ct = static_cast<int>((a.n + kPairTileN - 1) / kPairTileN);                        // 256-column tiles
+  KnnBlocks blocks;
+  blocks.n_blk = static_cast<int>((a.n + kTile - 1) / kTile);
+  blocks.third = (blocks.n_blk + 2) / 3;
+  // pass 1 walks the 256-column tiles in plain order
+  const int n_slots = PASS == 1 ? static_cast<int>((a.n + kPairTileN - 1) / kPairTileN) : blocks.tiles();
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (both CTAs; transactions complete on the leader's barriers) ==========
@@ -1139,8 +1177,10 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
       }
       __syncwarp();
       ++a_round;
-      for (int ct = 0; ct < n_ct; ++ct) {
-        const int col = ct * kPairTileN + static_cast<int>(rank) * kTileM;  // this CTA's half of B
+      for (int slot = 0; slot < n_slots; ++slot) {
+        // this CTA's half of B
+        const int col = PASS == 1 ? slot * kPairTileN + static_cast<int>(rank) * kTileM
+                                  : static_cast<int>(blocks.col(2 * slot + static_cast<int>(rank), a.n));
         for (int kb = 0; kb < n_kblocks; ++kb) {
           if (round > 0) mbar_wait_warp(&bars->b_empty[stage], (round - 1) & 1, &bars->error);
           if (elect_one()) {
@@ -1169,7 +1209,7 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
         mbar_wait_warp(&bars->a_full, a_round & 1, &bars->error);
         tc_fence_after();
         ++a_round;
-        for (int ct = 0; ct < n_ct; ++ct) {
+        for (int slot = 0; slot < n_slots; ++slot) {
           if (acc_round > 0) mbar_wait_warp(&bars->acc_empty[acc], (acc_round - 1) & 1, &bars->error);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * kPairTileN;
@@ -1203,37 +1243,43 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
     }
   } else {
     // ===================== epilogue =====================
-    PairStage& ws = stages[warp];
     const int group = warp / 4;
     const int gt = tid % kGroupThreads;  // row of the strip = TMEM lane
     uint8_t* my_panel = panel + group * kBlock;
-    const bool active = PASS == 1 || group == 0;  // pass 2: one group, every half tile in column order
-    uint32_t tile_seq = 0;
-    for (int sp = pair_id; sp < n_sp && active; sp += n_pairs_grid) {
+    uint32_t tile_seq = 0;               // tiles issued so far (every role counts the same sequence)
+    for (int sp = pair_id; sp < n_sp; sp += n_pairs_grid) {
       const long long row = a.row_begin + static_cast<long long>(2 * sp + static_cast<int>(rank)) * kTileM + gt;
       const bool row_ok = row < a.row_end;
       const long long loc = row - a.row_begin;
-      // pass 2: the row's plan and running state
+      // pass 2: the row's plan and this group's running state
       int cut = -1, budget = 0, seen = 0;
-      long long out_at = 0;
+      long long out_at = 0, out_first = 0;
       uint32_t zsel = 0, ztie = 0;  // classes whose zero-dot columns rank above / at the cut
       if (PASS == 2 && row_ok) {
         cut = __ldg(a.cut + loc);
         budget = __ldg(a.tie_left + loc);
-        out_at = __ldg(a.row_off + loc);
+        const long long r0 = __ldg(a.row_off + loc), r1 = __ldg(a.row_off + loc + 1);
+        out_first = out_at = 3 * r0 + group * (r1 - r0);   // this group's third of the row's staging space
         for (int c = 0; c < a.n_sq; ++c) {
-          const int r0 = rank_tab[c * tstride];
-          zsel |= static_cast<uint32_t>(r0 < cut) << c;   // 0xFFFF is above every cut
-          ztie |= static_cast<uint32_t>(r0 == cut) << c;
+          const int rk0 = rank_tab[c * tstride];
+          zsel |= static_cast<uint32_t>(rk0 < cut) << c;   // 0xFFFF is above every cut
+          ztie |= static_cast<uint32_t>(rk0 == cut) << c;
         }
       }
       int panel_block = -1;
-      for (int ct = 0; ct < n_ct; ++ct, ++tile_seq) {
+      uint32_t mask_buf = 0;  // pass 2: class-mask buffer of this group's next half tile
+      for (int slot = 0; slot < n_slots; ++slot) {
         const uint32_t acc = tile_seq % kPairAccStages;
         const uint32_t acc_parity = (tile_seq / kPairAccStages) & 1;
+        const uint32_t my_seq = tile_seq++;
         for (int half = 0; half < 2; ++half) {
-          if (PASS == 1 && (2 * tile_seq + half) % kEpiGroups != static_cast<uint32_t>(group)) continue;
-          const long long c0 = static_cast<long long>(ct) * kPairTileN + half * kTile;  // first column of the half tile
+          // pass 1: half tiles round-robin; pass 2: group g owns the halves of column third g
+          if ((PASS == 1 ? (2 * my_seq + half) : static_cast<uint32_t>(2 * slot + half)) % kEpiGroups !=
+              static_cast<uint32_t>(group))
+            continue;
+          // first column of the half tile
+          const long long c0 = PASS == 1 ? static_cast<long long>(slot) * kPairTileN + half * kTile
+                                         : blocks.col(2 * slot + half, a.n);
           const int jb = static_cast<int>(c0 / kBlock);
           if (jb != panel_block && c0 < a.n) {  // column classes of the next 1024 columns (uniform per group)
             bar_sync(2 + group, kGroupThreads);
@@ -1250,9 +1296,11 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
             panel_block = jb;
           }
           const int pc0 = static_cast<int>(c0 - static_cast<long long>(jb) * kBlock);  // panel index of the half tile
-          uint32_t* my_masks = clsmask + ((2 * tile_seq + half) & 1) * 4 * kKnnTcMaxSq;
+          uint32_t* my_masks = clsmask + (group * 2 + mask_buf) * 4 * kKnnTcMaxSq;
           if (PASS == 2 && c0 < a.n) {
-            // class masks of the four 32-column chunks: warp q of the group makes chunk q
+            // class masks of the four 32-column chunks: warp q of the group makes chunk q.  (Two buffers in turn: a
+            // warp that is still reading the masks of the previous half tile reads the other one.)
+            mask_buf ^= 1u;
             const int q = warp & 3;
             const uint32_t cls = my_panel[pc0 + q * 32 + lane];
             uint32_t mine = 0;
@@ -1272,44 +1320,55 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
             for (int cc = 0; cc < kTile; cc += 32) {
               uint32_t v[32];
               tc_ld32(taddr + cc, v);
-              uint32_t nzmask = 0;
+              uint32_t w[8];
 #pragma unroll
-              for (int b = 0; b < 32; ++b) nzmask |= static_cast<uint32_t>(v[b] != 0u) << b;
-              if (!row_ok) nzmask = 0;
-              const bool any_nz = __any_sync(0xFFFFFFFFu, nzmask != 0u);
-              if (any_nz) {
+              for (int j = 0; j < 8; ++j) w[j] = pack4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              uint32_t wmask = 0;  // non-zero words
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  ws.dotw[j][lane] = v[4 * j] | (v[4 * j + 1] << 8) | (v[4 * j + 2] << 16) | (v[4 * j + 3] << 24);
-              }
+              for (int j = 0; j < 8; ++j) wmask |= static_cast<uint32_t>(w[j] != 0u) << j;
+              if (!row_ok) wmask = 0;
               const long long cbase = c0 + cc;            // global column of bit 0
               const long long self = row - cbase;          // bit of the row's own column, if inside the chunk
               if (PASS == 1) {
-                for (uint32_t m2 = nzmask; m2; m2 &= m2 - 1) {
-                  const int b = __ffs(m2) - 1;
-                  const uint32_t cls = my_panel[pc0 + cc + b];
-                  if (cls >= static_cast<uint32_t>(a.n_sq)) continue;
-                  atomicAdd(nz + gt * a.n_sq + cls, 1u);   // the self pair too: it is not a zero-dot column
-                  if (b == self) continue;
-                  const uint32_t dot = stage_get_dot(ws, b, lane);
-                  const uint32_t r = rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
-                  if (r == kKnnNoRank) continue;
-                  if (a.hist16) atomicAdd(shist + gt * hwords + (r >> 1), 1u << ((r & 1u) * 16));
-                  else atomicAdd(shist + gt * hwords + r, 1u);
+                for (; wmask; wmask &= wmask - 1) {
+                  const int j = __ffs(wmask) - 1;
+                  const uint32_t word = pick8(w, j);
+                  for (uint32_t t = nonzero_bytes(word); t; t &= t - 1) {
+                    const int byte = (__ffs(t) - 1) >> 3, b = 4 * j + byte;
+                    const uint32_t cls = my_panel[pc0 + cc + b];
+                    atomicAdd(nz + gt * a.n_sq + cls, 1u);   // the self pair too: it is not a zero-dot column
+                    if (b == self) continue;
+                    const uint32_t r = rank_tab[cls * tstride + ((word >> (8 * byte)) & 0xFFu)];
+                    if (r == kKnnNoRank) continue;
+                    if (a.hist16) atomicAdd(shist + gt * hwords + (r >> 1), 1u << ((r & 1u) * 16));
+                    else atomicAdd(shist + gt * hwords + r, 1u);
+                  }
                 }
               } else {
-                uint32_t sel = 0, tie = 0;
-                for (uint32_t zm = zsel; zm; zm &= zm - 1) sel |= my_masks[(cc >> 5) * kKnnTcMaxSq + __ffs(zm) - 1];
-                for (uint32_t zm = ztie; zm; zm &= zm - 1) tie |= my_masks[(cc >> 5) * kKnnTcMaxSq + __ffs(zm) - 1];
-                sel &= ~nzmask;
-                tie &= ~nzmask;
-                for (uint32_t m2 = nzmask; m2; m2 &= m2 - 1) {
-                  const int b = __ffs(m2) - 1;
-                  const uint32_t cls = my_panel[pc0 + cc + b];
-                  const uint32_t dot = stage_get_dot(ws, b, lane);
-                  const int r = rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
-                  sel |= static_cast<uint32_t>(r < cut) << b;
-                  tie |= static_cast<uint32_t>(r == cut) << b;
+                PairStage& ws = stages[warp];
+                if (__any_sync(0xFFFFFFFFu, wmask != 0u)) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) ws.dotw[j][lane] = w[j];
+                }
+                uint32_t sel = 0, tie = 0, nzmask = 0;
+                for (; wmask; wmask &= wmask - 1) {
+                  const int j = __ffs(wmask) - 1;
+                  const uint32_t word = ws.dotw[j][lane];
+                  for (uint32_t t = nonzero_bytes(word); t; t &= t - 1) {
+                    const int byte = (__ffs(t) - 1) >> 3, b = 4 * j + byte;
+                    const uint32_t cls = my_panel[pc0 + cc + b];
+                    const int r = rank_tab[cls * tstride + ((word >> (8 * byte)) & 0xFFu)];
+                    nzmask |= 1u << b;
+                    sel |= static_cast<uint32_t>(r < cut) << b;
+                    tie |= static_cast<uint32_t>(r == cut) << b;
+                  }
+                }
+                if (zsel | ztie) {
+                  uint32_t zs = 0, zt = 0;
+                  for (uint32_t zm = zsel; zm; zm &= zm - 1) zs |= my_masks[(cc >> 5) * kKnnTcMaxSq + __ffs(zm) - 1];
+                  for (uint32_t zm = ztie; zm; zm &= zm - 1) zt |= my_masks[(cc >> 5) * kKnnTcMaxSq + __ffs(zm) - 1];
+                  sel |= zs & ~nzmask;
+                  tie |= zt & ~nzmask;
                 }
                 if (self >= 0 && self < 32) {
                   sel &= ~(1u << self);
@@ -1324,17 +1383,16 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
                     for (int x = t - room; x > 0; --x) tie &= ~(0x80000000u >> __clz(tie));
                   }
                 }
-                const uint32_t fin = sel | tie;
-                for (uint32_t m2 = fin; m2; m2 &= m2 - 1) {
+                for (uint32_t m2 = sel | tie; m2; m2 &= m2 - 1) {
                   const int b = __ffs(m2) - 1;
                   const uint32_t cls = my_panel[pc0 + cc + b];
                   const uint32_t dot = ((nzmask >> b) & 1u) ? stage_get_dot(ws, b, lane) : 0u;
-                  const uint32_t r = rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
+                  const uint32_t r = rank_tab[cls * tstride + dot];
                   a.recs[out_at++] = static_cast<uint64_t>(cbase + b) | static_cast<uint64_t>(dot) << 32 |
                                      static_cast<uint64_t>(r) << 48;
                 }
+                __syncwarp();  // the staged dots are rewritten by the next chunk
               }
-              __syncwarp();  // the staged dots are rewritten by the next chunk
             }
           }
           tc_fence_before();
@@ -1342,6 +1400,7 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
           if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->acc_empty[acc]), 0));
         }
       }
+      if (PASS == 2 && row_ok) a.third_cnt[3 * loc + group] = static_cast<uint32_t>(out_at - out_first);
       if (PASS == 1) {
         // the strip is finished: zero-dot members of every class, then the rows go out and the tables are cleared
         bar_sync(1, kEpiThreads);
@@ -1372,10 +1431,6 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
         for (int i = tid; i < kTileM * (a.n_sq + hwords); i += kEpiThreads) nz[i] = 0u;
         bar_sync(1, kEpiThreads);
       }
-    }
-    if (!active) {
-      // pass 2, groups 1 and 2: nothing to score; their share of the acc_empty arrivals is made by group 0 (it takes both
-      // halves of every tile)
     }
   }
 
@@ -1541,10 +1596,10 @@ static size_t knn_tc_fixed_smem(const KnnTcArgs& a, int pass) {
   const int n_kblocks = a.d / kMaxKBlock;
   const int tab_elems = (a.n_sq + 1) * (a.dot_max + 1);
   const int hwords = a.hist16 ? (a.n_ranks + 1) / 2 : a.n_ranks;
-  size_t bytes = static_cast<size_t>(n_kblocks) * kTileM * kMaxKBlock + kEpiGroups * kBlock +
-                 (kEpiThreads / 32) * sizeof(PairStage) + sizeof(Barriers) + 2 * static_cast<size_t>((tab_elems + 1) & ~1) +
-                 (kKnnTcMaxSq + 2 * 4 * kKnnTcMaxSq) * sizeof(uint32_t) + 1024;
+  size_t bytes = static_cast<size_t>(n_kblocks) * kTileM * kMaxKBlock + kEpiGroups * kBlock + sizeof(Barriers) +
+                 2 * static_cast<size_t>((tab_elems + 1) & ~1) + kKnnTcMaxSq * sizeof(uint32_t) + 1024;
   if (pass == 1) bytes += static_cast<size_t>(kTileM) * (a.n_sq + hwords) * sizeof(uint32_t);
+  else bytes += kEpiGroups * 2 * 4 * kKnnTcMaxSq * sizeof(uint32_t) + (kEpiThreads / 32) * sizeof(PairStage);
   return bytes;
 }
 

@@ -369,6 +369,68 @@ __global__ void __launch_bounds__(256) order_kernel(OrderArgs a) {
   }
 }
 
+// The same for the staging layout of the tcgen05 kernel (gg_knn_tc.cuh): a row's pairs come as three column thirds, each
+// in column order, each holding at most the row's tie budget of cut-rank members; walking the thirds in order and
+// keeping cut-rank members while the budget lasts reproduces the column-order rule over the whole row.
+struct Order3Args {
+  OrderArgs o;
+  const uint32_t* third_cnt;
+  const int32_t* cut;
+  const int32_t* tie_left;
+};
+
+__global__ void __launch_bounds__(256) order3_kernel(Order3Args a3) {
+  const OrderArgs& a = a3.o;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= a.n) return;
+  const int64_t base = a.row_off[row];
+  const int64_t cnt_row = a.row_off[row + 1] - base;
+  if (cnt_row == 0) return;
+  const int sqi = a.sqnorm[a.row_begin + row];
+  const float qmax_f = a.metric == 1 ? static_cast<float>(*a.qmax) : 1.0f;
+  uint32_t* cur = a.cursors + row * a.n_ranks;
+  const unsigned cut = static_cast<unsigned>(a3.cut[row]);
+  const int budget = a3.tie_left[row];
+  int seen = 0;
+  for (int g = 0; g < 3; ++g) {
+    const int cnt = static_cast<int>(a3.third_cnt[3 * row + g]);
+    const uint64_t* src = a.recs + 3 * base + g * cnt_row;
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < cnt;
+      const uint64_t rec = valid ? src[i] : ~0ull;
+      const unsigned rank = static_cast<unsigned>(rec >> 48);
+      const bool is_tie = valid && rank == cut;
+      const unsigned tb = __ballot_sync(0xFFFFFFFFu, is_tie);
+      const bool keep = valid && (!is_tie || seen + __popc(tb & ((1u << lane) - 1u)) < budget);
+      seen += __popc(tb);
+      const unsigned key = keep ? rank : 0x10000u + lane;  // dropped and idle lanes: groups of their own
+      const unsigned same = __match_any_sync(0xFFFFFFFFu, key);
+      const int leader = __ffs(same) - 1;
+      unsigned first = 0;
+      if (keep && lane == leader) first = atomicAdd(cur + rank, static_cast<unsigned>(__popc(same)));
+      first = __shfl_sync(0xFFFFFFFFu, first, leader);
+      if (keep) {
+        const int64_t slot = static_cast<int64_t>(first) + __popc(same & ((1u << lane) - 1u));
+        const int64_t col = static_cast<int64_t>(rec & 0xFFFFFFFFull);
+        const int dot = static_cast<int>((rec >> 32) & 0xFFFFu);
+        const int sqj = a.sqnorm[col];
+        float wv;
+        if (a.metric == 0) {
+          wv = fminf(static_cast<float>(static_cast<double>(dot) / sqrt(static_cast<double>(sqi) * sqj)), 1.0f);
+        } else {
+          wv = 1.0f - static_cast<float>(sqi + sqj - 2 * dot) / qmax_f;
+        }
+        a.src[slot] = a.row_begin + row;
+        a.dst[slot] = col;
+        a.w[slot] = wv;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ---- plan: cut rank, tie budget, rows' output counts -------------------------------------------------------------
 __global__ void cut_kernel(const uint32_t* hist, int64_t n, int n_ranks, int k_nn, int metric, const int32_t* sqnorm,
                            const int32_t* rank_q, int32_t* cut, int32_t* tie_left, uint32_t* before, int32_t* qmax) {
@@ -625,14 +687,23 @@ extern "C" int gg_knn_plan(int64_t n, int64_t row_begin, int64_t row_end, int n_
   return GG_OK;
 }
 
+/* 64-bit words of scratch gg_knn_write needs for a shard of n_rows rows and n_edges edges (the kernel that will serve
+ * the shape decides: the tcgen05 kernel stages every row three times over, plus three counters per row) */
+extern "C" size_t gg_knn_write_scratch_words(int pitch, int64_t n, int n_sq, int dot_max, int n_ranks, int64_t n_rows,
+                                             int64_t n_edges) {
+  if (n_rows < 0 || n_edges < 0) return 0;
+  const bool tc = g_knn_impl.load() != 1 && ggkf::knn_tc_eligible(pitch, n, n_sq, dot_max, n_ranks, 2);
+  return tc ? 3 * static_cast<size_t>(n_edges) + (3 * static_cast<size_t>(n_rows) + 1) / 2 : static_cast<size_t>(n_edges);
+}
+
 /* pass 2 + order for the row shard: edge_src / edge_dst / weight[row_offsets[m]], grouped by source row, most similar
- * first.  recs: scratch of row_offsets[m] 64-bit words (`capacity` of them). */
+ * first.  recs: scratch of gg_knn_write_scratch_words() 64-bit words (`recs_words` of them). */
 extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
                             const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq,
                             int dot_max, int n_ranks, int metric,
                             uint32_t* cursors, const int32_t* cut, const int32_t* tie_left,
-                            const int64_t* row_offsets, const int32_t* qmax, uint64_t* recs, int64_t* edge_src,
-                            int64_t* edge_dst, float* weight, int64_t capacity, gg_stream_t st) {
+                            const int64_t* row_offsets, const int32_t* qmax, uint64_t* recs, int64_t recs_words,
+                            int64_t* edge_src, int64_t* edge_dst, float* weight, int64_t capacity, gg_stream_t st) {
   KnnArgs a;
   const int rc =
       fill_args(a, counts, pitch, n, row_begin, row_end, sqnorm, sqid, sq_max, rank_tab, n_sq, dot_max, n_ranks);
@@ -649,21 +720,25 @@ extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t
   cudaStream_t s = gg::as_stream(st);
   bool tc = false;
   if (int rc3 = use_tc(a, 2, tc)) return rc3;
-  int rc2;
+  const int64_t m = row_end - row_begin;
+  GG_REQUIRE(recs_words >= static_cast<int64_t>(gg_knn_write_scratch_words(pitch, n, n_sq, dot_max, n_ranks, m, capacity)),
+             GG_ERR_WORKSPACE, "recs scratch smaller than gg_knn_write_scratch_words()");
+  OrderArgs o{recs, row_offsets, m, row_begin, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
+  const unsigned grid = static_cast<unsigned>((m * 32 + 255) / 256);
   if (tc) {
     ggkf::KnnTcArgs t = tc_args(a);
     t.cut = cut;
     t.tie_left = tie_left;
     t.row_off = row_offsets;
     t.recs = recs;
-    rc2 = ggkf::knn_tc_launch(t, 2, nullptr, s);
-  } else {
-    rc2 = launch_knn<2, kHistGlobal>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s);
+    t.third_cnt = reinterpret_cast<uint32_t*>(recs + 3 * capacity);
+    if (int rc2 = ggkf::knn_tc_launch(t, 2, nullptr, s)) return rc2;
+    Order3Args o3{o, t.third_cnt, cut, tie_left};
+    order3_kernel<<<grid, 256, 0, s>>>(o3);
+    GG_CUDA_CHECK(cudaGetLastError());
+    return GG_OK;
   }
-  if (rc2 != GG_OK) return rc2;
-  const int64_t m = row_end - row_begin;
-  OrderArgs o{recs, row_offsets, m, row_begin, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
-  const unsigned grid = static_cast<unsigned>((m * 32 + 255) / 256);
+  if (int rc2 = launch_knn<2, kHistGlobal>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s)) return rc2;
   order_kernel<<<grid, 256, 0, s>>>(o);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;

@@ -21,7 +21,11 @@ struct KnnTcArgs {
   const int32_t* cut;          // pass 2: the plan of gg_knn_plan
   const int32_t* tie_left;
   const int64_t* row_off;
-  uint64_t* recs;              // pass 2: column | dot << 32 | rank << 48, rows at row_off, column order
+  // pass 2 output: column | dot << 32 | rank << 48.  A row's staging space is 3 x (its edge count) words at
+  // 3 * row_off[row]; epilogue group g fills third g with the pairs it selects from the g-th third of the columns, in
+  // column order, and third_cnt[3 * row + g] says how many.  Every third keeps at most tie_left members of the cut rank.
+  uint64_t* recs;
+  uint32_t* third_cnt;
 };
 
 // true when the tensor path can serve this shape (gg_knn.cu falls back to its mma.sync kernel otherwise)

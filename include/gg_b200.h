@@ -40,7 +40,7 @@ typedef void* gg_stream_t; /* cudaStream_t */
 #define GG_API
 #endif
 
-#define GG_ABI_VERSION 2
+#define GG_ABI_VERSION 3
 #define GG_OK 0
 #define GG_ERR_ARG (-1)      /* null pointer, negative size, misaligned buffer */
 #define GG_ERR_K (-2)        /* k / small_k outside the supported range */
@@ -419,10 +419,14 @@ GG_API int gg_knn_plan(int64_t n, int64_t row_begin, int64_t row_end, int n_rank
                 int64_t* row_offsets, int32_t* qmax,
                 int phase /* 0 all; 1 cut ranks + the shard's qmax; 2 finish with the global qmax in place */,
                 void* workspace, size_t workspace_bytes, gg_stream_t st);
+/* 64-bit words of `recs` scratch for a shard of n_rows rows / n_edges edges (the tcgen05 kernel stages more) */
+GG_API size_t gg_knn_write_scratch_words(int pitch, int64_t n, int n_sq, int dot_max, int n_ranks, int64_t n_rows,
+                                  int64_t n_edges);
 GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
                  const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max,
                  int n_ranks, int metric, uint32_t* cursors, const int32_t* cut, const int32_t* tie_left,
-                 const int64_t* row_offsets, const int32_t* qmax, uint64_t* recs /* scratch: `capacity` words */,
+                 const int64_t* row_offsets, const int32_t* qmax,
+                 uint64_t* recs /* scratch */, int64_t recs_words /* >= gg_knn_write_scratch_words() */,
                  int64_t* edge_src, int64_t* edge_dst, float* weight, int64_t capacity /* = row_offsets[m] */,
                  gg_stream_t st);
 

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in gg_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == _declared()
     loaded = _lib.load()
-    assert loaded.gg_abi_version() == _lib.GG_ABI_VERSION == 2
+    assert loaded.gg_abi_version() == _lib.GG_ABI_VERSION == 3
     assert loaded.gg_hist_bins(8) == 4**9
     assert loaded.gg_stream_padded_bytes(150) == 176
 
