@@ -612,6 +612,36 @@ def run_ours(a):
                                            "stages": parts + [f"k6_expand_d{d}"],
                                            "note": "issue-bound sparse class sweeps; floor = edge bytes written once"}
     dominant = max(rooflines, key=lambda k_: rooflines[k_]["ms"]) if rooflines else None
+    # the per-row kNN mode of the KF edges (--representation_ss_faiss_ann: kf_faiss_to_edge_index_weight, k = int(p N)
+    # neighbours per node) is not part of the step; its two Gram passes run on the same tensor kernel family and are
+    # quoted beside it (widest set, metric "IP", full N x N matrix per pass)
+    knn_line = None
+    if rank == 0 and world == 1 and not big and not a.no_probes and a.top_k:
+        kc = max(built.kf_counts, key=lambda kc_: int(kc_.counts.shape[1]))
+        d_knn, k_nn = int(kc.counts.shape[1]), int(a.top_k * n_nodes)
+        if d_knn >= 128 and 1 <= k_nn < n_nodes:
+            for _ in range(2):
+                core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, "IP")
+            ktimer = core.StageTimer()
+            core.set_timer(ktimer)
+            reps = 3
+            for _ in range(reps):
+                flush.fill_(1)
+                res = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, "IP")
+            core.set_timer(None)
+            kms = {k_: sum(v) / reps for k_, v in ktimer.summary().items()}
+            gram_ms = kms.get(f"knn_count_d{d_knn}", 0.0) + kms.get(f"knn_write_d{d_knn}", 0.0)
+            kflops = 2 * 2.0 * d_knn * n_nodes * n_nodes
+            ach = kflops / (gram_ms * 1e-3) / 1e12
+            knn_line = {"bound": "tensor", "achieved": ach, "unit": "TFLOP/s", "ms": gram_ms, "stage_ms": kms,
+                        "algorithmic_flops": kflops, "gram_passes": 2, "k": k_nn, "metric": "IP", "nodes": n_nodes, "d": d_knn,
+                        "edges": int(res.edge_index.shape[1]), "pairs_per_s": 2.0 * n_nodes * (n_nodes - 1) / (gram_ms * 1e-3),
+                        "kernel": "knn_tc_pair_kernel<1|2> (tcgen05.mma.cta_group::2.kind::i8) + plan + reorder",
+                        "note": "epilogue-bound: per-pair work on the non-zero dots of every row (DESIGN.md section 7b)"}
+            if "tensor_i8" in probes:
+                knn_line.update({"peak": probes["tensor_i8"]["tops"], "frac": ach / probes["tensor_i8"]["tops"],
+                                 "peak_source": "measured in-process: " + probes["tensor_i8"]["how"]})
+            del res
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if rooflines and os.path.exists(traffic_file) and not big:  # per-launch DRAM bytes from the committed ncu --set full capture
         with open(traffic_file) as fh:
@@ -648,6 +678,7 @@ def run_ours(a):
         "probes": probes,
         "roofline": {"kernel": dominant, **rooflines[dominant]} if dominant else None,
         "rooflines": rooflines,
+        "knn_mode": knn_line,
         "clocks": clock_info,
     }
     if rank == 0 and world == 1 and not big and not a.no_e2e:

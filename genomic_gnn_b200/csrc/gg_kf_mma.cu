@@ -22,6 +22,8 @@
 //     the tensor pipe ahead of the epilogues.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "gg_kf_emit.cuh"
 #include "gg_knn_tc.cuh"
 
@@ -1116,7 +1118,8 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
     }
     for (int i = 0; i < kPairAccStages; ++i) {
       mbar_init(&bars->acc_full[i], 1);
-      mbar_init(&bars->acc_empty[i], 2 * 2 * (kGroupThreads / 32));  // 2 CTAs x 2 half tiles x 4 warps
+      // pass 1: every epilogue warp of both CTAs takes part in every tile; pass 2: 2 CTAs x 2 half tiles x 4 warps
+      mbar_init(&bars->acc_empty[i], PASS == 1 ? 2 * (kEpiThreads / 32) : 2 * 2 * (kGroupThreads / 32));
     }
     bars->error = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1273,10 +1276,10 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
         const uint32_t acc_parity = (tile_seq / kPairAccStages) & 1;
         const uint32_t my_seq = tile_seq++;
         for (int half = 0; half < 2; ++half) {
-          // pass 1: half tiles round-robin; pass 2: group g owns the halves of column third g
-          if ((PASS == 1 ? (2 * my_seq + half) : static_cast<uint32_t>(2 * slot + half)) % kEpiGroups !=
-              static_cast<uint32_t>(group))
-            continue;
+          // pass 2: group g owns the halves of column third g.  pass 1: every group works on both halves of every tile
+          // (the eight 32-column chunks of a tile are dealt round-robin below): with only two accumulator tiles the
+          // time one tile spends in the epilogue, not the epilogue's throughput, paces the tensor pipe
+          if (PASS == 2 && static_cast<uint32_t>(2 * slot + half) % kEpiGroups != static_cast<uint32_t>(group)) continue;
           // first column of the half tile
           const long long c0 = PASS == 1 ? static_cast<long long>(slot) * kPairTileN + half * kTile
                                          : blocks.col(2 * slot + half, a.n);
@@ -1318,6 +1321,8 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
                 tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + acc * kPairTileN + half * kTile;
 #pragma unroll 1
             for (int cc = 0; cc < kTile; cc += 32) {
+              if (PASS == 1 && (my_seq + 4 * half + (cc >> 5)) % kEpiGroups != static_cast<uint32_t>(group)) continue;
+              if (a.debug_skip == 1) continue;
               uint32_t v[32];
               tc_ld32(taddr + cc, v);
               uint32_t w[8];
@@ -1326,7 +1331,7 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
               uint32_t wmask = 0;  // non-zero words
 #pragma unroll
               for (int j = 0; j < 8; ++j) wmask |= static_cast<uint32_t>(w[j] != 0u) << j;
-              if (!row_ok) wmask = 0;
+              if (!row_ok || a.debug_skip == 2) wmask = 0;
               const long long cbase = c0 + cc;            // global column of bit 0
               const long long self = row - cbase;          // bit of the row's own column, if inside the chunk
               if (PASS == 1) {
@@ -1395,6 +1400,7 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
               }
             }
           }
+          if (PASS == 1 && half == 0) continue;   // pass 1: one arrival per warp and tile, after both halves
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->acc_empty[acc]), 0));
@@ -1674,7 +1680,12 @@ int knn_tc_launch(const KnnTcArgs& a, int pass, int* error_flag, cudaStream_t s)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, a, n_bstages, error_flag, g));
+  KnnTcArgs args = a;
+  {
+    const char* e = getenv("GG_KNN_DEBUG_SKIP");   // timing experiments only: 1 = no epilogue work, 2 = no per-pair work
+    args.debug_skip = e ? atoi(e) : 0;
+  }
+  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, args, n_bstages, error_flag, g));
   return GG_OK;
 }
 
