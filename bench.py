@@ -688,6 +688,12 @@ def run_ours(a):
         line["cpu_baseline"] = {"value": a.reads / sec, "unit": "reads/s", "cores": blas_threads(), "kind": "port",
                                 "sample": desc, "host_cpus": os.cpu_count(), "est_seconds_full_workload": sec,
                                 "detail": detail}
+    if world > 1:   # what every rank measured: the slowest rank of a stage is what the step waits for
+        import torch.distributed as dist
+
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {k_: round(v, 4) for k_, v in stage_ms.items()})
+        line["stage_ms_per_rank"] = per_rank
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -159,3 +159,18 @@ def test_swar_acgt_formula():
                 fixed = ((x & 0xE8E8E8E8) ^ 0x40404040) & m
                 ok = ((fixed >> (8 * lane)) & 0xFF) == 0 and ((low_bits(x) >> (8 * lane)) & 1) == 1
                 assert ok == (b in b"ACGT"), (lane, b)
+
+
+def test_round2_entry_points_validate_their_arguments_without_a_gpu():
+    from genomic_gnn_b200 import _lib
+
+    lib = _lib.load()
+    ERR_ARG = -1
+    assert lib.gg_kf_counts_upto(None, 16, None, 8, 2, None, None, None, None) == ERR_ARG      # the device row count
+    assert lib.gg_knn_set_impl(3) == ERR_ARG
+    assert lib.gg_knn_set_impl(1) == 0                                                        # mma.sync kernel: ...
+    assert lib.gg_knn_write_scratch_words(1024, 65536, 5, 16, 48, 65536, 1000) == 1000        # ... one word per edge
+    assert lib.gg_knn_set_impl(0) == 0
+    assert lib.gg_knn_write_scratch_words(16, 65536, 40, 49, 700, 65536, 1000) == 1000        # narrow rows: never tcgen05
+    assert lib.gg_knn_write(None, 1024, 4096, 0, 4096, None, None, 16, None, 5, 16, 48, 0, None, None, None, None, None,
+                            None, 0, None, None, None, 0, None) == ERR_ARG
