@@ -1479,7 +1479,7 @@ def knn_row_shard(n: int, world: int, rank: int):
     return min(lo, n), hi
 
 
-KNN_IMPL = {"auto": 0, "mma": 1, "tcgen05": 2}
+KNN_IMPL = {"auto": 0, "mma": 1, "tcgen05": 2, "sparse": 3}
 
 
 def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance: str = "L2", hist_mode: int = -1,
@@ -1491,14 +1491,15 @@ def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance
     knn_row_shard() of the rows against all columns, the ranks agree on the "L2" normaliser (max over ranks of one
     integer) and, unless ``gather=False``, all-gather their edge lists in rank order = the single-GPU result.
     ``rows=(lo, hi)`` computes one shard explicitly (``qmax_reduce``: callable mapping the shard's integer
-    maximum distance to the global one).  ``impl``: "auto" = both Gram passes on the tcgen05 CTA-pair kernel for rows
-    of 128..1024 bytes (small_k >= 4), the mma.sync kernel otherwise; "mma" / "tcgen05" force one (tests).
+    maximum distance to the global one).  ``impl``: "auto" = the sparse inverted-index join for rows of 64..1024 counts
+    with at most 16 non-zero entries on up to 200,000 nodes, else both Gram passes on the tcgen05 CTA-pair kernel for
+    rows of 128..1024 bytes, else the mma.sync kernel; "sparse" / "tcgen05" / "mma" force one (tests).
     ``hist_mode`` forces where pass 1 of the mma.sync kernel accumulates (tests): 0 global atomics, 1 / 2 shared memory
     16- / 32-bit."""
     if distance not in KNN_METRICS:
         raise ValueError("distance must be 'IP' or 'L2'")
     if impl not in KNN_IMPL:
-        raise ValueError("impl must be 'auto', 'mma' or 'tcgen05'")
+        raise ValueError("impl must be 'auto', 'mma', 'tcgen05' or 'sparse'")
     lib = _lib.load()
     check(lib.gg_knn_set_impl(KNN_IMPL[impl]), "gg_knn_set_impl")
     dev = counts.device
@@ -1529,11 +1530,32 @@ def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance
     st = _stream()
     n_edges, qmax_v = 0, 0
     qmax = torch.zeros(1, dtype=torch.int32, device=dev)
+    # rows of sub-k-mer counts are sparse (<= k - small_k + 1 non-zero entries): wide rows go through the inverted-index
+    # join, which never forms the zero dots; a forced histogram mode names the mma.sync kernel
+    index = None
+    # (below 128 columns the posting lists are so long that the join does more work than the dense kernels: 48 against
+    # 20 ms at 64 columns -- only on request there)
+    if (m > 0 and hist_mode < 0 and (impl == "sparse" or (impl == "auto" and pitch >= 128))
+            and lib.gg_knn_sparse_eligible(pitch, n, n_sq, n_ranks)):
+        ib = int(lib.gg_knn_sparse_index_bytes(n, pitch))
+        index = torch.empty(ib, dtype=torch.uint8, device=dev)
+        idx_status = torch.empty(2, dtype=torch.int64, device=dev)
+        with _stage(f"knn_index_d{pitch}"):
+            check(lib.gg_knn_sparse_index(ptr(counts), pitch, n, ptr(sqnorm), ptr(sqid_d), sq_max, n_sq, ptr(index), ib,
+                                          ptr(idx_status), st), "gg_knn_sparse_index")
+        if int(read_small(idx_status)[0]) != 0:      # a row with more than 16 non-zero counts: not k-mer count rows
+            index = None
+    if index is None and impl == "sparse":
+        raise GGError("the sparse kNN path cannot serve this shape (columns, nodes, classes or non-zero counts per row)")
     if m > 0:
         hist = torch.empty(m * n_ranks, dtype=torch.int32, device=dev)
         with _stage(f"knn_count_d{pitch}"):
-            check(lib.gg_knn_count(ptr(counts), pitch, n, lo, hi, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq,
-                                   dot_max, n_ranks, int(hist_mode), ptr(hist), st), "gg_knn_count")
+            if index is not None:
+                check(lib.gg_knn_sparse_count(ptr(index), ib, pitch, n, lo, hi, ptr(sqnorm), ptr(tab_d), n_sq, dot_max,
+                                              n_ranks, ptr(hist), st), "gg_knn_sparse_count")
+            else:
+                check(lib.gg_knn_count(ptr(counts), pitch, n, lo, hi, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq,
+                                       dot_max, n_ranks, int(hist_mode), ptr(hist), st), "gg_knn_count")
         cut = torch.empty(m, dtype=torch.int32, device=dev)
         tie_left = torch.empty(m, dtype=torch.int32, device=dev)
         row_off = torch.empty(m + 1, dtype=torch.int64, device=dev)
@@ -1565,14 +1587,21 @@ def kf_knn_edges(counts: torch.Tensor, sqnorm: torch.Tensor, k_nn: int, distance
     edge_index = torch.empty((2, n_edges), dtype=torch.int64, device=dev)
     weight = torch.empty(n_edges, dtype=torch.float32, device=dev)
     if n_edges:
-        words = int(lib.gg_knn_write_scratch_words(pitch, n, n_sq, dot_max, n_ranks, m, n_edges))
+        words = n_edges if index is not None else int(lib.gg_knn_write_scratch_words(pitch, n, n_sq, dot_max, n_ranks, m, n_edges))
         recs = torch.empty(words, dtype=torch.int64, device=dev)
         with _stage(f"knn_write_d{pitch}"):
-            check(lib.gg_knn_write(ptr(counts), pitch, n, lo, hi, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq,
-                                   dot_max, n_ranks, metric, ptr(hist), ptr(cut), ptr(tie_left), ptr(row_off), ptr(qmax),
-                                   ptr(recs), words, C.c_void_p(edge_index.data_ptr()),
-                                   C.c_void_p(edge_index.data_ptr() + 8 * n_edges), ptr(weight), n_edges, st),
-                  "gg_knn_write")
+            if index is not None:
+                check(lib.gg_knn_sparse_write(ptr(index), ib, pitch, n, lo, hi, ptr(sqnorm), ptr(tab_d), n_sq, dot_max,
+                                              n_ranks, metric, ptr(hist), ptr(cut), ptr(tie_left), ptr(row_off), ptr(qmax),
+                                              ptr(recs), C.c_void_p(edge_index.data_ptr()),
+                                              C.c_void_p(edge_index.data_ptr() + 8 * n_edges), ptr(weight), n_edges, st),
+                      "gg_knn_sparse_write")
+            else:
+                check(lib.gg_knn_write(ptr(counts), pitch, n, lo, hi, ptr(sqnorm), ptr(sqid_d), sq_max, ptr(tab_d), n_sq,
+                                       dot_max, n_ranks, metric, ptr(hist), ptr(cut), ptr(tie_left), ptr(row_off),
+                                       ptr(qmax), ptr(recs), words, C.c_void_p(edge_index.data_ptr()),
+                                       C.c_void_p(edge_index.data_ptr() + 8 * n_edges), ptr(weight), n_edges, st),
+                      "gg_knn_write")
     if sharded and gather:
         with _stage("c4_gather_knn_edges"):
             edge_index = comm.gather_cat(edge_index, dim=1)

@@ -565,6 +565,375 @@ int launch_knn(const KnnArgs& a, size_t smem, cudaStream_t s) {
   return GG_OK;
 }
 
+// =====================================================================================================================
+// Sparse path: an inverted-index join instead of a Gram matrix.
+//
+// A row of 4^s sub-k-mer counts has at most k - s + 1 non-zero entries (4 of 1024 at k = 8, s = 5), so two rows have a
+// non-zero dot only when they share a column: 1.5 % of the pairs at s = 5.  Both passes therefore never form the zero
+// dots: a CTA takes one row i, walks the posting lists of the row's non-zero columns (rows that hold the column,
+// ascending, with their counts) and accumulates dot(i, j) into a byte per column j in shared memory (N bytes: up to
+// ~200,000 nodes).  Pass 1 then visits the touched j once more, takes each accumulated dot out with an atomic AND (the
+// first visitor of a j gets it, later ones get zero: a j reached through two columns is counted once, and the
+// accumulator is clean again for the next row), and counts ranks; zero-dot members of a column class are its size minus
+// the row's non-zero count for that class, as on the tensor path.  Pass 2 accumulates the same way and then scans the
+// accumulator in COLUMN order (every thread a contiguous column range, two sweeps around a block scan: count, then
+// write), which is the order the tie rule needs; zero-dot columns are selected through the per-column class array.
+// The plan kernels and the reorder kernel are shared with the dense paths.
+// =====================================================================================================================
+constexpr int kSpMaxNnz = 16;        // non-zero entries per row the index holds (rows of k-mer counts: <= 15)
+constexpr int kSpThreads = 256;
+constexpr int kSpMaxNodes = 200000;  // accumulator bytes + tables must fit one CTA's shared memory
+
+constexpr int kKnnMaxSq = 64;
+
+struct SparseIndex {
+  // row side: entries of row i at rnz[i * kSpMaxNnz ...], column | count << 16
+  uint32_t* rnz;
+  uint8_t* rnz_n;
+  // column side (posting lists): rows of column c, ascending, at post[col_start[c] .. col_start[c + 1]), row | count << 24
+  uint32_t* col_start;   // [d + 1]
+  uint32_t* post;        // [n * kSpMaxNnz]
+  uint8_t* colcls;       // [n + 4] norm class of every node (n_sq: none)
+  uint32_t* colcount;    // [kKnnMaxSq] nodes per class
+  unsigned int* cursor;  // [4] row cursors of the two passes
+  // build-time scratch: (column, row | count << 24) pairs in row order -> stable radix sort by column
+  uint32_t* row_start;   // [n + 1]
+  uint16_t *key_in, *key_out;
+  uint32_t* val_in;
+  void* cub_temp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+struct U8ToU32 {
+  __host__ __device__ uint32_t operator()(uint8_t v) const { return v; }
+};
+
+size_t sparse_cub_bytes(int64_t n) {
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, static_cast<const uint16_t*>(nullptr), static_cast<uint16_t*>(nullptr),
+                                  static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<int>(n * kSpMaxNnz));
+  cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(nullptr, U8ToU32());
+  cub::DeviceScan::ExclusiveSum(nullptr, b, it, static_cast<uint32_t*>(nullptr), static_cast<int>(n + 1));
+  return a > b ? a : b;
+}
+
+SparseIndex sparse_carve(void* ws, int64_t n, int d) {
+  gg::Carver c(ws);
+  SparseIndex x;
+  const size_t cap = static_cast<size_t>(n) * kSpMaxNnz;
+  x.rnz = c.take<uint32_t>(cap);
+  x.rnz_n = c.take<uint8_t>(n + 1);
+  x.col_start = c.take<uint32_t>(d + 1);
+  x.post = c.take<uint32_t>(cap);
+  x.colcls = c.take<uint8_t>(n + 4);
+  x.colcount = c.take<uint32_t>(kKnnMaxSq);
+  x.cursor = c.take<unsigned int>(4);
+  x.row_start = c.take<uint32_t>(n + 1);
+  x.key_in = c.take<uint16_t>(cap);
+  x.key_out = c.take<uint16_t>(cap);
+  x.val_in = c.take<uint32_t>(cap);
+  x.cub_bytes = sparse_cub_bytes(n);
+  x.cub_temp = c.take<char>(x.cub_bytes);
+  x.total = c.used();
+  return x;
+}
+
+// one warp per row: non-zero entries of the row (ballot-compacted, ascending column), column histogram, norm class
+__global__ void __launch_bounds__(256) sparse_rows_kernel(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm,
+                                                          const uint8_t* sqid, int sq_max, int n_sq, SparseIndex x,
+                                                          unsigned long long* status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + row * pitch);
+  int found = 0;
+  for (int w0 = 0; w0 < pitch / 4; w0 += 32) {
+    const int w = w0 + lane;
+    const uint32_t v = w < pitch / 4 ? __ldg(src + w) : 0u;
+    for (uint32_t any = __ballot_sync(0xFFFFFFFFu, v != 0u); any; any &= any - 1) {
+      const int l = __ffs(any) - 1;
+      const uint32_t word = __shfl_sync(0xFFFFFFFFu, v, l);
+      if (lane == 0) {
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t cnt = (word >> (8 * b)) & 0xFFu;
+          if (!cnt) continue;
+          const uint32_t col = static_cast<uint32_t>(4 * (w0 + l) + b);
+          if (found < kSpMaxNnz) {
+            x.rnz[row * kSpMaxNnz + found] = col | (cnt << 16);
+            atomicAdd(x.col_start + col + 1, 1u);   // histogram, turned into offsets by the scan
+          }
+          ++found;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    x.rnz_n[row] = static_cast<uint8_t>(found < kSpMaxNnz ? found : kSpMaxNnz);
+    if (found > kSpMaxNnz) atomicMax(status, static_cast<unsigned long long>(found));  // the caller must not use this path
+    const int sq = sqnorm[row];
+    uint32_t cls = 0xFFu;
+    if (sq >= 0 && sq <= sq_max) cls = sqid[sq];
+    x.colcls[row] = static_cast<uint8_t>(cls == 0xFFu ? n_sq : cls);
+    if (cls != 0xFFu) atomicAdd(x.colcount + cls, 1u);
+  }
+}
+
+// col_start[c + 1] holds the size of column c: inclusive scan in place (one CTA; d <= 1024)
+__global__ void __launch_bounds__(1024) sparse_scan_kernel(uint32_t* col_start, int d) {
+  __shared__ uint32_t buf[1024];
+  const int t = threadIdx.x;
+  uint32_t v = t < d ? col_start[t + 1] : 0u;
+  buf[t] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t u = t >= o ? buf[t - o] : 0u;
+    __syncthreads();
+    buf[t] += u;
+    __syncthreads();
+  }
+  if (t < d) col_start[t + 1] = buf[t];
+  if (t == 0) col_start[0] = 0u;
+}
+
+// (column, row | count << 24) pairs in row order; unused slots keep the all-ones key and sort to the end
+__global__ void __launch_bounds__(256) sparse_pairs_kernel(int64_t n, SparseIndex x) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (row >= n) return;
+  const int cnt = x.rnz_n[row];
+  const uint32_t at = x.row_start[row];
+  for (int e = 0; e < cnt; ++e) {
+    const uint32_t ent = x.rnz[row * kSpMaxNnz + e];
+    x.key_in[at + e] = static_cast<uint16_t>(ent & 0xFFFFu);
+    x.val_in[at + e] = static_cast<uint32_t>(row) | ((ent >> 16) << 24);
+  }
+}
+
+struct SparseArgs {
+  SparseIndex x;
+  int64_t n, row_begin, row_end;
+  const int32_t* sqnorm;
+  const uint16_t* rank_tab;   // [n_sq][dot_max + 1]
+  int n_sq, dot_max, n_ranks;
+  uint32_t* hist;             // pass 1 out
+  const int32_t* cut;
+  const int32_t* tie_left;
+  const int64_t* row_off;
+  uint64_t* recs;
+  int per_log2;               // log2 of the accumulator words a thread of pass 2 scans (sp_phys)
+};
+
+// The accumulator holds one byte per node, four to a word.  Pass 2 lets thread t scan the words [t << per_log2,
+// (t + 1) << per_log2) in ascending order, which would put all 32 lanes of a warp on one bank; skewing the layout by one
+// word per thread range (word w lives at w + (w >> per_log2)) makes lane t hit bank (t + step) mod 32 instead.
+__device__ __forceinline__ int sp_phys(int w, int per_log2) { return w + (w >> per_log2); }
+// bit 7 of every non-zero byte
+__device__ __forceinline__ uint32_t nonzero_bytes_sp(uint32_t w) { return (((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u; }
+
+// accumulate dot(i, j) for every j that shares a column with row i: acc is one byte per node (dots are <= 255)
+__device__ __forceinline__ void sparse_accumulate(const SparseArgs& a, int64_t row, uint32_t* acc, uint32_t* lists,
+                                                  int& n_lists, int& total) {
+  // lists[3 e], [3 e + 1], [3 e + 2] = first posting entry, exclusive prefix of the lengths, this row's count
+  const int cnt = a.x.rnz_n[row];
+  if (threadIdx.x < 32) {
+    uint32_t len = 0;
+    if (static_cast<int>(threadIdx.x) < cnt) {
+      const uint32_t ent = a.x.rnz[row * kSpMaxNnz + threadIdx.x];
+      const uint32_t col = ent & 0xFFFFu;
+      const uint32_t first = a.x.col_start[col];
+      len = a.x.col_start[col + 1] - first;
+      lists[3 * threadIdx.x] = first;
+      lists[3 * threadIdx.x + 2] = ent >> 16;
+    }
+    uint32_t incl = len;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (static_cast<int>(threadIdx.x) >= o) incl += u;
+    }
+    if (static_cast<int>(threadIdx.x) < cnt) lists[3 * threadIdx.x + 1] = incl - len;
+    if (threadIdx.x == 31) {
+      lists[3 * kSpMaxNnz] = static_cast<uint32_t>(cnt);
+      lists[3 * kSpMaxNnz + 1] = incl;
+    }
+  }
+  __syncthreads();
+  n_lists = static_cast<int>(lists[3 * kSpMaxNnz]);
+  total = static_cast<int>(lists[3 * kSpMaxNnz + 1]);
+  for (int t = threadIdx.x; t < total; t += kSpThreads) {
+    int e = 0;
+    while (e + 1 < n_lists && lists[3 * (e + 1) + 1] <= static_cast<uint32_t>(t)) ++e;
+    const uint32_t p = __ldg(a.x.post + lists[3 * e] + (t - lists[3 * e + 1]));
+    const uint32_t j = p & 0xFFFFFFu;
+    atomicAdd(acc + sp_phys(static_cast<int>(j >> 2), a.per_log2), ((p >> 24) * lists[3 * e + 2]) << (8 * (j & 3u)));
+  }
+  __syncthreads();
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kSpThreads) knn_sparse_kernel(SparseArgs a, unsigned int* row_cursor) {
+  extern __shared__ __align__(16) uint32_t sp_smem[];
+  const int acc_words = static_cast<int>((a.n + 3) / 4);
+  const int acc_alloc = (sp_phys(acc_words, a.per_log2) + 4) & ~3;
+  uint32_t* acc = sp_smem;                                   // one byte per node, skewed (sp_phys)
+  uint32_t* lists = acc + acc_alloc;                         // [3 * kSpMaxNnz + 2]
+  uint32_t* shist = lists + 3 * kSpMaxNnz + 4;               // pass 1: [n_ranks] + [n_sq] non-zero counts per class
+  uint32_t* scan = lists + 3 * kSpMaxNnz + 4;                // pass 2: [2 * kSpThreads] block scan
+  __shared__ int s_row;
+  const int tstride = a.dot_max + 1;
+  for (int i = threadIdx.x; i < acc_alloc; i += kSpThreads) acc[i] = 0u;
+  if (PASS == 1)
+    for (int i = threadIdx.x; i < a.n_ranks + a.n_sq; i += kSpThreads) shist[i] = 0u;
+  __syncthreads();
+  while (true) {
+    if (threadIdx.x == 0) s_row = static_cast<int>(atomicAdd(row_cursor, 1u));
+    __syncthreads();
+    const int64_t row = a.row_begin + s_row;
+    __syncthreads();
+    if (row >= a.row_end) break;
+    int n_lists, total;
+    sparse_accumulate(a, row, acc, lists, n_lists, total);
+    const int64_t loc = row - a.row_begin;
+    if (PASS == 1) {
+      uint32_t* nzc = shist + a.n_ranks;
+      for (int t = threadIdx.x; t < total; t += kSpThreads) {
+        int e = 0;
+        while (e + 1 < n_lists && lists[3 * (e + 1) + 1] <= static_cast<uint32_t>(t)) ++e;
+        const uint32_t j = __ldg(a.x.post + lists[3 * e] + (t - lists[3 * e + 1])) & 0xFFFFFFu;
+        const int sh = 8 * (j & 3u);
+        const uint32_t old = atomicAnd(acc + sp_phys(static_cast<int>(j >> 2), a.per_log2), ~(0xFFu << sh));   // the first visitor of j takes the dot out
+        const uint32_t dot = (old >> sh) & 0xFFu;
+        if (!dot) continue;
+        const uint32_t cls = a.x.colcls[j];
+        if (cls >= static_cast<uint32_t>(a.n_sq)) continue;
+        atomicAdd(nzc + cls, 1u);            // the self pair too: it is not a zero-dot column
+        if (static_cast<int64_t>(j) == row) continue;
+        const uint32_t r = a.rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
+        if (r != kNoRank) atomicAdd(shist + r, 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x < a.n_sq) {   // zero-dot members of every class
+        const int c = threadIdx.x;
+        const uint32_t r0 = a.rank_tab[c * tstride];
+        if (r0 != kNoRank) {
+          const int sq_row = a.sqnorm[row];
+          const bool own = sq_row == 0 && a.x.colcls[row] == c;   // an all-zero row meets itself with dot 0
+          atomicAdd(shist + r0, a.x.colcount[c] - nzc[c] - (own ? 1u : 0u));
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < a.n_ranks; i += kSpThreads) {
+        a.hist[loc * a.n_ranks + i] = shist[i];
+        shist[i] = 0u;
+      }
+      if (threadIdx.x < a.n_sq) nzc[threadIdx.x] = 0u;
+      __syncthreads();
+    } else {
+      // column-ordered selection: thread t owns the words [t * per, (t + 1) * per) of the accumulator
+      const int cut = a.cut[loc], budget = a.tie_left[loc];
+      uint32_t zsel = 0, ztie = 0;   // classes whose zero-dot columns rank above / at the cut (n_sq <= 32 here)
+      for (int c = 0; c < a.n_sq; ++c) {
+        const int r0 = a.rank_tab[c * tstride];
+        zsel |= static_cast<uint32_t>(r0 < cut) << c;
+        ztie |= static_cast<uint32_t>(r0 == cut) << c;
+      }
+      const bool zeros = (zsel | ztie) != 0u;
+      const int per = 1 << a.per_log2;
+      const int w_lo = min(acc_words, static_cast<int>(threadIdx.x) * per), w_hi = min(acc_words, w_lo + per);
+      uint32_t* my_acc = acc + threadIdx.x;   // sp_phys(w) = w + threadIdx.x inside this thread's range
+      // A lane's range holds a handful of non-zero words, but some lane of the warp has one at nearly every step: walking
+      // the range word by word would run the per-column code 64 times per sweep with one or two lanes busy.  So the
+      // range is looked at once, 64 words at a time, for a bit mask of the words that matter (all of them when zero-dot
+      // columns can be selected), and both sweeps walk the set bits.
+      int n_sel = 0, n_tie = 0;
+      for (int pass2 = 0; pass2 < 2; ++pass2) {
+        int sel_before = 0, tie_before = 0, tie_room = 0;
+        long long out = 0;
+        if (pass2) {
+          sel_before = static_cast<int>(scan[threadIdx.x]);
+          tie_before = static_cast<int>(scan[kSpThreads + threadIdx.x]);
+          tie_room = budget - tie_before;   // members of the cut rank this thread may still take, in column order
+          out = a.row_off[loc] + sel_before + (tie_before < budget ? tie_before : budget);
+        }
+        for (int w0 = w_lo; w0 < w_hi; w0 += 64) {
+          const int span = min(64, w_hi - w0);
+          unsigned long long mask = 0;
+          if (zeros) {
+            mask = span == 64 ? ~0ull : ((1ull << span) - 1ull);
+          } else {
+            for (int i = 0; i < span; ++i) mask |= static_cast<unsigned long long>(my_acc[w0 + i] != 0u) << i;
+          }
+          for (; mask; mask &= mask - 1) {
+            const int w = w0 + __ffsll(static_cast<long long>(mask)) - 1;
+            const uint32_t word = my_acc[w];
+            if (pass2 && word) my_acc[w] = 0u;   // clean for the next row
+            const uint32_t cls4 = *reinterpret_cast<const uint32_t*>(a.x.colcls + 4 * w);
+            // the columns of the word that matter: non-zero dots, or all four when zero dots can be selected
+            for (uint32_t bm = zeros ? 0x80808080u : nonzero_bytes_sp(word); bm; bm &= bm - 1) {
+              const int b = (__ffs(bm) - 1) >> 3;
+              const int64_t j = 4ll * w + b;
+              if (j >= a.n || j == row) continue;
+              const uint32_t dot = (word >> (8 * b)) & 0xFFu, cls = (cls4 >> (8 * b)) & 0xFFu;
+              if (cls >= static_cast<uint32_t>(a.n_sq)) continue;
+              const int r = a.rank_tab[cls * tstride + min(dot, static_cast<uint32_t>(a.dot_max))];
+              if (!pass2) {
+                n_sel += r < cut;
+                n_tie += r == cut;
+              } else {
+                bool take = r < cut;
+                if (r == cut && tie_room > 0) {
+                  take = true;
+                  --tie_room;
+                }
+                if (take)
+                  a.recs[out++] = static_cast<uint64_t>(j) | static_cast<uint64_t>(dot) << 32 | static_cast<uint64_t>(r) << 48;
+              }
+            }
+          }
+        }
+        if (pass2) break;
+        scan[threadIdx.x] = static_cast<uint32_t>(n_sel);
+        scan[kSpThreads + threadIdx.x] = static_cast<uint32_t>(n_tie);
+        __syncthreads();
+        if (threadIdx.x < 32) {   // exclusive scans of both arrays by one warp
+          uint32_t run_s = 0, run_t = 0;
+          for (int i0 = 0; i0 < kSpThreads; i0 += 32) {
+            const uint32_t vs = scan[i0 + threadIdx.x], vt = scan[kSpThreads + i0 + threadIdx.x];
+            uint32_t is = vs, it = vt;
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t us = __shfl_up_sync(0xFFFFFFFFu, is, o), ut = __shfl_up_sync(0xFFFFFFFFu, it, o);
+              if (static_cast<int>(threadIdx.x) >= o) {
+                is += us;
+                it += ut;
+              }
+            }
+            scan[i0 + threadIdx.x] = run_s + is - vs;
+            scan[kSpThreads + i0 + threadIdx.x] = run_t + it - vt;
+            run_s += __shfl_sync(0xFFFFFFFFu, is, 31);
+            run_t += __shfl_sync(0xFFFFFFFFu, it, 31);
+          }
+        }
+        __syncthreads();
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int sparse_per_log2(int64_t n) {
+  const int64_t acc_words = (n + 3) / 4;
+  int lg = 0;
+  while ((static_cast<int64_t>(kSpThreads) << lg) < acc_words) ++lg;
+  return lg;
+}
+
+size_t sparse_smem(int64_t n, int n_ranks, int n_sq, int pass) {
+  const size_t acc_words = (static_cast<size_t>(n) + 3) / 4;
+  const size_t acc_alloc = (acc_words + (acc_words >> sparse_per_log2(n)) + 4) & ~static_cast<size_t>(3);
+  const size_t tail = pass == 1 ? static_cast<size_t>(n_ranks + n_sq) : 2 * kSpThreads;
+  return (acc_alloc + 3 * kSpMaxNnz + 4 + tail) * sizeof(uint32_t);
+}
+
 // the tcgen05 CTA-pair Gram serves rows of 128..1024 bytes (small_k >= 4) with at most 32 norm classes
 int use_tc(const KnnArgs& a, int pass, bool& yes) {
   const int impl = g_knn_impl.load();
@@ -594,7 +963,7 @@ ggkf::KnnTcArgs tc_args(const KnnArgs& a) {
 }  // namespace
 
 extern "C" int gg_knn_set_impl(int impl) {
-  GG_REQUIRE(impl >= 0 && impl <= 2, GG_ERR_ARG, "impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+  GG_REQUIRE(impl >= 0 && impl <= 3, GG_ERR_ARG, "impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05) or 3 (sparse)");
   g_knn_impl.store(impl);
   return GG_OK;
 }
@@ -740,6 +1109,130 @@ extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t
   }
   if (int rc2 = launch_knn<2, kHistGlobal>(a, knn_base_smem(a.kpad, a.chunk, n_sq, dot_max), s)) return rc2;
   order_kernel<<<grid, 256, 0, s>>>(o);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+/* ---- sparse (inverted-index) flavour of the two passes: rows with at most 16 non-zero counts, up to 200,000 nodes ------ */
+extern "C" int gg_knn_sparse_eligible(int pitch, int64_t n, int n_sq, int n_ranks) {
+  if (g_knn_impl.load() != 0 && g_knn_impl.load() != 3) return 0;
+  if (pitch < 64 || pitch > 1024 || pitch % 4 != 0 || n < 2 || n > kSpMaxNodes || n_sq < 1 || n_sq > 32) return 0;
+  const size_t worst = sparse_smem(n, n_ranks, n_sq, 1) > sparse_smem(n, n_ranks, n_sq, 2) ? sparse_smem(n, n_ranks, n_sq, 1)
+                                                                                             : sparse_smem(n, n_ranks, n_sq, 2);
+  return worst <= kSmemLimit ? 1 : 0;
+}
+
+extern "C" size_t gg_knn_sparse_index_bytes(int64_t n, int pitch) {
+  if (n < 1 || pitch < 4 || pitch > 1024) return 0;
+  return sparse_carve(nullptr, n, pitch).total;
+}
+
+/* status (device int64[2]): [0] the largest non-zero count of a row when it exceeds 16 (the index is then unusable) */
+extern "C" int gg_knn_sparse_index(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
+                                   int sq_max, int n_sq, void* index, size_t index_bytes, int64_t* status, gg_stream_t st) {
+  GG_REQUIRE(counts && sqnorm && sqid && index && status, GG_ERR_ARG, "null argument");
+  GG_REQUIRE(n >= 1 && n <= kSpMaxNodes && pitch >= 4 && pitch <= 1024 && pitch % 4 == 0, GG_ERR_ARG, "bad shape");
+  GG_REQUIRE(n_sq >= 1 && n_sq <= 32 && sq_max >= 0 && sq_max <= 254, GG_ERR_ARG, "bad class table");
+  SparseIndex x = sparse_carve(index, n, pitch);
+  GG_REQUIRE(index_bytes >= x.total, GG_ERR_WORKSPACE, "index workspace too small");
+  cudaStream_t s = gg::as_stream(st);
+  GG_CUDA_CHECK(cudaMemsetAsync(status, 0, 2 * sizeof(int64_t), s));
+  GG_CUDA_CHECK(cudaMemsetAsync(x.col_start, 0, (pitch + 1) * sizeof(uint32_t), s));
+  GG_CUDA_CHECK(cudaMemsetAsync(x.colcount, 0, kKnnMaxSq * sizeof(uint32_t), s));
+  GG_CUDA_CHECK(cudaMemsetAsync(x.key_in, 0xFF, static_cast<size_t>(n) * kSpMaxNnz * sizeof(uint16_t), s));
+  GG_CUDA_CHECK(cudaMemsetAsync(x.rnz_n + n, 0, 1, s));
+  const unsigned wgrid = static_cast<unsigned>((n * 32 + 255) / 256), grid = static_cast<unsigned>((n + 255) / 256);
+  sparse_rows_kernel<<<wgrid, 256, 0, s>>>(counts, pitch, n, sqnorm, sqid, sq_max, n_sq, x,
+                                           reinterpret_cast<unsigned long long*>(status));
+  GG_CUDA_CHECK(cudaGetLastError());
+  sparse_scan_kernel<<<1, 1024, 0, s>>>(x.col_start, pitch);
+  GG_CUDA_CHECK(cudaGetLastError());
+  size_t tb = x.cub_bytes;
+  cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> it(x.rnz_n, U8ToU32());
+  GG_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(x.cub_temp, tb, it, x.row_start, static_cast<int>(n + 1), s));
+  sparse_pairs_kernel<<<grid, 256, 0, s>>>(n, x);
+  GG_CUDA_CHECK(cudaGetLastError());
+  tb = x.cub_bytes;
+  int bits = 1;
+  while ((1 << bits) < pitch) ++bits;   // pads (0xFFFF) still sort behind every real column on one more bit
+  GG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(x.cub_temp, tb, x.key_in, x.key_out, x.val_in, x.post,
+                                                static_cast<int>(n * kSpMaxNnz), 0, bits + 1, s));
+  return GG_OK;
+}
+
+static int sparse_args(SparseArgs& a, void* index, size_t index_bytes, int pitch, int64_t n, int64_t row_begin,
+                       int64_t row_end, const int32_t* sqnorm, const uint16_t* rank_tab, int n_sq, int dot_max,
+                       int n_ranks) {
+  GG_REQUIRE(index && sqnorm && rank_tab, GG_ERR_ARG, "null argument");
+  GG_REQUIRE(n >= 2 && n <= kSpMaxNodes && pitch >= 4 && pitch <= 1024, GG_ERR_ARG, "bad shape");
+  GG_REQUIRE(row_begin >= 0 && row_begin < row_end && row_end <= n, GG_ERR_ARG, "bad row shard");
+  GG_REQUIRE(n_sq >= 1 && n_sq <= 32 && dot_max >= 0 && n_ranks >= 1 && n_ranks < 0xFFFF, GG_ERR_ARG, "bad class table");
+  a = SparseArgs{};
+  a.x = sparse_carve(index, n, pitch);
+  GG_REQUIRE(index_bytes >= a.x.total, GG_ERR_WORKSPACE, "index workspace too small");
+  a.n = n;
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  a.sqnorm = sqnorm;
+  a.rank_tab = rank_tab;
+  a.n_sq = n_sq;
+  a.dot_max = dot_max;
+  a.n_ranks = n_ranks;
+  a.per_log2 = sparse_per_log2(n);
+  return GG_OK;
+}
+
+template <int PASS>
+static int launch_sparse(const SparseArgs& a, cudaStream_t s) {
+  const size_t smem = sparse_smem(a.n, a.n_ranks, a.n_sq, PASS);
+  GG_REQUIRE(smem <= kSmemLimit, GG_ERR_ARG, "accumulator does not fit shared memory");
+  GG_CUDA_CHECK(cudaFuncSetAttribute(knn_sparse_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+  int per_sm = 0;
+  GG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, knn_sparse_kernel<PASS>, kSpThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t rows = a.row_end - a.row_begin;
+  const int64_t cap = static_cast<int64_t>(gg::sm_count()) * per_sm;
+  unsigned int* cursor = a.x.cursor + (PASS - 1);
+  GG_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(unsigned int), s));
+  knn_sparse_kernel<PASS><<<static_cast<unsigned>(rows < cap ? rows : cap), kSpThreads, smem, s>>>(a, cursor);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+extern "C" int gg_knn_sparse_count(void* index, size_t index_bytes, int pitch, int64_t n, int64_t row_begin,
+                                   int64_t row_end, const int32_t* sqnorm, const uint16_t* rank_tab, int n_sq, int dot_max,
+                                   int n_ranks, uint32_t* hist, gg_stream_t st) {
+  SparseArgs a;
+  if (int rc = sparse_args(a, index, index_bytes, pitch, n, row_begin, row_end, sqnorm, rank_tab, n_sq, dot_max, n_ranks))
+    return rc;
+  GG_REQUIRE(hist, GG_ERR_ARG, "null histogram");
+  a.hist = hist;
+  return launch_sparse<1>(a, gg::as_stream(st));
+}
+
+extern "C" int gg_knn_sparse_write(void* index, size_t index_bytes, int pitch, int64_t n, int64_t row_begin,
+                                   int64_t row_end, const int32_t* sqnorm, const uint16_t* rank_tab, int n_sq, int dot_max,
+                                   int n_ranks, int metric, uint32_t* cursors, const int32_t* cut, const int32_t* tie_left,
+                                   const int64_t* row_offsets, const int32_t* qmax, uint64_t* recs, int64_t* edge_src,
+                                   int64_t* edge_dst, float* weight, int64_t capacity, gg_stream_t st) {
+  SparseArgs a;
+  if (int rc = sparse_args(a, index, index_bytes, pitch, n, row_begin, row_end, sqnorm, rank_tab, n_sq, dot_max, n_ranks))
+    return rc;
+  GG_REQUIRE(metric == 0 || metric == 1, GG_ERR_ARG, "metric must be 0 (IP) or 1 (L2)");
+  GG_REQUIRE(cursors && cut && tie_left && row_offsets && qmax, GG_ERR_ARG, "null plan");
+  GG_REQUIRE(capacity >= 0 && (capacity == 0 || (recs && edge_src && edge_dst && weight)), GG_ERR_ARG, "null output");
+  GG_REQUIRE(capacity < (int64_t(1) << 32), GG_ERR_ARG, "more than 2^32 - 1 edges");
+  if (capacity == 0) return GG_OK;
+  a.cut = cut;
+  a.tie_left = tie_left;
+  a.row_off = row_offsets;
+  a.recs = recs;
+  cudaStream_t s = gg::as_stream(st);
+  if (int rc = launch_sparse<2>(a, s)) return rc;
+  const int64_t m = row_end - row_begin;
+  OrderArgs o{recs, row_offsets, m, row_begin, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
+  order_kernel<<<static_cast<unsigned>((m * 32 + 255) / 256), 256, 0, s>>>(o);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

@@ -407,7 +407,8 @@ GG_API int gg_spmm_csr_f32(const int64_t* row_ptr, const int32_t* col, const flo
  * pitch: bytes per row of counts: 4, 8, or a multiple of 16 (of 128 above 128) up to 1024.
  * ------------------------------------------------------------------------ */
 /* Which Gram kernel serves both passes: 0 = auto (the tcgen05 CTA-pair kernel for rows of 128..1024 bytes with at most
- * 32 norm classes, else the mma.sync kernel), 1 = mma.sync only, 2 = tcgen05 or an error.  Process-wide. */
+ * 32 norm classes, else the mma.sync kernel), 1 = mma.sync only, 2 = tcgen05 or an error, 3 = as 0 (names the sparse
+ * flavour below for gg_knn_sparse_eligible).  Process-wide. */
 GG_API int gg_knn_set_impl(int impl);
 GG_API int gg_knn_count(const uint8_t* counts, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
                  const int32_t* sqnorm, const uint8_t* sqid, int sq_max, const uint16_t* rank_tab, int n_sq, int dot_max,
@@ -429,6 +430,25 @@ GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row
                  uint64_t* recs /* scratch */, int64_t recs_words /* >= gg_knn_write_scratch_words() */,
                  int64_t* edge_src, int64_t* edge_dst, float* weight, int64_t capacity /* = row_offsets[m] */,
                  gg_stream_t st);
+
+/* Sparse flavour of the two passes (rows with at most 16 non-zero counts -- rows of sub-k-mer counts have at most
+ * k - small_k + 1 --, 64..1024 columns, up to 200,000 nodes): an inverted-index join that never forms the zero dots.
+ * gg_knn_sparse_index builds row lists + posting lists + norm classes into a caller-owned workspace
+ * (gg_knn_sparse_index_bytes); idx_status (device int64[2]): [0] != 0 = a row holds more than 16 non-zero counts, the
+ * index must not be used.  gg_knn_sparse_count / gg_knn_sparse_write replace gg_knn_count / gg_knn_write between the same
+ * gg_knn_plan calls (recs: row_offsets[m] words); results are identical. */
+GG_API int gg_knn_sparse_eligible(int pitch, int64_t n, int n_sq, int n_ranks);
+GG_API size_t gg_knn_sparse_index_bytes(int64_t n, int pitch);
+GG_API int gg_knn_sparse_index(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,
+                        int sq_max, int n_sq, void* index, size_t index_bytes, int64_t* idx_status, gg_stream_t st);
+GG_API int gg_knn_sparse_count(void* index, size_t index_bytes, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
+                        const int32_t* sqnorm, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, uint32_t* hist,
+                        gg_stream_t st);
+GG_API int gg_knn_sparse_write(void* index, size_t index_bytes, int pitch, int64_t n, int64_t row_begin, int64_t row_end,
+                        const int32_t* sqnorm, const uint16_t* rank_tab, int n_sq, int dot_max, int n_ranks, int metric,
+                        uint32_t* cursors, const int32_t* cut, const int32_t* tie_left, const int64_t* row_offsets,
+                        const int32_t* qmax, uint64_t* recs, int64_t* edge_src, int64_t* edge_dst, float* weight,
+                        int64_t capacity, gg_stream_t st);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU exchanges over NVLink peer memory (no reference counterpart: the reference is single-device).

@@ -167,10 +167,17 @@ def test_round2_entry_points_validate_their_arguments_without_a_gpu():
     lib = _lib.load()
     ERR_ARG = -1
     assert lib.gg_kf_counts_upto(None, 16, None, 8, 2, None, None, None, None) == ERR_ARG      # the device row count
-    assert lib.gg_knn_set_impl(3) == ERR_ARG
+    assert lib.gg_knn_set_impl(4) == ERR_ARG
     assert lib.gg_knn_set_impl(1) == 0                                                        # mma.sync kernel: ...
     assert lib.gg_knn_write_scratch_words(1024, 65536, 5, 16, 48, 65536, 1000) == 1000        # ... one word per edge
     assert lib.gg_knn_set_impl(0) == 0
     assert lib.gg_knn_write_scratch_words(16, 65536, 40, 49, 700, 65536, 1000) == 1000        # narrow rows: never tcgen05
     assert lib.gg_knn_write(None, 1024, 4096, 0, 4096, None, None, 16, None, 5, 16, 48, 0, None, None, None, None, None,
                             None, 0, None, None, None, 0, None) == ERR_ARG
+    # the sparse flavour: shapes it serves, index size, argument checks
+    assert lib.gg_knn_sparse_eligible(1024, 65536, 5, 48) == 1
+    assert lib.gg_knn_sparse_eligible(16, 65536, 40, 700) == 0            # narrow rows are dense
+    assert lib.gg_knn_sparse_eligible(1024, 1 << 20, 5, 48) == 0          # one byte per node must fit shared memory
+    assert lib.gg_knn_sparse_index_bytes(65536, 1024) > 65536 * 16 * 4
+    assert lib.gg_knn_sparse_index(None, 1024, 65536, None, None, 16, 5, None, 0, None, None) == ERR_ARG
+    assert lib.gg_knn_sparse_count(None, 0, 1024, 65536, 0, 65536, None, None, 5, 16, 48, None, None) == ERR_ARG

@@ -56,7 +56,7 @@ def test_knn_matches_exact_search(k, s, n_reads, frac, distance):
 ])
 @pytest.mark.parametrize("distance", ["IP", "L2"])
 def test_knn_tcgen05_matches_mma(k, s, n_reads, frac, distance):
-    """Both Gram passes on the tcgen05 CTA-pair kernel (rank histograms with the zero-dot classes by subtraction, pass 2
+    """The inverted-index join and both Gram passes on the tcgen05 CTA-pair kernel (rank histograms with the zero-dot classes by subtraction, pass 2
     by one epilogue group in column order) against the mma.sync kernel: identical edges, order and weights -- whole and
     as a 128-aligned row shard."""
     from genomic_gnn_b200 import core
@@ -68,12 +68,29 @@ def test_knn_tcgen05_matches_mma(k, s, n_reads, frac, distance):
     b = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, impl="tcgen05")
     assert a.edge_index.shape[1] > 0
     assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight, b.weight)
+    if n <= 200_000:   # the inverted-index join (the default for these shapes)
+        c = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, impl="sparse")
+        assert torch.equal(a.edge_index, c.edge_index) and torch.equal(a.weight, c.weight)
     if n >= 1024 and k <= 8:
         lo, hi = 384, min(n, 384 + 640)   # a shard that starts inside a strip pair
         fix = (lambda q: q) if distance == "L2" else None
         a1 = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, rows=(lo, hi), qmax_reduce=fix, impl="mma")
         b1 = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, rows=(lo, hi), qmax_reduce=fix, impl="tcgen05")
         assert torch.equal(a1.edge_index, b1.edge_index) and torch.equal(a1.weight, b1.weight)
+        c1 = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, distance, rows=(lo, hi), qmax_reduce=fix, impl="sparse")
+        assert torch.equal(a1.edge_index, c1.edge_index) and torch.equal(a1.weight, c1.weight)
+
+
+@pytest.mark.parametrize("distance", ["IP", "L2"])
+def test_knn_sparse_on_64_columns(distance):
+    """Rows of 64 counts (small_k = 3): too narrow for the tensor path, still sparse enough for the join."""
+    from genomic_gnn_b200 import core
+
+    built, kc = _built(6, 3, 4000)
+    a = core.kf_knn_edges(kc.counts, kc.sqnorm, 60, distance, impl="mma")
+    c = core.kf_knn_edges(kc.counts, kc.sqnorm, 60, distance, impl="sparse")
+    assert a.edge_index.shape[1] > 0
+    assert torch.equal(a.edge_index, c.edge_index) and torch.equal(a.weight, c.weight)
 
 
 @pytest.mark.parametrize("hist_mode", [0, 1, 2])

@@ -511,6 +511,28 @@ def test_internal_n_bridge(gg):
     assert pf[("CCC", "CCC")] == 2          # one overlapping bridge folded into the (k+1)-mer bin + one ordinary
 
 
+def test_more_bridge_records_than_the_default_room(gg):
+    """Every read holds an internal N run, so the one-read build (K1 + K2 + K3 behind one device read, assembled on the
+    assumption of a stream without bridge records) has to fall back twice: bridge records exist, and there are more of
+    them than the default 65,536 slots -- the stream is counted again with room for all."""
+    from genomic_gnn_b200 import core
+
+    rng = np.random.default_rng(17)
+    bases = np.frombuffer(b"ACGT", np.uint8)
+    reads = []
+    for _ in range(70_000):
+        a = bases[rng.integers(0, 4, 14)].tobytes().decode()
+        b = bases[rng.integers(0, 4, 14)].tobytes().decode()
+        reads.append(a + "N" * int(rng.integers(1, 3)) + b)
+    want = fast.build_graph(reads, 4, "2", edges_threshold=0.9)
+    got = core.build_graph(reads, 4, "2", edges_threshold=0.9)
+    assert np.array_equal(got.db.node_codes.cpu().numpy(), want["node_codes"])
+    assert np.array_equal(got.db.edge_index.cpu().numpy(), want["edge_index"])
+    assert np.array_equal(got.db.weight.cpu().numpy(), want["weight"])
+    assert np.array_equal(got.x[0].cpu().numpy(), want["y_0"])
+    assert np.array_equal(got.kf[0].edge_index.cpu().numpy(), want["edge_index_KF0"])
+
+
 def test_skewed_low_complexity_reads(gg):
     from genomic_gnn_b200 import core
 
