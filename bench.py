@@ -613,35 +613,45 @@ def run_ours(a):
                                            "note": "issue-bound sparse class sweeps; floor = edge bytes written once"}
     dominant = max(rooflines, key=lambda k_: rooflines[k_]["ms"]) if rooflines else None
     # the per-row kNN mode of the KF edges (--representation_ss_faiss_ann: kf_faiss_to_edge_index_weight, k = int(p N)
-    # neighbours per node) is not part of the step; its two Gram passes run on the same tensor kernel family and are
-    # quoted beside it (widest set, metric "IP", full N x N matrix per pass)
+    # neighbours per node) is not part of the step; it is quoted beside it for the widest set (metric "IP"): the default
+    # path for rows this sparse (an inverted-index join, shared-memory bound) and the two Gram passes on the tensor kernel
     knn_line = None
     if rank == 0 and world == 1 and not big and not a.no_probes and a.top_k:
         kc = max(built.kf_counts, key=lambda kc_: int(kc_.counts.shape[1]))
         d_knn, k_nn = int(kc.counts.shape[1]), int(a.top_k * n_nodes)
         if d_knn >= 128 and 1 <= k_nn < n_nodes:
-            for _ in range(2):
-                core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, "IP")
-            ktimer = core.StageTimer()
-            core.set_timer(ktimer)
-            reps = 3
-            for _ in range(reps):
-                flush.fill_(1)
-                res = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, "IP")
-            core.set_timer(None)
-            kms = {k_: sum(v) / reps for k_, v in ktimer.summary().items()}
-            gram_ms = kms.get(f"knn_count_d{d_knn}", 0.0) + kms.get(f"knn_write_d{d_knn}", 0.0)
-            kflops = 2 * 2.0 * d_knn * n_nodes * n_nodes
-            ach = kflops / (gram_ms * 1e-3) / 1e12
-            knn_line = {"bound": "tensor", "achieved": ach, "unit": "TFLOP/s", "ms": gram_ms, "stage_ms": kms,
-                        "algorithmic_flops": kflops, "gram_passes": 2, "k": k_nn, "metric": "IP", "nodes": n_nodes, "d": d_knn,
-                        "edges": int(res.edge_index.shape[1]), "pairs_per_s": 2.0 * n_nodes * (n_nodes - 1) / (gram_ms * 1e-3),
-                        "kernel": "knn_tc_pair_kernel<1|2> (tcgen05.mma.cta_group::2.kind::i8) + plan + reorder",
-                        "note": "epilogue-bound: per-pair work on the non-zero dots of every row (DESIGN.md section 7b)"}
-            if "tensor_i8" in probes:
-                knn_line.update({"peak": probes["tensor_i8"]["tops"], "frac": ach / probes["tensor_i8"]["tops"],
-                                 "peak_source": "measured in-process: " + probes["tensor_i8"]["how"]})
-            del res
+            def time_knn(impl, reps=3):
+                for _ in range(2):
+                    core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, "IP", impl=impl)
+                ktimer = core.StageTimer()
+                core.set_timer(ktimer)
+                for _ in range(reps):
+                    flush.fill_(1)
+                    res = core.kf_knn_edges(kc.counts, kc.sqnorm, k_nn, "IP", impl=impl)
+                core.set_timer(None)
+                kms = {k_: sum(v) / reps for k_, v in ktimer.summary().items()}
+                return kms, sum(kms.values()), int(res.edge_index.shape[1])
+
+            kms, total_ms, n_e = time_knn("auto")
+            knn_line = {"impl": "auto: inverted-index join (knn_sparse_kernel<1|2>) + plan + reorder", "ms": total_ms,
+                        "stage_ms": kms, "k": k_nn, "metric": "IP", "nodes": n_nodes, "d": d_knn, "edges": n_e,
+                        "pairs_per_s": n_nodes * (n_nodes - 1) / (total_ms * 1e-3), "edges_per_s": n_e / (total_ms * 1e-3),
+                        "bound": "shared memory / issue (sparse rows: only pairs with a non-zero dot are formed)"}
+            try:
+                tms, t_total, _ = time_knn("tcgen05")
+                gram_ms = tms.get(f"knn_count_d{d_knn}", 0.0) + tms.get(f"knn_write_d{d_knn}", 0.0)
+                kflops = 2 * 2.0 * d_knn * n_nodes * n_nodes
+                ach = kflops / (gram_ms * 1e-3) / 1e12
+                tline = {"ms": t_total, "stage_ms": tms, "bound": "tensor", "achieved": ach, "unit": "TFLOP/s",
+                         "algorithmic_flops": kflops, "gram_passes": 2,
+                         "kernel": "knn_tc_pair_kernel<1|2> (tcgen05.mma.cta_group::2.kind::i8) + plan + reorder",
+                         "note": "epilogue-bound: per-pair work on the non-zero dots of every row (DESIGN.md section 7b)"}
+                if "tensor_i8" in probes:
+                    tline.update({"peak": probes["tensor_i8"]["tops"], "frac": ach / probes["tensor_i8"]["tops"],
+                                  "peak_source": "measured in-process: " + probes["tensor_i8"]["how"]})
+                knn_line["tcgen05"] = tline
+            except Exception as exc:  # noqa: BLE001
+                knn_line["tcgen05"] = {"unavailable": str(exc)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if rooflines and os.path.exists(traffic_file) and not big:  # per-launch DRAM bytes from the committed ncu --set full capture
         with open(traffic_file) as fh:
