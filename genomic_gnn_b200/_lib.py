@@ -108,6 +108,7 @@ SIGNATURES = {
     "gg_knn_count": (_I32, [_P, _I32, _I64, _I64, _I64, _P, _P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "gg_knn_plan_workspace_bytes": (_SZ, [_I64]),
     "gg_knn_plan": (_I32, [_I64, _I64, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
+    "gg_kf_emit_sparse": (_I32, [_P, _SZ, _I32, _I64, _I32, _I32, _P, _P, _P, _I64, _P, _P, _P]),
     "gg_knn_sparse_eligible": (_I32, [_I32, _I64, _I32, _I32]),
     "gg_knn_sparse_index_bytes": (_SZ, [_I64, _I32]),
     "gg_knn_sparse_index": (_I32, [_P, _I32, _I64, _P, _P, _I32, _I32, _P, _SZ, _P, _P]),

@@ -701,8 +701,27 @@ def kf_hist_bins(sq_max: int) -> int:
     return (sq_max + 1) * (sq_max * sq_max + 1)
 
 
+def kf_sparse_index(counts: torch.Tensor, sqnorm: torch.Tensor):
+    """Row lists + posting lists of a count matrix with sparse rows (gg_knn_sparse_index), for gg_kf_emit_sparse.
+    Returns (index tensor, its size, device status int64[2]: [0] != 0 = a row has more than 16 non-zero counts)."""
+    lib = _lib.load()
+    dev = counts.device
+    n, pitch = int(counts.shape[0]), int(counts.shape[1])
+    ib = int(lib.gg_knn_sparse_index_bytes(n, pitch))
+    index = torch.empty(ib, dtype=torch.uint8, device=dev)
+    status = torch.empty(2, dtype=torch.int64, device=dev)
+    key = ("nocls", str(dev))
+    if key not in _DEVICE_LUTS:     # norm classes are a kNN matter: one empty table for every KF build
+        _DEVICE_LUTS[key] = torch.full((256,), 0xFF, dtype=torch.uint8, device=dev)
+    with _stage(f"k4_index_d{pitch}"):
+        check(lib.gg_knn_sparse_index(ptr(counts), pitch, n, ptr(sqnorm), ptr(_DEVICE_LUTS[key]), 254, 1, ptr(index), ib,
+                                      ptr(status), _stream()), "gg_knn_sparse_index")
+    return index, ib, status
+
+
 def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, iblock_begin=0,
-            iblock_end=None, impl="auto", rec_capacity=None, sync=True, class_hist=None, hist_m=0, retry=True):
+            iblock_end=None, impl="auto", rec_capacity=None, sync=True, class_hist=None, hist_m=0, retry=True,
+            sparse_index=None):
     """Score all pairs of the row-block shard and stage the candidates (``threshold``: float or ScoreTest).
     Returns (recs, n_recs, rowcnt, params, counts_scored): the last is the matrix the kernel read (zero-padded to a
     32-byte pitch for the tensor path on narrow rows), which kf_finalize needs to re-multiply narrow rows.
@@ -720,7 +739,11 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, 
     nb = _row_blocks(n)
     iblock_end = nb if iblock_end is None else iblock_end
     dmin_d, scale_d, shift, p_max = _device_tables(_as_test(threshold), int(sq_max), dev)
-    params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL[impl], d_valid, int(hist_m))
+    sparse = impl == "sparse"
+    if sparse and sparse_index is None:
+        sparse_index = kf_sparse_index(counts, sqnorm)
+    params = KfParams(n, d, iblock_begin, iblock_end, p_max, shift, _lib.KF_IMPL["auto" if sparse else impl], d_valid,
+                      int(hist_m))
     rc_elems = int(lib.gg_kf_rowcnt_elems(n, iblock_begin, iblock_end))
     rowcnt = torch.empty(max(rc_elems, 1), dtype=torch.int64, device=dev)
     status = torch.empty(4, dtype=torch.int64, device=dev)
@@ -729,13 +752,22 @@ def kf_emit(counts: torch.Tensor, sqnorm: torch.Tensor, threshold, sq_max: int, 
     while True:
         recs = torch.empty((max(rec_capacity, 1), 4), dtype=torch.int32, device=dev)
         with _stage(f"k4_emit_d{d}"):
-            check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
-                                 rec_capacity, ptr(rowcnt), ptr(status), ptr(class_hist), _stream()), "gg_kf_emit")
+            if sparse:   # inverted-index join: only pairs that share a column can pass a threshold >= 0
+                check(lib.gg_kf_emit_sparse(ptr(sparse_index[0]), sparse_index[1], d, n, iblock_begin, iblock_end,
+                                            ptr(sqnorm), ptr(dmin_d), ptr(recs), rec_capacity, ptr(rowcnt), ptr(status),
+                                            _stream()), "gg_kf_emit_sparse")
+                status[3:4].copy_(sparse_index[2][0:1], non_blocking=True)   # [3] != 0: rows were not sparse after all
+            else:
+                check(lib.gg_kf_emit(C.byref(params), ptr(counts), ptr(sqnorm), ptr(dmin_d), ptr(scale_d), ptr(recs),
+                                     rec_capacity, ptr(rowcnt), ptr(status), ptr(class_hist), _stream()), "gg_kf_emit")
         if not sync:
             return recs, None, rowcnt, params, counts, status
         st_host = read_small(status).tolist()
         if int(st_host[2]) != 0:
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
+        if sparse and int(st_host[3]) != 0:   # not k-mer count rows: the dense kernels take over
+            return kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, "auto", rec_capacity, sync,
+                           class_hist, hist_m, retry)
         found, slots = int(st_host[0]), max(int(st_host[0]), int(st_host[1]))
         if slots <= rec_capacity or not retry:
             out = _Emit((recs[:min(slots, rec_capacity)], found, rowcnt, params, counts))
@@ -766,6 +798,7 @@ class StagedRecords:
         self.status4 = status      # device int64[4] while n_recs has not been read: [0] found, [2] pipeline error
         self.redo = redo           # re-scores the shard with room for a given number of records
         self.found = self.slots = None
+        self.sparse = False        # scored by the inverted-index join (status word [3]: rows were not sparse)
 
     def after_counts(self, mine):
         """``mine`` = this rank's status words as read by kf_resolve."""
@@ -773,6 +806,8 @@ class StagedRecords:
             raise GGError("KF tcgen05 kernel reported a pipeline time-out (mbarrier protocol error)")
         self.found = int(mine[0])
         self.slots = max(self.found, int(mine[1]))
+        if self.sparse and int(mine[3]) != 0:   # the sparse join met rows that are not sparse: score again, densely
+            self.slots = int(self.recs.shape[0]) + 1
         self.status4 = None
 
     def complete(self):
@@ -1056,16 +1091,32 @@ def kf_stage(counts: torch.Tensor, sqnorm: torch.Tensor, threshold: float = 0.0,
         guess = int(n**2 * keep_top_k) if keep_top_k is not None else 1 << 22
         # ... capped at 2 GB of records: at k=10 the budget alone would be 1.1e10 records (176 GB)
         rec_capacity = max(1 << 16, min(n_pairs, max(guess, 1 << 20), 1 << 27))
-        if keep_top_k is not None and pair_kernel_serves(d_valid, impl):
+        # impl="sparse": wide rows of k-mer counts are sparse (at most row_sum non-zero entries), and the inverted-index
+        # join scores only the pairs that share a column -- 1.5 % of them at small_k = 5 -- up to 200,000 nodes (one
+        # accumulator byte per node in shared memory).  On request only: at BASELINE config 4 it takes 1.28 + 0.12 ms
+        # (one row per CTA iteration, latency-bound) against 1.15 ms for the CTA-pair tensor kernel, which stays the default
+        lib = _lib.load()
+        use_sparse = impl == "sparse"
+        if use_sparse and not lib.gg_knn_sparse_eligible(d_valid, n, 1, 1):
+            raise ValueError("the sparse KF path needs 64..1024 columns and at most 200,000 nodes")
+        emit_impl = "sparse" if use_sparse else impl
+        sparse_index = kf_sparse_index(counts, sqnorm) if use_sparse else None
+        if keep_top_k is not None and not use_sparse and pair_kernel_serves(d_valid, impl):
             st.class_hist = torch.zeros(kf_hist_bins(int(sq_max)), dtype=torch.int64, device=counts.device)
         recs, _, rowcnt, params, scored, status = kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end,
-                                                          impl, rec_capacity=rec_capacity, sync=False,
-                                                          class_hist=st.class_hist, hist_m=row_sum)
+                                                          emit_impl, rec_capacity=rec_capacity, sync=False,
+                                                          class_hist=st.class_hist, hist_m=row_sum,
+                                                          sparse_index=sparse_index)
 
         def redo(room):
-            return kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, impl, rec_capacity=room)
+            # (a sparse staging whose rows turned out dense comes back here too: kf_emit then falls back by itself)
+            return kf_emit(counts, sqnorm, threshold, sq_max, iblock_begin, iblock_end, emit_impl, rec_capacity=room,
+                           sparse_index=sparse_index)
 
         st.staged = StagedRecords(recs, None, rowcnt, params, scored, status, redo)
+        st.staged.sparse = use_sparse
+        if use_sparse:
+            st.impl = "auto"   # what a later re-emission of this set (binding top-n, chunked) may use
     return st
 
 

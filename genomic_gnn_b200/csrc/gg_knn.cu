@@ -920,6 +920,149 @@ __global__ void __launch_bounds__(kSpThreads) knn_sparse_kernel(SparseArgs a, un
   }
 }
 
+// ---- the KF threshold edges of sparse wide rows through the same join (gg_kf_emit_sparse) ----------------------------
+// cos(i, j) > threshold needs dot(i, j) >= dmin[sq_i sq_j] >= 1, so only pairs that share a column can be edges.  One CTA
+// per row i accumulates dot(i, j) for the j > i of its posting lists, then every thread scans whole 128-column tiles of
+// the accumulator in column order (its range is at least one tile, so a candidate's rank inside its tile is a running
+// count of the thread): sweep 1 tests, clears what fails, counts per tile (rowcnt) and per thread; a warp scan + one
+// atomic reserves the record slots; sweep 2 writes the records {s, t, rank in tile, dot} and clears.  Same outputs as
+// gg_kf_emit: unordered records + per-(block pair, row, tile) counts for gg_kf_place.
+struct KfSparseArgs {
+  SparseIndex x;
+  int64_t n;
+  int ib0, ib1, n_jblocks, per_log2;
+  const int32_t* sqnorm;
+  const uint16_t* dmin;
+  uint8_t* rowcnt;
+  uint4* recs;
+  long long capacity;
+  unsigned long long* status;
+};
+
+__global__ void __launch_bounds__(kSpThreads) kf_sparse_kernel(KfSparseArgs a, unsigned int* row_cursor) {
+  extern __shared__ __align__(16) uint32_t sp_smem[];
+  const int acc_words = static_cast<int>((a.n + 3) / 4);
+  const int acc_alloc = (sp_phys(acc_words, a.per_log2) + 4) & ~3;
+  uint32_t* acc = sp_smem;
+  uint32_t* lists = acc + acc_alloc;
+  __shared__ int s_row;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < acc_alloc; i += kSpThreads) acc[i] = 0u;
+  __syncthreads();
+  const int64_t row_lo = static_cast<int64_t>(a.ib0) * GG_KF_BLOCK;
+  const int64_t row_hi = min(a.n, static_cast<int64_t>(a.ib1) * GG_KF_BLOCK);
+  unsigned long long found = 0;
+  while (true) {
+    if (threadIdx.x == 0) s_row = static_cast<int>(atomicAdd(row_cursor, 1u));
+    __syncthreads();
+    const int64_t row = row_lo + s_row;
+    __syncthreads();
+    if (row >= row_hi) break;
+    // posting lists of the row's columns (as sparse_accumulate), entries j > row only
+    const int cnt = a.x.rnz_n[row];
+    if (threadIdx.x < 32) {
+      uint32_t len = 0;
+      if (lane < cnt) {
+        const uint32_t ent = a.x.rnz[row * kSpMaxNnz + lane];
+        const uint32_t col = ent & 0xFFFFu;
+        const uint32_t first = a.x.col_start[col];
+        len = a.x.col_start[col + 1] - first;
+        lists[3 * lane] = first;
+        lists[3 * lane + 2] = ent >> 16;
+      }
+      uint32_t incl = len;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (lane < cnt) lists[3 * lane + 1] = incl - len;
+      if (lane == 31) {
+        lists[3 * kSpMaxNnz] = static_cast<uint32_t>(cnt);
+        lists[3 * kSpMaxNnz + 1] = incl;
+      }
+    }
+    __syncthreads();
+    const int n_lists = static_cast<int>(lists[3 * kSpMaxNnz]), total = static_cast<int>(lists[3 * kSpMaxNnz + 1]);
+    for (int t = threadIdx.x; t < total; t += kSpThreads) {
+      int e = 0;
+      while (e + 1 < n_lists && lists[3 * (e + 1) + 1] <= static_cast<uint32_t>(t)) ++e;
+      const uint32_t p = __ldg(a.x.post + lists[3 * e] + (t - lists[3 * e + 1]));
+      const uint32_t j = p & 0xFFFFFFu;
+      if (static_cast<int64_t>(j) <= row) continue;
+      atomicAdd(acc + sp_phys(static_cast<int>(j >> 2), a.per_log2), ((p >> 24) * lists[3 * e + 2]) << (8 * (j & 3u)));
+    }
+    __syncthreads();
+    const int per = 1 << a.per_log2;
+    const int w_lo = min(acc_words, static_cast<int>(threadIdx.x) * per), w_hi = min(acc_words, w_lo + per);
+    uint32_t* my_acc = acc + threadIdx.x;
+    const uint32_t sq_i = static_cast<uint32_t>(a.sqnorm[row]);
+    const int i_local = static_cast<int>(row >> 10) - a.ib0, r = static_cast<int>(row & (GG_KF_BLOCK - 1));
+    // sweep 1: exact test per non-zero column; what fails is cleared; per-tile counts go to rowcnt
+    int mine = 0;
+    for (int t0 = w_lo; t0 < w_hi; t0 += 32) {   // one 128-column tile = 32 words
+      unsigned int mask = 0;
+      const int span = min(32, w_hi - t0);
+      for (int i = 0; i < span; ++i) mask |= static_cast<unsigned int>(my_acc[t0 + i] != 0u) << i;
+      int tile_cnt = 0;
+      for (; mask; mask &= mask - 1) {
+        const int w = t0 + __ffs(mask) - 1;
+        uint32_t word = my_acc[w];
+        for (uint32_t bm = nonzero_bytes_sp(word); bm; bm &= bm - 1) {
+          const int b = (__ffs(bm) - 1) >> 3;
+          const uint32_t dot = (word >> (8 * b)) & 0xFFu;
+          const uint32_t sq_j = static_cast<uint32_t>(__ldg(a.sqnorm + 4 * w + b));
+          if (dot >= __ldg(a.dmin + sq_i * sq_j)) ++tile_cnt;
+          else word &= ~(0xFFu << (8 * b));
+        }
+        my_acc[w] = word;
+      }
+      if (tile_cnt) {
+        const int tile_g = t0 >> 5;   // global tile index: column block = tile_g / 8, tile inside it = tile_g % 8
+        a.rowcnt[((static_cast<long long>(i_local) * a.n_jblocks + (tile_g >> 3)) * GG_KF_BLOCK + r) * 8 + (tile_g & 7)] =
+            static_cast<uint8_t>(tile_cnt);
+        mine += tile_cnt;
+      }
+    }
+    // record slots: one atomic per warp
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long base = 0;
+    if (warp_total) {
+      if (lane == 31) base = atomicAdd(a.status, static_cast<unsigned long long>(warp_total));
+      base = __shfl_sync(0xFFFFFFFFu, base, 31) + (incl - mine);
+    }
+    found += mine;
+    // sweep 2: what is left in the accumulator are the candidates
+    if (mine) {
+      for (int t0 = w_lo; t0 < w_hi; t0 += 32) {
+        unsigned int mask = 0;
+        const int span = min(32, w_hi - t0);
+        for (int i = 0; i < span; ++i) mask |= static_cast<unsigned int>(my_acc[t0 + i] != 0u) << i;
+        uint32_t rank = 0;
+        for (; mask; mask &= mask - 1) {
+          const int w = t0 + __ffs(mask) - 1;
+          const uint32_t word = my_acc[w];
+          my_acc[w] = 0u;
+          for (uint32_t bm = nonzero_bytes_sp(word); bm; bm &= bm - 1) {
+            const int b = (__ffs(bm) - 1) >> 3;
+            if (static_cast<long long>(base) < a.capacity)
+              a.recs[base] = make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>(4 * w + b), rank,
+                                        (word >> (8 * b)) & 0xFFu);
+            ++base;
+            ++rank;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  (void)found;
+}
+
 int sparse_per_log2(int64_t n) {
   const int64_t acc_words = (n + 3) / 4;
   int lg = 0;
@@ -1115,7 +1258,6 @@ extern "C" int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t
 
 /* ---- sparse (inverted-index) flavour of the two passes: rows with at most 16 non-zero counts, up to 200,000 nodes ------ */
 extern "C" int gg_knn_sparse_eligible(int pitch, int64_t n, int n_sq, int n_ranks) {
-  if (g_knn_impl.load() != 0 && g_knn_impl.load() != 3) return 0;
   if (pitch < 64 || pitch > 1024 || pitch % 4 != 0 || n < 2 || n > kSpMaxNodes || n_sq < 1 || n_sq > 32) return 0;
   const size_t worst = sparse_smem(n, n_ranks, n_sq, 1) > sparse_smem(n, n_ranks, n_sq, 2) ? sparse_smem(n, n_ranks, n_sq, 1)
                                                                                              : sparse_smem(n, n_ranks, n_sq, 2);
@@ -1233,6 +1375,56 @@ extern "C" int gg_knn_sparse_write(void* index, size_t index_bytes, int pitch, i
   const int64_t m = row_end - row_begin;
   OrderArgs o{recs, row_offsets, m, row_begin, n_ranks, cursors, sqnorm, metric, qmax, edge_src, edge_dst, weight};
   order_kernel<<<static_cast<unsigned>((m * 32 + 255) / 256), 256, 0, s>>>(o);
+  GG_CUDA_CHECK(cudaGetLastError());
+  return GG_OK;
+}
+
+/* KF threshold edges of sparse wide rows (an index of gg_knn_sparse_index over the same counts): the outputs of gg_kf_emit
+ * -- unordered records + per-(block pair, row, tile) counts, kf_status[0] = candidates found (may exceed rec_capacity:
+ * score again with more room) -- without forming the zero dots.  dmin as for gg_kf_emit (p_max + 1 entries). */
+extern "C" int gg_kf_emit_sparse(void* index, size_t index_bytes, int pitch, int64_t n, int iblock_begin, int iblock_end,
+                                 const int32_t* sqnorm, const uint16_t* dmin, gg_kf_rec_t* recs, int64_t rec_capacity,
+                                 uint64_t* rowcnt, int64_t* kf_status, gg_stream_t st) {
+  GG_REQUIRE(index && sqnorm && dmin && rowcnt && kf_status, GG_ERR_ARG, "null argument");
+  GG_REQUIRE(n >= 2 && n <= kSpMaxNodes && pitch >= 4 && pitch <= 1024, GG_ERR_ARG, "bad shape");
+  const int nb = static_cast<int>((n + GG_KF_BLOCK - 1) / GG_KF_BLOCK);
+  GG_REQUIRE(iblock_begin >= 0 && iblock_begin <= iblock_end && iblock_end <= nb, GG_ERR_ARG, "bad row-block shard");
+  GG_REQUIRE(rec_capacity >= 0 && (rec_capacity == 0 || recs), GG_ERR_ARG, "record buffer");
+  cudaStream_t s = gg::as_stream(st);
+  GG_CUDA_CHECK(cudaMemsetAsync(kf_status, 0, 4 * sizeof(int64_t), s));
+  const size_t rc_elems = gg_kf_rowcnt_elems(n, iblock_begin, iblock_end);
+  if (rc_elems == 0) return GG_OK;
+  GG_CUDA_CHECK(cudaMemsetAsync(rowcnt, 0, rc_elems * sizeof(uint64_t), s));
+  KfSparseArgs a{};
+  a.x = sparse_carve(index, n, pitch);
+  GG_REQUIRE(index_bytes >= a.x.total, GG_ERR_WORKSPACE, "index workspace too small");
+  a.n = n;
+  a.ib0 = iblock_begin;
+  a.ib1 = iblock_end;
+  a.n_jblocks = nb;
+  a.per_log2 = sparse_per_log2(n) < 5 ? 5 : sparse_per_log2(n);   // a thread scans whole 128-column tiles
+  a.sqnorm = sqnorm;
+  a.dmin = dmin;
+  a.rowcnt = reinterpret_cast<uint8_t*>(rowcnt);
+  a.recs = reinterpret_cast<uint4*>(recs);
+  a.capacity = rec_capacity;
+  a.status = reinterpret_cast<unsigned long long*>(kf_status);
+  const size_t acc_words = (static_cast<size_t>(n) + 3) / 4;
+  const size_t smem = (((acc_words + (acc_words >> a.per_log2) + 4) & ~static_cast<size_t>(3)) + 3 * kSpMaxNnz + 4) *
+                      sizeof(uint32_t);
+  GG_REQUIRE(smem <= kSmemLimit, GG_ERR_ARG, "accumulator does not fit shared memory");
+  GG_CUDA_CHECK(cudaFuncSetAttribute(kf_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  GG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kf_sparse_kernel, kSpThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t row_lo = static_cast<int64_t>(iblock_begin) * GG_KF_BLOCK;
+  const int64_t row_hi = n < static_cast<int64_t>(iblock_end) * GG_KF_BLOCK ? n : static_cast<int64_t>(iblock_end) * GG_KF_BLOCK;
+  const int64_t rows = row_hi - row_lo;
+  if (rows <= 0) return GG_OK;
+  const int64_t cap = static_cast<int64_t>(gg::sm_count()) * per_sm;
+  unsigned int* cursor = a.x.cursor + 2;
+  GG_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(unsigned int), s));
+  kf_sparse_kernel<<<static_cast<unsigned>(rows < cap ? rows : cap), kSpThreads, smem, s>>>(a, cursor);
   GG_CUDA_CHECK(cudaGetLastError());
   return GG_OK;
 }

@@ -437,6 +437,11 @@ GG_API int gg_knn_write(const uint8_t* counts, int pitch, int64_t n, int64_t row
  * (gg_knn_sparse_index_bytes); idx_status (device int64[2]): [0] != 0 = a row holds more than 16 non-zero counts, the
  * index must not be used.  gg_knn_sparse_count / gg_knn_sparse_write replace gg_knn_count / gg_knn_write between the same
  * gg_knn_plan calls (recs: row_offsets[m] words); results are identical. */
+/* The KF THRESHOLD edges (gg_kf_emit's job) of the same sparse wide rows through the same index: a pair can only be an
+ * edge when it shares a column.  Outputs as gg_kf_emit (records + rowcnt + kf_status[0]); feed them to gg_kf_place. */
+GG_API int gg_kf_emit_sparse(void* index, size_t index_bytes, int pitch, int64_t n, int iblock_begin, int iblock_end,
+                      const int32_t* sqnorm, const uint16_t* dmin, gg_kf_rec_t* recs, int64_t rec_capacity, uint64_t* rowcnt,
+                      int64_t* kf_status, gg_stream_t st);
 GG_API int gg_knn_sparse_eligible(int pitch, int64_t n, int n_sq, int n_ranks);
 GG_API size_t gg_knn_sparse_index_bytes(int64_t n, int pitch);
 GG_API int gg_knn_sparse_index(const uint8_t* counts, int pitch, int64_t n, const int32_t* sqnorm, const uint8_t* sqid,

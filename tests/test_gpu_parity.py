@@ -271,6 +271,40 @@ def test_kf_tcgen05_matches_generic(gg, k, s, n_reads, thr):
 
 
 @pytest.mark.parametrize("k,s,n_reads,thr", [
+    (6, 4, 4000, 0.5),     # D = 256, N = 4096: a thread scans one tile
+    (6, 5, 4000, 0.0),     # D = 1024, threshold 0: every pair that shares a column is an edge
+    (7, 5, 150, 0.3),      # ragged N: partial last tile and row block
+    (8, 5, 3000, 0.7),     # N ~ 65k: the BASELINE config 4 shape
+    (8, 3, 3000, 0.9),     # D = 64: long posting lists (on request only)
+])
+def test_kf_sparse_join_matches_tensor_path(gg, k, s, n_reads, thr):
+    """KF threshold edges of wide, sparse rows through the inverted-index join (impl="sparse") against the tensor / generic
+    kernels: identical edges, order and weights, whole and as a shard."""
+    from genomic_gnn_b200 import core
+
+    reads = fast.synthetic_reads(n_reads, 150, seed=21 + k + s)
+    built = core.build_graph(reads, k, str(s), with_kf=False)
+    kc = built.kf_counts[0]
+    ref_impl = "tcgen05x2" if 4**s >= 128 else "naive"
+    a = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl=ref_impl)
+    b = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="sparse", row_sum=kc.m)
+    assert a.edge_index.shape[1] > 0
+    assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.weight64, b.weight64)
+    nb = (built.db.num_nodes + 1023) // 1024
+    if nb >= 3:
+        a1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl=ref_impl, iblock_begin=1, iblock_end=3)
+        b1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="sparse", iblock_begin=1, iblock_end=3,
+                           row_sum=kc.m)
+        assert torch.equal(a1.edge_index, b1.edge_index) and torch.equal(a1.weight64, b1.weight64)
+    # a binding top-n on the join's candidates: placed, histogrammed and selected as packed words
+    top = 0.002
+    ei, w = fast.kf_edges_exact(kc.counts.cpu().numpy(), thr, top) if built.db.num_nodes <= 4096 else (None, None)
+    if ei is not None:
+        cut = core.kf_edges(kc.counts, kc.sqnorm, thr, top, sq_max=kc.m**2, impl="sparse", row_sum=kc.m)
+        assert np.array_equal(cut.edge_index.cpu().numpy(), ei) and np.array_equal(cut.weight64.cpu().numpy(), w)
+
+
+@pytest.mark.parametrize("k,s,n_reads,thr", [
     (9, 2, 400_000, 0.93),   # N ~ 262k: 256 column blocks = four 64-block windows per class, shard across windows
     (8, 1, 200_000, 0.995),  # 4 columns: a few hundred classes with thousands of members (member sweeps, dense rows)
 ])
