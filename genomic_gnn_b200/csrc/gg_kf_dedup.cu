@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(RowsCfg<PLACE, BIG>::kRowThreads) class_rows_k
     const int m0 = __ldg(a.class_start + c), m1 = __ldg(a.class_start + c + 1);
     // members ascend: skip classes without a row in this shard (uniform across the CTA).  The first member at or
     // after row_lo decides: shards of a few row blocks (top-n chunks) hold a member of only a few percent of the classes
-    {
+    if (a.ib0 > 0 || a.ib1 < a.n_jblocks) {  // a shard that holds every row needs no search (two dependent loads per class)
       const int first_in = m1 - members_at_or_after(a.members, m0, m1, row_lo);
       if (first_in >= m1 || __ldg(a.members + first_in) >= row_hi) {
         __syncthreads();  // s_class is rewritten at the top of the loop
