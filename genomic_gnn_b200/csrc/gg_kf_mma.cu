@@ -22,8 +22,6 @@
 //     the tensor pipe ahead of the epilogues.
 #include <cuda.h>
 
-#include <cstdlib>
-
 #include "gg_kf_emit.cuh"
 #include "gg_knn_tc.cuh"
 
@@ -1322,7 +1320,6 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
 #pragma unroll 1
             for (int cc = 0; cc < kTile; cc += 32) {
               if (PASS == 1 && (my_seq + 4 * half + (cc >> 5)) % kEpiGroups != static_cast<uint32_t>(group)) continue;
-              if (a.debug_skip == 1) continue;
               uint32_t v[32];
               tc_ld32(taddr + cc, v);
               uint32_t w[8];
@@ -1331,7 +1328,7 @@ knn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, KnnTcArgs a, int n_
               uint32_t wmask = 0;  // non-zero words
 #pragma unroll
               for (int j = 0; j < 8; ++j) wmask |= static_cast<uint32_t>(w[j] != 0u) << j;
-              if (!row_ok || a.debug_skip == 2) wmask = 0;
+              if (!row_ok) wmask = 0;
               const long long cbase = c0 + cc;            // global column of bit 0
               const long long self = row - cbase;          // bit of the row's own column, if inside the chunk
               if (PASS == 1) {
@@ -1680,12 +1677,7 @@ int knn_tc_launch(const KnnTcArgs& a, int pass, int* error_flag, cudaStream_t s)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  KnnTcArgs args = a;
-  {
-    const char* e = getenv("GG_KNN_DEBUG_SKIP");   // timing experiments only: 1 = no epilogue work, 2 = no per-pair work
-    args.debug_skip = e ? atoi(e) : 0;
-  }
-  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, args, n_bstages, error_flag, g));
+  GG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmap, a, n_bstages, error_flag, g));
   return GG_OK;
 }
 

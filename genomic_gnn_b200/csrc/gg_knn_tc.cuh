@@ -26,7 +26,6 @@ struct KnnTcArgs {
   // column order, and third_cnt[3 * row + g] says how many.  Every third keeps at most tie_left members of the cut rank.
   uint64_t* recs;
   uint32_t* third_cnt;
-  int debug_skip;              // GG_KNN_DEBUG_SKIP (timing experiments; results are wrong when set)
 };
 
 // true when the tensor path can serve this shape (gg_knn.cu falls back to its mma.sync kernel otherwise)

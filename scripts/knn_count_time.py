@@ -28,4 +28,4 @@ a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 a.record()
 for _ in range(5): run()
 b.record(); torch.cuda.synchronize()
-print(f"skip={os.environ.get('GG_KNN_DEBUG_SKIP','0')} N {n} D {pitch} n_ranks {n_ranks} n_sq {tab.shape[0]}: pass 1 {a.elapsed_time(b)/5:.3f} ms")
+print(f"N {n} D {pitch} n_ranks {n_ranks} n_sq {tab.shape[0]}: pass 1 (tcgen05) {a.elapsed_time(b)/5:.3f} ms")
