@@ -1733,9 +1733,17 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
             from . import dist
 
             b0, b1 = dist.kf_block_range(_row_blocks(db.num_nodes), comm.world, comm.rank)
-        # every set is scored first; ONE exchange / device read then brings the candidate counts of all of them
-        stages = [kf_stage(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl,
-                           iblock_begin=b0, iblock_end=b1, row_sum=kc.m) for kc in kcs]
+        # every set is scored first; ONE exchange / device read then brings the candidate counts of all of them.  Wide
+        # sets are queued first and the narrow (duplicate-row) sets only start their class kernels: the host then waits
+        # for the class count while the tensor kernel of the wide set runs (kf_stage(defer=True))
+        stages = [None] * len(kcs)
+        for i in sorted(range(len(kcs)), key=lambda j: -int(kcs[j].counts.shape[1])):
+            kc = kcs[i]
+            stages[i] = kf_stage(kc.counts, kc.sqnorm, edges_threshold, edges_keep_top_k, sq_max=kc.m * kc.m, impl=kf_impl,
+                                 iblock_begin=b0, iblock_end=b1, row_sum=kc.m, defer=True)
+        for st in stages:
+            if st.finish_stage is not None:
+                st.finish_stage()
         kf_resolve(stages, comm)
         out.kf = [kf_finish(st, comm, gather=kf_gather, chunk_records=kf_chunk_records, sink=kf_sink) for st in stages]
         for kf in out.kf:  # multi-GPU: the edge exchanges of earlier sets ran underneath the scoring of later ones
