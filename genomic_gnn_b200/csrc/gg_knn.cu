@@ -846,6 +846,7 @@ __global__ void __launch_bounds__(kSpThreads) knn_sparse_kernel(SparseArgs a, un
       // range is looked at once, 64 words at a time, for a bit mask of the words that matter (all of them when zero-dot
       // columns can be selected), and both sweeps walk the set bits.
       int n_sel = 0, n_tie = 0;
+      unsigned long long masks[4] = {0ull, 0ull, 0ull, 0ull};
       for (int pass2 = 0; pass2 < 2; ++pass2) {
         int sel_before = 0, tie_before = 0, tie_room = 0;
         long long out = 0;
@@ -855,15 +856,21 @@ __global__ void __launch_bounds__(kSpThreads) knn_sparse_kernel(SparseArgs a, un
           tie_room = budget - tie_before;   // members of the cut rank this thread may still take, in column order
           out = a.row_off[loc] + sel_before + (tie_before < budget ? tie_before : budget);
         }
-        for (int w0 = w_lo; w0 < w_hi; w0 += 64) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {   // a thread's range is at most 256 words: four masks, kept for the second sweep
+          const int w0 = w_lo + 64 * ch;
+          if (w0 >= w_hi) continue;
           const int span = min(64, w_hi - w0);
-          unsigned long long mask = 0;
-          if (zeros) {
-            mask = span == 64 ? ~0ull : ((1ull << span) - 1ull);
-          } else {
-            for (int i = 0; i < span; ++i) mask |= static_cast<unsigned long long>(my_acc[w0 + i] != 0u) << i;
+          if (!pass2) {
+            unsigned long long m0 = 0;
+            if (zeros) {
+              m0 = span == 64 ? ~0ull : ((1ull << span) - 1ull);
+            } else {
+              for (int i = 0; i < span; ++i) m0 |= static_cast<unsigned long long>(my_acc[w0 + i] != 0u) << i;
+            }
+            masks[ch] = m0;
           }
-          for (; mask; mask &= mask - 1) {
+          for (unsigned long long mask = masks[ch]; mask; mask &= mask - 1) {
             const int w = w0 + __ffsll(static_cast<long long>(mask)) - 1;
             const uint32_t word = my_acc[w];
             if (pass2 && word) my_acc[w] = 0u;   // clean for the next row
