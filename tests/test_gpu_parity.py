@@ -296,6 +296,9 @@ def test_kf_sparse_join_matches_tensor_path(gg, k, s, n_reads, thr):
         b1 = core.kf_edges(kc.counts, kc.sqnorm, thr, None, sq_max=kc.m**2, impl="sparse", iblock_begin=1, iblock_end=3,
                            row_sum=kc.m)
         assert torch.equal(a1.edge_index, b1.edge_index) and torch.equal(a1.weight64, b1.weight64)
+    # a record buffer that is too small: the join reports the exact count and is run again with room for it
+    small = core.kf_emit(kc.counts, kc.sqnorm, thr, kc.m**2, impl="sparse", rec_capacity=64)
+    assert small[1] == a.edge_index.shape[1] and small[0].shape[0] >= small[1] > 64
     # a binding top-n on the join's candidates: placed, histogrammed and selected as packed words
     top = 0.002
     ei, w = fast.kf_edges_exact(kc.counts.cpu().numpy(), thr, top) if built.db.num_nodes <= 4096 else (None, None)
