@@ -1704,9 +1704,7 @@ def build_graph(sequences, k: int, small_k="2", create_all_kmers=False, edges_th
         # than the default room is counted again with room for all
         db, fused_kcs, cr = count_db_counts(stream, k, [int(s) for s in str(small_k).split(",")], create_all_kmers)
         if db is None:
-            try:
-                if cr.n_bridges == -1 and int(read_small(cr.status)[_lib.ST_BRIDGES]) > int(cr.bridges.shape[0]):
-                    raise _NeedBridges(int(read_small(cr.status)[_lib.ST_BRIDGES]))
+            try:   # (a count whose status is still unread, n_bridges == -1, is assembled speculatively once more)
                 db = build_db(cr, normalise=True, create_all_kmers=create_all_kmers)
             except _NeedBridges as need:
                 cr = count_kp1mers(stream, k, bridge_capacity=int(need.args[0]))
