@@ -958,7 +958,6 @@ __global__ void __launch_bounds__(kSpThreads) kf_sparse_kernel(KfSparseArgs a, u
   __syncthreads();
   const int64_t row_lo = static_cast<int64_t>(a.ib0) * GG_KF_BLOCK;
   const int64_t row_hi = min(a.n, static_cast<int64_t>(a.ib1) * GG_KF_BLOCK);
-  unsigned long long found = 0;
   while (true) {
     if (threadIdx.x == 0) s_row = static_cast<int>(atomicAdd(row_cursor, 1u));
     __syncthreads();
@@ -1042,7 +1041,6 @@ __global__ void __launch_bounds__(kSpThreads) kf_sparse_kernel(KfSparseArgs a, u
       if (lane == 31) base = atomicAdd(a.status, static_cast<unsigned long long>(warp_total));
       base = __shfl_sync(0xFFFFFFFFu, base, 31) + (incl - mine);
     }
-    found += mine;
     // sweep 2: what is left in the accumulator are the candidates
     if (mine) {
       for (int t0 = w_lo; t0 < w_hi; t0 += 32) {
@@ -1067,7 +1065,6 @@ __global__ void __launch_bounds__(kSpThreads) kf_sparse_kernel(KfSparseArgs a, u
     }
     __syncthreads();
   }
-  (void)found;
 }
 
 int sparse_per_log2(int64_t n) {
